@@ -1,0 +1,629 @@
+// api.cu -- the C ABI of libgpad_b200.so (include/gpad.h): handle management, operator
+// conversion, path selection and the host loop that drives the kernels.  Replaces the body of
+// the reference's main() between readData and the D2H copies (main.cu:108-180).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "batch_common.cuh"
+#include "batch_tc.h"
+#include "gpad_internal.h"
+#include "latency.h"
+
+namespace gpad {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    cudaGetLastError();
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? GPAD_ERR_NO_DEVICE : GPAD_ERR_CUDA;
+}
+
+}  // namespace gpad
+
+using namespace gpad;
+
+struct gpad_handle_s {
+    gpad_config_t cfg{};
+    int n = 0, device = 0, num_sms = 0;
+    size_t smem_optin = 0;
+    std::string desc;
+    long long launches = 0;
+    cudaStream_t own_stream = nullptr;
+    std::vector<void*> allocs;
+
+    // ---- latency mode ----
+    lat::Params lp{};
+    int sync_mode = 0, G = 1, threads = 256;
+    bool ops_smem = false;
+    float *d_gP = nullptr, *d_pD = nullptr, *d_f = nullptr, *d_y0 = nullptr, *d_yprev0 = nullptr;
+    float *d_theta = nullptr, *d_beta = nullptr;
+    int sched_cap = 0;
+    std::vector<float> h_theta, h_beta;       // last uploaded schedule
+    float *o_ynext = nullptr, *o_y = nullptr, *o_z = nullptr, *o_zhat = nullptr, *o_w = nullptr;
+    int *o_iters = nullptr, *o_status = nullptr;
+    float *o_viol = nullptr, *o_gap = nullptr;
+    unsigned* d_flags = nullptr;              // [0] barrier counter, [1] nonfinite flag
+
+    // ---- batch mode ----
+    Operators op;
+    BatchState st;
+    tc::GemmDesc g1, g2;
+    float* stage_in = nullptr;                // staging for host-memory inputs/outputs [max_batch][max(n,m)]
+    int* h_active = nullptr;                  // pinned
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(gpad_handle_s* h, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        cudaGetLastError();
+        return GPAD_ERR_ALLOC;
+    }
+    h->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return GPAD_OK;
+}
+#define GPAD_TRY(expr) do { int rc__ = (expr); if (rc__ != GPAD_OK) return rc__; } while (0)
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// operators -> host, sequential layout (M_G [n][m], G_L [m][n])
+int fetch_operators(const gpad_config_t& c, const float* M_G, const float* G_L, size_t count_each, int copies,
+                    std::vector<float>& MG, std::vector<float>& GL) {
+    const size_t total = count_each * copies;
+    std::vector<float> a(total), b(total);
+    if (c.operators_mem == GPAD_MEM_DEVICE) {
+        GPAD_CUDA(cudaMemcpy(a.data(), M_G, total * sizeof(float), cudaMemcpyDeviceToHost));
+        GPAD_CUDA(cudaMemcpy(b.data(), G_L, total * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+        memcpy(a.data(), M_G, total * sizeof(float));
+        memcpy(b.data(), G_L, total * sizeof(float));
+    }
+    if (c.layout == GPAD_LAYOUT_SEQUENTIAL) { MG.swap(a); GL.swap(b); return GPAD_OK; }
+    const int n = c.n_u * c.N, m = c.m;
+    MG.resize(total); GL.resize(total);
+    for (int k = 0; k < copies; ++k) {
+        const float* fa = a.data() + k * count_each; const float* fb = b.data() + k * count_each;
+        float* sa = MG.data() + k * count_each; float* sb = GL.data() + k * count_each;
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i < n; ++i) sa[(size_t)i * m + j] = fa[(size_t)j * n + i];    // flipped M_G is [m][n]
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < m; ++i) sb[(size_t)i * n + j] = fb[(size_t)j * m + i];    // flipped G_L is [n][m]
+    }
+    return GPAD_OK;
+}
+
+// rows x cols (ld = cols) -> device rows_pad x ld_pad, zero padded
+int upload_padded(gpad_handle_s* h, const float* src, int rows, int cols, int rows_pad, int ld_pad, float** out) {
+    std::vector<float> tmp((size_t)rows_pad * ld_pad, 0.f);
+    for (int r = 0; r < rows; ++r) memcpy(&tmp[(size_t)r * ld_pad], src + (size_t)r * cols, sizeof(float) * cols);
+    GPAD_TRY(dev_alloc(h, out, tmp.size()));
+    GPAD_CUDA(cudaMemcpy(*out, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return GPAD_OK;
+}
+
+// ------------------------------------------------------------------ latency mode
+int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vector<float>& GL) {
+    const int n = h->n, m = h->cfg.m;
+    lat::Params& p = h->lp;
+    p.n = n; p.m = m; p.nld = round_up(n, 4); p.mld = round_up(m, 4);
+    float *dMG, *dGL;
+    GPAD_TRY(upload_padded(h, MG.data(), n, m, n, p.mld, &dMG));
+    GPAD_TRY(upload_padded(h, GL.data(), m, n, m, p.nld, &dGL));
+    p.M_G = dMG; p.G_L = dGL;
+    p.L = h->cfg.L;
+
+    // ---- plan: how many CTAs cooperate, how they synchronise, where the operators live ----
+    const size_t limit = h->smem_optin;
+    auto configure = [&](int G) {
+        p.rows_a = (n + G - 1) / G; p.rows_b = (m + G - 1) / G;
+        p.rows_a_pad = round_up(p.rows_a, 4); p.rows_b_pad = round_up(p.rows_b, 4);
+        p.g_pad = round_up(G, 4);
+    };
+    const size_t op_elems = (size_t)n * p.mld + (size_t)m * p.nld;
+    int sync = -1, G = 1; bool ops = false;
+    const char* env = getenv("GPAD_LATENCY_PLAN");    // "block" | "cluster:<C>" | "grid:<G>" (experiments)
+    if (env && !strncmp(env, "block", 5)) { sync = lat::SYNC_BLOCK; G = 1; }
+    else if (env && !strncmp(env, "cluster:", 8)) { sync = lat::SYNC_CLUSTER; G = atoi(env + 8); }
+    else if (env && !strncmp(env, "grid:", 5)) { sync = lat::SYNC_GRID; G = atoi(env + 5); }
+    if (sync < 0) {
+        configure(1);
+        if (op_elems <= 16384 && lat::smem_bytes(p, true) <= limit) { sync = lat::SYNC_BLOCK; G = 1; }
+    }
+    if (sync < 0) {
+        // largest co-schedulable cluster whose per-CTA operator slice fits in shared memory
+        for (int C : {16, 8, 4, 2}) {
+            configure(C);
+            const size_t need = lat::smem_bytes(p, true);
+            if (need > limit || p.rows_b < 8) continue;
+            if (C > lat::max_cluster_size(true, lat::kMaxThreads, need)) continue;
+            sync = lat::SYNC_CLUSTER; G = C;
+            break;
+        }
+    }
+    if (sync < 0) { sync = lat::SYNC_GRID; G = h->num_sms; }
+    if (G < 1) G = 1;
+    if (sync == lat::SYNC_GRID) G = std::min(G, h->num_sms);
+    if (sync == lat::SYNC_CLUSTER) G = std::min(G, 16);
+    configure(G);
+    ops = lat::smem_bytes(p, true) <= limit;
+    if (getenv("GPAD_LATENCY_NO_SMEM_OPS")) ops = false;
+    if (lat::smem_bytes(p, ops) > limit) {
+        set_error("latency mode: vectors of n=%d, m=%d do not fit in shared memory", n, m);
+        return GPAD_ERR_UNSUPPORTED;
+    }
+    h->sync_mode = sync; h->G = G; h->ops_smem = ops;
+    p.lpr_a = std::min(32, next_pow2(std::max(1, p.mld / 4)));
+    p.lpr_b = std::min(32, next_pow2(std::max(1, p.nld / 4)));
+    const int want = std::max(p.rows_a * p.lpr_a, p.rows_b * p.lpr_b);
+    h->threads = std::min(lat::kMaxThreads, std::max(64, round_up(want, 32)));
+    if (const char* t = getenv("GPAD_LATENCY_THREADS")) h->threads = std::max(32, std::min(lat::kMaxThreads, atoi(t) / 32 * 32));
+
+    // per-solve device buffers
+    GPAD_TRY(dev_alloc(h, &h->d_gP, n)); GPAD_TRY(dev_alloc(h, &h->d_pD, m)); GPAD_TRY(dev_alloc(h, &h->d_f, n));
+    GPAD_TRY(dev_alloc(h, &h->d_y0, m)); GPAD_TRY(dev_alloc(h, &h->d_yprev0, m));
+    GPAD_TRY(dev_alloc(h, &h->o_ynext, m)); GPAD_TRY(dev_alloc(h, &h->o_y, m)); GPAD_TRY(dev_alloc(h, &h->o_w, m));
+    GPAD_TRY(dev_alloc(h, &h->o_z, n)); GPAD_TRY(dev_alloc(h, &h->o_zhat, n));
+    GPAD_TRY(dev_alloc(h, &h->o_iters, 1)); GPAD_TRY(dev_alloc(h, &h->o_status, 1));
+    GPAD_TRY(dev_alloc(h, &h->o_viol, 1)); GPAD_TRY(dev_alloc(h, &h->o_gap, 1));
+    GPAD_TRY(dev_alloc(h, &p.x_w, p.mld)); GPAD_TRY(dev_alloc(h, &p.x_zhat, p.nld));
+    GPAD_TRY(dev_alloc(h, &p.x_red, 3 * 8 * p.g_pad));
+    GPAD_TRY(dev_alloc(h, &h->d_flags, 2));
+    p.barrier = h->d_flags; p.nonfinite_flag = reinterpret_cast<int*>(h->d_flags + 1);
+
+    char buf[256];
+    snprintf(buf, sizeof(buf), "latency: persistent kernel, %s x%d CTAs, %d threads, operators %s, smem %zu B/CTA",
+             sync == lat::SYNC_BLOCK ? "single-CTA" : sync == lat::SYNC_CLUSTER ? "cluster(DSMEM)" : "cooperative-grid",
+             G, h->threads, ops ? "in shared memory" : "streamed from L2", lat::smem_bytes(p, ops));
+    h->desc = buf;
+    return GPAD_OK;
+}
+
+int upload_schedule(gpad_handle_s* h, const float* theta, const float* beta, int count, cudaStream_t s) {
+    if ((int)h->h_theta.size() == count && !memcmp(h->h_theta.data(), theta, sizeof(float) * count) &&
+        !memcmp(h->h_beta.data(), beta, sizeof(float) * count))
+        return GPAD_OK;
+    if (count > h->sched_cap) {
+        const int cap = std::max(count, 256);
+        GPAD_TRY(dev_alloc(h, &h->d_theta, cap)); GPAD_TRY(dev_alloc(h, &h->d_beta, cap));
+        h->sched_cap = cap;
+    }
+    h->h_theta.assign(theta, theta + count);
+    h->h_beta.assign(beta, beta + count);
+    GPAD_CUDA(cudaMemcpyAsync(h->d_theta, h->h_theta.data(), sizeof(float) * count, cudaMemcpyHostToDevice, s));
+    GPAD_CUDA(cudaMemcpyAsync(h->d_beta, h->h_beta.data(), sizeof(float) * count, cudaMemcpyHostToDevice, s));
+    return GPAD_OK;
+}
+
+int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
+    const int n = h->n, m = h->cfg.m;
+    const bool host = a->mem == GPAD_MEM_HOST;
+    cudaStream_t s = host ? h->own_stream : static_cast<cudaStream_t>(a->stream);
+    GPAD_TRY(upload_schedule(h, a->theta, a->beta, a->max_iter, s));
+    lat::Params p = h->lp;
+    if (host) {
+        GPAD_CUDA(cudaMemcpyAsync(h->d_gP, a->g_P, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+        GPAD_CUDA(cudaMemcpyAsync(h->d_pD, a->p_D, sizeof(float) * m, cudaMemcpyHostToDevice, s));
+        if (a->f) GPAD_CUDA(cudaMemcpyAsync(h->d_f, a->f, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+        if (a->y0) GPAD_CUDA(cudaMemcpyAsync(h->d_y0, a->y0, sizeof(float) * m, cudaMemcpyHostToDevice, s));
+        if (a->y_prev0) GPAD_CUDA(cudaMemcpyAsync(h->d_yprev0, a->y_prev0, sizeof(float) * m, cudaMemcpyHostToDevice, s));
+        p.g_P = h->d_gP; p.p_D = h->d_pD; p.f = a->f ? h->d_f : nullptr;
+        p.y0 = a->y0 ? h->d_y0 : nullptr; p.y_prev0 = a->y_prev0 ? h->d_yprev0 : nullptr;
+    } else {
+        p.g_P = a->g_P; p.p_D = a->p_D; p.f = a->f; p.y0 = a->y0; p.y_prev0 = a->y_prev0;
+    }
+    p.theta = h->d_theta; p.beta = h->d_beta;
+    p.max_iter = a->max_iter; p.check_every = a->check_every > 0 ? a->check_every : 0;
+    p.eps_g = a->eps_g; p.eps_V = a->eps_V;
+    // in device mode the kernel writes straight into the caller's buffers; the two vectors the
+    // dual-gap branch parks (w, zhat) always need real storage
+    const bool dev = !host;
+    p.out_y_next = dev && a->y_next ? a->y_next : h->o_ynext;
+    p.out_y = dev && a->y ? a->y : h->o_y;
+    p.out_z = dev && a->z ? a->z : h->o_z;
+    p.out_zhat = dev && a->zhat ? a->zhat : h->o_zhat;
+    p.out_w = dev && a->w ? a->w : h->o_w;
+    p.out_iters = dev && a->iters ? a->iters : h->o_iters;
+    p.out_status = dev && a->status ? a->status : h->o_status;
+    p.out_max_viol = dev && a->max_viol ? a->max_viol : h->o_viol;
+    p.out_gap = dev && a->gap ? a->gap : h->o_gap;
+    GPAD_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned), s));
+    GPAD_TRY(lat::launch(p, h->sync_mode, h->ops_smem, h->G, h->threads, s));
+    h->launches += 1;
+    if (host) {
+        if (a->y_next) GPAD_CUDA(cudaMemcpyAsync(a->y_next, h->o_ynext, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
+        if (a->y) GPAD_CUDA(cudaMemcpyAsync(a->y, h->o_y, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
+        if (a->w) GPAD_CUDA(cudaMemcpyAsync(a->w, h->o_w, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
+        if (a->z) GPAD_CUDA(cudaMemcpyAsync(a->z, h->o_z, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+        if (a->zhat) GPAD_CUDA(cudaMemcpyAsync(a->zhat, h->o_zhat, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+        if (a->iters) GPAD_CUDA(cudaMemcpyAsync(a->iters, h->o_iters, sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (a->status) GPAD_CUDA(cudaMemcpyAsync(a->status, h->o_status, sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (a->max_viol) GPAD_CUDA(cudaMemcpyAsync(a->max_viol, h->o_viol, sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (a->gap) GPAD_CUDA(cudaMemcpyAsync(a->gap, h->o_gap, sizeof(float), cudaMemcpyDeviceToHost, s));
+        GPAD_CUDA(cudaStreamSynchronize(s));
+    }
+    return GPAD_OK;
+}
+
+// ------------------------------------------------------------------ batch (shared operators)
+int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vector<float>& GL) {
+    const int n = h->n, m = h->cfg.m;
+    const bool tcp = h->cfg.precision == GPAD_PREC_TF32X3;
+    BatchState& st = h->st;
+    st.n = n; st.m = m; st.np = round_up(n, 32); st.mp = round_up(m, 32);
+    st.Bp = round_up(h->cfg.max_batch, 128);
+    int bn1 = 0, nt1 = 0, bn2 = 0, nt2 = 0;
+    tc::plan_tiles(n, &bn1, &nt1);
+    tc::plan_tiles(m, &bn2, &nt2);
+    h->op.n_rows_pad = round_up(std::max(bn1 * nt1, n), 128);
+    h->op.m_rows_pad = round_up(std::max(bn2 * nt2, m), 128);
+    GPAD_TRY(upload_padded(h, MG.data(), n, m, h->op.n_rows_pad, st.mp, &h->op.M_G));
+    GPAD_TRY(upload_padded(h, GL.data(), m, n, h->op.m_rows_pad, st.np, &h->op.G_L));
+    const size_t bm = (size_t)st.Bp * st.mp, bnn = (size_t)st.Bp * st.np;
+    GPAD_TRY(dev_alloc(h, &st.g_P, bnn)); GPAD_TRY(dev_alloc(h, &st.p_D, bm)); GPAD_TRY(dev_alloc(h, &st.f, bnn));
+    GPAD_TRY(dev_alloc(h, &st.y[0], bm)); GPAD_TRY(dev_alloc(h, &st.y[1], bm)); GPAD_TRY(dev_alloc(h, &st.w, bm));
+    GPAD_TRY(dev_alloc(h, &st.z, bnn)); GPAD_TRY(dev_alloc(h, &st.zhat, bnn)); GPAD_TRY(dev_alloc(h, &st.sbar, bm));
+    GPAD_TRY(dev_alloc(h, &st.red, (size_t)st.Bp * kRedStride));
+    GPAD_TRY(dev_alloc(h, &st.done, st.Bp)); GPAD_TRY(dev_alloc(h, &st.iters, st.Bp)); GPAD_TRY(dev_alloc(h, &st.status, st.Bp));
+    GPAD_TRY(dev_alloc(h, &st.max_viol, st.Bp)); GPAD_TRY(dev_alloc(h, &st.gap, st.Bp));
+    GPAD_TRY(dev_alloc(h, &st.active_count, 1));
+    GPAD_TRY(dev_alloc(h, &h->stage_in, (size_t)h->cfg.max_batch * std::max(n, m)));
+    GPAD_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_active), sizeof(int)));
+    char buf[320];
+    if (tcp) {
+        GPAD_TRY(dev_alloc(h, &st.w_hi, bm)); GPAD_TRY(dev_alloc(h, &st.w_lo, bm));
+        GPAD_TRY(dev_alloc(h, &st.zh_hi, bnn)); GPAD_TRY(dev_alloc(h, &st.zh_lo, bnn));
+        GPAD_CUDA(cudaMemset(st.zh_hi, 0, bnn * sizeof(float))); GPAD_CUDA(cudaMemset(st.zh_lo, 0, bnn * sizeof(float)));
+        const size_t c1 = (size_t)h->op.n_rows_pad * st.mp, c2 = (size_t)h->op.m_rows_pad * st.np;
+        GPAD_TRY(dev_alloc(h, &h->op.M_G_lo, c1)); GPAD_TRY(dev_alloc(h, &h->op.G_L_lo, c2));
+        GPAD_TRY(tc::launch_split(h->op.M_G, h->op.M_G, h->op.M_G_lo, c1, nullptr));
+        GPAD_TRY(tc::launch_split(h->op.G_L, h->op.G_L, h->op.G_L_lo, c2, nullptr));
+        GPAD_CUDA(cudaDeviceSynchronize());
+        int bk = 16;
+        if (const char* e = getenv("GPAD_TC_BK")) bk = atoi(e) == 32 ? 32 : 16;
+        tc::GemmDesc& g1 = h->g1; tc::GemmDesc& g2 = h->g2;
+        g1.bk = g2.bk = bk;
+        g1.k_pad = st.mp; g1.bn = bn1; g1.n_tiles = nt1; g1.ncols_valid = n;
+        g2.k_pad = st.np; g2.bn = bn2; g2.n_tiles = nt2; g2.ncols_valid = m;
+        g1.stages = tc::pick_stages(bk, bn1, h->smem_optin);
+        g2.stages = tc::pick_stages(bk, bn2, h->smem_optin);
+        if (const char* e = getenv("GPAD_TC_STAGES")) { g1.stages = std::min(g1.stages, std::max(2, atoi(e))); g2.stages = std::min(g2.stages, std::max(2, atoi(e))); }
+        GPAD_TRY(tc::make_tmap(&g1.tmA_hi, st.w_hi, st.mp, st.Bp, st.mp, bk, 128));
+        GPAD_TRY(tc::make_tmap(&g1.tmA_lo, st.w_lo, st.mp, st.Bp, st.mp, bk, 128));
+        GPAD_TRY(tc::make_tmap(&g1.tmB_hi, h->op.M_G, st.mp, h->op.n_rows_pad, st.mp, bk, bn1));
+        GPAD_TRY(tc::make_tmap(&g1.tmB_lo, h->op.M_G_lo, st.mp, h->op.n_rows_pad, st.mp, bk, bn1));
+        GPAD_TRY(tc::make_tmap(&g2.tmA_hi, st.zh_hi, st.np, st.Bp, st.np, bk, 128));
+        GPAD_TRY(tc::make_tmap(&g2.tmA_lo, st.zh_lo, st.np, st.Bp, st.np, bk, 128));
+        GPAD_TRY(tc::make_tmap(&g2.tmB_hi, h->op.G_L, st.np, h->op.m_rows_pad, st.np, bk, bn2));
+        GPAD_TRY(tc::make_tmap(&g2.tmB_lo, h->op.G_L_lo, st.np, h->op.m_rows_pad, st.np, bk, bn2));
+        snprintf(buf, sizeof(buf),
+                 "batch-shared: tcgen05 kind::tf32 x3 (hi/lo split), TMA ring bk=%d, product1 tiles 128x%d x%d (%d stages), "
+                 "product2 tiles 128x%d x%d (%d stages), TMEM 2x256 cols, persistent over %d SMs",
+                 bk, bn1, nt1, g1.stages, bn2, nt2, g2.stages, h->num_sms);
+    } else {
+        snprintf(buf, sizeof(buf), "batch-shared: CUDA-core fp32 GEMM 128x128x16 tiles with fused GPAD epilogues");
+    }
+    h->desc = buf;
+    return GPAD_OK;
+}
+
+// user vector [B][len] (host or device) -> padded device rows [Bp][ld]; null src -> zeros
+int ingest(gpad_handle_s* h, float* dst, int ld, const float* src, int len, int B, bool host, cudaStream_t s) {
+    const float* dsrc = src;
+    if (src && host) {
+        GPAD_CUDA(cudaMemcpyAsync(h->stage_in, src, sizeof(float) * (size_t)B * len, cudaMemcpyHostToDevice, s));
+        dsrc = h->stage_in;
+    }
+    GPAD_TRY(launch_pad_rows(dst, ld, h->st.Bp, dsrc, len, B, s));
+    h->launches += 1;
+    return GPAD_OK;
+}
+
+int emit(gpad_handle_s* h, float* dst, int len, int B, const float* src, int ld, bool host, cudaStream_t s) {
+    if (!dst) return GPAD_OK;
+    float* ddst = host ? h->stage_in : dst;
+    GPAD_TRY(launch_unpad_rows(ddst, len, B, src, ld, s));
+    h->launches += 1;
+    if (host) GPAD_CUDA(cudaMemcpyAsync(dst, ddst, sizeof(float) * (size_t)B * len, cudaMemcpyDeviceToHost, s));
+    return GPAD_OK;
+}
+
+int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
+    BatchState& st = h->st;
+    const int n = st.n, m = st.m, B = a->batch;
+    const bool host = a->mem == GPAD_MEM_HOST;
+    const bool tcp = h->cfg.precision == GPAD_PREC_TF32X3;
+    const bool checking = a->check_every > 0;
+    cudaStream_t s = host ? h->own_stream : static_cast<cudaStream_t>(a->stream);
+    st.B = B;
+    GPAD_TRY(ingest(h, st.g_P, st.np, a->g_P, n, B, host, s));
+    GPAD_TRY(ingest(h, st.p_D, st.mp, a->p_D, m, B, host, s));
+    if (a->f) GPAD_TRY(ingest(h, st.f, st.np, a->f, n, B, host, s));
+    GPAD_TRY(ingest(h, st.y[0], st.mp, a->y0, m, B, host, s));
+    GPAD_TRY(ingest(h, st.y[1], st.mp, a->y_prev0, m, B, host, s));
+    GPAD_TRY(launch_batch_init(st, st.y[0], st.y[1], a->max_iter > 0 ? a->beta[0] : 0.f, tcp, checking, s));
+    GPAD_TRY(launch_batch_reset_term(st, a->max_iter, s));
+    h->launches += 2;
+
+    BatchKernelArgs k{};
+    k.n = n; k.m = m; k.np = st.np; k.mp = st.mp; k.B = B; k.checking = checking ? 1 : 0; k.L = h->cfg.L;
+    k.g_P = st.g_P; k.p_D = st.p_D; k.f = a->f ? st.f : nullptr;
+    k.w = st.w; k.w_hi = st.w_hi; k.w_lo = st.w_lo; k.z = st.z; k.zhat = st.zhat; k.zh_hi = st.zh_hi; k.zh_lo = st.zh_lo;
+    k.sbar = st.sbar; k.red = st.red; k.done = checking ? st.done : nullptr;
+    const int m_tiles = round_up(B, 128) / 128;
+    h->g1.m_tiles = m_tiles; h->g2.m_tiles = m_tiles;
+    const int Bp_call = m_tiles * 128;
+
+    int executed = 0;
+    for (int v = 0; v < a->max_iter; ++v) {
+        const bool check = checking && ((v + 1) % a->check_every == 0);
+        const bool last = v + 1 == a->max_iter;
+        k.it.theta = a->theta[v];
+        k.it.beta_next = last ? 0.f : a->beta[v + 1];
+        k.it.check = check ? 1 : 0;
+        k.it.last = (last || check) ? 1 : 0;     // on check iterations w advances after the decision
+        k.y_cur = st.y[v & 1];
+        k.y_next = st.y[(v + 1) & 1];
+        if (tcp) {
+            GPAD_TRY(tc::launch_gemm(1, h->g1, k, nullptr, 0, h->num_sms, s));
+            GPAD_TRY(tc::launch_gemm(2, h->g2, k, nullptr, 0, h->num_sms, s));
+        } else {
+            GPAD_TRY(launch_simt_iteration(h->op, k, Bp_call, s));
+        }
+        h->launches += 2;
+        executed = v + 1;
+        if (check) {
+            GPAD_TRY(launch_batch_decide(st, v + 1, h->cfg.L, a->eps_g, a->eps_V, a->f != nullptr, s));
+            h->launches += 1;
+            GPAD_CUDA(cudaMemcpyAsync(h->h_active, st.active_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+            GPAD_CUDA(cudaStreamSynchronize(s));
+            if (*h->h_active <= 0) break;
+            if (!last) {
+                GPAD_TRY(launch_batch_advance_w(st, k.y_next, k.y_cur, k.it.beta_next, tcp, s));
+                h->launches += 1;
+            }
+        }
+    }
+    (void)executed;
+    if (!checking && a->max_iter > 0) {
+        GPAD_TRY(launch_batch_finite(st, st.y[a->max_iter & 1], s));
+        h->launches += 1;
+    }
+
+    // ---- outputs ----
+    if (a->y_next || a->y) {
+        float* d_next = a->y_next ? (host ? h->stage_in : a->y_next) : nullptr;
+        // host mode stages one vector at a time
+        if (host) {
+            if (a->y_next) {
+                GPAD_TRY(launch_unpad_y(h->stage_in, nullptr, m, B, st.y[0], st.y[1], st.mp, st.iters, s));
+                GPAD_CUDA(cudaMemcpyAsync(a->y_next, h->stage_in, sizeof(float) * (size_t)B * m, cudaMemcpyDeviceToHost, s));
+                h->launches += 1;
+            }
+            if (a->y) {
+                GPAD_TRY(launch_unpad_y(nullptr, h->stage_in, m, B, st.y[0], st.y[1], st.mp, st.iters, s));
+                GPAD_CUDA(cudaMemcpyAsync(a->y, h->stage_in, sizeof(float) * (size_t)B * m, cudaMemcpyDeviceToHost, s));
+                h->launches += 1;
+            }
+        } else {
+            GPAD_TRY(launch_unpad_y(d_next, a->y, m, B, st.y[0], st.y[1], st.mp, st.iters, s));
+            h->launches += 1;
+        }
+    }
+    GPAD_TRY(emit(h, a->z, n, B, st.z, st.np, host, s));
+    GPAD_TRY(emit(h, a->zhat, n, B, st.zhat, st.np, host, s));
+    GPAD_TRY(emit(h, a->w, m, B, st.w, st.mp, host, s));
+    const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (a->iters) GPAD_CUDA(cudaMemcpyAsync(a->iters, st.iters, sizeof(int) * B, kind, s));
+    if (a->status) GPAD_CUDA(cudaMemcpyAsync(a->status, st.status, sizeof(int) * B, kind, s));
+    if (a->max_viol) GPAD_CUDA(cudaMemcpyAsync(a->max_viol, st.max_viol, sizeof(float) * B, kind, s));
+    if (a->gap) GPAD_CUDA(cudaMemcpyAsync(a->gap, st.gap, sizeof(float) * B, kind, s));
+    if (host) GPAD_CUDA(cudaStreamSynchronize(s));
+    return GPAD_OK;
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+const char* gpad_status_string(int status) {
+    switch (status) {
+        case GPAD_OK: return "ok";
+        case GPAD_ERR_INVALID_ARG: return "invalid argument";
+        case GPAD_ERR_CUDA: return "CUDA error";
+        case GPAD_ERR_UNSUPPORTED: return "unsupported configuration";
+        case GPAD_ERR_ALLOC: return "allocation failed";
+        case GPAD_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+        case GPAD_ERR_IO: return "I/O error";
+        default: return "unknown status";
+    }
+}
+
+const char* gpad_last_error(void) { return g_last_error.c_str(); }
+int gpad_api_version(void) { return GPAD_API_VERSION; }
+
+int gpad_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int usable = 0;
+    for (int d = 0; d < count; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++usable;
+    }
+    return usable;
+}
+
+static int stream_of(void* s, cudaStream_t* out) { *out = static_cast<cudaStream_t>(s); return GPAD_OK; }
+
+int gpad_step_one(const float* y, const float* y_prev, float* w, float beta, int m, void* stream) {
+    GPAD_REQUIRE(y && y_prev && w && m > 0, "gpad_step_one: null pointer or m <= 0");
+    cudaStream_t s; stream_of(stream, &s);
+    return launch_step_one(y, y_prev, w, beta, m, s);
+}
+
+int gpad_step_two(const float* M_G, const float* w_v, const float* g_P, float* zhat, int N, int n_u, int m, void* stream) {
+    GPAD_REQUIRE(M_G && w_v && g_P && zhat && N > 0 && n_u > 0 && m > 0, "gpad_step_two: bad argument");
+    cudaStream_t s; stream_of(stream, &s);
+    return launch_gemv_t(M_G, w_v, m, N * n_u, 0, g_P, nullptr, zhat, s);      // flipped M_G: [m][n]
+}
+
+int gpad_array_copy(float* dest, const float* src, int size, void* stream) {
+    GPAD_REQUIRE(dest && src && size > 0, "gpad_array_copy: bad argument");
+    cudaStream_t s; stream_of(stream, &s);
+    return launch_copy(dest, src, size, s);
+}
+
+int gpad_step_three(float theta, const float* zhat_v, float* z_v, int length, void* stream) {
+    GPAD_REQUIRE(zhat_v && z_v && length > 0, "gpad_step_three: bad argument");
+    cudaStream_t s; stream_of(stream, &s);
+    return launch_step_three(theta, zhat_v, z_v, length, s);
+}
+
+int gpad_step_four(const float* G_L, float* y_vp1, const float* w_v, const float* p_D, const float* zhat_v, int N, int n_u,
+                   int m, int max_threads, void* stream) {
+    (void)max_threads;
+    GPAD_REQUIRE(G_L && y_vp1 && w_v && p_D && zhat_v && N > 0 && n_u > 0 && m > 0, "gpad_step_four: bad argument");
+    cudaStream_t s; stream_of(stream, &s);
+    return launch_gemv_t(G_L, zhat_v, N * n_u, m, 1, w_v, p_D, y_vp1, s);      // flipped G_L: [n][m]
+}
+
+int gpad_setup(const gpad_config_t* cfg, const float* M_G, const float* G_L, gpad_handle_t* out) {
+    GPAD_REQUIRE(cfg && M_G && G_L && out, "gpad_setup: null argument");
+    GPAD_REQUIRE(cfg->n_u > 0 && cfg->N > 0 && cfg->m > 0, "gpad_setup: n_u, N, m must be positive");
+    GPAD_REQUIRE(cfg->layout == GPAD_LAYOUT_FLIPPED || cfg->layout == GPAD_LAYOUT_SEQUENTIAL, "gpad_setup: bad layout");
+    GPAD_REQUIRE(cfg->mode >= GPAD_MODE_LATENCY && cfg->mode <= GPAD_MODE_BATCH_PER_INSTANCE, "gpad_setup: bad mode");
+    GPAD_REQUIRE(cfg->precision == GPAD_PREC_FP32 || cfg->precision == GPAD_PREC_TF32X3, "gpad_setup: bad precision");
+    GPAD_REQUIRE(cfg->max_batch >= 1, "gpad_setup: max_batch must be >= 1");
+    GPAD_REQUIRE(cfg->mode != GPAD_MODE_LATENCY || cfg->max_batch == 1, "gpad_setup: latency mode solves one QP (max_batch = 1)");
+    GPAD_REQUIRE(cfg->precision == GPAD_PREC_FP32 || cfg->mode == GPAD_MODE_BATCH_SHARED,
+                 "gpad_setup: GPAD_PREC_TF32X3 is only available in GPAD_MODE_BATCH_SHARED");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device: %s (libgpad_b200 has no CPU fallback)", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return GPAD_ERR_NO_DEVICE;
+    }
+    int dev = cfg->device;
+    if (dev < 0) GPAD_CUDA(cudaGetDevice(&dev));
+    GPAD_REQUIRE(dev < count, "gpad_setup: device %d out of range (%d devices)", dev, count);
+    GPAD_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    GPAD_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; libgpad_b200 contains sm_100a code only", dev, prop.major, prop.minor);
+        return GPAD_ERR_UNSUPPORTED;
+    }
+    if (cfg->mode == GPAD_MODE_BATCH_PER_INSTANCE) {
+        set_error("GPAD_MODE_BATCH_PER_INSTANCE is not implemented yet");
+        return GPAD_ERR_UNSUPPORTED;
+    }
+    gpad_handle_s* h = new gpad_handle_s;
+    h->cfg = *cfg; h->cfg.device = dev;
+    h->n = cfg->n_u * cfg->N; h->device = dev; h->num_sms = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    int rc = GPAD_OK;
+    std::vector<float> MG, GL;
+    do {
+        if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = GPAD_ERR_CUDA; set_error("stream creation failed"); break; }
+        rc = fetch_operators(*cfg, M_G, G_L, (size_t)h->n * cfg->m, 1, MG, GL);
+        if (rc != GPAD_OK) break;
+        rc = cfg->mode == GPAD_MODE_LATENCY ? setup_latency(h, MG, GL) : setup_batch(h, MG, GL);
+    } while (0);
+    if (rc != GPAD_OK) { gpad_destroy(h); return rc; }
+    *out = h;
+    return GPAD_OK;
+}
+
+int gpad_destroy(gpad_handle_t h) {
+    if (!h) return GPAD_OK;
+    cudaSetDevice(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->h_active) cudaFreeHost(h->h_active);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    cudaGetLastError();
+    delete h;
+    return GPAD_OK;
+}
+
+int gpad_solve(gpad_handle_t h, const gpad_solve_args_t* a) {
+    GPAD_REQUIRE(h && a, "gpad_solve: null argument");
+    GPAD_REQUIRE(a->batch >= 1 && a->batch <= h->cfg.max_batch, "gpad_solve: batch %d outside 1..%d", a->batch, h->cfg.max_batch);
+    GPAD_REQUIRE(a->mem == GPAD_MEM_HOST || a->mem == GPAD_MEM_DEVICE, "gpad_solve: bad memspace");
+    GPAD_REQUIRE(a->g_P && a->p_D, "gpad_solve: g_P and p_D are required");
+    GPAD_REQUIRE(a->max_iter >= 1 && a->theta && a->beta, "gpad_solve: max_iter >= 1 and theta/beta are required");
+    GPAD_REQUIRE(a->check_every <= 0 || (a->eps_g >= 0.f && a->eps_V >= 0.f), "gpad_solve: negative tolerance");
+    if (h->cfg.mode == GPAD_MODE_BATCH_SHARED && a->check_every > 0 && a->f) {
+        set_error("gpad_solve: the relative / dual gap tests (f != NULL) are evaluated in latency mode only");
+        return GPAD_ERR_UNSUPPORTED;
+    }
+    GPAD_CUDA(cudaSetDevice(h->device));
+    return h->cfg.mode == GPAD_MODE_LATENCY ? solve_latency(h, a) : solve_batch(h, a);
+}
+
+long long gpad_launch_count(gpad_handle_t h) { return h ? h->launches : 0; }
+const char* gpad_describe(gpad_handle_t h) { return h ? h->desc.c_str() : ""; }
+
+int gpad_debug_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int K, void* stream) {
+    GPAD_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "gpad_debug_gemm_tf32x3: bad argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0;
+    GPAD_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    GPAD_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) { set_error("sm_100 device required"); return GPAD_ERR_UNSUPPORTED; }
+    int bk = 16;
+    if (const char* e = getenv("GPAD_TC_BK")) bk = atoi(e) == 32 ? 32 : 16;
+    tc::GemmDesc g;
+    g.bk = bk;
+    g.k_pad = round_up(K, 32);
+    tc::plan_tiles(N, &g.bn, &g.n_tiles);
+    g.m_tiles = round_up(M, 128) / 128;
+    g.ncols_valid = N;
+    g.stages = tc::pick_stages(bk, g.bn, prop.sharedMemPerBlockOptin);
+    if (const char* e = getenv("GPAD_TC_STAGES")) g.stages = std::min(g.stages, std::max(2, atoi(e)));
+    const int Mp = g.m_tiles * 128, Np = round_up(g.bn * g.n_tiles, 128);
+    float *Ap, *Al, *Bp, *Bl;
+    const size_t ca = (size_t)Mp * g.k_pad, cb = (size_t)Np * g.k_pad;
+    GPAD_CUDA(cudaMalloc(&Ap, ca * 4)); GPAD_CUDA(cudaMalloc(&Al, ca * 4));
+    GPAD_CUDA(cudaMalloc(&Bp, cb * 4)); GPAD_CUDA(cudaMalloc(&Bl, cb * 4));
+    int rc = GPAD_OK;
+    do {
+        if ((rc = launch_pad_rows(Ap, g.k_pad, Mp, A, K, M, s)) != GPAD_OK) break;
+        if ((rc = launch_pad_rows(Bp, g.k_pad, Np, B, K, N, s)) != GPAD_OK) break;
+        if ((rc = tc::launch_split(Ap, Ap, Al, ca, s)) != GPAD_OK) break;
+        if ((rc = tc::launch_split(Bp, Bp, Bl, cb, s)) != GPAD_OK) break;
+        if ((rc = tc::make_tmap(&g.tmA_hi, Ap, g.k_pad, Mp, g.k_pad, bk, 128)) != GPAD_OK) break;
+        if ((rc = tc::make_tmap(&g.tmA_lo, Al, g.k_pad, Mp, g.k_pad, bk, 128)) != GPAD_OK) break;
+        if ((rc = tc::make_tmap(&g.tmB_hi, Bp, g.k_pad, Np, g.k_pad, bk, g.bn)) != GPAD_OK) break;
+        if ((rc = tc::make_tmap(&g.tmB_lo, Bl, g.k_pad, Np, g.k_pad, bk, g.bn)) != GPAD_OK) break;
+        BatchKernelArgs k{};
+        k.B = M;
+        rc = tc::launch_gemm(0, g, k, C, N, prop.multiProcessorCount, s);
+    } while (0);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(Ap); cudaFree(Al); cudaFree(Bp); cudaFree(Bl);
+    if (rc == GPAD_OK && e != cudaSuccess) return cuda_fail(e, "gpad_debug_gemm_tf32x3", __FILE__, __LINE__);
+    return rc;
+}
+
+}  // extern "C"

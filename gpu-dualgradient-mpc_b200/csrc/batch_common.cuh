@@ -1,0 +1,129 @@
+// batch_common.cuh -- per-element epilogues of the two batched products, shared by the
+// CUDA-core (batch_simt.cu) and tcgen05 (batch_tc.cu) paths, so both apply exactly the same
+// arithmetic after the accumulator:
+//
+//   product 1 (step 2 + 3, kernel_functions.cu:16-72):   acc = <M_G[i,:], w_b>
+//        zhat = acc - g_P;  z = (1-theta) z + theta zhat
+//   product 2 (step 4 + next step 1, kernel_functions.cu:142-200, 7-14):  acc = <G_L[i,:], zhat_b>
+//        s = acc + (w + p_D);  y+ = (s + |s|)/2;  w+ = y+ + beta_{v+1} (y+ - y)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gpad_internal.h"
+
+namespace gpad {
+
+// red[b][k]: 0 max sbar, 1 max rhat, 2 min w, 3 sum w*rhat, 4 sum w*dot, 5 sum f*zhat, 6 nonfinite
+constexpr int kRedStride = 8;
+
+struct BatchKernelArgs {
+    // leading dimensions
+    int n, m, np, mp;
+    int B;                 // valid instances
+    IterScalars it;
+    int checking;          // termination enabled for this solve (sbar recurrence maintained)
+    float L;
+    // state (see BatchState)
+    const float* g_P;
+    const float* p_D;
+    const float* f;
+    const float* y_cur;
+    float* y_next;
+    float* w;
+    float* w_hi;
+    float* w_lo;
+    float* z;
+    float* zhat;
+    float* zh_hi;
+    float* zh_lo;
+    float* sbar;
+    float* red;
+    const int* done;       // per-instance "stopped" flag (null in fixed-iteration mode)
+};
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// x = hi + lo + O(2^-22 |x|): hi = RN_tf32(x), lo = RN_tf32(x - hi) (x - hi is exact in fp32)
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = tf32_rn(x);
+    lo = tf32_rn(x - hi);
+}
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    // monotone int mapping: valid for any mix of signs
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// ---- product 1 epilogue for one element (instance b, row i of M_G) ----
+template <bool SPLIT>
+__device__ __forceinline__ void epilogue1(const BatchKernelArgs& a, int b, int i, float acc, float& f_zhat) {
+    const size_t o = (size_t)b * a.np + i;
+    const float zh = acc - a.g_P[o];
+    a.z[o] = (1.0f - a.it.theta) * a.z[o] + a.it.theta * zh;
+    a.zhat[o] = zh;
+    if (SPLIT) {
+        float hi, lo;
+        split_tf32(zh, hi, lo);
+        a.zh_hi[o] = hi;
+        a.zh_lo[o] = lo;
+    }
+    if (a.it.check && a.f) f_zhat = fmaf(a.f[o], zh, f_zhat);
+}
+
+struct Red2 {
+    float max_sbar = -INFINITY, max_rhat = -INFINITY, min_w = INFINITY, w_rhat = 0.f, w_dot = 0.f, bad = 0.f;
+};
+
+// ---- product 2 epilogue for one element (instance b, row i of G_L) ----
+template <bool SPLIT>
+__device__ __forceinline__ void epilogue2(const BatchKernelArgs& a, int b, int i, float acc, Red2& r) {
+    const size_t o = (size_t)b * a.mp + i;
+    const float wv = a.w[o], pd = a.p_D[o];
+    const float s = acc + (wv + pd);
+    const float yn = 0.5f * (s + fabsf(s));
+    a.y_next[o] = yn;
+    if (a.checking) {
+        const float rhat = acc + pd;
+        const float sb = (1.0f - a.it.theta) * a.sbar[o] + a.it.theta * rhat;
+        a.sbar[o] = sb;
+        if (a.it.check) {
+            r.max_sbar = fmaxf(r.max_sbar, sb);
+            r.max_rhat = fmaxf(r.max_rhat, rhat);
+            r.min_w = fminf(r.min_w, wv);
+            r.w_rhat = fmaf(wv, rhat, r.w_rhat);
+            r.w_dot = fmaf(wv, acc, r.w_dot);
+            if (!isfinite(yn)) r.bad = 1.f;
+        }
+    }
+    if (!a.it.last) {
+        const float yv = a.y_cur[o];
+        const float wn = yn + a.it.beta_next * (yn - yv);
+        a.w[o] = wn;
+        if (SPLIT) {
+            float hi, lo;
+            split_tf32(wn, hi, lo);
+            a.w_hi[o] = hi;
+            a.w_lo[o] = lo;
+        }
+    }
+}
+
+__device__ __forceinline__ void flush_red2(const BatchKernelArgs& a, int b, const Red2& r) {
+    float* red = a.red + (size_t)b * kRedStride;
+    atomic_max_float(red + 0, r.max_sbar);
+    atomic_max_float(red + 1, r.max_rhat);
+    atomic_min_float(red + 2, r.min_w);
+    atomicAdd(red + 3, r.w_rhat);
+    atomicAdd(red + 4, r.w_dot);
+    if (r.bad > 0.f) atomicExch(red + 6, 1.0f);
+}
+
+}  // namespace gpad

@@ -1,0 +1,305 @@
+// batch_simt.cu -- throughput mode on CUDA cores (GPAD_PREC_FP32) plus the batch bookkeeping
+// kernels both precisions share (init / pad / decide / gather outputs).
+//
+// Each GPAD iteration over a batch of B QPs that share M_G and G_L is two GEMMs with the batch
+// on the M dimension:
+//     Zhat[B x n] = W[B x m]    * M_G^T[m x n]   (+ epilogue1: -g_P, z average)
+//     Y+  [B x m] = Zhat[B x n] * G_L^T[n x m]   (+ epilogue2: +w+p_D, projection, momentum)
+// Both operands are K-contiguous (instance-major state, sequential-layout operators), all
+// buffers are zero padded to the tile sizes, so the mainloop has no bounds checks.
+// Tile 128x128x16, 256 threads, 8x8 outputs per thread, double-buffered shared memory.
+#include "batch_common.cuh"
+#include "gpad_internal.h"
+
+namespace gpad {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
+
+// C[b][i] = sum_k A[b*lda + k] * Bop[i*ldb + k], K multiple of BK, rows padded to BM / BN.
+template <int PHASE>
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const float* __restrict__ A, int lda,
+                                                        const float* __restrict__ Bop, int ldb, int K,
+                                                        const BatchKernelArgs args) {
+    __shared__ __align__(16) float As[2][BK][BM + PAD];
+    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 thread grid, 8x8 outputs each
+    const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    // global -> register staging: 2 float4 per operand per thread
+    const int lr0 = tid >> 2, lk = (tid & 3) * 4;    // rows lr0 and lr0+64, k offset lk
+    const float* Ag = A + (size_t)(row0 + lr0) * lda + lk;
+    const float* Bg = Bop + (size_t)(col0 + lr0) * ldb + lk;
+    float4 ra0, ra1, rb0, rb1;
+    auto load_g = [&](int k0) {
+        ra0 = *reinterpret_cast<const float4*>(Ag + k0);
+        ra1 = *reinterpret_cast<const float4*>(Ag + (size_t)64 * lda + k0);
+        rb0 = __ldg(reinterpret_cast<const float4*>(Bg + k0));
+        rb1 = __ldg(reinterpret_cast<const float4*>(Bg + (size_t)64 * ldb + k0));
+    };
+    auto store_s = [&](int buf) {
+        As[buf][lk + 0][lr0] = ra0.x; As[buf][lk + 1][lr0] = ra0.y; As[buf][lk + 2][lr0] = ra0.z; As[buf][lk + 3][lr0] = ra0.w;
+        As[buf][lk + 0][lr0 + 64] = ra1.x; As[buf][lk + 1][lr0 + 64] = ra1.y; As[buf][lk + 2][lr0 + 64] = ra1.z; As[buf][lk + 3][lr0 + 64] = ra1.w;
+        Bs[buf][lk + 0][lr0] = rb0.x; Bs[buf][lk + 1][lr0] = rb0.y; Bs[buf][lk + 2][lr0] = rb0.z; Bs[buf][lk + 3][lr0] = rb0.w;
+        Bs[buf][lk + 0][lr0 + 64] = rb1.x; Bs[buf][lk + 1][lr0 + 64] = rb1.y; Bs[buf][lk + 2][lr0 + 64] = rb1.z; Bs[buf][lk + 3][lr0 + 64] = rb1.w;
+    };
+
+    load_g(0);
+    store_s(0);
+    __syncthreads();
+    const int nk = K / BK;
+    for (int kb = 0; kb < nk; ++kb) {
+        const int buf = kb & 1;
+        if (kb + 1 < nk) load_g((kb + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            // thread owns rows ty*4..+3 and 64+ty*4..+3, cols tx*4..+3 and 64+tx*4..+3
+            const float4 a_lo = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            const float4 a_hi = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+            const float4 b_lo = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float4 b_hi = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+            const float av[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+            const float bv[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kb + 1 < nk) {
+            store_s(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+    // ---- fused epilogue ----
+    const int ncols = PHASE == 1 ? args.n : args.m;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int b = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (b >= args.B) continue;
+        if (args.done && args.done[b]) continue;
+        float f_zhat = 0.f;
+        Red2 red;
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (c >= ncols) continue;
+            any = true;
+            if (PHASE == 1) epilogue1<false>(args, b, c, acc[i][j], f_zhat);
+            else epilogue2<false>(args, b, c, acc[i][j], red);
+        }
+        if (args.it.check && any) {
+            if (PHASE == 1) { if (args.f) atomicAdd(args.red + (size_t)b * kRedStride + 5, f_zhat); }
+            else flush_red2(args, b, red);
+        }
+    }
+}
+
+// dst[Bp][ld] <- src[B][len] (zero padding), src may be null (all zeros)
+__global__ void pad_rows_kernel(float* __restrict__ dst, int ld, int rows_total, const float* __restrict__ src,
+                                int len, int B) {
+    const size_t total = (size_t)rows_total * ld;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / ld), i = (int)(idx % ld);
+        dst[idx] = (src && b < B && i < len) ? src[(size_t)b * len + i] : 0.f;
+    }
+}
+
+// dst[B][len] <- src[Bp][ld]
+__global__ void unpad_rows_kernel(float* __restrict__ dst, int len, int B, const float* __restrict__ src, int ld) {
+    const size_t total = (size_t)B * len;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / len), i = (int)(idx % len);
+        dst[idx] = src[(size_t)b * ld + i];
+    }
+}
+
+// w_0 = y_0 + beta_0 (y_0 - y_{-1}) (step 1 of iteration 0), its tf32 split, zeroed z / sbar
+__global__ void batch_init_kernel(int Bp, int np, int mp, const float* __restrict__ y0, const float* __restrict__ yprev0,
+                                  float beta0, float* __restrict__ w, float* __restrict__ w_hi, float* __restrict__ w_lo,
+                                  float* __restrict__ z, float* __restrict__ zhat, float* __restrict__ sbar) {
+    const size_t tm = (size_t)Bp * mp, tn = (size_t)Bp * np;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tm; idx += (size_t)gridDim.x * blockDim.x) {
+        const float y = y0[idx], yp = yprev0[idx];
+        const float wv = y + beta0 * (y - yp);
+        w[idx] = wv;
+        if (w_hi) { float hi, lo; split_tf32(wv, hi, lo); w_hi[idx] = hi; w_lo[idx] = lo; }
+        if (sbar) sbar[idx] = 0.f;
+    }
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tn; idx += (size_t)gridDim.x * blockDim.x) {
+        z[idx] = 0.f;
+        zhat[idx] = 0.f;
+    }
+}
+
+__global__ void batch_reset_term_kernel(int Bp, float* __restrict__ red, int* __restrict__ done, int* __restrict__ iters,
+                                        int* __restrict__ status, float* __restrict__ max_viol, float* __restrict__ gap,
+                                        int* __restrict__ active, int B, int max_iter) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) *active = B;
+    if (b >= Bp) return;
+    float* r = red + (size_t)b * kRedStride;
+    r[0] = -INFINITY; r[1] = -INFINITY; r[2] = INFINITY; r[3] = 0.f; r[4] = 0.f; r[5] = 0.f; r[6] = 0.f; r[7] = 0.f;
+    done[b] = 0;
+    iters[b] = max_iter;
+    status[b] = GPAD_STATUS_MAX_ITER;
+    max_viol[b] = __int_as_float(0x7fc00000);
+    gap[b] = __int_as_float(0x7fc00000);
+}
+
+// termination decision per instance after a check iteration.  The dual-gap
+// branch (w has a negative entry) needs two more operator products and is only evaluated in
+// latency mode; here such instances keep iterating.
+__global__ void batch_decide_kernel(int B, int iter_done, float L, float eps_g, float eps_V, int have_f,
+                                    float* __restrict__ red, int* __restrict__ done, int* __restrict__ iters,
+                                    int* __restrict__ status, float* __restrict__ max_viol, float* __restrict__ gap,
+                                    int* __restrict__ active) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || done[b]) return;
+    float* r = red + (size_t)b * kRedStride;
+    const float viol_z = L * r[0], viol_zhat = L * r[1];
+    int st = -1;
+    float mv = viol_z, gp = gap[b];
+    if (r[6] > 0.f) st = GPAD_STATUS_NONFINITE;
+    else if (viol_z <= eps_g) st = GPAD_STATUS_CONVERGED_Z;
+    else if (viol_zhat <= eps_g && r[2] >= 0.f) {
+        gp = -L * r[3];
+        const float V = 0.5f * (r[5] - L * r[4]);
+        if (gp <= eps_V || (have_f && gp <= V * eps_V / (1.0f + eps_V))) { st = GPAD_STATUS_CONVERGED_ZHAT; mv = viol_zhat; }
+    }
+    max_viol[b] = mv;
+    gap[b] = gp;
+    if (st >= 0) {
+        status[b] = st;
+        iters[b] = iter_done;
+        done[b] = 1;
+        atomicSub(active, 1);
+    }
+    r[0] = -INFINITY; r[1] = -INFINITY; r[2] = INFINITY; r[3] = 0.f; r[4] = 0.f; r[5] = 0.f; r[6] = 0.f;
+}
+
+// after a check iteration: w_{v+1} = y+ + beta_{v+1} (y+ - y) for the instances still running
+// (product 2 does not advance w on check iterations so that stopped instances keep w_v)
+__global__ void batch_advance_w_kernel(int B, int m, int mp, const float* __restrict__ y_next, const float* __restrict__ y_cur,
+                                       float beta_next, const int* __restrict__ done, float* __restrict__ w,
+                                       float* __restrict__ w_hi, float* __restrict__ w_lo) {
+    const size_t total = (size_t)B * mp;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / mp), i = (int)(idx % mp);
+        if (i >= m || done[b]) continue;
+        const float yn = y_next[idx], yv = y_cur[idx];
+        const float wn = yn + beta_next * (yn - yv);
+        w[idx] = wn;
+        if (w_hi) { float hi, lo; split_tf32(wn, hi, lo); w_hi[idx] = hi; w_lo[idx] = lo; }
+    }
+}
+
+// y_I / y_{I-1} of instance b live in ping-pong buffer (iters_b & 1) / ((iters_b - 1) & 1)
+__global__ void unpad_y_kernel(float* __restrict__ dst_next, float* __restrict__ dst_cur, int m, int B,
+                               const float* __restrict__ ybuf0, const float* __restrict__ ybuf1, int mp,
+                               const int* __restrict__ iters) {
+    const size_t total = (size_t)B * m;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / m), i = (int)(idx % m);
+        const int par = iters[b] & 1;
+        const float* nx = par ? ybuf1 : ybuf0;
+        const float* cu = par ? ybuf0 : ybuf1;
+        if (dst_next) dst_next[idx] = nx[(size_t)b * mp + i];
+        if (dst_cur) dst_cur[idx] = cu[(size_t)b * mp + i];
+    }
+}
+
+// fixed-iteration mode: MAX_ITER unless an iterate went non-finite
+__global__ void batch_finite_kernel(int B, int mp, int m, const float* __restrict__ y_next, int* __restrict__ status) {
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    int bad = 0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x)
+        if (!isfinite(y_next[(size_t)b * mp + i])) bad = 1;
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0 && bad) status[b] = GPAD_STATUS_NONFINITE;
+}
+
+inline int grid_for(size_t total) {
+    size_t g = (total + 255) / 256;
+    return (int)(g > 148 * 16 ? 148 * 16 : (g ? g : 1));
+}
+
+}  // namespace
+
+int launch_pad_rows(float* dst, int ld, int rows_total, const float* src, int len, int B, cudaStream_t s) {
+    pad_rows_kernel<<<grid_for((size_t)rows_total * ld), 256, 0, s>>>(dst, ld, rows_total, src, len, B);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+int launch_unpad_rows(float* dst, int len, int B, const float* src, int ld, cudaStream_t s) {
+    unpad_rows_kernel<<<grid_for((size_t)B * len), 256, 0, s>>>(dst, len, B, src, ld);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+int launch_batch_init(const BatchState& st, const float* y0p, const float* yprev0p, float beta0, bool split,
+                      bool checking, cudaStream_t s) {
+    batch_init_kernel<<<grid_for((size_t)st.Bp * st.mp), 256, 0, s>>>(st.Bp, st.np, st.mp, y0p, yprev0p, beta0, st.w,
+                                                                      split ? st.w_hi : nullptr, split ? st.w_lo : nullptr,
+                                                                      st.z, st.zhat, checking ? st.sbar : nullptr);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+int launch_batch_reset_term(const BatchState& st, int max_iter, cudaStream_t s) {
+    batch_reset_term_kernel<<<(st.Bp + 255) / 256, 256, 0, s>>>(st.Bp, st.red, st.done, st.iters, st.status, st.max_viol,
+                                                              st.gap, st.active_count, st.B, max_iter);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+int launch_batch_decide(const BatchState& st, int iter_done, float L, float eps_g, float eps_V, bool have_f, cudaStream_t s) {
+    batch_decide_kernel<<<(st.B + 255) / 256, 256, 0, s>>>(st.B, iter_done, L, eps_g, eps_V, have_f ? 1 : 0, st.red, st.done,
+                                                          st.iters, st.status, st.max_viol, st.gap, st.active_count);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+int launch_batch_advance_w(const BatchState& st, const float* y_next, const float* y_cur, float beta_next, bool split,
+                           cudaStream_t s) {
+    batch_advance_w_kernel<<<grid_for((size_t)st.B * st.mp), 256, 0, s>>>(st.B, st.m, st.mp, y_next, y_cur, beta_next, st.done,
+                                                                         st.w, split ? st.w_hi : nullptr, split ? st.w_lo : nullptr);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+int launch_unpad_y(float* dst_next, float* dst_cur, int m, int B, const float* ybuf0, const float* ybuf1, int mp,
+                   const int* iters, cudaStream_t s) {
+    unpad_y_kernel<<<grid_for((size_t)B * m), 256, 0, s>>>(dst_next, dst_cur, m, B, ybuf0, ybuf1, mp, iters);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+int launch_batch_finite(const BatchState& st, const float* y_next, cudaStream_t s) {
+    batch_finite_kernel<<<st.B, 128, 0, s>>>(st.B, st.mp, st.m, y_next, st.status);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+// one GPAD iteration on CUDA cores: two fused GEMM launches
+int launch_simt_iteration(const Operators& op, const BatchKernelArgs& args, int Bp, cudaStream_t s) {
+    dim3 g1((args.n + BN - 1) / BN, Bp / BM), g2((args.m + BN - 1) / BN, Bp / BM);
+    simt_gemm_kernel<1><<<g1, 256, 0, s>>>(args.w, args.mp, op.M_G, args.mp, args.mp, args);
+    GPAD_CUDA(cudaGetLastError());
+    simt_gemm_kernel<2><<<g2, 256, 0, s>>>(args.zhat, args.np, op.G_L, args.np, args.np, args);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+}  // namespace gpad

@@ -1,0 +1,387 @@
+// batch_tc.cu -- throughput mode on the 5th-generation tensor cores (GPAD_PREC_TF32X3).
+//
+// Each GPAD iteration over a batch of B QPs sharing M_G / G_L is two GEMMs with the batch on
+// the MMA M dimension:
+//     Zhat[B x n] = W[B x m]    * M_G^T      (epilogue1: -g_P, z average, tf32 split of zhat)
+//     Y+  [B x m] = Zhat[B x n] * G_L^T      (epilogue2: +(w+p_D), projection, momentum, split of w+)
+// fp32 accuracy from kind::tf32: both operands are split x = hi + lo (hi = RN_tf32(x),
+// lo = RN_tf32(x - hi)) and every product is three MMAs into the same fp32 TMEM accumulator:
+//     hi*lo + lo*hi + hi*hi          (lo*lo ~ 2^-22 relative is dropped: "3xTF32")
+//
+// Kernel anatomy (one CTA per SM, persistent over output tiles of 128 x bn, bn <= 256):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of A_hi/A_lo [128 x BK] and B_hi/B_lo [bn x BK]
+//               into a `stages`-deep shared-memory ring (K-major, hardware swizzle), mbarrier tx-count
+//   warp 1      TMEM allocator + MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::tf32,
+//               tcgen05.commit releases ring slots and publishes finished accumulators
+//   warps 2..9  epilogue: tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> coalesced
+//               global reads/writes of the fused GPAD epilogue (batch_common.cuh)
+//   TMEM: 512 columns = 2 accumulator stages x 256 fp32 columns, so the epilogue of tile t
+//   overlaps the mainloop of tile t+1.
+#include <cuda.h>
+
+#include "batch_common.cuh"
+#include "gpad_internal.h"
+#include "batch_tc.h"
+
+namespace gpad {
+namespace tc {
+
+namespace {
+
+constexpr int kBM = 128;            // batch rows per tile == UMMA M
+constexpr int kAccStride = 256;     // TMEM columns per accumulator stage
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (2 + kEpiWarps);
+constexpr int kEpiBufFloats = 32 * 33;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor of a K-major operand tile whose rows are BK floats wide and
+// hardware-swizzled with a span of one row (BK = 32: SWIZZLE_128B, BK = 16: SWIZZLE_64B);
+// canonical layout ((8,rows/8),(T,2)) : ((row bytes, SBO),(1, LBO)) -- cute mma_sm100_desc.hpp
+template <int BK>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    constexpr uint64_t row_bytes = BK * 4;
+    constexpr uint64_t sbo = 8 * row_bytes;                     // next group of 8 rows
+    constexpr uint64_t layout = (BK == 32) ? 2 : (BK == 16 ? 4 : 6);  // SWIZZLE_128B / 64B / 32B
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                    // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                                     // LBO (unused for swizzled K-major)
+    d |= (sbo >> 4) << 32;                                      // SBO, bits [32,46)
+    d |= (uint64_t)1 << 46;                                     // descriptor version (Blackwell)
+    d |= layout << 61;                                          // swizzle mode, bits [61,64)
+    return d;
+}
+
+// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = bn
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+struct TileSched {
+    int tile, step, total, n_tiles;
+    __device__ TileSched(int total_, int n_tiles_) : tile(blockIdx.x), step(gridDim.x), total(total_), n_tiles(n_tiles_) {}
+    __device__ bool valid() const { return tile < total; }
+    __device__ void next() { tile += step; }
+    __device__ int m_tile() const { return tile / n_tiles; }
+    __device__ int n_tile() const { return tile % n_tiles; }
+};
+
+// PHASE 0: plain store of C (test hook); 1: GPAD product 1; 2: GPAD product 2
+template <int PHASE, int BK>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               int num_k_blocks, int m_tiles, int n_tiles, int bn, int stages,
+               const BatchKernelArgs args, float* __restrict__ Cdbg, int ldc, int ncols_valid) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t a_bytes = kBM * BK * 4, b_bytes = (uint32_t)bn * BK * 4;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    float* epi_buf = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kEpiWarps * kEpiBufFloats);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + stages;
+    uint64_t* tfull_bar = bars + 2 * stages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = m_tiles * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+        for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), kEpiWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================ TMA producer ============================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (TileSched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
+                const int row_a = ts.m_tile() * kBM, row_b = ts.n_tile() * bn;
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+                    const uint32_t fb = smem_u32(full_bar + stage);
+                    mbar_expect_tx(fb, stage_bytes);
+                    const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
+                    tma_load_2d(base, &tmA_hi, kb * BK, row_a, fb);
+                    tma_load_2d(base + a_bytes, &tmA_lo, kb * BK, row_a, fb);
+                    tma_load_2d(base + 2 * a_bytes, &tmB_hi, kb * BK, row_b, fb);
+                    tma_load_2d(base + 2 * a_bytes + b_bytes, &tmB_lo, kb * BK, row_b, fb);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================ MMA issuer ============================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(bn);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (TileSched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
+                mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(smem_u32(full_bar + stage), phase);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint64_t a_hi = make_smem_desc<BK>(base + ks * 32);
+                        const uint64_t a_lo = make_smem_desc<BK>(base + a_bytes + ks * 32);
+                        const uint64_t b_hi = make_smem_desc<BK>(base + 2 * a_bytes + ks * 32);
+                        const uint64_t b_lo = make_smem_desc<BK>(base + 2 * a_bytes + b_bytes + ks * 32);
+                        umma_tf32(d_tmem, a_hi, b_lo, idesc, (kb | ks) != 0 ? 1u : 0u);
+                        umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
+                        umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+                    }
+                    umma_commit(smem_u32(empty_bar + stage));      // frees the ring slot when these MMAs retire
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(smem_u32(tfull_bar + acc));            // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ============================ epilogue warps ============================
+        const int ew = warp - 2;
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int half = ew >> 2;               // two warps share a quarter and alternate column blocks
+        float* buf = epi_buf + ew * kEpiBufFloats;
+        const int nblk = (bn + 31) / 32;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (TileSched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
+            mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+            tc_fence_after();
+            const int row_base = ts.m_tile() * kBM + q * 32;
+            for (int blk = half; blk < nblk; blk += 2) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride + blk * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = __uint_as_float(v[j]);
+                __syncwarp();
+                const int cin = blk * 32 + lane;            // column inside the tile
+                const int c = ts.n_tile() * bn + cin;       // global output column
+                const bool col_ok = cin < bn && c < ncols_valid;
+#pragma unroll 4
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int b = row_base + rr;
+                    const float val = buf[rr * 33 + lane];
+                    bool ok = col_ok && b < args.B;
+                    if (PHASE != 0 && ok && args.done) ok = args.done[b] == 0;
+                    if (PHASE == 0) {
+                        if (ok) Cdbg[(size_t)b * ldc + c] = val;
+                    } else if (PHASE == 1) {
+                        float f_zhat = 0.f;
+                        if (ok) epilogue1<true>(args, b, c, val, f_zhat);
+                        if (args.it.check && args.f) {
+#pragma unroll
+                            for (int o = 16; o; o >>= 1) f_zhat += __shfl_xor_sync(0xffffffffu, f_zhat, o);
+                            if (lane == 0 && b < args.B) atomicAdd(args.red + (size_t)b * kRedStride + 5, f_zhat);
+                        }
+                    } else {
+                        Red2 red;
+                        if (ok) epilogue2<true>(args, b, c, val, red);
+                        if (args.it.check) {
+#pragma unroll
+                            for (int o = 16; o; o >>= 1) {
+                                red.max_sbar = fmaxf(red.max_sbar, __shfl_xor_sync(0xffffffffu, red.max_sbar, o));
+                                red.max_rhat = fmaxf(red.max_rhat, __shfl_xor_sync(0xffffffffu, red.max_rhat, o));
+                                red.min_w = fminf(red.min_w, __shfl_xor_sync(0xffffffffu, red.min_w, o));
+                                red.w_rhat += __shfl_xor_sync(0xffffffffu, red.w_rhat, o);
+                                red.w_dot += __shfl_xor_sync(0xffffffffu, red.w_dot, o);
+                                red.bad = fmaxf(red.bad, __shfl_xor_sync(0xffffffffu, red.bad, o));
+                            }
+                            if (lane == 0 && b < args.B && !(args.done && args.done[b])) flush_red2(args, b, red);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// x -> (RN_tf32(x), RN_tf32(x - hi)), elementwise
+__global__ void split_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, size_t count) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        float h, l;
+        split_tf32(src[i], h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+int make_tmap(CUtensorMap* map, const float* ptr, int k_elems, int rows, int ld, int box_k, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return GPAD_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)k_elems, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = box_k == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : box_k == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return GPAD_ERR_CUDA; }
+    return GPAD_OK;
+}
+
+void plan_tiles(int ncols, int* bn, int* n_tiles) {
+    const int nt = (ncols + 255) / 256;
+    int b = ((ncols + nt - 1) / nt + 15) / 16 * 16;
+    if (b < 16) b = 16;
+    *bn = b;
+    *n_tiles = nt;
+}
+
+size_t smem_bytes(int bk, int bn, int stages) {
+    const size_t stage = (size_t)(2 * kBM + 2 * bn) * bk * 4;
+    return 1024 + stages * stage + (size_t)kEpiWarps * kEpiBufFloats * 4 + (2 * stages + 4) * 8 + 16;
+}
+
+int pick_stages(int bk, int bn, size_t smem_limit) {
+    int s = 8;
+    while (s > 2 && smem_bytes(bk, bn, s) > smem_limit) --s;
+    return s;
+}
+
+template <int PHASE, int BK>
+static int launch_one(const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s) {
+    auto kern = tc_gemm_kernel<PHASE, BK>;
+    const size_t smem = smem_bytes(BK, g.bn, g.stages);
+    GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = g.m_tiles * g.n_tiles;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    kern<<<grid, kThreads, smem, s>>>(g.tmA_hi, g.tmA_lo, g.tmB_hi, g.tmB_lo, g.k_pad / BK, g.m_tiles, g.n_tiles, g.bn,
+                                      g.stages, args, C, ldc, g.ncols_valid);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+int launch_gemm(int phase, const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s) {
+    if (g.bk == 16) {
+        if (phase == 0) return launch_one<0, 16>(g, args, C, ldc, num_sms, s);
+        if (phase == 1) return launch_one<1, 16>(g, args, C, ldc, num_sms, s);
+        return launch_one<2, 16>(g, args, C, ldc, num_sms, s);
+    }
+    if (phase == 0) return launch_one<0, 32>(g, args, C, ldc, num_sms, s);
+    if (phase == 1) return launch_one<1, 32>(g, args, C, ldc, num_sms, s);
+    return launch_one<2, 32>(g, args, C, ldc, num_sms, s);
+}
+
+int launch_split(const float* src, float* hi, float* lo, size_t count, cudaStream_t s) {
+    size_t g = (count + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g == 0) g = 1;
+    split_kernel<<<(int)g, 256, 0, s>>>(src, hi, lo, count);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+}  // namespace tc
+}  // namespace gpad

@@ -1,0 +1,28 @@
+// batch_tc.h -- host interface of the tcgen05 3xTF32 GEMM path (batch_tc.cu)
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "batch_common.cuh"
+
+namespace gpad {
+namespace tc {
+
+struct GemmDesc {
+    CUtensorMap tmA_hi, tmA_lo;   // A [rows = batch][K] tiles of 128 x bk
+    CUtensorMap tmB_hi, tmB_lo;   // B [rows = outputs][K] tiles of bn x bk
+    int bk = 16;                  // K block in floats: 16 (SWIZZLE_64B) or 32 (SWIZZLE_128B)
+    int k_pad = 0;                // K rounded up to bk
+    int m_tiles = 0, n_tiles = 0, bn = 0, stages = 0;
+    int ncols_valid = 0;          // output columns that exist (n or m)
+};
+
+int make_tmap(CUtensorMap* map, const float* ptr, int k_elems, int rows, int ld, int box_k, int box_rows);
+void plan_tiles(int ncols, int* bn, int* n_tiles);
+size_t smem_bytes(int bk, int bn, int stages);
+int pick_stages(int bk, int bn, size_t smem_limit);
+int launch_gemm(int phase, const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s);
+int launch_split(const float* src, float* hi, float* lo, size_t count, cudaStream_t s);
+
+}  // namespace tc
+}  // namespace gpad

@@ -1,0 +1,101 @@
+// gpad_internal.h -- shared declarations of libgpad_b200.so (not part of the public C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "gpad.h"
+
+namespace gpad {
+
+// ---- error plumbing: every failure records a thread-local message and returns a status ----
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define GPAD_CUDA(call)                                                         \
+    do {                                                                        \
+        cudaError_t e__ = (call);                                               \
+        if (e__ != cudaSuccess) return ::gpad::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define GPAD_REQUIRE(cond, ...)                     \
+    do {                                            \
+        if (!(cond)) {                              \
+            ::gpad::set_error(__VA_ARGS__);         \
+            return GPAD_ERR_INVALID_ARG;            \
+        }                                           \
+    } while (0)
+
+inline int round_up(int v, int q) { return (v + q - 1) / q * q; }
+inline size_t round_up_sz(size_t v, size_t q) { return (v + q - 1) / q * q; }
+
+// ---- per-iteration scalars handed to kernels by value (main.cu:163,170 does the same) ----
+struct IterScalars {
+    float theta;      // theta_v
+    float beta_next;  // beta_{v+1} (0 on the last iteration)
+    int last;         // 1 on the final iteration: do not advance w
+    int check;        // 1 when the termination quantities are reduced this iteration
+};
+
+// ---- device state of a batched (shared-operator) solve; all row-major [rows][ld] ----
+struct BatchState {
+    int B = 0;        // instances in this call
+    int Bp = 0;       // capacity rounded up to the batch tile
+    int n = 0, m = 0;
+    int np = 0, mp = 0;  // leading dimensions (padded to 32 floats)
+    float* g_P = nullptr;   // [Bp][np]
+    float* p_D = nullptr;   // [Bp][mp]
+    float* f = nullptr;     // [Bp][np] (optional)
+    float* y[2] = {nullptr, nullptr};  // ping-pong y_v / y_{v+1}  [Bp][mp]
+    float* w = nullptr;     // [Bp][mp] exact fp32 w_v
+    float* w_hi = nullptr;  // TF32X3 only: RN-tf32(w) and the tf32-rounded remainder
+    float* w_lo = nullptr;
+    float* z = nullptr;     // [Bp][np]
+    float* zhat = nullptr;  // [Bp][np]
+    float* zh_hi = nullptr; // TF32X3 only
+    float* zh_lo = nullptr;
+    float* sbar = nullptr;  // [Bp][mp] averaged residual (termination only)
+    float* red = nullptr;   // [Bp][8] per-instance reductions (termination only)
+    int* done = nullptr;    // [Bp] instance stopped (termination mode)
+    int* iters = nullptr;   // [Bp]
+    int* status = nullptr;  // [Bp]
+    float* max_viol = nullptr;
+    float* gap = nullptr;
+    int* active_count = nullptr;  // [1] instances still iterating
+};
+
+struct Operators {
+    // fp32 operators in the sequential (K-contiguous) layout, zero padded:
+    float* M_G = nullptr;   // [n_rows_pad][mp]   rows = outputs of GEMM 1 (n), K = m
+    float* G_L = nullptr;   // [m_rows_pad][np]   rows = outputs of GEMM 2 (m), K = n
+    float* M_G_lo = nullptr;  // TF32X3: M_G holds RN-tf32(M_G), *_lo the tf32-rounded remainder
+    float* G_L_lo = nullptr;
+    int n_rows_pad = 0, m_rows_pad = 0;
+};
+
+struct BatchKernelArgs;
+
+// ---- kernel launchers (defined in the .cu files) ----
+int launch_pad_rows(float* dst, int ld, int rows_total, const float* src, int len, int B, cudaStream_t s);
+int launch_unpad_rows(float* dst, int len, int B, const float* src, int ld, cudaStream_t s);
+int launch_unpad_y(float* dst_next, float* dst_cur, int m, int B, const float* ybuf0, const float* ybuf1, int mp,
+                   const int* iters, cudaStream_t s);
+int launch_batch_init(const BatchState& st, const float* y0p, const float* yprev0p, float beta0, bool split,
+                      bool checking, cudaStream_t s);
+int launch_batch_reset_term(const BatchState& st, int max_iter, cudaStream_t s);
+int launch_batch_decide(const BatchState& st, int iter_done, float L, float eps_g, float eps_V, bool have_f, cudaStream_t s);
+int launch_batch_advance_w(const BatchState& st, const float* y_next, const float* y_cur, float beta_next, bool split,
+                           cudaStream_t s);
+int launch_batch_finite(const BatchState& st, const float* y_next, cudaStream_t s);
+int launch_simt_iteration(const Operators& op, const BatchKernelArgs& args, int Bp, cudaStream_t s);
+int launch_step_one(const float* y, const float* y_prev, float* w, float beta, int m, cudaStream_t s);
+int launch_gemv_t(const float* A, const float* x, int rows, int cols, int mode, const float* v1,
+                  const float* v2, float* out, cudaStream_t s);
+int launch_copy(float* dst, const float* src, int n, cudaStream_t s);
+int launch_step_three(float theta, const float* zhat, float* z, int n, cudaStream_t s);
+
+}  // namespace gpad

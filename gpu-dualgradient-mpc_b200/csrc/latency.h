@@ -1,0 +1,46 @@
+// latency.h -- parameters of the persistent single-QP kernel (latency.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+namespace gpad {
+namespace lat {
+
+enum { SYNC_BLOCK = 0, SYNC_CLUSTER = 1, SYNC_GRID = 2 };
+constexpr int kMaxThreads = 512;
+
+struct Params {
+    int n, m;
+    int nld, mld;            // n, m rounded up to 4 floats (row strides of G_L / M_G)
+    int rows_a, rows_b;      // rows of M_G / G_L per CTA (ceil(n/G), ceil(m/G))
+    int rows_a_pad, rows_b_pad;  // rounded up to 4
+    int g_pad;               // G rounded up to 4
+    int lpr_a, lpr_b;        // lanes per row in phase A / B
+    const float* M_G;        // [n][mld] sequential layout, zero padded
+    const float* G_L;        // [m][nld]
+    const float* g_P;        // [n]
+    const float* p_D;        // [m]
+    const float* f;          // [n] or null
+    const float* y0;         // [m] or null
+    const float* y_prev0;    // [m] or null
+    const float* theta;      // device [max_iter]
+    const float* beta;       // device [max_iter]
+    int max_iter, check_every;
+    float eps_g, eps_V, L;
+    // outputs (device, always valid)
+    float *out_y_next, *out_y, *out_z, *out_zhat, *out_w;
+    int *out_iters, *out_status;
+    float *out_max_viol, *out_gap;
+    // grid-mode exchange buffers
+    float* x_w;              // [m]
+    float* x_zhat;           // [n]
+    float* x_red;            // [3][8][g_pad]
+    unsigned* barrier;       // zeroed before launch
+    int* nonfinite_flag;     // zeroed before launch
+};
+
+size_t smem_bytes(const Params& p, bool ops_smem);
+int launch(const Params& p, int sync_mode, bool ops_smem, int G, int threads, cudaStream_t stream);
+int max_cluster_size(bool ops_smem, int threads, size_t smem);
+
+}  // namespace lat
+}  // namespace gpad

@@ -1,0 +1,306 @@
+"""gpad_b200 -- thin ctypes binding of libgpad_b200.so (include/gpad.h).
+
+Python is plumbing only: every solve goes through the C ABI into the hand-written sm_100a
+kernels.  There is no CPU or PyTorch fallback: if the shared library is missing, or no B200 is
+present, the calls raise.  Device buffers are passed as raw pointers (torch tensors'
+``data_ptr()``), host buffers as numpy arrays.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgpad_b200.so")
+
+# enums of include/gpad.h
+LAYOUT_FLIPPED, LAYOUT_SEQUENTIAL = 0, 1
+MODE_LATENCY, MODE_BATCH_SHARED, MODE_BATCH_PER_INSTANCE = 1, 2, 3
+PREC_FP32, PREC_TF32X3 = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+SCHEDULE_PAPER, SCHEDULE_MATLAB_LAG = 0, 1
+STATUS_NAMES = {0: "max_iter", 1: "converged_z", 2: "converged_zhat", 3: "converged_dual", 4: "nonfinite"}
+
+EXPORTS = [
+    "gpad_status_string", "gpad_last_error", "gpad_api_version", "gpad_device_count",
+    "gpad_step_one", "gpad_step_two", "gpad_array_copy", "gpad_step_three", "gpad_step_four",
+    "gpad_setup", "gpad_destroy", "gpad_solve", "gpad_launch_count", "gpad_describe",
+    "gpad_problem_battery", "gpad_problem_quadrotor", "gpad_problem_destroy", "gpad_problem_dims",
+    "gpad_problem_operators", "gpad_problem_instances", "gpad_problem_plant", "gpad_schedule",
+    "gpad_file_read", "gpad_file_write", "gpad_file_free", "gpad_debug_gemm_tf32x3",
+]
+
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+_dp = C.POINTER(C.c_double)
+
+
+class GpadError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("n_u", C.c_int), ("N", C.c_int), ("m", C.c_int), ("L", C.c_float), ("layout", C.c_int),
+                ("mode", C.c_int), ("precision", C.c_int), ("max_batch", C.c_int), ("device", C.c_int),
+                ("operators_mem", C.c_int), ("reserved", C.c_int * 6)]
+
+
+class SolveArgs(C.Structure):
+    _fields_ = [("batch", C.c_int), ("mem", C.c_int),
+                ("g_P", C.c_void_p), ("p_D", C.c_void_p), ("f", C.c_void_p), ("y0", C.c_void_p), ("y_prev0", C.c_void_p),
+                ("theta", _fp), ("beta", _fp), ("max_iter", C.c_int), ("check_every", C.c_int),
+                ("eps_g", C.c_float), ("eps_V", C.c_float),
+                ("y_next", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p), ("zhat", C.c_void_p), ("w", C.c_void_p),
+                ("iters", C.c_void_p), ("status", C.c_void_p), ("max_viol", C.c_void_p), ("gap", C.c_void_p),
+                ("stream", C.c_void_p), ("reserved", C.c_int * 4)]
+
+
+class FileData(C.Structure):
+    _fields_ = [("n_u", C.c_int), ("N", C.c_int), ("m", C.c_int), ("num_iterations", C.c_int), ("L", C.c_float),
+                ("M_G", _fp), ("g_P", _fp), ("G_L", _fp), ("p_D", _fp), ("theta", _fp), ("beta", _fp)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libgpad_b200.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GpadError(f"{LIB_PATH} is missing: run `make` (or __graft_entry__.build()); there is no fallback path")
+        L = C.CDLL(LIB_PATH)
+        L.gpad_status_string.restype = C.c_char_p
+        L.gpad_last_error.restype = C.c_char_p
+        L.gpad_describe.restype = C.c_char_p
+        L.gpad_describe.argtypes = [C.c_void_p]
+        L.gpad_launch_count.restype = C.c_longlong
+        L.gpad_launch_count.argtypes = [C.c_void_p]
+        L.gpad_setup.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.gpad_destroy.argtypes = [C.c_void_p]
+        L.gpad_solve.argtypes = [C.c_void_p, C.POINTER(SolveArgs)]
+        L.gpad_step_one.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+        L.gpad_step_two.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.gpad_array_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.gpad_step_three.argtypes = [C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.gpad_step_four.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_void_p]
+        L.gpad_problem_battery.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.gpad_problem_quadrotor.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.gpad_problem_destroy.argtypes = [C.c_void_p]
+        L.gpad_problem_dims.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip, _fp]
+        L.gpad_problem_operators.argtypes = [C.c_void_p, C.c_int, _fp, _fp]
+        L.gpad_problem_instances.argtypes = [C.c_void_p, C.c_int, _dp, _fp, _fp, _fp]
+        L.gpad_problem_plant.argtypes = [C.c_void_p, _ip, _dp, _dp]
+        L.gpad_schedule.argtypes = [_fp, _fp, C.c_int, C.c_int]
+        L.gpad_file_read.argtypes = [C.c_char_p, C.POINTER(FileData)]
+        L.gpad_file_write.argtypes = [C.c_char_p, C.POINTER(FileData)]
+        L.gpad_file_free.argtypes = [C.POINTER(FileData)]
+        L.gpad_debug_gemm_tf32x3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc, what="gpad call"):
+    if rc != 0:
+        L = lib()
+        raise GpadError(f"{what}: {L.gpad_status_string(rc).decode()} -- {L.gpad_last_error().decode()}")
+
+
+def device_count():
+    return lib().gpad_device_count()
+
+
+def _f32p(a):
+    return a.ctypes.data_as(_fp)
+
+
+def _ptr(x):
+    """raw address of a numpy array / torch tensor / int / None"""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if isinstance(x, int):
+        return x
+    return x.data_ptr()
+
+
+def schedule(count, variant=SCHEDULE_PAPER):
+    th = np.zeros(count, np.float32)
+    be = np.zeros(count, np.float32)
+    check(lib().gpad_schedule(_f32p(th), _f32p(be), count, variant), "gpad_schedule")
+    return th, be
+
+
+class Problem:
+    """Host-side condensed MPC problem (C++ restatement of gpad.m / acceldualgrad.m precompute)."""
+
+    def __init__(self, kind, **kw):
+        self._h = C.c_void_p()
+        L = lib()
+        if kind == "battery":
+            check(L.gpad_problem_battery(kw["n_u"], kw["N"], C.byref(self._h)), "gpad_problem_battery")
+        elif kind == "quadrotor":
+            check(L.gpad_problem_quadrotor(kw.get("N", 100), C.byref(self._h)), "gpad_problem_quadrotor")
+        else:
+            raise ValueError(kind)
+        nu, N, m, npar, Lc = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_float()
+        check(L.gpad_problem_dims(self._h, C.byref(nu), C.byref(N), C.byref(m), C.byref(npar), C.byref(Lc)))
+        self.kind, self.n_u, self.N, self.m, self.n_par, self.L = kind, nu.value, N.value, m.value, npar.value, Lc.value
+        self.n = self.n_u * self.N
+
+    def operators(self, layout=LAYOUT_SEQUENTIAL):
+        M_G = np.empty(self.n * self.m, np.float32)
+        G_L = np.empty(self.n * self.m, np.float32)
+        check(lib().gpad_problem_operators(self._h, layout, _f32p(M_G), _f32p(G_L)), "gpad_problem_operators")
+        if layout == LAYOUT_SEQUENTIAL:
+            return M_G.reshape(self.n, self.m), G_L.reshape(self.m, self.n)
+        return M_G.reshape(self.m, self.n), G_L.reshape(self.n, self.m)
+
+    def instances(self, params, want_f=True):
+        params = np.ascontiguousarray(np.atleast_2d(params), np.float64)
+        B = params.shape[0]
+        assert params.shape[1] == self.n_par
+        g_P = np.empty((B, self.n), np.float32)
+        p_D = np.empty((B, self.m), np.float32)
+        f = np.empty((B, self.n), np.float32) if want_f else None
+        check(lib().gpad_problem_instances(self._h, B, params.ctypes.data_as(_dp), _f32p(g_P), _f32p(p_D),
+                                           _f32p(f) if want_f else None), "gpad_problem_instances")
+        return g_P, p_D, f
+
+    def plant(self):
+        nx = C.c_int()
+        check(lib().gpad_problem_plant(self._h, C.byref(nx), None, None))
+        A = np.empty((nx.value, nx.value)); Bm = np.empty((nx.value, self.n_u))
+        check(lib().gpad_problem_plant(self._h, C.byref(nx), A.ctypes.data_as(_dp), Bm.ctypes.data_as(_dp)))
+        return A, Bm
+
+    def close(self):
+        if self._h:
+            lib().gpad_problem_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Solver:
+    """gpad_setup / gpad_solve / gpad_destroy."""
+
+    def __init__(self, n_u, N, m, L, M_G, G_L, layout=LAYOUT_SEQUENTIAL, mode=MODE_LATENCY, precision=PREC_FP32,
+                 max_batch=1, device=-1, operators_mem=MEM_HOST):
+        cfg = Config(n_u, N, m, float(L), layout, mode, precision, max_batch, device, operators_mem)
+        if operators_mem == MEM_HOST:
+            M_G = np.ascontiguousarray(M_G, np.float32)
+            G_L = np.ascontiguousarray(G_L, np.float32)
+            if n_u > 0 and N > 0 and m > 0:
+                assert M_G.size == n_u * N * m and G_L.size == n_u * N * m
+        self._keep = (M_G, G_L)
+        self._h = C.c_void_p()
+        check(lib().gpad_setup(C.byref(cfg), _ptr(M_G), _ptr(G_L), C.byref(self._h)), "gpad_setup")
+        self.n_u, self.N, self.m, self.n, self.mode, self.max_batch = n_u, N, m, n_u * N, mode, max_batch
+
+    @property
+    def description(self):
+        return lib().gpad_describe(self._h).decode()
+
+    @property
+    def launches(self):
+        return lib().gpad_launch_count(self._h)
+
+    def solve_host(self, g_P, p_D, theta, beta, max_iter=None, f=None, y0=None, y_prev0=None, check_every=0,
+                   eps_g=0.0, eps_V=0.0, outputs=("y_next", "y", "z", "zhat", "w")):
+        """numpy in, numpy out (GPAD_MEM_HOST): H2D + solve + D2H + sync inside the call."""
+        n, m = self.n, self.m
+        g_P = np.ascontiguousarray(g_P, np.float32).reshape(-1, n)
+        B = g_P.shape[0]
+        p_D = np.ascontiguousarray(p_D, np.float32).reshape(B, m)
+        opt = {k: (None if v is None else np.ascontiguousarray(v, np.float32).reshape(B, -1))
+               for k, v in (("f", f), ("y0", y0), ("y_prev0", y_prev0))}
+        theta = np.ascontiguousarray(theta, np.float32); beta = np.ascontiguousarray(beta, np.float32)
+        max_iter = len(theta) if max_iter is None else max_iter
+        out = {k: np.empty((B, m if k in ("y_next", "y", "w") else n), np.float32) for k in outputs}
+        iters = np.zeros(B, np.int32); status = np.zeros(B, np.int32)
+        viol = np.zeros(B, np.float32); gap = np.zeros(B, np.float32)
+        a = SolveArgs(B, MEM_HOST, _ptr(g_P), _ptr(p_D), _ptr(opt["f"]), _ptr(opt["y0"]), _ptr(opt["y_prev0"]),
+                      _f32p(theta), _f32p(beta), max_iter, check_every, eps_g, eps_V,
+                      _ptr(out.get("y_next")), _ptr(out.get("y")), _ptr(out.get("z")), _ptr(out.get("zhat")),
+                      _ptr(out.get("w")), _ptr(iters), _ptr(status), _ptr(viol), _ptr(gap), None)
+        check(lib().gpad_solve(self._h, C.byref(a)), "gpad_solve")
+        if B == 1 and self.mode == MODE_LATENCY:
+            out = {k: v[0] for k, v in out.items()}
+            out.update(iters=int(iters[0]), status=int(status[0]), max_viol=float(viol[0]), gap=float(gap[0]))
+        else:
+            out.update(iters=iters, status=status, max_viol=viol, gap=gap)
+        return out
+
+    def solve_device(self, batch, g_P, p_D, theta, beta, max_iter, stream=None, f=None, y0=None, y_prev0=None,
+                     check_every=0, eps_g=0.0, eps_V=0.0, y_next=None, y=None, z=None, zhat=None, w=None,
+                     iters=None, status=None, max_viol=None, gap=None):
+        """device pointers (torch tensors or ints) in and out (GPAD_MEM_DEVICE): enqueue only."""
+        theta = np.ascontiguousarray(theta, np.float32); beta = np.ascontiguousarray(beta, np.float32)
+        a = SolveArgs(batch, MEM_DEVICE, _ptr(g_P), _ptr(p_D), _ptr(f), _ptr(y0), _ptr(y_prev0),
+                      _f32p(theta), _f32p(beta), max_iter, check_every, eps_g, eps_V,
+                      _ptr(y_next), _ptr(y), _ptr(z), _ptr(zhat), _ptr(w), _ptr(iters), _ptr(status),
+                      _ptr(max_viol), _ptr(gap), stream)
+        check(lib().gpad_solve(self._h, C.byref(a)), "gpad_solve")
+
+    def close(self):
+        if self._h:
+            lib().gpad_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- step shims (device pointers) ----
+def step_one(y, y_prev, w, beta, m, stream=None):
+    check(lib().gpad_step_one(_ptr(y), _ptr(y_prev), _ptr(w), beta, m, stream), "gpad_step_one")
+
+
+def step_two(M_G, w, g_P, zhat, N, n_u, m, stream=None):
+    check(lib().gpad_step_two(_ptr(M_G), _ptr(w), _ptr(g_P), _ptr(zhat), N, n_u, m, stream), "gpad_step_two")
+
+
+def array_copy(dst, src, size, stream=None):
+    check(lib().gpad_array_copy(_ptr(dst), _ptr(src), size, stream), "gpad_array_copy")
+
+
+def step_three(theta, zhat, z, length, stream=None):
+    check(lib().gpad_step_three(theta, _ptr(zhat), _ptr(z), length, stream), "gpad_step_three")
+
+
+def step_four(G_L, y_vp1, w, p_D, zhat, N, n_u, m, max_threads=0, stream=None):
+    check(lib().gpad_step_four(_ptr(G_L), _ptr(y_vp1), _ptr(w), _ptr(p_D), _ptr(zhat), N, n_u, m, max_threads, stream),
+          "gpad_step_four")
+
+
+def debug_gemm_tf32x3(A, B, Cout, M, N, K, stream=None):
+    check(lib().gpad_debug_gemm_tf32x3(_ptr(A), _ptr(B), _ptr(Cout), M, N, K, stream), "gpad_debug_gemm_tf32x3")
+
+
+# ---- reference data file (main.cu:29-67) ----
+def file_write(path, n_u, N, m, L, M_G, g_P, G_L, p_D, theta, beta):
+    arrs = [np.ascontiguousarray(a, np.float32).ravel() for a in (M_G, g_P, G_L, p_D, theta, beta)]
+    fd = FileData(n_u, N, m, arrs[4].size, float(L), *[_f32p(a) for a in arrs])
+    check(lib().gpad_file_write(path.encode(), C.byref(fd)), "gpad_file_write")
+
+
+def file_read(path):
+    fd = FileData()
+    check(lib().gpad_file_read(path.encode(), C.byref(fd)), "gpad_file_read")
+    n, m, it = fd.n_u * fd.N, fd.m, fd.num_iterations
+    take = lambda p, cnt: np.ctypeslib.as_array(p, shape=(cnt,)).copy()
+    out = dict(n_u=fd.n_u, N=fd.N, m=m, num_iterations=it, L=fd.L, M_G=take(fd.M_G, n * m), g_P=take(fd.g_P, n),
+               G_L=take(fd.G_L, n * m), p_D=take(fd.p_D, m), theta=take(fd.theta, max(it, 1))[:it],
+               beta=take(fd.beta, max(it, 1))[:it])
+    lib().gpad_file_free(C.byref(fd))
+    return out

@@ -1,0 +1,216 @@
+/*
+ * gpad.h -- C ABI of libgpad_b200.so, the B200-native (sm_100a) GPAD solver.
+ *
+ * This is the drop-in boundary for the GPAD hot path of shreyasren/GPU-DualGradient-MPC.
+ * The reference has no plugin/FFI layer: its boundary is "the symbols main.cu links against"
+ * (the five __global__ kernels of Code/CUDA/FinalProject/include/kernel_functions.h:9-39,
+ * launched by the loop at main.cu:160-175 on caller-owned device buffers) plus the text data
+ * file main.cu:29-67 reads.  Every entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every function returns a gpad_status (0 = ok) and never exits.
+ *   - n = n_u*N decision variables, m constraints (file header "n_u N m num_iterations L").
+ *   - operators follow the C/CUDA sign convention of the reference: zhat = M_G w - g_P
+ *     (kernel_functions.cu:62, seq_functions.cpp:63), y+ = max(G_L zhat + (w + p_D), 0).
+ *   - batched vectors are instance-major: v[b*len + i] (a batch is B reference problems'
+ *     vectors back to back).
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point
+ *     returns GPAD_ERR_NO_DEVICE / GPAD_ERR_CUDA.
+ *   - a handle is not thread-safe; distinct handles are independent.  The caller owns every
+ *     buffer it passes; the library owns its handle and its converted operator copies.
+ */
+#ifndef GPAD_H
+#define GPAD_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPAD_API_VERSION 1
+
+typedef enum {
+    GPAD_OK = 0,
+    GPAD_ERR_INVALID_ARG = 1,
+    GPAD_ERR_CUDA = 2,
+    GPAD_ERR_UNSUPPORTED = 3,
+    GPAD_ERR_ALLOC = 4,
+    GPAD_ERR_NO_DEVICE = 5,
+    GPAD_ERR_IO = 6
+} gpad_status;
+
+/* operator storage of the pointers given to gpad_setup / the step shims */
+typedef enum {
+    GPAD_LAYOUT_FLIPPED = 0,    /* M_G [m][n], G_L [n][m]: what the reference kernels read
+                                   (ENABLE_FLIPPING, kernel_functions.cu:50,180)            */
+    GPAD_LAYOUT_SEQUENTIAL = 1  /* M_G [n][m], G_L [m][n]: what seq_functions.cpp:61,82 read */
+} gpad_layout;
+
+typedef enum {
+    GPAD_MODE_LATENCY = 1,            /* one QP, persistent kernel, operators resident on chip */
+    GPAD_MODE_BATCH_SHARED = 2,       /* B QPs sharing M_G/G_L: per-iteration GEMMs            */
+    GPAD_MODE_BATCH_PER_INSTANCE = 3  /* B QPs each with its own M_G/G_L: batched GEMV         */
+} gpad_mode;
+
+typedef enum {
+    GPAD_PREC_FP32 = 0,    /* CUDA-core FFMA, fp32 accumulate                                   */
+    GPAD_PREC_TF32X3 = 1   /* tcgen05 kind::tf32, hi/lo split of both operands (3 MMAs/product),
+                              fp32 accumulate in TMEM -- BATCH_SHARED only                      */
+} gpad_precision;
+
+typedef enum { GPAD_MEM_HOST = 0, GPAD_MEM_DEVICE = 1 } gpad_memspace;
+
+/* per-instance termination status (iters/status/max_viol/gap are the termination outputs the
+ * reference never had; SURVEY section 8a row T, acceldualgrad.m:66-79, paper Alg. 1) */
+typedef enum {
+    GPAD_STATUS_MAX_ITER = 0,
+    GPAD_STATUS_CONVERGED_Z = 1,
+    GPAD_STATUS_CONVERGED_ZHAT = 2,
+    GPAD_STATUS_CONVERGED_DUAL = 3,
+    GPAD_STATUS_NONFINITE = 4
+} gpad_solve_status;
+
+typedef enum { GPAD_SCHEDULE_PAPER = 0, GPAD_SCHEDULE_MATLAB_LAG = 1 } gpad_schedule_variant;
+
+const char* gpad_status_string(int status);
+/* message of the last failure on the calling thread (CUDA error text included) */
+const char* gpad_last_error(void);
+int gpad_api_version(void);
+/* number of usable sm_100 devices (0 without a GPU; never fails) */
+int gpad_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * 1. Step-compatible shims: host-callable replacements of the five kernel launches of the
+ *    reference loop body, same argument lists plus a stream (the reference uses the default
+ *    stream and cudaDeviceSynchronize, main.cu:164,168,172; here nothing synchronises).
+ *    All pointers are DEVICE pointers; operators are in GPAD_LAYOUT_FLIPPED like the
+ *    reference's data files.  stream is a cudaStream_t (NULL = default stream).
+ * ---------------------------------------------------------------------------------------- */
+/* replaces StepOneGPADKernel<<<>>>            kernel_functions.h:9,  main.cu:163 */
+int gpad_step_one(const float* y_vec_in, const float* y_vec_minus_1_in, float* w_vec_out,
+                  float beta_v, int m, void* stream);
+/* replaces StepTwoGPADKernel<<<>>>            kernel_functions.h:10-20, main.cu:166 */
+int gpad_step_two(const float* M_G, const float* w_v, const float* g_P, float* zhat,
+                  int N, int n_u, int m, void* stream);
+/* replaces DeviceArrayCopy<<<>>>              kernel_functions.h:39, main.cu:167 */
+int gpad_array_copy(float* dest, const float* src, int size, void* stream);
+/* replaces StepThreeGPADKernel<<<>>>          kernel_functions.h:21, main.cu:170 */
+int gpad_step_three(float theta, const float* zhat_v, float* z_v, int length, void* stream);
+/* replaces StepFourGPADFlippedParRows<<<>>>   kernel_functions.h:26-38, main.cu:171
+ * (max_threads is accepted and ignored, as in the reference kernel) */
+int gpad_step_four(const float* G_L, float* y_vp1, const float* w_v, const float* p_D,
+                   const float* zhat_v, int N, int n_u, int m, int max_threads, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Whole-solve entry points: replace the body of main() between readData and the D2H copies
+ *    (main.cu:108-180): allocation, H2D, the iteration loop, D2H.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gpad_handle_s* gpad_handle_t;
+
+typedef struct {
+    int n_u, N, m;          /* file header, main.cu:34                                        */
+    float L;                /* Lipschitz constant from the file header (used by termination)  */
+    int layout;             /* gpad_layout of M_G / G_L passed to gpad_setup                  */
+    int mode;               /* gpad_mode                                                       */
+    int precision;          /* gpad_precision                                                  */
+    int max_batch;          /* capacity in instances (1 for GPAD_MODE_LATENCY)                 */
+    int device;             /* CUDA device ordinal, -1 = current device                        */
+    int operators_mem;      /* gpad_memspace of M_G / G_L                                      */
+    int reserved[6];        /* must be zero                                                    */
+} gpad_config_t;
+
+/* Uploads / converts the operators once (the cudaMalloc + cudaMemcpy H2D block main.cu:126-147).
+ * GPAD_MODE_BATCH_PER_INSTANCE: M_G / G_L hold max_batch operators back to back. */
+int gpad_setup(const gpad_config_t* cfg, const float* M_G, const float* G_L, gpad_handle_t* out);
+int gpad_destroy(gpad_handle_t h);
+
+typedef struct {
+    int batch;              /* instances in this call, 1..max_batch                            */
+    int mem;                /* gpad_memspace of every in/out pointer below except theta/beta   */
+    /* inputs */
+    const float* g_P;       /* [batch][n]                                                      */
+    const float* p_D;       /* [batch][m]                                                      */
+    const float* f;         /* [batch][n] or NULL; enables the relative / dual gap tests       */
+    const float* y0;        /* [batch][m] or NULL (zeros, main.cu:69-77): y_0   (warm start)   */
+    const float* y_prev0;   /* [batch][m] or NULL (zeros): y_{-1}                              */
+    const float* theta;     /* HOST [max_iter]  (passed by value per launch in main.cu:170)    */
+    const float* beta;      /* HOST [max_iter]  (main.cu:163)                                  */
+    int max_iter;           /* N_v = 100 in main.cu:87                                         */
+    int check_every;        /* <= 0: fixed iteration count (the reference's behaviour)         */
+    float eps_g, eps_V;     /* acceldualgrad.m:12-13                                           */
+    /* outputs, any may be NULL: the five vectors main.cu:176-180 copies back ...              */
+    float* y_next;          /* [batch][m]  y_I       (main.cu: y_vp1)                          */
+    float* y;               /* [batch][m]  y_{I-1}   (main.cu: y_v)                            */
+    float* z;               /* [batch][n]  z_{I-1}   (main.cu: z_v)                            */
+    float* zhat;            /* [batch][n]  zhat_{I-1}                                          */
+    float* w;               /* [batch][m]  w_{I-1}                                             */
+    /* ... and the termination outputs */
+    int* iters;             /* [batch] iterations executed                                     */
+    int* status;            /* [batch] gpad_solve_status                                       */
+    float* max_viol;        /* [batch] max_i g(.)_i at the last check (NaN if never checked)   */
+    float* gap;             /* [batch] duality-gap figure at the last check (NaN if none)      */
+    void* stream;           /* cudaStream_t for GPAD_MEM_DEVICE calls (NULL = default stream)  */
+    int reserved[4];        /* must be zero                                                    */
+} gpad_solve_args_t;
+
+/* GPAD_MEM_HOST: copies in, solves, copies out and synchronises before returning.
+ * GPAD_MEM_DEVICE: enqueues everything on args->stream and returns without synchronising
+ * (iteration-count early exit in tolerance mode synchronises that stream every check). */
+int gpad_solve(gpad_handle_t h, const gpad_solve_args_t* args);
+
+/* kernels launched by this handle since setup (bench.py's gpu_launches claim) */
+long long gpad_launch_count(gpad_handle_t h);
+/* human-readable description of the kernel path chosen for this handle */
+const char* gpad_describe(gpad_handle_t h);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Host-side problem setup (C++ restatement of the MATLAB offline stage: gpad.m:4-85,
+ *    acceldualgrad.m:9-23) and the theta/beta schedule the data file carries (main.cu:61-64).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gpad_problem_s* gpad_problem_t;
+
+/* battery balancing, n_u cells, horizon N: m = 4 n_u N + 2 N, L = ||H||_F^2 */
+int gpad_problem_battery(int n_u, int N, gpad_problem_t* out);
+/* hover-linearised quadrotor, nx = 12, nu = 4, horizon N: m = 24 N, L = 1.02 lambda_max(G H^-1 G') */
+int gpad_problem_quadrotor(int N, gpad_problem_t* out);
+int gpad_problem_destroy(gpad_problem_t p);
+/* n_par = length of the per-instance parameter vector (battery: x0 [n_u]; quadrotor: [x0;xref] [24]) */
+int gpad_problem_dims(gpad_problem_t p, int* n_u, int* N, int* m, int* n_par, float* L);
+/* operators to host buffers of n*m floats each, in the requested gpad_layout */
+int gpad_problem_operators(gpad_problem_t p, int layout, float* M_G, float* G_L);
+/* per-instance vectors from parameters [B][n_par] (double): g_P [B][n], p_D [B][m], f [B][n]
+ * (f may be NULL) -- all host buffers */
+int gpad_problem_instances(gpad_problem_t p, int B, const double* params, float* g_P, float* p_D,
+                           float* f);
+/* plant matrices for closed-loop simulation: A [nx][nx], B [nx][n_u] row-major (double) */
+int gpad_problem_plant(gpad_problem_t p, int* nx, double* A, double* B);
+
+/* theta_v, beta_v for v = 0..count-1 (paper eq. 8e / acceldualgrad.m:55-56) */
+int gpad_schedule(float* theta, float* beta, int count, int variant);
+
+/* ------------------------------------------------------------------------------------------
+ * 4. The reference's text data file (main.cu:29-67): header "n_u N m num_iterations L", then
+ *    M_G (n*m), g_P (n), G_L (n*m), p_D (m), theta[num_iterations], beta[num_iterations].
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int n_u, N, m, num_iterations;
+    float L;
+    float *M_G, *g_P, *G_L, *p_D, *theta, *beta;   /* malloc'ed by gpad_file_read */
+} gpad_file_t;
+
+int gpad_file_read(const char* path, gpad_file_t* out);
+int gpad_file_write(const char* path, const gpad_file_t* in);
+void gpad_file_free(gpad_file_t* f);
+
+/* ------------------------------------------------------------------------------------------
+ * 5. Test hook: C[M][N] = A[M][K] * B[N][K]^T through the tcgen05 3xTF32 mainloop used by
+ *    GPAD_PREC_TF32X3 (device pointers, row-major, any M,N,K >= 1).
+ * ---------------------------------------------------------------------------------------- */
+int gpad_debug_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int K,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPAD_H */

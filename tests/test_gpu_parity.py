@@ -1,0 +1,360 @@
+"""GPU parity tests (-m gpu): every CUDA path of libgpad_b200.so, called through the C ABI, against
+the CPU oracle (oracle/gpad_oracle.c, pinned by tests/test_oracle.py) on identical seeded inputs.
+
+Tolerance (north star: <= 1e-5 relative for fp32 problems), metric rel_inf = ||a-b||_inf/||b||_inf:
+  * GPU vs fp64 arbiter  <= 1e-5  on every vector, every size;
+  * GPU vs oracle        <= 1e-5 + rel_inf(oracle, fp64 arbiter): the oracle's strict left-to-right
+    fp32 sums are themselves up to ~1.3e-5 from fp64 at m >= 600 ("tolerance vs
+    oracle noise"), so its own distance from the arbiter is added rather than hidden;
+  * active set (pattern of y_I > 0) and iteration count / status: exact (flips are counted and
+    must be zero, except entries below 1e-6 in the fp64 arbiter, which are reported).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import problems as P
+from oracle import Oracle, schedule
+
+pytestmark = pytest.mark.gpu
+
+VECS = ("y_next", "y", "z", "zhat", "w")
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpad_b200
+    return gpad_b200
+
+
+def check_parity(gpu, ora, f64, label=""):
+    worst = 0.0
+    for k in VECS:
+        e64 = P.rel_inf(gpu[k], f64[k])
+        eor = P.rel_inf(gpu[k], ora[k])
+        noise = P.rel_inf(ora[k], f64[k])
+        assert e64 <= TOL, f"{label} {k}: GPU vs fp64 {e64:.3e}"
+        assert eor <= TOL + noise, f"{label} {k}: GPU vs oracle {eor:.3e} (oracle noise {noise:.3e})"
+        worst = max(worst, e64)
+    act_g, act_o = gpu["y_next"] > 0, ora["y_next"] > 0
+    flips = np.flatnonzero(act_g != act_o)
+    tiny = [i for i in flips if abs(f64["y_next"].ravel()[i]) < 1e-6]
+    assert len(flips) == len(tiny), f"{label}: {len(flips)} active-set flips, {len(tiny)} of them below 1e-6"
+    return worst
+
+
+def battery_case(n_u, N, seed=0):
+    pb = P.battery(n_u, N)
+    rng = np.random.default_rng(seed)
+    g_P, p_D, f = pb.instance(P.battery_x0(n_u, rng))
+    return pb, g_P, p_D, f
+
+
+# ------------------------------------------------------------------------------------ step shims
+@pytest.mark.parametrize("case", ["b3x4", "b4x3", "b10x15"])
+def test_step_shims_against_reference_golden(torch_cuda, G, golden_dir, case):
+    """the transliterated reference loop body (main.cu:163-171) on the flipped operators the
+    reference kernels read, against outputs of the reference's own seq_functions.cpp"""
+    t = torch_cuda
+    g = np.load(os.path.join(golden_dir, f"ref_steps_{case}.npz"))
+    n_u, N, m = (int(v) for v in g["dims"])
+    n = n_u * N
+    dev = lambda a: t.from_numpy(np.ascontiguousarray(a, np.float32)).cuda()
+    M_G_f, G_L_f = dev(g["M_G"].reshape(n, m).T), dev(g["G_L"].reshape(m, n).T)
+    y, y_prev, g_P, p_D = dev(g["y"]), dev(g["y_prev"]), dev(g["g_P"]), dev(g["p_D"])
+    w, zhat, y_next, z = t.empty(m, device="cuda"), t.empty(n, device="cuda"), t.empty(m, device="cuda"), t.zeros(n, device="cuda")
+    G.step_one(y, y_prev, w, float(g["beta"]), m)
+    G.step_two(M_G_f, w, g_P, zhat, N, n_u, m)
+    G.array_copy(y_prev, y, m)
+    G.step_three(0.25, zhat, z, n)
+    G.step_four(G_L_f, y_next, w, p_D, zhat, N, n_u, m, 3660)
+    t.cuda.synchronize()
+    assert np.array_equal(w.cpu().numpy(), g["w"])                    # elementwise: bit-exact
+    assert np.array_equal(y_prev.cpu().numpy(), g["y"])
+    assert P.rel_inf(zhat.cpu().numpy(), g["zhat"]) <= TOL
+    assert P.rel_inf(y_next.cpu().numpy(), g["y_next"]) <= TOL
+    assert np.allclose(z.cpu().numpy(), 0.25 * zhat.cpu().numpy(), rtol=1e-6, atol=0)
+    assert np.array_equal(y_next.cpu().numpy() > 0, g["y_next"] > 0)
+
+
+def test_step_shim_loop_equals_oracle_solve(torch_cuda, G, oracle):
+    t = torch_cuda
+    pb, g_P, p_D, _ = battery_case(10, 15)
+    n_u, N, n, m = 10, 15, pb.n, pb.m
+    theta, beta = schedule(100)
+    dev = lambda a: t.from_numpy(np.ascontiguousarray(a, np.float32)).cuda()
+    dM_G, dG_L, dg_P, dp_D = dev(pb.M_G_flipped()), dev(pb.G_L_flipped()), dev(g_P), dev(p_D)
+    dy_vp1, dy_v, dw_v = t.zeros(m, device="cuda"), t.zeros(m, device="cuda"), t.zeros(m, device="cuda")
+    dz_v, dzhat_v = t.zeros(n, device="cuda"), t.zeros(n, device="cuda")
+    for v in range(100):                                              # main.cu:160-175, 1:1
+        G.step_one(dy_vp1, dy_v, dw_v, float(beta[v]), m)
+        G.step_two(dM_G, dw_v, dg_P, dzhat_v, N, n_u, m)
+        G.array_copy(dy_v, dy_vp1, m)
+        G.step_three(float(theta[v]), dzhat_v, dz_v, n)
+        G.step_four(dG_L, dy_vp1, dw_v, dp_D, dzhat_v, N, n_u, m, 3660)
+    t.cuda.synchronize()
+    gpu = dict(y_next=dy_vp1.cpu().numpy(), y=dy_v.cpu().numpy(), z=dz_v.cpu().numpy(), zhat=dzhat_v.cpu().numpy(),
+               w=dw_v.cpu().numpy())
+    ora = oracle.solve(n_u, N, m, pb.M_G, pb.G_L, g_P, p_D, theta, beta)
+    f64 = oracle.solve_f64(n_u, N, m, pb.M_G, pb.G_L, g_P, p_D, theta, beta)
+    check_parity(gpu, ora, f64, "shim loop (10,15)")
+
+
+# ------------------------------------------------------------------------------------ latency mode
+LADDER = [(3, 4), (4, 3), (10, 15), (15, 10), (30, 30), (10, 100)]
+
+
+@pytest.mark.parametrize("dims", LADDER)
+def test_latency_fixed_iterations_match_oracle(torch_cuda, G, oracle, dims):
+    n_u, N = dims
+    pb, g_P, p_D, _ = battery_case(n_u, N)
+    theta, beta = schedule(100)
+    s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, layout=G.LAYOUT_SEQUENTIAL, mode=G.MODE_LATENCY)
+    print("\n", dims, s.description)
+    gpu = s.solve_host(g_P, p_D, theta, beta)
+    ora = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta)
+    f64 = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta)
+    worst = check_parity(gpu, ora, f64, f"latency {dims}")
+    assert gpu["iters"] == 100 and gpu["status"] == 0
+    print(f"   worst GPU-vs-fp64 rel_inf {worst:.2e}")
+    # idempotence: a second solve on the same handle reproduces the first bit for bit
+    again = s.solve_host(g_P, p_D, theta, beta)
+    for k in VECS:
+        assert np.array_equal(gpu[k], again[k])
+    s.close()
+
+
+@pytest.mark.parametrize("plan", ["block", "cluster:2", "cluster:8", "grid:16", "grid:148"])
+def test_latency_every_synchronisation_variant(torch_cuda, G, oracle, plan, monkeypatch):
+    """the same QP through single-CTA, cluster/DSMEM and cooperative-grid variants, operators in
+    shared memory and streamed from L2"""
+    n_u, N = 10, 15
+    pb, g_P, p_D, f = battery_case(n_u, N)
+    theta, beta = schedule(100)
+    ora = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta)
+    f64 = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta)
+    for no_smem in ([True] if plan == "block" else [False, True]):
+        monkeypatch.setenv("GPAD_LATENCY_PLAN", plan)
+        if no_smem:
+            monkeypatch.setenv("GPAD_LATENCY_NO_SMEM_OPS", "1")
+        else:
+            monkeypatch.delenv("GPAD_LATENCY_NO_SMEM_OPS", raising=False)
+        s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G_flipped(), pb.G_L_flipped(), layout=G.LAYOUT_FLIPPED, mode=G.MODE_LATENCY)
+        print("\n", plan, s.description)
+        gpu = s.solve_host(g_P, p_D, theta, beta)
+        check_parity(gpu, ora, f64, f"latency plan {plan} no_smem={no_smem}")
+        s.close()
+
+
+@pytest.mark.parametrize("case", ["b3x4", "b4x3", "b10x15"])
+def test_latency_against_reference_golden(torch_cuda, G, golden_dir, case):
+    g = np.load(os.path.join(golden_dir, f"ref_solve_{case}.npz"))
+    n_u, N, m = (int(v) for v in g["dims"])
+    s = G.Solver(n_u, N, m, float(g["L"]), g["M_G"], g["G_L"], mode=G.MODE_LATENCY)
+    gpu = s.solve_host(g["g_P"], g["p_D"], g["theta"], g["beta"])
+    for k in VECS:
+        assert P.rel_inf(gpu[k], g[k]) <= 2.5e-5, k      # vs the reference's own serial-fp32 output
+    assert np.array_equal(gpu["y_next"] > 0, g["y_next"] > 0)
+    s.close()
+
+
+@pytest.mark.parametrize("dims,eps", [((3, 4), 1e-2), ((3, 4), 1e-3), ((3, 4), 1e-4), ((10, 15), 1e-2),
+                                      ((10, 15), 1e-3), ((15, 10), 1e-3), ((10, 15), 1e-4)])
+@pytest.mark.parametrize("with_f", [False, True])
+def test_latency_termination_matches_oracle(torch_cuda, G, oracle, dims, eps, with_f):
+    n_u, N = dims
+    pb, g_P, p_D, f = battery_case(n_u, N)
+    theta, beta = schedule(2000)
+    kw = dict(check_every=1, eps_g=eps, eps_V=eps)
+    s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_LATENCY)
+    gpu = s.solve_host(g_P, p_D, theta, beta, f=f if with_f else None, **kw)
+    ora = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, f=f if with_f else None, **kw)
+    slack = 0 if eps >= 1e-3 else 1           # counts are exact away from the fp32 floor
+    assert gpu["status"] == ora["status"], (gpu["status"], ora["status"])
+    assert abs(gpu["iters"] - ora["iters"]) <= slack, (gpu["iters"], ora["iters"])
+    if gpu["iters"] == ora["iters"]:
+        for k in VECS:
+            assert P.rel_inf(gpu[k], ora[k]) <= 3e-5, k
+        assert abs(gpu["max_viol"] - ora["max_viol"]) <= 1e-5 + 1e-3 * abs(ora["max_viol"])
+    # check_every = 7 stops on a multiple of 7 and agrees with the oracle under the same setting
+    gpu7 = s.solve_host(g_P, p_D, theta, beta, f=f if with_f else None, check_every=7, eps_g=eps, eps_V=eps)
+    ora7 = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, f=f if with_f else None,
+                        check_every=7, eps_g=eps, eps_V=eps)
+    assert gpu7["iters"] % 7 == 0 and abs(gpu7["iters"] - ora7["iters"]) <= 7 * slack
+    s.close()
+
+
+def test_latency_dual_gap_branch(torch_cuda, G, oracle):
+    """instances that reach a check with a negative entry in w take the V(zhat) - Phi(y) branch"""
+    hit = 0
+    theta, beta = schedule(3000)
+    for seed in range(12):
+        n_u, N = 4, 6
+        pb = P.battery(n_u, N)
+        rng = np.random.default_rng(100 + seed)
+        g_P, p_D, f = pb.instance(rng.random(n_u) - 0.5)
+        kw = dict(check_every=1, eps_g=5e-2, eps_V=5e-2)
+        ora = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, f=f, **kw)
+        s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_LATENCY)
+        gpu = s.solve_host(g_P, p_D, theta, beta, f=f, **kw)
+        s.close()
+        assert gpu["status"] == ora["status"] and gpu["iters"] == ora["iters"], (seed, gpu["status"], ora["status"], gpu["iters"], ora["iters"])
+        for k in VECS:
+            assert P.rel_inf(gpu[k], ora[k]) <= 3e-5
+        hit += ora["status"] == 3
+    print("\n dual-gap terminations:", hit)
+
+
+def test_latency_warm_start_and_device_buffers(torch_cuda, G, oracle):
+    t = torch_cuda
+    n_u, N = 10, 15
+    pb, g_P, p_D, _ = battery_case(n_u, N, seed=4)
+    theta, beta = schedule(40)
+    cold = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta)
+    warm_o = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, y0=cold["y_next"], y_prev0=cold["y"])
+    warm_d = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, y0=cold["y_next"], y_prev0=cold["y"])
+    s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_LATENCY)
+    dev = lambda a: t.from_numpy(np.ascontiguousarray(a, np.float32)).cuda()
+    out = {k: t.empty(pb.m if k in ("y_next", "y", "w") else pb.n, device="cuda") for k in VECS}
+    iters = t.zeros(1, dtype=t.int32, device="cuda"); status = t.zeros(1, dtype=t.int32, device="cuda")
+    stream = t.cuda.Stream()
+    with t.cuda.stream(stream):
+        s.solve_device(1, dev(g_P), dev(p_D), theta, beta, 40, stream=stream.cuda_stream, y0=dev(cold["y_next"]),
+                       y_prev0=dev(cold["y"]), iters=iters, status=status, **out)
+    stream.synchronize()
+    gpu = {k: v.cpu().numpy() for k, v in out.items()}
+    check_parity(gpu, warm_o, warm_d, "warm start, device buffers")
+    assert int(iters.item()) == 40 and int(status.item()) == 0
+    s.close()
+
+
+# ------------------------------------------------------------------------------------ tensor-core GEMM hook
+@pytest.mark.parametrize("shape", [(128, 16, 16), (128, 256, 64), (300, 200, 1000), (1000, 416, 2400), (257, 2400, 400)])
+def test_tf32x3_gemm_reaches_fp32_accuracy(torch_cuda, G, shape):
+    t = torch_cuda
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    dA, dB = t.from_numpy(A).cuda(), t.from_numpy(B).cuda()
+    dC = t.full((M, N), float("nan"), device="cuda")
+    G.debug_gemm_tf32x3(dA, dB, dC, M, N, K)
+    t.cuda.synchronize()
+    C = dC.cpu().numpy()
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T     # sum |a||b|
+    err = np.max(np.abs(C - ref) / scale)
+    fp32 = np.max(np.abs((A @ B.T).astype(np.float64) - ref) / scale)
+    print(f"\n {shape}: 3xTF32 err {err:.2e} of sum|a||b|  (numpy fp32 {fp32:.2e})")
+    assert np.isfinite(C).all()
+    assert err <= 2e-6
+
+
+# ------------------------------------------------------------------------------------ batch, shared operators
+def batch_reference(oracle, pb, n_u, N, g_P, p_D, theta, beta, **kw):
+    ora = oracle.solve_batch(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, **kw)
+    f64 = {k: np.zeros_like(ora[k], dtype=np.float64) for k in VECS}
+    for b in range(g_P.shape[0]):
+        d = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P[b], p_D[b], theta, beta)
+        for k in VECS:
+            f64[k][b] = d[k]
+    return ora, f64
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("dims,B", [((3, 4), 300), ((10, 15), 130), ((15, 10), 129)])
+def test_batch_battery_matches_oracle(torch_cuda, G, oracle, prec, dims, B):
+    n_u, N = dims
+    pb = P.battery(n_u, N)
+    X0 = np.random.default_rng(B).random((B, n_u)) - 0.5
+    g_P, p_D, _ = pb.instance(X0)
+    theta, beta = schedule(100)
+    s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED,
+                 precision=G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32, max_batch=B)
+    print("\n", s.description)
+    gpu = s.solve_host(g_P, p_D, theta, beta)
+    ora, f64 = batch_reference(oracle, pb, n_u, N, g_P, p_D, theta, beta)
+    worst = check_parity(gpu, ora, f64, f"batch {prec} {dims}")
+    print(f"   worst GPU-vs-fp64 rel_inf {worst:.2e}")
+    assert (gpu["iters"] == 100).all() and (gpu["status"] == 0).all()
+    # a smaller batch on the same handle: instance results do not depend on the batch they ride in
+    sub = s.solve_host(g_P[:7], p_D[:7], theta, beta)
+    for k in VECS:
+        assert np.array_equal(sub[k], gpu[k][:7]), k
+    s.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_batch_quadrotor_matches_oracle(torch_cuda, G, oracle, prec):
+    N = 20
+    pb = P.quadrotor(N)
+    B = 140
+    par = P.quadrotor_params(B, np.random.default_rng(7))
+    g_P, p_D, _ = pb.instance(par)
+    theta, beta = schedule(100)
+    s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED,
+                 precision=G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32, max_batch=B)
+    gpu = s.solve_host(g_P, p_D, theta, beta)
+    ora, f64 = batch_reference(oracle, pb, 4, N, g_P, p_D, theta, beta)
+    worst = check_parity(gpu, ora, f64, f"batch {prec} quadrotor N={N}")
+    print(f"\n quadrotor N={N} {prec}: worst GPU-vs-fp64 rel_inf {worst:.2e}")
+    s.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_batch_termination_matches_oracle(torch_cuda, G, oracle, prec):
+    n_u, N, B = 3, 4, 200
+    pb = P.battery(n_u, N)
+    X0 = np.random.default_rng(11).random((B, n_u)) - 0.5
+    g_P, p_D, _ = pb.instance(X0)
+    theta, beta = schedule(400)
+    kw = dict(check_every=2, eps_g=1e-3, eps_V=1e-3)
+    s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED,
+                 precision=G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32, max_batch=B)
+    gpu = s.solve_host(g_P, p_D, theta, beta, **kw)
+    ora = oracle.solve_batch(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, **kw)
+    assert np.array_equal(gpu["status"], ora["status"])
+    assert np.array_equal(gpu["iters"], ora["iters"]), np.flatnonzero(gpu["iters"] != ora["iters"])
+    assert len(set(ora["iters"].tolist())) > 3          # instances really stop at different iterations
+    for k in VECS:
+        assert P.rel_inf(gpu[k], ora[k]) <= 3e-5, k
+    s.close()
+
+
+def test_full_size_quadrotor_properties(torch_cuda, G, oracle):
+    """BASELINE config 4 shapes (n=400, m=2400) at a batch the oracle cannot follow: size-independent
+    properties instead -- the tensor-core path agrees with the CUDA-core path, duplicate instances
+    give identical results wherever they sit in the batch, and a handful of instances are checked
+    against the oracle."""
+    N, B = 100, 1024
+    pb = G.Problem("quadrotor", N=N)
+    M_G, G_L = pb.operators()
+    rng = np.random.default_rng(3)
+    par = P.quadrotor_params(B, rng)
+    par[B - 5:] = par[:5]                                   # duplicates at the far end of the batch
+    g_P, p_D, _ = pb.instances(par, want_f=False)
+    theta, beta = schedule(30)
+    res = {}
+    for prec, code in (("fp32", G.PREC_FP32), ("tf32x3", G.PREC_TF32X3)):
+        s = G.Solver(4, N, pb.m, pb.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=code, max_batch=B)
+        res[prec] = s.solve_host(g_P, p_D, theta, beta)
+        s.close()
+    for k in VECS:
+        assert P.rel_inf(res["tf32x3"][k], res["fp32"][k]) <= TOL, k
+        assert np.array_equal(res["tf32x3"][k][B - 5:], res["tf32x3"][k][:5]), k
+    assert np.array_equal(res["tf32x3"]["y_next"] > 0, res["fp32"]["y_next"] > 0) or \
+        (np.abs(res["fp32"]["y_next"][(res["tf32x3"]["y_next"] > 0) != (res["fp32"]["y_next"] > 0)]) < 1e-6).all()
+    for b in (0, 517):
+        d = oracle.solve_f64(4, N, pb.m, M_G, G_L, g_P[b], p_D[b], theta, beta)
+        for k in VECS:
+            assert P.rel_inf(res["tf32x3"][k][b], d[k]) <= TOL, (b, k)
