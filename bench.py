@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- GPAD QP solves/sec at batch 64K (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3]): quadrotor-style MPC, nx=12, nu=4, horizon N=100 (n=400 decision
+variables, m=2400 box + polytopic constraints), a batch of 65536 independent QPs per GPU sharing
+M_G / G_L, random initial states and set-points (seeded), fixed 100 GPAD iterations per solve
+(main.cu:87).  A STEP is one whole solve of the batch: 100 iterations of the hot path
+(main.cu:160-175 loop body) through gpad_solve() in throughput mode (tcgen05 3xTF32).
+
+  value     device-resident: inputs already in HBM, CUDA events around K gpad_solve() calls on the
+            launching stream, max over ranks;  solves/s = N_gpus * 65536 * K / T
+  e2e       the same K solves through the C ABI with HOST (pinned) buffers: H2D of g_P / p_D and
+            D2H of the five vectors main.cu:176-180 copies back are inside the timed region
+  roofline  dominant kernel = the tcgen05 3xTF32 GEMM (both products are the same kernel template):
+            algorithmic FLOPs per launch 2*n*m*B divided by its mean launch duration measured with
+            CUDA events inside the library (gpad_profile_*), against the tensor-pipe peak for this
+            precision scheme: MEASURED_PEAKS.json bf16 sustained / 2 (tf32) / 3 (three MMAs/product)
+  cpu_baseline  the reference's own seq_functions.cpp (oracle/_ref, kind "reference") or the C
+            restatement (kind "port") on all host cores, bounded sample of the same workload
+  --impl reference  times that CPU path as the whole arm (no GPU code involved)
+Inputs (2.9 GB per GPU per solve with state) are far larger than the 126 MB L2, so no flush is needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "gpu-dualgradient-mpc_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "GPAD QP solves/sec at batch 64K"
+UNIT = "solves/s"
+BATCH = 65536
+HORIZON = 100
+ITERS = 100           # N_v, main.cu:87
+WORKLOAD = ("quadrotor MPC nx=12 nu=4 N=100: n=400, m=2400 (box + polytopic), 65536 QPs per GPU sharing M_G/G_L, "
+            "random x0/set-points (seed 0), fixed 100 GPAD iterations per solve")
+
+
+def quad_params(B, seed):
+    """per-instance [x0 (12); xref (12)], same distribution as tests/problems.py:quadrotor_params"""
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros((B, 12)); xr = np.zeros((B, 12))
+    x0[:, 0:3] = rng.uniform(-1.0, 1.0, (B, 3)); x0[:, 3:6] = rng.uniform(-1.0, 1.0, (B, 3))
+    x0[:, 6:8] = rng.uniform(-0.2, 0.2, (B, 2)); x0[:, 8] = rng.uniform(-0.5, 0.5, B)
+    x0[:, 9:12] = rng.uniform(-0.5, 0.5, (B, 3))
+    xr[:, 0:3] = rng.uniform(-2.0, 2.0, (B, 3)); xr[:, 8] = rng.uniform(-0.5, 0.5, B)
+    return np.hstack([x0, xr])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                smax = float(f[1])
+                if t0 - 0.05 <= ts <= t1 + 0.05:
+                    sm.append(float(f[0]))
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("bf16_tflops_sustained", 1388.8), d.get("hbm_gbs", 6545.3), "MEASURED_PEAKS.json"
+    return 1400.0, 6650.0, "B200_PROFILING.md fallback"
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_solver():
+    """(callable, kind): batch solve on all host cores through the reference's own compiled
+    seq_functions.cpp when oracle/_ref exists, else the C restatement"""
+    import oracle
+    oracle.build()
+    if oracle.have_ref():
+        ref = oracle.RefLib()
+        return (lambda pb, g, p, th, be, nt: ref.solve_batch(pb["n_u"], pb["N"], pb["m"], pb["M_G"], pb["G_L"], g, p, th, be,
+                                                             nthreads=nt)), "reference"
+    ora = oracle.Oracle()
+    return (lambda pb, g, p, th, be, nt: ora.solve_batch(pb["n_u"], pb["N"], pb["m"], pb["M_G"], pb["G_L"], g, p, th, be,
+                                                         nthreads=nt)), "port"
+
+
+def host_problem():
+    import gpad_b200 as G
+    prob = G.Problem("quadrotor", N=HORIZON)
+    M_G, G_L = prob.operators(G.LAYOUT_SEQUENTIAL)
+    return prob, dict(n_u=prob.n_u, N=prob.N, m=prob.m, n=prob.n, L=prob.L, M_G=M_G, G_L=G_L)
+
+
+def cpu_rate(budget_s, cores=None):
+    """solves/s of the CPU path on `cores` threads over a sample sized to ~budget_s seconds"""
+    import gpad_b200 as G
+    solve, kind = cpu_solver()
+    prob, pb = host_problem()
+    theta, beta = G.schedule(ITERS)
+    cores = cores or os.cpu_count() or 1
+    g1, p1, _ = prob.instances(quad_params(cores, 99), want_f=False)
+    t0 = time.perf_counter(); solve(pb, g1, p1, theta, beta, cores); t_probe = time.perf_counter() - t0   # one solve per core
+    count = int(max(cores, min(65536, budget_s / max(t_probe, 1e-3) * cores)))
+    g, p, _ = prob.instances(quad_params(count, 7), want_f=False)
+    t0 = time.perf_counter(); out = solve(pb, g, p, theta, beta, cores); dt = time.perf_counter() - t0
+    return count / dt, dict(kind=kind, cores=int(out["threads"]),
+                            sample=f"{count} of the workload's QPs, 100 iterations each, {dt:.1f} s on {out['threads']} threads")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import gpad_b200 as G
+    solve, kind = cpu_solver()
+    prob, pb = host_problem()
+    theta, beta = G.schedule(ITERS)
+    cores = os.cpu_count() or 1
+    g1, p1, _ = prob.instances(quad_params(cores, 99), want_f=False)
+    t0 = time.perf_counter(); solve(pb, g1, p1, theta, beta, cores); t_probe = time.perf_counter() - t0
+    total_steps = args.steps + args.warmup
+    per_step_s = max(1.0, min(15.0, 150.0 / max(total_steps, 1)))
+    count = int(max(cores, per_step_s / max(t_probe, 1e-3) * cores))
+    g, p, _ = prob.instances(quad_params(count, 7), want_f=False)
+    for _ in range(args.warmup):
+        solve(pb, g, p, theta, beta, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = solve(pb, g, p, theta, beta, cores)
+    dt = time.perf_counter() - t0
+    value = count * args.steps / dt
+    sample = f"{count} of the workload's QPs per step, 100 iterations each, on {out['threads']} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "step": "bounded sample: " + sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(out["threads"]), "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def latency_probe(torch, G):
+    """single-QP p50 solve latency (second half of the BASELINE metric), latency mode, device-resident"""
+    out = {}
+    for n_u, N in ((3, 4), (10, 100)):
+        prob = G.Problem("battery", n_u=n_u, N=N)
+        M_G, G_L = prob.operators()
+        x0 = np.array([[-0.1, 0.45, -0.09, 0.05, 0, -0.05, 0.3, 0.2, 0.25, -0.45]]) if n_u == 10 else np.array([[0.31, -0.12, 0.44]])
+        g_P, p_D, _ = prob.instances(x0, want_f=False)
+        theta, beta = G.schedule(ITERS)
+        s = G.Solver(n_u, N, prob.m, prob.L, M_G, G_L, mode=G.MODE_LATENCY)
+        dg, dp = torch.from_numpy(g_P[0]).cuda(), torch.from_numpy(p_D[0]).cuda()
+        dz = torch.empty(prob.n, device="cuda"); dy = torch.empty(prob.m, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for _ in range(10):
+            s.solve_device(1, dg, dp, theta, beta, ITERS, stream=st, z=dz, y_next=dy)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(300):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); s.solve_device(1, dg, dp, theta, beta, ITERS, stream=st, z=dz, y_next=dy); e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        out[f"battery({n_u},{N}) n={prob.n} m={prob.m}"] = {"p50_us": float(np.median(ts)), "p99_us": float(np.percentile(ts, 99)),
+                                                            "iterations": ITERS, "path": s.description}
+        s.close()
+    return out
+
+
+def run_ours(args):
+    import torch
+    import gpad_b200 as G
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device and no CPU fallback exists for the product path "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    prob, pb = host_problem()
+    n, m, B = prob.n, prob.m, args.batch
+    theta, beta = G.schedule(ITERS)
+    g_P, p_D, _ = prob.instances(quad_params(B, seed=rank), want_f=False)
+    prec = G.PREC_FP32 if args.precision == "fp32" else G.PREC_TF32X3
+    solver = G.Solver(prob.n_u, prob.N, m, prob.L, pb["M_G"], pb["G_L"], mode=G.MODE_BATCH_SHARED, precision=prec,
+                      max_batch=B, device=local)
+    stream = torch.cuda.current_stream()
+    st = stream.cuda_stream
+    d_gP, d_pD = torch.from_numpy(g_P).cuda(), torch.from_numpy(p_D).cuda()
+    names = ("y_next", "y", "z", "zhat", "w")
+    d_out = {k: torch.empty((B, m if k in ("y_next", "y", "w") else n), device="cuda") for k in names}
+    d_it = torch.zeros(B, dtype=torch.int32, device="cuda"); d_st = torch.zeros(B, dtype=torch.int32, device="cuda")
+
+    def step_device():
+        solver.solve_device(B, d_gP, d_pD, theta, beta, ITERS, stream=st, iters=d_it, status=d_st, **d_out)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    solver.profile(True)
+    solver.profile_read(1); solver.profile_read(2)
+    launches0 = solver.launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    if dist is not None:
+        # the only exchange of the path: final gather of the first control move u0 = z[:, :n_u] and the status
+        u0 = d_out["z"][:, :prob.n_u].contiguous()
+        gathered = [torch.empty_like(u0) for _ in range(world)] if rank == 0 else None
+        dist.gather(u0, gathered, dst=0)
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    elapsed_ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(elapsed_ms.item())
+    launches = solver.launches - launches0
+    ms1, c1 = solver.profile_read(1)
+    ms2, c2 = solver.profile_read(2)
+    solver.profile(False)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region ----
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    h_gP, h_pD = pin(g_P), pin(p_D)
+    h_out = {k: torch.empty((B, m if k in ("y_next", "y", "w") else n), pin_memory=True).numpy() for k in names}
+    from gpad_b200 import SolveArgs, MEM_HOST, _ptr, _f32p, check, lib
+    import ctypes as C
+    h_it = np.zeros(B, np.int32); h_st = np.zeros(B, np.int32)
+    a = SolveArgs(B, MEM_HOST, _ptr(h_gP), _ptr(h_pD), None, None, None, _f32p(theta), _f32p(beta), ITERS, 0, 0.0, 0.0,
+                  _ptr(h_out["y_next"]), _ptr(h_out["y"]), _ptr(h_out["z"]), _ptr(h_out["zhat"]), _ptr(h_out["w"]),
+                  _ptr(h_it), _ptr(h_st), None, None, None)
+    e2e_steps = max(1, min(args.steps, 3))
+    check(lib().gpad_solve(solver._h, C.byref(a)), "gpad_solve (e2e warm-up)")
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        check(lib().gpad_solve(solver._h, C.byref(a)), "gpad_solve (e2e)")      # synchronises before returning
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    t_e2e = float(t_e2e.item())
+    h2d = (g_P.nbytes + p_D.nbytes)
+    d2h = sum(v.nbytes for v in h_out.values()) + h_it.nbytes + h_st.nbytes
+    ok = bool(np.isfinite(h_out["z"]).all() and (h_st == 0).all() and (h_it == ITERS).all())
+    same = bool(np.array_equal(h_out["z"], d_out["z"].cpu().numpy()))
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+    e2e_value = world * B * e2e_steps / t_e2e
+    bf16_sus, hbm, peak_src = measured_peaks()
+    peak = bf16_sus / 2.0 / 3.0 if prec == G.PREC_TF32X3 else None
+    flops_per_launch = 2.0 * n * m * B
+    k_ms = (ms1 + ms2) / max(c1 + c2, 1)
+    achieved = flops_per_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    if prec == G.PREC_TF32X3:
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "kernel": "tc_gemm_kernel (tcgen05 kind::tf32 x3)", "algorithmic_flops_per_launch": flops_per_launch,
+                "mean_launch_ms": k_ms, "launches_timed": int(c1 + c2), "product1_ms": ms1 / max(c1, 1), "product2_ms": ms2 / max(c2, 1),
+                "kernel_share_of_step": (ms1 + ms2) / elapsed_ms,
+                "peak_basis": f"{peak_src}: bf16 sustained {bf16_sus} TF/s / 2 (tf32) / 3 (hi*lo + lo*hi + hi*hi MMAs per product), of measured"}
+    else:
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if achieved else None,
+                "traffic": traffic, "kernel": "simt_gemm_kernel (CUDA-core FFMA)", "peak_basis": "148 SMs x 128 FMA/clk x 1.965 GHz (nominal fp32)"}
+
+    cpu_val, cpu_info = cpu_rate(args.cpu_budget)
+    lat = latency_probe(torch, G) if not args.no_latency else None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (tf32 x3 split products, fp32 accumulate)" if prec == G.PREC_TF32X3 else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "iters_per_solve": ITERS, "n": n, "m": m,
+                   "step": "one gpad_solve() of the whole batch = 100 GPAD iterations", "l2": "inputs (>2.9 GB/GPU) exceed the 126 MB L2; no flush",
+                   "precision": args.precision, "path": solver.description},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                "results_finite_and_complete": ok, "matches_device_resident_run": same},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "cpu_baseline": dict(value=cpu_val, unit=UNIT, **cpu_info),
+        "clocks": clocks,
+        "single_qp_latency": lat,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "fp32"])
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-latency", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

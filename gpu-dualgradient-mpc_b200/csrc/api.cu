@@ -45,6 +45,27 @@ struct gpad_handle_s {
     cudaStream_t own_stream = nullptr;
     std::vector<void*> allocs;
 
+    // ---- optional per-kernel event timing (gpad_profile_*) ----
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_used[3];
+    cudaEvent_t prof_begin(cudaStream_t s) {
+        if (!profile) return nullptr;
+        cudaEvent_t e = take_event();
+        cudaEventRecord(e, s);
+        return e;
+    }
+    void prof_end(int which, cudaEvent_t begin, cudaStream_t s) {
+        if (!profile || !begin) return;
+        cudaEvent_t e = take_event();
+        cudaEventRecord(e, s);
+        ev_used[which].push_back({begin, e});
+    }
+    cudaEvent_t take_event() {
+        if (ev_pool.empty()) { cudaEvent_t e; cudaEventCreate(&e); return e; }
+        cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e;
+    }
+
     // ---- latency mode ----
     lat::Params lp{};
     int sync_mode = 0, G = 1, threads = 256;
@@ -246,7 +267,9 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
     p.out_max_viol = dev && a->max_viol ? a->max_viol : h->o_viol;
     p.out_gap = dev && a->gap ? a->gap : h->o_gap;
     GPAD_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned), s));
+    cudaEvent_t pe = h->prof_begin(s);
     GPAD_TRY(lat::launch(p, h->sync_mode, h->ops_smem, h->G, h->threads, s));
+    h->prof_end(0, pe, s);
     h->launches += 1;
     if (host) {
         if (a->y_next) GPAD_CUDA(cudaMemcpyAsync(a->y_next, h->o_ynext, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
@@ -372,7 +395,6 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
     h->g1.m_tiles = m_tiles; h->g2.m_tiles = m_tiles;
     const int Bp_call = m_tiles * 128;
 
-    int executed = 0;
     for (int v = 0; v < a->max_iter; ++v) {
         const bool check = checking && ((v + 1) % a->check_every == 0);
         const bool last = v + 1 == a->max_iter;
@@ -383,13 +405,21 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
         k.y_cur = st.y[v & 1];
         k.y_next = st.y[(v + 1) & 1];
         if (tcp) {
+            cudaEvent_t pe = h->prof_begin(s);
             GPAD_TRY(tc::launch_gemm(1, h->g1, k, nullptr, 0, h->num_sms, s));
+            h->prof_end(1, pe, s);
+            pe = h->prof_begin(s);
             GPAD_TRY(tc::launch_gemm(2, h->g2, k, nullptr, 0, h->num_sms, s));
+            h->prof_end(2, pe, s);
         } else {
-            GPAD_TRY(launch_simt_iteration(h->op, k, Bp_call, s));
+            cudaEvent_t pe = h->prof_begin(s);
+            GPAD_TRY(launch_simt_product(1, h->op, k, Bp_call, s));
+            h->prof_end(1, pe, s);
+            pe = h->prof_begin(s);
+            GPAD_TRY(launch_simt_product(2, h->op, k, Bp_call, s));
+            h->prof_end(2, pe, s);
         }
         h->launches += 2;
-        executed = v + 1;
         if (check) {
             GPAD_TRY(launch_batch_decide(st, v + 1, h->cfg.L, a->eps_g, a->eps_V, a->f != nullptr, s));
             h->launches += 1;
@@ -402,7 +432,6 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
             }
         }
     }
-    (void)executed;
     if (!checking && a->max_iter > 0) {
         GPAD_TRY(launch_batch_finite(st, st.y[a->max_iter & 1], s));
         h->launches += 1;
@@ -558,6 +587,9 @@ int gpad_destroy(gpad_handle_t h) {
     if (!h) return GPAD_OK;
     cudaSetDevice(h->device);
     for (void* p : h->allocs) cudaFree(p);
+    for (int k = 0; k < 3; ++k)
+        for (auto& pr : h->ev_used[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->h_active) cudaFreeHost(h->h_active);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     cudaGetLastError();
@@ -578,6 +610,30 @@ int gpad_solve(gpad_handle_t h, const gpad_solve_args_t* a) {
     }
     GPAD_CUDA(cudaSetDevice(h->device));
     return h->cfg.mode == GPAD_MODE_LATENCY ? solve_latency(h, a) : solve_batch(h, a);
+}
+
+int gpad_profile_enable(gpad_handle_t h, int enable) {
+    GPAD_REQUIRE(h, "gpad_profile_enable: null handle");
+    h->profile = enable != 0;
+    return GPAD_OK;
+}
+
+int gpad_profile_read(gpad_handle_t h, int which, double* total_ms, long long* launches) {
+    GPAD_REQUIRE(h && which >= 0 && which < 3, "gpad_profile_read: bad argument");
+    GPAD_CUDA(cudaSetDevice(h->device));
+    double ms = 0.0;
+    for (auto& pr : h->ev_used[which]) {
+        GPAD_CUDA(cudaEventSynchronize(pr.second));
+        float t = 0.f;
+        GPAD_CUDA(cudaEventElapsedTime(&t, pr.first, pr.second));
+        ms += t;
+        h->ev_pool.push_back(pr.first);
+        h->ev_pool.push_back(pr.second);
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = (long long)h->ev_used[which].size();
+    h->ev_used[which].clear();
+    return GPAD_OK;
 }
 
 long long gpad_launch_count(gpad_handle_t h) { return h ? h->launches : 0; }

@@ -67,7 +67,7 @@ template <bool SPLIT>
 __device__ __forceinline__ void epilogue1(const BatchKernelArgs& a, int b, int i, float acc, float& f_zhat) {
     const size_t o = (size_t)b * a.np + i;
     const float zh = acc - a.g_P[o];
-    a.z[o] = (1.0f - a.it.theta) * a.z[o] + a.it.theta * zh;
+    a.z[o] = __fadd_rn(__fmul_rn(1.0f - a.it.theta, a.z[o]), __fmul_rn(a.it.theta, zh));   // unfused like the CPU build
     a.zhat[o] = zh;
     if (SPLIT) {
         float hi, lo;
@@ -92,7 +92,7 @@ __device__ __forceinline__ void epilogue2(const BatchKernelArgs& a, int b, int i
     a.y_next[o] = yn;
     if (a.checking) {
         const float rhat = acc + pd;
-        const float sb = (1.0f - a.it.theta) * a.sbar[o] + a.it.theta * rhat;
+        const float sb = __fadd_rn(__fmul_rn(1.0f - a.it.theta, a.sbar[o]), __fmul_rn(a.it.theta, rhat));
         a.sbar[o] = sb;
         if (a.it.check) {
             r.max_sbar = fmaxf(r.max_sbar, sb);
@@ -105,7 +105,7 @@ __device__ __forceinline__ void epilogue2(const BatchKernelArgs& a, int b, int i
     }
     if (!a.it.last) {
         const float yv = a.y_cur[o];
-        const float wn = yn + a.it.beta_next * (yn - yv);
+        const float wn = __fadd_rn(yn, __fmul_rn(a.it.beta_next, __fsub_rn(yn, yv)));
         a.w[o] = wn;
         if (SPLIT) {
             float hi, lo;

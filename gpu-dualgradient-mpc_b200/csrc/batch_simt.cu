@@ -130,7 +130,7 @@ __global__ void batch_init_kernel(int Bp, int np, int mp, const float* __restric
     const size_t tm = (size_t)Bp * mp, tn = (size_t)Bp * np;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tm; idx += (size_t)gridDim.x * blockDim.x) {
         const float y = y0[idx], yp = yprev0[idx];
-        const float wv = y + beta0 * (y - yp);
+        const float wv = __fadd_rn(y, __fmul_rn(beta0, __fsub_rn(y, yp)));
         w[idx] = wv;
         if (w_hi) { float hi, lo; split_tf32(wv, hi, lo); w_hi[idx] = hi; w_lo[idx] = lo; }
         if (sbar) sbar[idx] = 0.f;
@@ -197,7 +197,7 @@ __global__ void batch_advance_w_kernel(int B, int m, int mp, const float* __rest
         const int b = (int)(idx / mp), i = (int)(idx % mp);
         if (i >= m || done[b]) continue;
         const float yn = y_next[idx], yv = y_cur[idx];
-        const float wn = yn + beta_next * (yn - yv);
+        const float wn = __fadd_rn(yn, __fmul_rn(beta_next, __fsub_rn(yn, yv)));
         w[idx] = wn;
         if (w_hi) { float hi, lo; split_tf32(wn, hi, lo); w_hi[idx] = hi; w_lo[idx] = lo; }
     }
@@ -292,12 +292,15 @@ int launch_batch_finite(const BatchState& st, const float* y_next, cudaStream_t 
     return GPAD_OK;
 }
 
-// one GPAD iteration on CUDA cores: two fused GEMM launches
-int launch_simt_iteration(const Operators& op, const BatchKernelArgs& args, int Bp, cudaStream_t s) {
-    dim3 g1((args.n + BN - 1) / BN, Bp / BM), g2((args.m + BN - 1) / BN, Bp / BM);
-    simt_gemm_kernel<1><<<g1, 256, 0, s>>>(args.w, args.mp, op.M_G, args.mp, args.mp, args);
-    GPAD_CUDA(cudaGetLastError());
-    simt_gemm_kernel<2><<<g2, 256, 0, s>>>(args.zhat, args.np, op.G_L, args.np, args.np, args);
+// one product of a GPAD iteration on CUDA cores (fused GEMM + epilogue)
+int launch_simt_product(int phase, const Operators& op, const BatchKernelArgs& args, int Bp, cudaStream_t s) {
+    if (phase == 1) {
+        dim3 g1((args.n + BN - 1) / BN, Bp / BM);
+        simt_gemm_kernel<1><<<g1, 256, 0, s>>>(args.w, args.mp, op.M_G, args.mp, args.mp, args);
+    } else {
+        dim3 g2((args.m + BN - 1) / BN, Bp / BM);
+        simt_gemm_kernel<2><<<g2, 256, 0, s>>>(args.zhat, args.np, op.G_L, args.np, args.np, args);
+    }
     GPAD_CUDA(cudaGetLastError());
     return GPAD_OK;
 }

@@ -91,7 +91,7 @@ int launch_batch_decide(const BatchState& st, int iter_done, float L, float eps_
 int launch_batch_advance_w(const BatchState& st, const float* y_next, const float* y_cur, float beta_next, bool split,
                            cudaStream_t s);
 int launch_batch_finite(const BatchState& st, const float* y_next, cudaStream_t s);
-int launch_simt_iteration(const Operators& op, const BatchKernelArgs& args, int Bp, cudaStream_t s);
+int launch_simt_product(int phase, const Operators& op, const BatchKernelArgs& args, int Bp, cudaStream_t s);
 int launch_step_one(const float* y, const float* y_prev, float* w, float beta, int m, cudaStream_t s);
 int launch_gemv_t(const float* A, const float* x, int rows, int cols, int mode, const float* v1,
                   const float* v2, float* out, cudaStream_t s);

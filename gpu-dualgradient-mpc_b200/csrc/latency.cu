@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
         float wv = 0.f;
         if (i < m) {
             const float y = p.y0 ? p.y0[i] : 0.f, yp = p.y_prev0 ? p.y_prev0[i] : 0.f;
-            wv = y + beta0 * (y - yp);                       // step 1 of iteration 0
+            wv = __fadd_rn(y, __fmul_rn(beta0, __fsub_rn(y, yp)));   // step 1 of iteration 0 (unfused like the CPU build)
         }
         w_s[i] = wv;
     }
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
                 const float d = row_dot<OPS_SMEM>(row, w_s, mld4, sub, lpr_a);
                 if (valid && sub == 0) {
                     const float zh = d - p.g_P[a0 + r];
-                    z_s[r] = one_minus * z_s[r] + theta * zh;
+                    z_s[r] = __fadd_rn(__fmul_rn(one_minus, z_s[r]), __fmul_rn(theta, zh));
                     publish<SYNC>(zh_s, p.x_zhat, a0 + r, zh);
                     if (check && p.f) f_zhat = fmaf(p.f[a0 + r], zh, f_zhat);
                 }
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
                     dt_s[r] = d;
                     if (checking) {
                         const float rhat = d + pd;
-                        const float sb = one_minus * sb_s[r] + theta * rhat;
+                        const float sb = __fadd_rn(__fmul_rn(one_minus, sb_s[r]), __fmul_rn(theta, rhat));
                         sb_s[r] = sb;
                         if (check) {
                             r_max_sbar = fmaxf(r_max_sbar, sb);
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
                 __syncthreads();   // every row of this CTA has read its w_s[i] / finished yn_s
                 for (int r = tid; r < nb; r += nthr) {
                     const float yn = yn_s[r], yv = yv_s[r];
-                    publish<SYNC>(w_s, p.x_w, b0 + r, yn + beta_next * (yn - yv));
+                    publish<SYNC>(w_s, p.x_w, b0 + r, __fadd_rn(yn, __fmul_rn(beta_next, __fsub_rn(yn, yv))));
                     yp_s[r] = yv;
                     yv_s[r] = yn;
                 }
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
             __syncthreads();
             for (int r = tid; r < nb; r += nthr) {
                 const float yn = yn_s[r], yv = yv_s[r];
-                publish<SYNC>(w_s, p.x_w, b0 + r, yn + beta_next * (yn - yv));
+                publish<SYNC>(w_s, p.x_w, b0 + r, __fadd_rn(yn, __fmul_rn(beta_next, __fsub_rn(yn, yv))));
                 yp_s[r] = yv;
                 yv_s[r] = yn;
             }

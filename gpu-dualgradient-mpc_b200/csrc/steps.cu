@@ -19,14 +19,14 @@ __global__ void step_one_kernel(const float* __restrict__ y, const float* __rest
                                 float* __restrict__ w, float beta, int m) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
         const float yi = y[i];
-        w[i] = yi + beta * (yi - y_prev[i]);
+        w[i] = __fadd_rn(yi, __fmul_rn(beta, __fsub_rn(yi, y_prev[i])));   // unfused, like the CPU build
     }
 }
 
 __global__ void step_three_kernel(float theta, const float* __restrict__ zhat, float* __restrict__ z, int n) {
     const float one_minus = 1.0f - theta;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        z[i] = one_minus * z[i] + theta * zhat[i];
+        z[i] = __fadd_rn(__fmul_rn(one_minus, z[i]), __fmul_rn(theta, zhat[i]));
 }
 
 __global__ void copy_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {

@@ -25,6 +25,7 @@ EXPORTS = [
     "gpad_status_string", "gpad_last_error", "gpad_api_version", "gpad_device_count",
     "gpad_step_one", "gpad_step_two", "gpad_array_copy", "gpad_step_three", "gpad_step_four",
     "gpad_setup", "gpad_destroy", "gpad_solve", "gpad_launch_count", "gpad_describe",
+    "gpad_profile_enable", "gpad_profile_read",
     "gpad_problem_battery", "gpad_problem_quadrotor", "gpad_problem_destroy", "gpad_problem_dims",
     "gpad_problem_operators", "gpad_problem_instances", "gpad_problem_plant", "gpad_schedule",
     "gpad_file_read", "gpad_file_write", "gpad_file_free", "gpad_debug_gemm_tf32x3",
@@ -76,6 +77,8 @@ def lib():
         L.gpad_describe.argtypes = [C.c_void_p]
         L.gpad_launch_count.restype = C.c_longlong
         L.gpad_launch_count.argtypes = [C.c_void_p]
+        L.gpad_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        L.gpad_profile_read.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
         L.gpad_setup.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.gpad_destroy.argtypes = [C.c_void_p]
         L.gpad_solve.argtypes = [C.c_void_p, C.POINTER(SolveArgs)]
@@ -211,6 +214,15 @@ class Solver:
     @property
     def launches(self):
         return lib().gpad_launch_count(self._h)
+
+    def profile(self, enable=True):
+        check(lib().gpad_profile_enable(self._h, 1 if enable else 0), "gpad_profile_enable")
+
+    def profile_read(self, which):
+        """(total_ms, launches) of kernel `which` (0 latency, 1 product 1, 2 product 2) since last read"""
+        ms, cnt = C.c_double(), C.c_longlong()
+        check(lib().gpad_profile_read(self._h, which, C.byref(ms), C.byref(cnt)), "gpad_profile_read")
+        return ms.value, cnt.value
 
     def solve_host(self, g_P, p_D, theta, beta, max_iter=None, f=None, y0=None, y_prev0=None, check_every=0,
                    eps_g=0.0, eps_V=0.0, outputs=("y_next", "y", "z", "zhat", "w")):

@@ -159,6 +159,14 @@ typedef struct {
  * (iteration-count early exit in tolerance mode synchronises that stream every check). */
 int gpad_solve(gpad_handle_t h, const gpad_solve_args_t* args);
 
+/* Optional per-kernel device timing: when enabled, every hot-path kernel launch of this handle is
+ * bracketed by CUDA events on the launching stream (bench.py's roofline figure).
+ * which: 0 = latency persistent kernel, 1 = product-1 kernel, 2 = product-2 kernel.
+ * gpad_profile_read synchronises, returns the accumulated milliseconds and launch count since the
+ * last read, and resets them. */
+int gpad_profile_enable(gpad_handle_t h, int enable);
+int gpad_profile_read(gpad_handle_t h, int which, double* total_ms, long long* launches);
+
 /* kernels launched by this handle since setup (bench.py's gpu_launches claim) */
 long long gpad_launch_count(gpad_handle_t h);
 /* human-readable description of the kernel path chosen for this handle */
