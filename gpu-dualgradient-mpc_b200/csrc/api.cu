@@ -302,7 +302,7 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
     GPAD_TRY(upload_padded(h, GL.data(), m, n, h->op.m_rows_pad, st.np, &h->op.G_L));
     const size_t bm = (size_t)st.Bp * st.mp, bnn = (size_t)st.Bp * st.np;
     GPAD_TRY(dev_alloc(h, &st.g_P, bnn)); GPAD_TRY(dev_alloc(h, &st.p_D, bm)); GPAD_TRY(dev_alloc(h, &st.f, bnn));
-    GPAD_TRY(dev_alloc(h, &st.y[0], bm)); GPAD_TRY(dev_alloc(h, &st.y[1], bm)); GPAD_TRY(dev_alloc(h, &st.w, bm));
+    GPAD_TRY(dev_alloc(h, &st.yb[0], bm)); GPAD_TRY(dev_alloc(h, &st.yb[1], bm)); GPAD_TRY(dev_alloc(h, &st.yb[2], bm));
     GPAD_TRY(dev_alloc(h, &st.z, bnn)); GPAD_TRY(dev_alloc(h, &st.zhat, bnn)); GPAD_TRY(dev_alloc(h, &st.sbar, bm));
     GPAD_TRY(dev_alloc(h, &st.red, (size_t)st.Bp * kRedStride));
     GPAD_TRY(dev_alloc(h, &st.done, st.Bp)); GPAD_TRY(dev_alloc(h, &st.iters, st.Bp)); GPAD_TRY(dev_alloc(h, &st.status, st.Bp));
@@ -312,7 +312,6 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
     GPAD_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_active), sizeof(int)));
     char buf[320];
     if (tcp) {
-        GPAD_TRY(dev_alloc(h, &st.w_hi, bm)); GPAD_TRY(dev_alloc(h, &st.w_lo, bm));
         GPAD_TRY(dev_alloc(h, &st.zh_hi, bnn)); GPAD_TRY(dev_alloc(h, &st.zh_lo, bnn));
         GPAD_CUDA(cudaMemset(st.zh_hi, 0, bnn * sizeof(float))); GPAD_CUDA(cudaMemset(st.zh_lo, 0, bnn * sizeof(float)));
         const size_t c1 = (size_t)h->op.n_rows_pad * st.mp, c2 = (size_t)h->op.m_rows_pad * st.np;
@@ -329,8 +328,7 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         g1.stages = tc::pick_stages(bk, bn1, h->smem_optin);
         g2.stages = tc::pick_stages(bk, bn2, h->smem_optin);
         if (const char* e = getenv("GPAD_TC_STAGES")) { g1.stages = std::min(g1.stages, std::max(2, atoi(e))); g2.stages = std::min(g2.stages, std::max(2, atoi(e))); }
-        GPAD_TRY(tc::make_tmap(&g1.tmA_hi, st.w_hi, st.mp, st.Bp, st.mp, bk, 128));
-        GPAD_TRY(tc::make_tmap(&g1.tmA_lo, st.w_lo, st.mp, st.Bp, st.mp, bk, 128));
+        for (int k = 0; k < 3; ++k) GPAD_TRY(tc::make_tmap(&g1.tmY[k], st.yb[k], st.mp, st.Bp, st.mp, bk, 128));
         GPAD_TRY(tc::make_tmap(&g1.tmB_hi, h->op.M_G, st.mp, h->op.n_rows_pad, st.mp, bk, bn1));
         GPAD_TRY(tc::make_tmap(&g1.tmB_lo, h->op.M_G_lo, st.mp, h->op.n_rows_pad, st.mp, bk, bn1));
         GPAD_TRY(tc::make_tmap(&g2.tmA_hi, st.zh_hi, st.np, st.Bp, st.np, bk, 128));
@@ -338,8 +336,8 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         GPAD_TRY(tc::make_tmap(&g2.tmB_hi, h->op.G_L, st.np, h->op.m_rows_pad, st.np, bk, bn2));
         GPAD_TRY(tc::make_tmap(&g2.tmB_lo, h->op.G_L_lo, st.np, h->op.m_rows_pad, st.np, bk, bn2));
         snprintf(buf, sizeof(buf),
-                 "batch-shared: tcgen05 kind::tf32 x3 (hi/lo split), TMA ring bk=%d, product1 tiles 128x%d x%d (%d stages), "
-                 "product2 tiles 128x%d x%d (%d stages), TMEM 2x256 cols, persistent over %d SMs",
+                 "batch-shared: tcgen05 kind::tf32 x3 (hi/lo split, w built in-kernel), TMA ring bk=%d, product1 tiles 128x%d x%d "
+                 "(%d stages), product2 tiles 128x%d x%d (%d stages), TMEM 2x256 cols, persistent over %d SMs",
                  bk, bn1, nt1, g1.stages, bn2, nt2, g2.stages, h->num_sms);
     } else {
         snprintf(buf, sizeof(buf), "batch-shared: CUDA-core fp32 GEMM 128x128x16 tiles with fused GPAD epilogues");
@@ -380,16 +378,17 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
     GPAD_TRY(ingest(h, st.g_P, st.np, a->g_P, n, B, host, s));
     GPAD_TRY(ingest(h, st.p_D, st.mp, a->p_D, m, B, host, s));
     if (a->f) GPAD_TRY(ingest(h, st.f, st.np, a->f, n, B, host, s));
-    GPAD_TRY(ingest(h, st.y[0], st.mp, a->y0, m, B, host, s));
-    GPAD_TRY(ingest(h, st.y[1], st.mp, a->y_prev0, m, B, host, s));
-    GPAD_TRY(launch_batch_init(st, st.y[0], st.y[1], a->max_iter > 0 ? a->beta[0] : 0.f, tcp, checking, s));
+    GPAD_TRY(ingest(h, st.yb[0], st.mp, a->y0, m, B, host, s));         // y_0
+    GPAD_TRY(ingest(h, st.yb[2], st.mp, a->y_prev0, m, B, host, s));    // y_{-1}
+    GPAD_TRY(launch_batch_init(st, checking, s));
     GPAD_TRY(launch_batch_reset_term(st, a->max_iter, s));
+    GPAD_TRY(upload_schedule(h, a->theta, a->beta, a->max_iter, s));    // beta[] on the device for the w output
     h->launches += 2;
 
     BatchKernelArgs k{};
     k.n = n; k.m = m; k.np = st.np; k.mp = st.mp; k.B = B; k.checking = checking ? 1 : 0; k.L = h->cfg.L;
     k.g_P = st.g_P; k.p_D = st.p_D; k.f = a->f ? st.f : nullptr;
-    k.w = st.w; k.w_hi = st.w_hi; k.w_lo = st.w_lo; k.z = st.z; k.zhat = st.zhat; k.zh_hi = st.zh_hi; k.zh_lo = st.zh_lo;
+    k.z = st.z; k.zhat = st.zhat; k.zh_hi = st.zh_hi; k.zh_lo = st.zh_lo;
     k.sbar = st.sbar; k.red = st.red; k.done = checking ? st.done : nullptr;
     const int m_tiles = round_up(B, 128) / 128;
     h->g1.m_tiles = m_tiles; h->g2.m_tiles = m_tiles;
@@ -397,13 +396,13 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
 
     for (int v = 0; v < a->max_iter; ++v) {
         const bool check = checking && ((v + 1) % a->check_every == 0);
-        const bool last = v + 1 == a->max_iter;
         k.it.theta = a->theta[v];
-        k.it.beta_next = last ? 0.f : a->beta[v + 1];
+        k.it.beta = a->beta[v];
         k.it.check = check ? 1 : 0;
-        k.it.last = (last || check) ? 1 : 0;     // on check iterations w advances after the decision
-        k.y_cur = st.y[v & 1];
-        k.y_next = st.y[(v + 1) & 1];
+        k.y_prev = st.yb[(v + 2) % 3];           // y_{v-1}
+        k.y_cur = st.yb[v % 3];                  // y_v
+        k.y_next = st.yb[(v + 1) % 3];           // y_{v+1} overwrites y_{v-2}
+        if (tcp) { h->g1.tmA_hi = h->g1.tmY[v % 3]; h->g1.tmA_lo = h->g1.tmY[(v + 2) % 3]; }
         if (tcp) {
             cudaEvent_t pe = h->prof_begin(s);
             GPAD_TRY(tc::launch_gemm(1, h->g1, k, nullptr, 0, h->num_sms, s));
@@ -426,40 +425,29 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
             GPAD_CUDA(cudaMemcpyAsync(h->h_active, st.active_count, sizeof(int), cudaMemcpyDeviceToHost, s));
             GPAD_CUDA(cudaStreamSynchronize(s));
             if (*h->h_active <= 0) break;
-            if (!last) {
-                GPAD_TRY(launch_batch_advance_w(st, k.y_next, k.y_cur, k.it.beta_next, tcp, s));
-                h->launches += 1;
-            }
         }
     }
     if (!checking && a->max_iter > 0) {
-        GPAD_TRY(launch_batch_finite(st, st.y[a->max_iter & 1], s));
+        GPAD_TRY(launch_batch_finite(st, st.yb[a->max_iter % 3], s));
         h->launches += 1;
     }
 
     // ---- outputs ----
-    if (a->y_next || a->y) {
-        float* d_next = a->y_next ? (host ? h->stage_in : a->y_next) : nullptr;
-        // host mode stages one vector at a time
-        if (host) {
-            if (a->y_next) {
-                GPAD_TRY(launch_unpad_y(h->stage_in, nullptr, m, B, st.y[0], st.y[1], st.mp, st.iters, s));
-                GPAD_CUDA(cudaMemcpyAsync(a->y_next, h->stage_in, sizeof(float) * (size_t)B * m, cudaMemcpyDeviceToHost, s));
-                h->launches += 1;
-            }
-            if (a->y) {
-                GPAD_TRY(launch_unpad_y(nullptr, h->stage_in, m, B, st.y[0], st.y[1], st.mp, st.iters, s));
-                GPAD_CUDA(cudaMemcpyAsync(a->y, h->stage_in, sizeof(float) * (size_t)B * m, cudaMemcpyDeviceToHost, s));
-                h->launches += 1;
-            }
-        } else {
-            GPAD_TRY(launch_unpad_y(d_next, a->y, m, B, st.y[0], st.y[1], st.mp, st.iters, s));
+    if (host) {      // host mode stages one vector at a time
+        float* dst[3] = {a->y_next, a->y, a->w};
+        for (int k3 = 0; k3 < 3; ++k3) {
+            if (!dst[k3]) continue;
+            GPAD_TRY(launch_unpad_y(k3 == 0 ? h->stage_in : nullptr, k3 == 1 ? h->stage_in : nullptr, k3 == 2 ? h->stage_in : nullptr,
+                                    m, B, st.yb[0], st.yb[1], st.yb[2], st.mp, st.iters, h->d_beta, s));
+            GPAD_CUDA(cudaMemcpyAsync(dst[k3], h->stage_in, sizeof(float) * (size_t)B * m, cudaMemcpyDeviceToHost, s));
             h->launches += 1;
         }
+    } else if (a->y_next || a->y || a->w) {
+        GPAD_TRY(launch_unpad_y(a->y_next, a->y, a->w, m, B, st.yb[0], st.yb[1], st.yb[2], st.mp, st.iters, h->d_beta, s));
+        h->launches += 1;
     }
     GPAD_TRY(emit(h, a->z, n, B, st.z, st.np, host, s));
     GPAD_TRY(emit(h, a->zhat, n, B, st.zhat, st.np, host, s));
-    GPAD_TRY(emit(h, a->w, m, B, st.w, st.mp, host, s));
     const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     if (a->iters) GPAD_CUDA(cudaMemcpyAsync(a->iters, st.iters, sizeof(int) * B, kind, s));
     if (a->status) GPAD_CUDA(cudaMemcpyAsync(a->status, st.status, sizeof(int) * B, kind, s));

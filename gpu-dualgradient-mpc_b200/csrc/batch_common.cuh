@@ -4,8 +4,10 @@
 //
 //   product 1 (step 2 + 3, kernel_functions.cu:16-72):   acc = <M_G[i,:], w_b>
 //        zhat = acc - g_P;  z = (1-theta) z + theta zhat
-//   product 2 (step 4 + next step 1, kernel_functions.cu:142-200, 7-14):  acc = <G_L[i,:], zhat_b>
-//        s = acc + (w + p_D);  y+ = (s + |s|)/2;  w+ = y+ + beta_{v+1} (y+ - y)
+//   product 2 (step 1 + 4, kernel_functions.cu:7-14, 142-200):  acc = <G_L[i,:], zhat_b>
+//        w = y + beta (y - y_prev);  s = acc + (w + p_D);  y+ = (s + |s|)/2
+// w is never stored: product 1 rebuilds it (and its tf32 split) while staging its A operand,
+// product 2 rebuilds it here, which saves three m-sized HBM arrays per iteration.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -27,11 +29,9 @@ struct BatchKernelArgs {
     const float* g_P;
     const float* p_D;
     const float* f;
-    const float* y_cur;
-    float* y_next;
-    float* w;
-    float* w_hi;
-    float* w_lo;
+    const float* y_prev;   // y_{v-1}
+    const float* y_cur;    // y_v
+    float* y_next;         // y_{v+1}
     float* z;
     float* zhat;
     float* zh_hi;
@@ -82,11 +82,14 @@ struct Red2 {
     float max_sbar = -INFINITY, max_rhat = -INFINITY, min_w = INFINITY, w_rhat = 0.f, w_dot = 0.f, bad = 0.f;
 };
 
+__device__ __forceinline__ float momentum(float y, float y_prev, float beta) {
+    return __fadd_rn(y, __fmul_rn(beta, __fsub_rn(y, y_prev)));      // step 1, unfused like the CPU build
+}
+
 // ---- product 2 epilogue for one element (instance b, row i of G_L) ----
-template <bool SPLIT>
 __device__ __forceinline__ void epilogue2(const BatchKernelArgs& a, int b, int i, float acc, Red2& r) {
     const size_t o = (size_t)b * a.mp + i;
-    const float wv = a.w[o], pd = a.p_D[o];
+    const float wv = momentum(a.y_cur[o], a.y_prev[o], a.it.beta), pd = a.p_D[o];
     const float s = acc + (wv + pd);
     const float yn = 0.5f * (s + fabsf(s));
     a.y_next[o] = yn;
@@ -101,17 +104,6 @@ __device__ __forceinline__ void epilogue2(const BatchKernelArgs& a, int b, int i
             r.w_rhat = fmaf(wv, rhat, r.w_rhat);
             r.w_dot = fmaf(wv, acc, r.w_dot);
             if (!isfinite(yn)) r.bad = 1.f;
-        }
-    }
-    if (!a.it.last) {
-        const float yv = a.y_cur[o];
-        const float wn = __fadd_rn(yn, __fmul_rn(a.it.beta_next, __fsub_rn(yn, yv)));
-        a.w[o] = wn;
-        if (SPLIT) {
-            float hi, lo;
-            split_tf32(wn, hi, lo);
-            a.w_hi[o] = hi;
-            a.w_lo[o] = lo;
         }
     }
 }

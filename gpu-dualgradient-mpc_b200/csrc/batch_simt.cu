@@ -18,8 +18,9 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
 
 // C[b][i] = sum_k A[b*lda + k] * Bop[i*ldb + k], K multiple of BK, rows padded to BM / BN.
+// PHASE 1: A = w_v built on the fly from y_v (A) and y_{v-1} (A2): step 1 fused into the operand load.
 template <int PHASE>
-__global__ void __launch_bounds__(256) simt_gemm_kernel(const float* __restrict__ A, int lda,
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const float* __restrict__ A, const float* __restrict__ A2, int lda,
                                                         const float* __restrict__ Bop, int ldb, int K,
                                                         const BatchKernelArgs args) {
     __shared__ __align__(16) float As[2][BK][BM + PAD];
@@ -37,11 +38,19 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const float* __restrict_
     // global -> register staging: 2 float4 per operand per thread
     const int lr0 = tid >> 2, lk = (tid & 3) * 4;    // rows lr0 and lr0+64, k offset lk
     const float* Ag = A + (size_t)(row0 + lr0) * lda + lk;
+    const float* Ag2 = PHASE == 1 ? A2 + (size_t)(row0 + lr0) * lda + lk : nullptr;
     const float* Bg = Bop + (size_t)(col0 + lr0) * ldb + lk;
     float4 ra0, ra1, rb0, rb1;
+    const float beta = args.it.beta;
     auto load_g = [&](int k0) {
         ra0 = *reinterpret_cast<const float4*>(Ag + k0);
         ra1 = *reinterpret_cast<const float4*>(Ag + (size_t)64 * lda + k0);
+        if (PHASE == 1) {
+            const float4 p0 = *reinterpret_cast<const float4*>(Ag2 + k0);
+            const float4 p1 = *reinterpret_cast<const float4*>(Ag2 + (size_t)64 * lda + k0);
+            ra0 = make_float4(momentum(ra0.x, p0.x, beta), momentum(ra0.y, p0.y, beta), momentum(ra0.z, p0.z, beta), momentum(ra0.w, p0.w, beta));
+            ra1 = make_float4(momentum(ra1.x, p1.x, beta), momentum(ra1.y, p1.y, beta), momentum(ra1.z, p1.z, beta), momentum(ra1.w, p1.w, beta));
+        }
         rb0 = __ldg(reinterpret_cast<const float4*>(Bg + k0));
         rb1 = __ldg(reinterpret_cast<const float4*>(Bg + (size_t)64 * ldb + k0));
     };
@@ -95,7 +104,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const float* __restrict_
             if (c >= ncols) continue;
             any = true;
             if (PHASE == 1) epilogue1<false>(args, b, c, acc[i][j], f_zhat);
-            else epilogue2<false>(args, b, c, acc[i][j], red);
+            else epilogue2(args, b, c, acc[i][j], red);
         }
         if (args.it.check && any) {
             if (PHASE == 1) { if (args.f) atomicAdd(args.red + (size_t)b * kRedStride + 5, f_zhat); }
@@ -123,18 +132,12 @@ __global__ void unpad_rows_kernel(float* __restrict__ dst, int len, int B, const
     }
 }
 
-// w_0 = y_0 + beta_0 (y_0 - y_{-1}) (step 1 of iteration 0), its tf32 split, zeroed z / sbar
-__global__ void batch_init_kernel(int Bp, int np, int mp, const float* __restrict__ y0, const float* __restrict__ yprev0,
-                                  float beta0, float* __restrict__ w, float* __restrict__ w_hi, float* __restrict__ w_lo,
-                                  float* __restrict__ z, float* __restrict__ zhat, float* __restrict__ sbar) {
+// zeroed z / zhat / sbar (y_0, y_{-1} were written into yb[0], yb[2] by the padding copies)
+__global__ void batch_init_kernel(int Bp, int np, int mp, float* __restrict__ z, float* __restrict__ zhat,
+                                  float* __restrict__ sbar) {
     const size_t tm = (size_t)Bp * mp, tn = (size_t)Bp * np;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tm; idx += (size_t)gridDim.x * blockDim.x) {
-        const float y = y0[idx], yp = yprev0[idx];
-        const float wv = __fadd_rn(y, __fmul_rn(beta0, __fsub_rn(y, yp)));
-        w[idx] = wv;
-        if (w_hi) { float hi, lo; split_tf32(wv, hi, lo); w_hi[idx] = hi; w_lo[idx] = lo; }
-        if (sbar) sbar[idx] = 0.f;
-    }
+    if (sbar)
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tm; idx += (size_t)gridDim.x * blockDim.x) sbar[idx] = 0.f;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tn; idx += (size_t)gridDim.x * blockDim.x) {
         z[idx] = 0.f;
         zhat[idx] = 0.f;
@@ -187,34 +190,21 @@ __global__ void batch_decide_kernel(int B, int iter_done, float L, float eps_g, 
     r[0] = -INFINITY; r[1] = -INFINITY; r[2] = INFINITY; r[3] = 0.f; r[4] = 0.f; r[5] = 0.f; r[6] = 0.f;
 }
 
-// after a check iteration: w_{v+1} = y+ + beta_{v+1} (y+ - y) for the instances still running
-// (product 2 does not advance w on check iterations so that stopped instances keep w_v)
-__global__ void batch_advance_w_kernel(int B, int m, int mp, const float* __restrict__ y_next, const float* __restrict__ y_cur,
-                                       float beta_next, const int* __restrict__ done, float* __restrict__ w,
-                                       float* __restrict__ w_hi, float* __restrict__ w_lo) {
-    const size_t total = (size_t)B * mp;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(idx / mp), i = (int)(idx % mp);
-        if (i >= m || done[b]) continue;
-        const float yn = y_next[idx], yv = y_cur[idx];
-        const float wn = __fadd_rn(yn, __fmul_rn(beta_next, __fsub_rn(yn, yv)));
-        w[idx] = wn;
-        if (w_hi) { float hi, lo; split_tf32(wn, hi, lo); w_hi[idx] = hi; w_lo[idx] = lo; }
-    }
-}
-
-// y_I / y_{I-1} of instance b live in ping-pong buffer (iters_b & 1) / ((iters_b - 1) & 1)
-__global__ void unpad_y_kernel(float* __restrict__ dst_next, float* __restrict__ dst_cur, int m, int B,
-                               const float* __restrict__ ybuf0, const float* __restrict__ ybuf1, int mp,
-                               const int* __restrict__ iters) {
+// outputs of instance b after I_b iterations: y_I in yb[I % 3], y_{I-1} in yb[(I-1) % 3], and
+// w_{I-1} = y_{I-1} + beta_{I-1} (y_{I-1} - y_{I-2}) with y_{I-2} in yb[(I+1) % 3]
+__global__ void unpad_y_kernel(float* __restrict__ dst_next, float* __restrict__ dst_cur, float* __restrict__ dst_w, int m, int B,
+                               const float* __restrict__ yb0, const float* __restrict__ yb1, const float* __restrict__ yb2,
+                               int mp, const int* __restrict__ iters, const float* __restrict__ beta) {
     const size_t total = (size_t)B * m;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(idx / m), i = (int)(idx % m);
-        const int par = iters[b] & 1;
-        const float* nx = par ? ybuf1 : ybuf0;
-        const float* cu = par ? ybuf0 : ybuf1;
-        if (dst_next) dst_next[idx] = nx[(size_t)b * mp + i];
-        if (dst_cur) dst_cur[idx] = cu[(size_t)b * mp + i];
+        const int I = iters[b];
+        const float* buf[3] = {yb0, yb1, yb2};
+        const size_t o = (size_t)b * mp + i;
+        const float yI = buf[I % 3][o], yIm1 = buf[(I + 2) % 3][o], yIm2 = buf[(I + 1) % 3][o];
+        if (dst_next) dst_next[idx] = yI;
+        if (dst_cur) dst_cur[idx] = yIm1;
+        if (dst_w) dst_w[idx] = I > 0 ? momentum(yIm1, yIm2, beta[I - 1]) : 0.f;
     }
 }
 
@@ -248,11 +238,8 @@ int launch_unpad_rows(float* dst, int len, int B, const float* src, int ld, cuda
     return GPAD_OK;
 }
 
-int launch_batch_init(const BatchState& st, const float* y0p, const float* yprev0p, float beta0, bool split,
-                      bool checking, cudaStream_t s) {
-    batch_init_kernel<<<grid_for((size_t)st.Bp * st.mp), 256, 0, s>>>(st.Bp, st.np, st.mp, y0p, yprev0p, beta0, st.w,
-                                                                      split ? st.w_hi : nullptr, split ? st.w_lo : nullptr,
-                                                                      st.z, st.zhat, checking ? st.sbar : nullptr);
+int launch_batch_init(const BatchState& st, bool checking, cudaStream_t s) {
+    batch_init_kernel<<<grid_for((size_t)st.Bp * st.mp), 256, 0, s>>>(st.Bp, st.np, st.mp, st.z, st.zhat, checking ? st.sbar : nullptr);
     GPAD_CUDA(cudaGetLastError());
     return GPAD_OK;
 }
@@ -271,17 +258,9 @@ int launch_batch_decide(const BatchState& st, int iter_done, float L, float eps_
     return GPAD_OK;
 }
 
-int launch_batch_advance_w(const BatchState& st, const float* y_next, const float* y_cur, float beta_next, bool split,
-                           cudaStream_t s) {
-    batch_advance_w_kernel<<<grid_for((size_t)st.B * st.mp), 256, 0, s>>>(st.B, st.m, st.mp, y_next, y_cur, beta_next, st.done,
-                                                                         st.w, split ? st.w_hi : nullptr, split ? st.w_lo : nullptr);
-    GPAD_CUDA(cudaGetLastError());
-    return GPAD_OK;
-}
-
-int launch_unpad_y(float* dst_next, float* dst_cur, int m, int B, const float* ybuf0, const float* ybuf1, int mp,
-                   const int* iters, cudaStream_t s) {
-    unpad_y_kernel<<<grid_for((size_t)B * m), 256, 0, s>>>(dst_next, dst_cur, m, B, ybuf0, ybuf1, mp, iters);
+int launch_unpad_y(float* dst_next, float* dst_cur, float* dst_w, int m, int B, const float* yb0, const float* yb1,
+                   const float* yb2, int mp, const int* iters, const float* beta_dev, cudaStream_t s) {
+    unpad_y_kernel<<<grid_for((size_t)B * m), 256, 0, s>>>(dst_next, dst_cur, dst_w, m, B, yb0, yb1, yb2, mp, iters, beta_dev);
     GPAD_CUDA(cudaGetLastError());
     return GPAD_OK;
 }
@@ -296,10 +275,10 @@ int launch_batch_finite(const BatchState& st, const float* y_next, cudaStream_t 
 int launch_simt_product(int phase, const Operators& op, const BatchKernelArgs& args, int Bp, cudaStream_t s) {
     if (phase == 1) {
         dim3 g1((args.n + BN - 1) / BN, Bp / BM);
-        simt_gemm_kernel<1><<<g1, 256, 0, s>>>(args.w, args.mp, op.M_G, args.mp, args.mp, args);
+        simt_gemm_kernel<1><<<g1, 256, 0, s>>>(args.y_cur, args.y_prev, args.mp, op.M_G, args.mp, args.mp, args);
     } else {
         dim3 g2((args.m + BN - 1) / BN, Bp / BM);
-        simt_gemm_kernel<2><<<g2, 256, 0, s>>>(args.zhat, args.np, op.G_L, args.np, args.np, args);
+        simt_gemm_kernel<2><<<g2, 256, 0, s>>>(args.zhat, nullptr, args.np, op.G_L, args.np, args.np, args);
     }
     GPAD_CUDA(cudaGetLastError());
     return GPAD_OK;

@@ -9,12 +9,16 @@
 //     hi*lo + lo*hi + hi*hi          (lo*lo ~ 2^-22 relative is dropped: "3xTF32")
 //
 // Kernel anatomy (one CTA per SM, persistent over output tiles of 128 x bn, bn <= 256):
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d of A_hi/A_lo [128 x BK] and B_hi/B_lo [bn x BK]
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of two A tiles [128 x BK] and B_hi/B_lo [bn x BK]
 //               into a `stages`-deep shared-memory ring (K-major, hardware swizzle), mbarrier tx-count
 //   warp 1      TMEM allocator + MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::tf32,
 //               tcgen05.commit releases ring slots and publishes finished accumulators
-//   warps 2..9  epilogue: tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> coalesced
-//               global reads/writes of the fused GPAD epilogue (batch_common.cuh)
+//   warps 2..13 product 2 / test hook: 12 epilogue warps: tcgen05.ld 32x32b -> registers -> per-warp
+//               smem transpose -> coalesced global reads/writes of the fused GPAD epilogue
+//               product 1: warps 2..5 are TRANSFORM warps -- the two A tiles that arrive are y_v and
+//               y_{v-1}; they rewrite them in place as hi/lo of w = y + beta (y - y_prev) (step 1 and
+//               the tf32 split fused into operand staging, so w never exists in HBM), fence the
+//               generic->async proxy and hand the slot to the MMA warp; warps 6..13 are the epilogue
 //   TMEM: 512 columns = 2 accumulator stages x 256 fp32 columns, so the epilogue of tile t
 //   overlaps the mainloop of tile t+1.
 #include <cuda.h>
@@ -30,8 +34,9 @@ namespace {
 
 constexpr int kBM = 128;            // batch rows per tile == UMMA M
 constexpr int kAccStride = 256;     // TMEM columns per accumulator stage
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 32 * (2 + kEpiWarps);
+constexpr int kXformWarps = 4;      // product 1 only
+constexpr int kWorkWarps = 12;      // warps 2..13: 12 epilogue warps, or 4 transform + 8 epilogue
+constexpr int kThreads = 32 * (2 + kWorkWarps);
 constexpr int kEpiBufFloats = 32 * 33;
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -57,6 +62,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -143,11 +151,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t a_bytes = kBM * BK * 4, b_bytes = (uint32_t)bn * BK * 4;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    constexpr bool kXform = PHASE == 1;                       // A tiles are y_v / y_{v-1}: build w hi/lo in place
+    constexpr int kEpi = kXform ? kWorkWarps - kXformWarps : kWorkWarps;
+    constexpr int kFirstEpiWarp = 2 + (kXform ? kXformWarps : 0);
     float* epi_buf = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kEpiWarps * kEpiBufFloats);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kWorkWarps * kEpiBufFloats);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + stages;
-    uint64_t* tfull_bar = bars + 2 * stages;
+    uint64_t* ready_bar = bars + 2 * stages;                  // product 1: transform warps -> MMA warp
+    uint64_t* tfull_bar = bars + 3 * stages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -156,8 +168,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
-        for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), kEpiWarps); }
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); mbar_init(smem_u32(ready_bar + s), kXformWarps);
+        }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), kEpi); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -196,7 +210,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
-                    mbar_wait(smem_u32(full_bar + stage), phase);
+                    mbar_wait(smem_u32((kXform ? ready_bar : full_bar) + stage), phase);
                     tc_fence_after();
                     const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
 #pragma unroll
@@ -216,19 +230,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
+    } else if (kXform && warp < kFirstEpiWarp) {
+        // ============================ transform warps (product 1) ============================
+        // slot layout: [y_v tile | y_{v-1} tile | B_hi | B_lo]; both A tiles carry the same swizzle, so
+        // the rewrite is purely elementwise: tile0 <- RN_tf32(w), tile1 <- RN_tf32(w - tile0)
+        const int xt = threadIdx.x - 64;                        // 0..127
+        const float beta = args.it.beta;
+        constexpr int kVec = kBM * BK / 4;                      // float4 per A tile
+        int stage = 0; uint32_t phase = 0;
+        for (TileSched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                mbar_wait(smem_u32(full_bar + stage), phase);
+                float4* t0 = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
+                float4* t1 = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + a_bytes);
+#pragma unroll
+                for (int i = xt; i < kVec; i += 32 * kXformWarps) {
+                    const float4 y = t0[i], yp = t1[i];
+                    float4 hi, lo;
+                    split_tf32(momentum(y.x, yp.x, beta), hi.x, lo.x);
+                    split_tf32(momentum(y.y, yp.y, beta), hi.y, lo.y);
+                    split_tf32(momentum(y.z, yp.z, beta), hi.z, lo.z);
+                    split_tf32(momentum(y.w, yp.w, beta), hi.w, lo.w);
+                    t0[i] = hi;
+                    t1[i] = lo;
+                }
+                fence_proxy_async_smem();                       // generic-proxy writes -> visible to the MMA (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(ready_bar + stage));
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+        }
     } else {
         // ============================ epilogue warps ============================
-        const int ew = warp - 2;
+        const int ew = warp - kFirstEpiWarp;
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
-        const int half = ew >> 2;               // two warps share a quarter and alternate column blocks
-        float* buf = epi_buf + ew * kEpiBufFloats;
+        const int part = ew >> 2;               // warps sharing a quarter alternate over column blocks
+        constexpr int kParts = kEpi / 4;
+        float* buf = epi_buf + (warp - 2) * kEpiBufFloats;
         const int nblk = (bn + 31) / 32;
         int acc = 0; uint32_t acc_phase = 0;
         for (TileSched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tc_fence_after();
             const int row_base = ts.m_tile() * kBM + q * 32;
-            for (int blk = half; blk < nblk; blk += 2) {
+            for (int blk = part; blk < nblk; blk += kParts) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride + blk * 32), v);
 #pragma unroll
@@ -237,36 +282,95 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const int cin = blk * 32 + lane;            // column inside the tile
                 const int c = ts.n_tile() * bn + cin;       // global output column
                 const bool col_ok = cin < bn && c < ncols_valid;
-#pragma unroll 4
-                for (int rr = 0; rr < 32; ++rr) {
-                    const int b = row_base + rr;
-                    const float val = buf[rr * 33 + lane];
-                    bool ok = col_ok && b < args.B;
-                    if (PHASE != 0 && ok && args.done) ok = args.done[b] == 0;
-                    if (PHASE == 0) {
-                        if (ok) Cdbg[(size_t)b * ldc + c] = val;
-                    } else if (PHASE == 1) {
-                        float f_zhat = 0.f;
-                        if (ok) epilogue1<true>(args, b, c, val, f_zhat);
-                        if (args.it.check && args.f) {
+                if (PHASE == 0) {
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int b = row_base + rr;
+                        if (col_ok && b < args.B) Cdbg[(size_t)b * ldc + c] = buf[rr * 33 + lane];
+                    }
+                } else if (!args.it.check && !args.done) {
+                    // fast path (fixed-iteration solves): rows in chunks of kChunk with every global
+                    // load of the chunk issued before the first use, so each warp keeps
+                    // kChunk * (2 or 3) x 128 B in flight; streaming cache hints keep the operators in L2
+                    constexpr int kChunk = 16;
+#pragma unroll 1
+                    for (int r0 = 0; r0 < 32; r0 += kChunk) {
+                        if (PHASE == 1) {
+                            float gp[kChunk], zo[kChunk];
 #pragma unroll
-                            for (int o = 16; o; o >>= 1) f_zhat += __shfl_xor_sync(0xffffffffu, f_zhat, o);
-                            if (lane == 0 && b < args.B) atomicAdd(args.red + (size_t)b * kRedStride + 5, f_zhat);
-                        }
-                    } else {
-                        Red2 red;
-                        if (ok) epilogue2<true>(args, b, c, val, red);
-                        if (args.it.check) {
-#pragma unroll
-                            for (int o = 16; o; o >>= 1) {
-                                red.max_sbar = fmaxf(red.max_sbar, __shfl_xor_sync(0xffffffffu, red.max_sbar, o));
-                                red.max_rhat = fmaxf(red.max_rhat, __shfl_xor_sync(0xffffffffu, red.max_rhat, o));
-                                red.min_w = fminf(red.min_w, __shfl_xor_sync(0xffffffffu, red.min_w, o));
-                                red.w_rhat += __shfl_xor_sync(0xffffffffu, red.w_rhat, o);
-                                red.w_dot += __shfl_xor_sync(0xffffffffu, red.w_dot, o);
-                                red.bad = fmaxf(red.bad, __shfl_xor_sync(0xffffffffu, red.bad, o));
+                            for (int j = 0; j < kChunk; ++j) {
+                                const int b = row_base + r0 + j;
+                                const bool ok = col_ok && b < args.B;
+                                const size_t o = (size_t)b * args.np + c;
+                                gp[j] = ok ? __ldcs(args.g_P + o) : 0.f;
+                                zo[j] = ok ? __ldcs(args.z + o) : 0.f;
                             }
-                            if (lane == 0 && b < args.B && !(args.done && args.done[b])) flush_red2(args, b, red);
+#pragma unroll
+                            for (int j = 0; j < kChunk; ++j) {
+                                const int b = row_base + r0 + j;
+                                if (!(col_ok && b < args.B)) continue;
+                                const size_t o = (size_t)b * args.np + c;
+                                const float zh = buf[(r0 + j) * 33 + lane] - gp[j];
+                                __stcs(args.z + o, __fadd_rn(__fmul_rn(1.0f - args.it.theta, zo[j]), __fmul_rn(args.it.theta, zh)));
+                                __stcs(args.zhat + o, zh);
+                                float hi, lo;
+                                split_tf32(zh, hi, lo);
+                                args.zh_hi[o] = hi;      // re-read by product 2 of this iteration: default caching
+                                args.zh_lo[o] = lo;
+                            }
+                        } else {
+                            float yc[kChunk], yp[kChunk], pd[kChunk];
+#pragma unroll
+                            for (int j = 0; j < kChunk; ++j) {
+                                const int b = row_base + r0 + j;
+                                const bool ok = col_ok && b < args.B;
+                                const size_t o = (size_t)b * args.mp + c;
+                                yc[j] = ok ? __ldcs(args.y_cur + o) : 0.f;
+                                yp[j] = ok ? __ldcs(args.y_prev + o) : 0.f;
+                                pd[j] = ok ? __ldcs(args.p_D + o) : 0.f;
+                            }
+#pragma unroll
+                            for (int j = 0; j < kChunk; ++j) {
+                                const int b = row_base + r0 + j;
+                                if (!(col_ok && b < args.B)) continue;
+                                const size_t o = (size_t)b * args.mp + c;
+                                const float wv = momentum(yc[j], yp[j], args.it.beta);
+                                const float sacc = buf[(r0 + j) * 33 + lane] + (wv + pd[j]);
+                                args.y_next[o] = 0.5f * (sacc + fabsf(sacc));   // read back by the next two kernels
+                            }
+                        }
+                    }
+                } else {
+                    // general path: termination bookkeeping (per-row reductions, stopped instances)
+#pragma unroll 2
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int b = row_base + rr;
+                        const float val = buf[rr * 33 + lane];
+                        bool ok = col_ok && b < args.B;
+                        if (ok && args.done) ok = args.done[b] == 0;
+                        if (PHASE == 1) {
+                            float f_zhat = 0.f;
+                            if (ok) epilogue1<true>(args, b, c, val, f_zhat);
+                            if (args.it.check && args.f) {
+#pragma unroll
+                                for (int o = 16; o; o >>= 1) f_zhat += __shfl_xor_sync(0xffffffffu, f_zhat, o);
+                                if (lane == 0 && b < args.B) atomicAdd(args.red + (size_t)b * kRedStride + 5, f_zhat);
+                            }
+                        } else {
+                            Red2 red;
+                            if (ok) epilogue2(args, b, c, val, red);
+                            if (args.it.check) {
+#pragma unroll
+                                for (int o = 16; o; o >>= 1) {
+                                    red.max_sbar = fmaxf(red.max_sbar, __shfl_xor_sync(0xffffffffu, red.max_sbar, o));
+                                    red.max_rhat = fmaxf(red.max_rhat, __shfl_xor_sync(0xffffffffu, red.max_rhat, o));
+                                    red.min_w = fminf(red.min_w, __shfl_xor_sync(0xffffffffu, red.min_w, o));
+                                    red.w_rhat += __shfl_xor_sync(0xffffffffu, red.w_rhat, o);
+                                    red.w_dot += __shfl_xor_sync(0xffffffffu, red.w_dot, o);
+                                    red.bad = fmaxf(red.bad, __shfl_xor_sync(0xffffffffu, red.bad, o));
+                                }
+                                if (lane == 0 && b < args.B && !(args.done && args.done[b])) flush_red2(args, b, red);
+                            }
                         }
                     }
                 }
@@ -341,7 +445,7 @@ void plan_tiles(int ncols, int* bn, int* n_tiles) {
 
 size_t smem_bytes(int bk, int bn, int stages) {
     const size_t stage = (size_t)(2 * kBM + 2 * bn) * bk * 4;
-    return 1024 + stages * stage + (size_t)kEpiWarps * kEpiBufFloats * 4 + (2 * stages + 4) * 8 + 16;
+    return 1024 + stages * stage + (size_t)kWorkWarps * kEpiBufFloats * 4 + (3 * stages + 4) * 8 + 16;
 }
 
 int pick_stages(int bk, int bn, size_t smem_limit) {

@@ -9,7 +9,8 @@ namespace gpad {
 namespace tc {
 
 struct GemmDesc {
-    CUtensorMap tmA_hi, tmA_lo;   // A [rows = batch][K] tiles of 128 x bk
+    CUtensorMap tmA_hi, tmA_lo;   // A [rows = batch][K] tiles of 128 x bk (product 1: y_v and y_{v-1}, split in-kernel)
+    CUtensorMap tmY[3];           // product 1: the three rotating y buffers
     CUtensorMap tmB_hi, tmB_lo;   // B [rows = outputs][K] tiles of bn x bk
     int bk = 16;                  // K block in floats: 16 (SWIZZLE_64B) or 32 (SWIZZLE_128B)
     int k_pad = 0;                // K rounded up to bk

@@ -36,8 +36,7 @@ inline size_t round_up_sz(size_t v, size_t q) { return (v + q - 1) / q * q; }
 // ---- per-iteration scalars handed to kernels by value (main.cu:163,170 does the same) ----
 struct IterScalars {
     float theta;      // theta_v
-    float beta_next;  // beta_{v+1} (0 on the last iteration)
-    int last;         // 1 on the final iteration: do not advance w
+    float beta;       // beta_v: w_v = y_v + beta_v (y_v - y_{v-1}) is recomputed wherever it is needed
     int check;        // 1 when the termination quantities are reduced this iteration
 };
 
@@ -50,10 +49,7 @@ struct BatchState {
     float* g_P = nullptr;   // [Bp][np]
     float* p_D = nullptr;   // [Bp][mp]
     float* f = nullptr;     // [Bp][np] (optional)
-    float* y[2] = {nullptr, nullptr};  // ping-pong y_v / y_{v+1}  [Bp][mp]
-    float* w = nullptr;     // [Bp][mp] exact fp32 w_v
-    float* w_hi = nullptr;  // TF32X3 only: RN-tf32(w) and the tf32-rounded remainder
-    float* w_lo = nullptr;
+    float* yb[3] = {nullptr, nullptr, nullptr};  // rotating y_{v-1} / y_v / y_{v+1}  [Bp][mp]; y_v lives in yb[v % 3]
     float* z = nullptr;     // [Bp][np]
     float* zhat = nullptr;  // [Bp][np]
     float* zh_hi = nullptr; // TF32X3 only
@@ -82,14 +78,11 @@ struct BatchKernelArgs;
 // ---- kernel launchers (defined in the .cu files) ----
 int launch_pad_rows(float* dst, int ld, int rows_total, const float* src, int len, int B, cudaStream_t s);
 int launch_unpad_rows(float* dst, int len, int B, const float* src, int ld, cudaStream_t s);
-int launch_unpad_y(float* dst_next, float* dst_cur, int m, int B, const float* ybuf0, const float* ybuf1, int mp,
-                   const int* iters, cudaStream_t s);
-int launch_batch_init(const BatchState& st, const float* y0p, const float* yprev0p, float beta0, bool split,
-                      bool checking, cudaStream_t s);
+int launch_unpad_y(float* dst_next, float* dst_cur, float* dst_w, int m, int B, const float* yb0, const float* yb1,
+                   const float* yb2, int mp, const int* iters, const float* beta_dev, cudaStream_t s);
+int launch_batch_init(const BatchState& st, bool checking, cudaStream_t s);
 int launch_batch_reset_term(const BatchState& st, int max_iter, cudaStream_t s);
 int launch_batch_decide(const BatchState& st, int iter_done, float L, float eps_g, float eps_V, bool have_f, cudaStream_t s);
-int launch_batch_advance_w(const BatchState& st, const float* y_next, const float* y_cur, float beta_next, bool split,
-                           cudaStream_t s);
 int launch_batch_finite(const BatchState& st, const float* y_next, cudaStream_t s);
 int launch_simt_product(int phase, const Operators& op, const BatchKernelArgs& args, int Bp, cudaStream_t s);
 int launch_step_one(const float* y, const float* y_prev, float* w, float beta, int m, cudaStream_t s);

@@ -157,8 +157,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
     float* yn_s = yp_s + p.rows_b_pad;     // [rows_b] own y_{v+1}
     float* sb_s = yn_s + p.rows_b_pad;     // [rows_b] own sbar
     float* dt_s = sb_s + p.rows_b_pad;     // [rows_b] own dot = (G_L zhat)_i
-    float* z_s = dt_s + p.rows_b_pad;      // [rows_a] own z
-    float* red_s = z_s + p.rows_a_pad;     // [kNumRed * G_pad] reductions of all CTAs + [32*kNumRed] scratch
+    float* pd_s = dt_s + p.rows_b_pad;     // [rows_b] own p_D rows (no global loads inside the loop)
+    float* z_s = pd_s + p.rows_b_pad;      // [rows_a] own z
+    float* gp_s = z_s + p.rows_a_pad;      // [rows_a] own g_P rows
+    float* f_s = gp_s + p.rows_a_pad;      // [rows_a] own f rows (termination only)
+    float* red_s = f_s + p.rows_a_pad;     // [kNumRed * G_pad] reductions of all CTAs + [32*kNumRed] scratch
     float* scr_s = red_s + kNumRed * p.g_pad;
     float* ops_s = scr_s + 32 * kNumRed;   // OPS_SMEM: [rows_a][mld] then [rows_b][nld]
     const float* MGrows = OPS_SMEM ? ops_s : p.M_G + (size_t)a0 * mld;
@@ -189,8 +192,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
         yn_s[i] = yv_s[i];
         sb_s[i] = 0.f;
         dt_s[i] = 0.f;
+        pd_s[i] = p.p_D[b0 + i];
     }
-    for (int i = tid; i < na; i += nthr) z_s[i] = 0.f;
+    for (int i = tid; i < na; i += nthr) {
+        z_s[i] = 0.f;
+        gp_s[i] = p.g_P[a0 + i];
+        f_s[i] = p.f ? p.f[a0 + i] : 0.f;
+    }
     Sync<SYNC> sync;
     if (SYNC == SYNC_CLUSTER) cg::this_cluster().sync();   // peers' smem must exist before remote stores
     else __syncthreads();
@@ -201,11 +209,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
     int iters = 0, status = GPAD_STATUS_MAX_ITER;
     float out_viol = __int_as_float(0x7fc00000), out_gap = __int_as_float(0x7fc00000);
 
+    // theta_v / beta_{v+1} are fetched one iteration ahead so their latency never sits on the
+    // critical path (cluster / grid barriers invalidate L1)
+    float theta_pf = p.theta[0];
+    float beta_pf = p.max_iter > 1 ? p.beta[1] : 0.f;
     for (int v = 0; v < p.max_iter; ++v) {
-        const float theta = p.theta[v];
+        const float theta = theta_pf;
         const float one_minus = 1.0f - theta;
         const bool last = (v + 1 == p.max_iter);
-        const float beta_next = last ? 0.f : p.beta[v + 1];
+        const float beta_next = last ? 0.f : beta_pf;
+        if (!last) {
+            theta_pf = __ldg(p.theta + v + 1);
+            beta_pf = (v + 2 < p.max_iter) ? __ldg(p.beta + v + 2) : 0.f;
+        }
         const bool check = checking && ((v + 1) % p.check_every == 0);
 
         // ---------------- phase A: zhat rows, z average ----------------
@@ -219,10 +235,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
                 const float* row = MGrows + (size_t)(valid ? r : 0) * mld;
                 const float d = row_dot<OPS_SMEM>(row, w_s, mld4, sub, lpr_a);
                 if (valid && sub == 0) {
-                    const float zh = d - p.g_P[a0 + r];
+                    const float zh = d - gp_s[r];
                     z_s[r] = __fadd_rn(__fmul_rn(one_minus, z_s[r]), __fmul_rn(theta, zh));
                     publish<SYNC>(zh_s, p.x_zhat, a0 + r, zh);
-                    if (check && p.f) f_zhat = fmaf(p.f[a0 + r], zh, f_zhat);
+                    if (check && p.f) f_zhat = fmaf(f_s[r], zh, f_zhat);
                 }
             }
         }
@@ -251,11 +267,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
                 const float d = row_dot<OPS_SMEM>(row, zh_s, nld4, sub, lpr_b);
                 if (valid && sub == 0) {
                     const int i = b0 + r;
-                    const float wi = w_s[i], pd = p.p_D[i];
+                    const float wi = w_s[i], pd = pd_s[r];
                     float s = d + (wi + pd);
                     const float yn = 0.5f * (s + fabsf(s));
                     yn_s[r] = yn;
                     dt_s[r] = d;
+                    if (!check && !last) {
+                        // advance in place: w_{v+1} (only this lane reads w_s[i] during phase B),
+                        // y_{v-1} <- y_v <- y_{v+1}.  Not on the last iteration: w_v / y_v are outputs.
+                        const float yv = yv_s[r];
+                        publish<SYNC>(w_s, p.x_w, i, __fadd_rn(yn, __fmul_rn(beta_next, __fsub_rn(yn, yv))));
+                        yp_s[r] = yv;
+                        yv_s[r] = yn;
+                    }
                     if (checking) {
                         const float rhat = d + pd;
                         const float sb = __fadd_rn(__fmul_rn(one_minus, sb_s[r]), __fmul_rn(theta, rhat));
@@ -275,16 +299,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
         iters = v + 1;
 
         if (!check) {
-            // advance: w <- w_{v+1}, rotate own y registers.  (Not on the last iteration: w_v,
-            // y_v stay as the outputs main.cu:176-180 copies back.)
             if (!last) {
-                __syncthreads();   // every row of this CTA has read its w_s[i] / finished yn_s
-                for (int r = tid; r < nb; r += nthr) {
-                    const float yn = yn_s[r], yv = yv_s[r];
-                    publish<SYNC>(w_s, p.x_w, b0 + r, __fadd_rn(yn, __fmul_rn(beta_next, __fsub_rn(yn, yv))));
-                    yp_s[r] = yv;
-                    yv_s[r] = yn;
-                }
                 sync.barrier(p);
                 gather<SYNC>(w_s, p.x_w, m);
             }
@@ -359,9 +374,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
                         const float* row = MGrows + (size_t)(valid ? r : 0) * mld;
                         const float d = row_dot<OPS_SMEM>(row, w_s, mld4, sub, lpr_a);
                         if (valid && sub == 0) {
-                            const float zy = d - p.g_P[a0 + r];
+                            const float zy = d - gp_s[r];
                             publish<SYNC>(zh_s, p.x_zhat, a0 + r, zy);
-                            fzy = fmaf(p.f[a0 + r], zy, fzy);
+                            fzy = fmaf(f_s[r], zy, fzy);
                         }
                     }
                 }
@@ -377,7 +392,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
                         const float d = row_dot<OPS_SMEM>(row, zh_s, nld4, sub, lpr_b);
                         if (valid && sub == 0) {
                             y_gz = fmaf(yn_s[r], d, y_gz);
-                            y_pd = fmaf(yn_s[r], p.p_D[b0 + r], y_pd);
+                            y_pd = fmaf(yn_s[r], pd_s[r], y_pd);
                         }
                     }
                 }
@@ -455,7 +470,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gpad_latency_kernel(const Para
 }  // namespace
 
 size_t smem_bytes(const Params& p, bool ops_smem) {
-    size_t fl = (size_t)p.mld + p.nld + 5 * (size_t)p.rows_b_pad + p.rows_a_pad + (size_t)kNumRed * p.g_pad + 32 * kNumRed;
+    size_t fl = (size_t)p.mld + p.nld + 6 * (size_t)p.rows_b_pad + 3 * (size_t)p.rows_a_pad + (size_t)kNumRed * p.g_pad + 32 * kNumRed;
     if (ops_smem) fl += (size_t)p.rows_a * p.mld + (size_t)p.rows_b * p.nld;
     return fl * sizeof(float);
 }

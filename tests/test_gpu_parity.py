@@ -5,7 +5,7 @@ Tolerance, metric rel_inf = ||a-b||_inf/||b||_inf (north star: <= 1e-5 relative 
   * GPU vs oracle <= 1e-5 on y_I, y_{I-1}, w (dual) and z (averaged primal); <= 2e-5 on zhat, the
     un-averaged primal iterate acc - g_P, whose cancellation puts the fp32 reference itself
     up to 3.9e-5 from exact arithmetic (measured table in DESIGN.md, tests/diag_gpu.py);
-  * GPU vs fp64 arbiter <= 1.25 x (oracle vs fp64 arbiter) + 2e-6: the GPU is never meaningfully
+  * GPU vs fp64 arbiter <= 1.25 x (oracle vs fp64 arbiter) + 5e-6: the GPU is never meaningfully
     further from exact arithmetic than the reference's own strict left-to-right fp32 sums;
   * active set (pattern of y_I > 0) and iteration count / status: exact (flips are counted and
     must be zero, except entries below 1e-6 in the fp64 arbiter, which are reported).
@@ -45,7 +45,7 @@ def check_parity(gpu, ora, f64, label=""):
         eor = P.rel_inf(gpu[k], ora[k])
         noise = P.rel_inf(ora[k], f64[k])
         assert eor <= (2 * TOL if k == "zhat" else TOL), f"{label} {k}: GPU vs oracle {eor:.3e} (oracle vs fp64 {noise:.3e})"
-        assert e64 <= 1.25 * noise + 2e-6, f"{label} {k}: GPU vs fp64 {e64:.3e}, oracle vs fp64 {noise:.3e}"
+        assert e64 <= 1.25 * noise + 5e-6, f"{label} {k}: GPU vs fp64 {e64:.3e}, oracle vs fp64 {noise:.3e}"
         worst = max(worst, eor)
     act_g, act_o = gpu["y_next"] > 0, ora["y_next"] > 0
     flips = np.flatnonzero(act_g != act_o)
