@@ -229,7 +229,8 @@ def run_ours(args):
     prob, pb = host_problem()
     n, m, B = prob.n, prob.m, args.batch
     theta, beta = G.schedule(ITERS)
-    g_P, p_D, _ = prob.instances(quad_params(B, seed=rank), want_f=False)
+    from gpad_b200 import sharding
+    g_P, p_D, _ = prob.instances(quad_params(B, seed=sharding.shard_seed(0, rank)), want_f=False)
     prec = G.PREC_FP32 if args.precision == "fp32" else G.PREC_TF32X3
     solver = G.Solver(prob.n_u, prob.N, m, prob.L, pb["M_G"], pb["G_L"], mode=G.MODE_BATCH_SHARED, precision=prec,
                       max_batch=B, device=local)
@@ -265,18 +266,13 @@ def run_ours(args):
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
-    if dist is not None:
-        # the only exchange of the path: final gather of the first control move u0 = z[:, :n_u] and the status
-        u0 = d_out["z"][:, :prob.n_u].contiguous()
-        gathered = [torch.empty_like(u0) for _ in range(world)] if rank == 0 else None
-        dist.gather(u0, gathered, dst=0)
+    # the only exchange of the path: final gather of the first control move u0 = z[:, :n_u] on rank 0
+    u0_all = sharding.gather_first_moves(d_out["z"], prob.n_u, dst=0)
     e1.record(stream)
     barrier()
     t_wall1 = time.time()
-    elapsed_ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if dist is not None:
-        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(elapsed_ms.item())
+    elapsed_ms = sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    assert rank != 0 or u0_all.shape[0] == world * B
     launches = solver.launches - launches0
     ms1, c1 = solver.profile_read(1)
     ms2, c2 = solver.profile_read(2)
@@ -300,10 +296,7 @@ def run_ours(args):
     for _ in range(e2e_steps):
         check(lib().gpad_solve(solver._h, C.byref(a)), "gpad_solve (e2e)")      # synchronises before returning
     torch.cuda.synchronize()
-    t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    t_e2e = float(t_e2e.item())
+    t_e2e = sharding.max_over_ranks(time.perf_counter() - t0, device="cuda")
     h2d = (g_P.nbytes + p_D.nbytes)
     d2h = sum(v.nbytes for v in h_out.values()) + h_it.nbytes + h_st.nbytes
     ok = bool(np.isfinite(h_out["z"]).all() and (h_st == 0).all() and (h_it == ITERS).all())
