@@ -170,7 +170,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = count * args.steps / dt
     sample = f"{count} of the workload's QPs per step, 100 iterations each, on {out['threads']} host threads"
-    print(json.dumps({
+    emit_line({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -178,7 +178,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(out["threads"]), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -252,6 +252,7 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step_device()
+    sharding.gather_first_moves(d_out["z"], prob.n_u, dst=0, equal_shards=True)   # NCCL connections set up outside the timed region
     barrier()
     solver.profile(True)
     solver.profile_read(1); solver.profile_read(2)
@@ -267,7 +268,7 @@ def run_ours(args):
     for _ in range(args.steps):
         step_device()
     # the only exchange of the path: final gather of the first control move u0 = z[:, :n_u] on rank 0
-    u0_all = sharding.gather_first_moves(d_out["z"], prob.n_u, dst=0)
+    u0_all = sharding.gather_first_moves(d_out["z"], prob.n_u, dst=0, equal_shards=True)
     e1.record(stream)
     barrier()
     t_wall1 = time.time()
@@ -348,12 +349,28 @@ def run_ours(args):
         "clocks": clocks,
         "single_qp_latency": lat,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit_line(obj):
+    """exactly one JSON line on the real stdout (library banners, e.g. NCCL's, go to stderr)"""
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                     # anything printed by libraries from here on lands on stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -79,6 +79,12 @@ struct gpad_handle_s {
     float *o_viol = nullptr, *o_gap = nullptr;
     unsigned* d_flags = nullptr;              // [0] barrier counter, [1] nonfinite flag
 
+    // ---- per-instance mode (one CTA per QP, latency kernel in SYNC_BLOCK) ----
+    float *pi_gP = nullptr, *pi_pD = nullptr, *pi_f = nullptr, *pi_y0 = nullptr, *pi_yprev0 = nullptr;   // host-mode staging
+    float *pi_ynext = nullptr, *pi_y = nullptr, *pi_z = nullptr, *pi_zhat = nullptr, *pi_w = nullptr;
+    int *pi_iters = nullptr, *pi_status = nullptr;
+    float *pi_viol = nullptr, *pi_gap = nullptr;
+
     // ---- batch mode ----
     Operators op;
     BatchState st;
@@ -104,7 +110,7 @@ int dev_alloc(gpad_handle_s* h, T** p, size_t count) {
 }
 #define GPAD_TRY(expr) do { int rc__ = (expr); if (rc__ != GPAD_OK) return rc__; } while (0)
 
-int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
 
 // operators -> host, sequential layout (M_G [n][m], G_L [m][n])
 int fetch_operators(const gpad_config_t& c, const float* M_G, const float* G_L, size_t count_each, int copies,
@@ -141,62 +147,102 @@ int upload_padded(gpad_handle_s* h, const float* src, int rows, int cols, int ro
     return GPAD_OK;
 }
 
+// ---- latency plan: how many CTAs cooperate, how they synchronise, where the operators live ----
+struct LatPlan {
+    int sync = -1, G = 1, threads = 64;
+    bool regs = false;
+    lat::Params p{};
+};
+
+int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// fills row split, lanes-per-row, strides, residency for G cooperating CTAs; returns false if infeasible
+bool plan_for(int n, int m, int G, bool want_regs, size_t smem_limit, bool no_resident, LatPlan& out) {
+    lat::Params& p = out.p;
+    p.n = n; p.m = m;
+    p.rows_a = (n + G - 1) / G; p.rows_b = (m + G - 1) / G;
+    p.rows_a_pad = round_up(p.rows_a, 4); p.rows_b_pad = round_up(p.rows_b, 4);
+    p.g_pad = round_up(G, 4);
+    const int m4 = (m + 3) / 4, n4 = (n + 3) / 4;
+    out.G = G;
+    if (want_regs) {
+        // one pass per phase, operator fragments in registers: lanes-per-row = smallest power of two that
+        // leaves <= 4 (else <= kRegChunks) float4 per lane while all rows of the CTA fit in 512 threads
+        auto pick = [&](int len4, int rows, int& lg) {
+            for (int target : {4, lat::kRegChunks})
+                for (lg = 0; lg <= 5; ++lg)
+                    if (((len4 + (1 << lg) - 1) >> lg) <= target && (rows << lg) <= lat::kMaxThreads) return true;
+            return false;
+        };
+        if (!pick(m4, p.rows_a, p.lg_a) || !pick(n4, p.rows_b, p.lg_b)) return false;
+        out.threads = std::max(32, round_up(std::max(p.rows_a << p.lg_a, p.rows_b << p.lg_b), 32));
+        p.res_a = p.res_b = 0;
+        out.regs = true;
+    } else {
+        p.lg_a = std::min(5, ilog2_ceil(m4)); p.lg_b = std::min(5, ilog2_ceil(n4));
+        out.threads = std::min(lat::kMaxThreads, std::max(64, round_up(std::max(p.rows_a << p.lg_a, p.rows_b << p.lg_b), 32)));
+        out.regs = false;
+    }
+    p.mld = round_up(m, 4 << p.lg_a); p.nld = round_up(n, 4 << p.lg_b);
+    if (!out.regs) {
+        // partial residency: as many own rows as fit next to the vectors, split evenly between the operators
+        p.res_a = p.res_b = 0;
+        const size_t fixed = lat::smem_bytes(p, false);
+        if (fixed > smem_limit) return false;
+        if (!no_resident) {
+            const size_t budget = smem_limit - fixed;
+            const size_t want = ((size_t)p.rows_a * p.mld + (size_t)p.rows_b * p.nld) * sizeof(float);
+            const double frac = want ? std::min(1.0, (double)budget / (double)want) : 1.0;
+            p.res_a = (int)(p.rows_a * frac);
+            size_t left = budget - (size_t)p.res_a * p.mld * sizeof(float);
+            p.res_b = (int)std::min<size_t>(p.rows_b, left / ((size_t)p.nld * sizeof(float)));
+        }
+    }
+    return lat::smem_bytes(p, out.regs) <= smem_limit;
+}
+
 // ------------------------------------------------------------------ latency mode
 int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vector<float>& GL) {
     const int n = h->n, m = h->cfg.m;
+    const size_t limit = h->smem_optin;
+    const bool no_res = getenv("GPAD_LATENCY_NO_SMEM_OPS") != nullptr;
+    LatPlan plan;
+    const char* env = getenv("GPAD_LATENCY_PLAN");    // "block" | "cluster:<C>" | "grid:<G>" (experiments)
+    bool ok = false;
+    if (env) {
+        int sync = lat::SYNC_GRID, G = h->num_sms;
+        if (!strncmp(env, "block", 5)) { sync = lat::SYNC_BLOCK; G = 1; }
+        else if (!strncmp(env, "cluster:", 8)) { sync = lat::SYNC_CLUSTER; G = std::max(1, std::min(16, atoi(env + 8))); }
+        else if (!strncmp(env, "grid:", 5)) { G = std::max(1, std::min(h->num_sms, atoi(env + 5))); }
+        ok = (!no_res && plan_for(n, m, G, true, limit, no_res, plan)) || plan_for(n, m, G, false, limit, no_res, plan);
+        plan.sync = sync;
+    } else {
+        // 1. one CTA with register-resident operators; 2. the smallest cluster that allows it;
+        // 3. the whole chip, operators in shared memory as far as they fit
+        if (plan_for(n, m, 1, true, limit, false, plan)) { plan.sync = lat::SYNC_BLOCK; ok = true; }
+        for (int C : {2, 4, 8, 16}) {
+            if (ok) break;
+            if (!plan_for(n, m, C, true, limit, false, plan)) continue;
+            if (C > lat::max_cluster_size(plan.threads, lat::smem_bytes(plan.p, true))) continue;
+            plan.sync = lat::SYNC_CLUSTER; ok = true;
+        }
+        if (!ok) { ok = plan_for(n, m, h->num_sms, false, limit, no_res, plan); plan.sync = lat::SYNC_GRID; }
+    }
+    if (!ok) {
+        set_error("latency mode: vectors of n=%d, m=%d do not fit in shared memory", n, m);
+        return GPAD_ERR_UNSUPPORTED;
+    }
+    if (const char* t = getenv("GPAD_LATENCY_THREADS"))
+        if (!plan.regs && atoi(t) > 0) plan.threads = std::max(32, std::min(lat::kMaxThreads, atoi(t) / 32 * 32));
     lat::Params& p = h->lp;
-    p.n = n; p.m = m; p.nld = round_up(n, 4); p.mld = round_up(m, 4);
+    p = plan.p;
+    h->sync_mode = plan.sync; h->G = plan.G; h->threads = plan.threads; h->ops_smem = plan.regs;
+    p.L = h->cfg.L;
+    p.batch = 1; p.op_stride_a = p.op_stride_b = 0;
     float *dMG, *dGL;
     GPAD_TRY(upload_padded(h, MG.data(), n, m, n, p.mld, &dMG));
     GPAD_TRY(upload_padded(h, GL.data(), m, n, m, p.nld, &dGL));
     p.M_G = dMG; p.G_L = dGL;
-    p.L = h->cfg.L;
-
-    // ---- plan: how many CTAs cooperate, how they synchronise, where the operators live ----
-    const size_t limit = h->smem_optin;
-    auto configure = [&](int G) {
-        p.rows_a = (n + G - 1) / G; p.rows_b = (m + G - 1) / G;
-        p.rows_a_pad = round_up(p.rows_a, 4); p.rows_b_pad = round_up(p.rows_b, 4);
-        p.g_pad = round_up(G, 4);
-    };
-    const size_t op_elems = (size_t)n * p.mld + (size_t)m * p.nld;
-    int sync = -1, G = 1; bool ops = false;
-    const char* env = getenv("GPAD_LATENCY_PLAN");    // "block" | "cluster:<C>" | "grid:<G>" (experiments)
-    if (env && !strncmp(env, "block", 5)) { sync = lat::SYNC_BLOCK; G = 1; }
-    else if (env && !strncmp(env, "cluster:", 8)) { sync = lat::SYNC_CLUSTER; G = atoi(env + 8); }
-    else if (env && !strncmp(env, "grid:", 5)) { sync = lat::SYNC_GRID; G = atoi(env + 5); }
-    if (sync < 0) {
-        configure(1);
-        if (op_elems <= 16384 && lat::smem_bytes(p, true) <= limit) { sync = lat::SYNC_BLOCK; G = 1; }
-    }
-    if (sync < 0) {
-        // largest co-schedulable cluster whose per-CTA operator slice fits in shared memory
-        for (int C : {16, 8, 4, 2}) {
-            configure(C);
-            const size_t need = lat::smem_bytes(p, true);
-            if (need > limit || p.rows_b < 8) continue;
-            if (C > lat::max_cluster_size(true, lat::kMaxThreads, need)) continue;
-            sync = lat::SYNC_CLUSTER; G = C;
-            break;
-        }
-    }
-    if (sync < 0) { sync = lat::SYNC_GRID; G = h->num_sms; }
-    if (G < 1) G = 1;
-    if (sync == lat::SYNC_GRID) G = std::min(G, h->num_sms);
-    if (sync == lat::SYNC_CLUSTER) G = std::min(G, 16);
-    configure(G);
-    ops = lat::smem_bytes(p, true) <= limit;
-    if (getenv("GPAD_LATENCY_NO_SMEM_OPS")) ops = false;
-    if (lat::smem_bytes(p, ops) > limit) {
-        set_error("latency mode: vectors of n=%d, m=%d do not fit in shared memory", n, m);
-        return GPAD_ERR_UNSUPPORTED;
-    }
-    h->sync_mode = sync; h->G = G; h->ops_smem = ops;
-    p.lpr_a = std::min(32, next_pow2(std::max(1, p.mld / 4)));
-    p.lpr_b = std::min(32, next_pow2(std::max(1, p.nld / 4)));
-    const int want = std::max(p.rows_a * p.lpr_a, p.rows_b * p.lpr_b);
-    h->threads = std::min(lat::kMaxThreads, std::max(64, round_up(want, 32)));
-    if (const char* t = getenv("GPAD_LATENCY_THREADS")) h->threads = std::max(32, std::min(lat::kMaxThreads, atoi(t) / 32 * 32));
 
     // per-solve device buffers
     GPAD_TRY(dev_alloc(h, &h->d_gP, n)); GPAD_TRY(dev_alloc(h, &h->d_pD, m)); GPAD_TRY(dev_alloc(h, &h->d_f, n));
@@ -206,14 +252,19 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
     GPAD_TRY(dev_alloc(h, &h->o_iters, 1)); GPAD_TRY(dev_alloc(h, &h->o_status, 1));
     GPAD_TRY(dev_alloc(h, &h->o_viol, 1)); GPAD_TRY(dev_alloc(h, &h->o_gap, 1));
     GPAD_TRY(dev_alloc(h, &p.x_w, p.mld)); GPAD_TRY(dev_alloc(h, &p.x_zhat, p.nld));
+    GPAD_CUDA(cudaMemset(p.x_w, 0, sizeof(float) * p.mld));          // the zero padding is gathered too
+    GPAD_CUDA(cudaMemset(p.x_zhat, 0, sizeof(float) * p.nld));
     GPAD_TRY(dev_alloc(h, &p.x_red, 3 * 8 * p.g_pad));
     GPAD_TRY(dev_alloc(h, &h->d_flags, 2));
     p.barrier = h->d_flags; p.nonfinite_flag = reinterpret_cast<int*>(h->d_flags + 1);
 
-    char buf[256];
-    snprintf(buf, sizeof(buf), "latency: persistent kernel, %s x%d CTAs, %d threads, operators %s, smem %zu B/CTA",
-             sync == lat::SYNC_BLOCK ? "single-CTA" : sync == lat::SYNC_CLUSTER ? "cluster(DSMEM)" : "cooperative-grid",
-             G, h->threads, ops ? "in shared memory" : "streamed from L2", lat::smem_bytes(p, ops));
+    char where[96];
+    if (plan.regs) snprintf(where, sizeof(where), "in registers");
+    else snprintf(where, sizeof(where), "%d/%d + %d/%d rows per CTA in shared memory, rest streamed from L2", p.res_a, p.rows_a, p.res_b, p.rows_b);
+    char buf[320];
+    snprintf(buf, sizeof(buf), "latency: persistent kernel, %s x%d CTAs, %d threads, lanes/row %d|%d, operators %s, smem %zu B/CTA",
+             plan.sync == lat::SYNC_BLOCK ? "single-CTA" : plan.sync == lat::SYNC_CLUSTER ? "cluster(DSMEM)" : "cooperative-grid",
+             plan.G, plan.threads, 1 << p.lg_a, 1 << p.lg_b, where, lat::smem_bytes(p, plan.regs));
     h->desc = buf;
     return GPAD_OK;
 }
@@ -281,6 +332,120 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
         if (a->status) GPAD_CUDA(cudaMemcpyAsync(a->status, h->o_status, sizeof(int), cudaMemcpyDeviceToHost, s));
         if (a->max_viol) GPAD_CUDA(cudaMemcpyAsync(a->max_viol, h->o_viol, sizeof(float), cudaMemcpyDeviceToHost, s));
         if (a->gap) GPAD_CUDA(cudaMemcpyAsync(a->gap, h->o_gap, sizeof(float), cudaMemcpyDeviceToHost, s));
+        GPAD_CUDA(cudaStreamSynchronize(s));
+    }
+    return GPAD_OK;
+}
+
+// ------------------------------------------------------------------ batch, per-instance operators
+// Every QP has its own M_G / G_L, so there is nothing to share between instances: each CTA runs
+// the persistent latency kernel on one QP (batched GEMV).  Operators are read from HBM once per
+// solve (into registers when the plan allows), not once per iteration.
+int setup_per_instance(gpad_handle_s* h, const float* M_G, const float* G_L) {
+    const int n = h->n, m = h->cfg.m, B = h->cfg.max_batch;
+    LatPlan plan;
+    if (plan_for(n, m, 1, true, h->smem_optin, false, plan)) plan.sync = lat::SYNC_BLOCK;
+    else if (plan_for(n, m, 1, false, h->smem_optin, false, plan)) plan.sync = lat::SYNC_BLOCK;
+    else { set_error("per-instance mode: n=%d, m=%d does not fit one CTA", n, m); return GPAD_ERR_UNSUPPORTED; }
+    lat::Params& p = h->lp;
+    p = plan.p;
+    h->sync_mode = lat::SYNC_BLOCK; h->G = 1; h->threads = plan.threads; h->ops_smem = plan.regs;
+    p.L = h->cfg.L;
+    p.batch = B;
+    p.op_stride_a = (size_t)n * p.mld; p.op_stride_b = (size_t)m * p.nld;
+    float *dMG, *dGL;
+    GPAD_TRY(dev_alloc(h, &dMG, (size_t)B * p.op_stride_a));
+    GPAD_TRY(dev_alloc(h, &dGL, (size_t)B * p.op_stride_b));
+    const bool flipped = h->cfg.layout == GPAD_LAYOUT_FLIPPED;
+    const size_t per = (size_t)n * m;
+    if (h->cfg.operators_mem == GPAD_MEM_DEVICE) {
+        GPAD_TRY(lat::launch_convert_ops(dMG, M_G, B, n, m, p.mld, flipped, nullptr));
+        GPAD_TRY(lat::launch_convert_ops(dGL, G_L, B, m, n, p.nld, flipped, nullptr));
+    } else {
+        // stage through a bounded device buffer
+        const int chunk = (int)std::max<size_t>(1, std::min<size_t>(B, (size_t)(256u << 20) / (per * sizeof(float))));
+        float* tmp = nullptr;
+        GPAD_CUDA(cudaMalloc(&tmp, (size_t)chunk * per * sizeof(float)));
+        int rc = GPAD_OK;
+        for (int b0 = 0; b0 < B && rc == GPAD_OK; b0 += chunk) {
+            const int nb = std::min(chunk, B - b0);
+            for (int which = 0; which < 2 && rc == GPAD_OK; ++which) {
+                const float* src = (which == 0 ? M_G : G_L) + (size_t)b0 * per;
+                if (cudaMemcpy(tmp, src, (size_t)nb * per * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { rc = GPAD_ERR_CUDA; break; }
+                rc = which == 0 ? lat::launch_convert_ops(dMG + (size_t)b0 * p.op_stride_a, tmp, nb, n, m, p.mld, flipped, nullptr)
+                                : lat::launch_convert_ops(dGL + (size_t)b0 * p.op_stride_b, tmp, nb, m, n, p.nld, flipped, nullptr);
+                if (cudaDeviceSynchronize() != cudaSuccess) rc = GPAD_ERR_CUDA;
+            }
+        }
+        cudaFree(tmp);
+        if (rc != GPAD_OK) { set_error("per-instance operator upload failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
+    }
+    GPAD_CUDA(cudaDeviceSynchronize());
+    p.M_G = dMG; p.G_L = dGL;
+    const size_t bn_ = (size_t)B * n, bm_ = (size_t)B * m;
+    GPAD_TRY(dev_alloc(h, &h->pi_gP, bn_)); GPAD_TRY(dev_alloc(h, &h->pi_pD, bm_)); GPAD_TRY(dev_alloc(h, &h->pi_f, bn_));
+    GPAD_TRY(dev_alloc(h, &h->pi_y0, bm_)); GPAD_TRY(dev_alloc(h, &h->pi_yprev0, bm_));
+    GPAD_TRY(dev_alloc(h, &h->pi_ynext, bm_)); GPAD_TRY(dev_alloc(h, &h->pi_y, bm_)); GPAD_TRY(dev_alloc(h, &h->pi_w, bm_));
+    GPAD_TRY(dev_alloc(h, &h->pi_z, bn_)); GPAD_TRY(dev_alloc(h, &h->pi_zhat, bn_));
+    GPAD_TRY(dev_alloc(h, &h->pi_iters, B)); GPAD_TRY(dev_alloc(h, &h->pi_status, B));
+    GPAD_TRY(dev_alloc(h, &h->pi_viol, B)); GPAD_TRY(dev_alloc(h, &h->pi_gap, B));
+    GPAD_TRY(dev_alloc(h, &p.x_w, 4)); GPAD_TRY(dev_alloc(h, &p.x_zhat, 4)); GPAD_TRY(dev_alloc(h, &p.x_red, 4));
+    GPAD_TRY(dev_alloc(h, &h->d_flags, 2));
+    p.barrier = h->d_flags; p.nonfinite_flag = reinterpret_cast<int*>(h->d_flags + 1);
+    char buf[320];
+    snprintf(buf, sizeof(buf), "batch-per-instance: one CTA per QP (batched GEMV), %d threads, lanes/row %d|%d, operators %s, smem %zu B/CTA",
+             plan.threads, 1 << p.lg_a, 1 << p.lg_b,
+             plan.regs ? "read once into registers" : "in shared memory / streamed", lat::smem_bytes(p, plan.regs));
+    h->desc = buf;
+    return GPAD_OK;
+}
+
+int solve_per_instance(gpad_handle_s* h, const gpad_solve_args_t* a) {
+    const int n = h->n, m = h->cfg.m, B = a->batch;
+    const bool host = a->mem == GPAD_MEM_HOST;
+    cudaStream_t s = host ? h->own_stream : static_cast<cudaStream_t>(a->stream);
+    GPAD_TRY(upload_schedule(h, a->theta, a->beta, a->max_iter, s));
+    lat::Params p = h->lp;
+    p.batch = B;
+    const size_t bn_ = (size_t)B * n * sizeof(float), bm_ = (size_t)B * m * sizeof(float);
+    if (host) {
+        GPAD_CUDA(cudaMemcpyAsync(h->pi_gP, a->g_P, bn_, cudaMemcpyHostToDevice, s));
+        GPAD_CUDA(cudaMemcpyAsync(h->pi_pD, a->p_D, bm_, cudaMemcpyHostToDevice, s));
+        if (a->f) GPAD_CUDA(cudaMemcpyAsync(h->pi_f, a->f, bn_, cudaMemcpyHostToDevice, s));
+        if (a->y0) GPAD_CUDA(cudaMemcpyAsync(h->pi_y0, a->y0, bm_, cudaMemcpyHostToDevice, s));
+        if (a->y_prev0) GPAD_CUDA(cudaMemcpyAsync(h->pi_yprev0, a->y_prev0, bm_, cudaMemcpyHostToDevice, s));
+        p.g_P = h->pi_gP; p.p_D = h->pi_pD; p.f = a->f ? h->pi_f : nullptr;
+        p.y0 = a->y0 ? h->pi_y0 : nullptr; p.y_prev0 = a->y_prev0 ? h->pi_yprev0 : nullptr;
+    } else {
+        p.g_P = a->g_P; p.p_D = a->p_D; p.f = a->f; p.y0 = a->y0; p.y_prev0 = a->y_prev0;
+    }
+    p.theta = h->d_theta; p.beta = h->d_beta;
+    p.max_iter = a->max_iter; p.check_every = a->check_every > 0 ? a->check_every : 0;
+    p.eps_g = a->eps_g; p.eps_V = a->eps_V;
+    const bool dev = !host;
+    p.out_y_next = dev ? a->y_next : (a->y_next ? h->pi_ynext : nullptr);
+    p.out_y = dev ? a->y : (a->y ? h->pi_y : nullptr);
+    p.out_z = dev ? a->z : (a->z ? h->pi_z : nullptr);
+    p.out_zhat = dev && a->zhat ? a->zhat : h->pi_zhat;       // also the scratch of the dual-gap branch
+    p.out_w = dev && a->w ? a->w : h->pi_w;
+    p.out_iters = dev ? a->iters : (a->iters ? h->pi_iters : nullptr);
+    p.out_status = dev ? a->status : (a->status ? h->pi_status : nullptr);
+    p.out_max_viol = dev ? a->max_viol : (a->max_viol ? h->pi_viol : nullptr);
+    p.out_gap = dev ? a->gap : (a->gap ? h->pi_gap : nullptr);
+    cudaEvent_t pe = h->prof_begin(s);
+    GPAD_TRY(lat::launch(p, lat::SYNC_BLOCK, h->ops_smem, 1, h->threads, s));
+    h->prof_end(0, pe, s);
+    h->launches += 1;
+    if (host) {
+        if (a->y_next) GPAD_CUDA(cudaMemcpyAsync(a->y_next, h->pi_ynext, bm_, cudaMemcpyDeviceToHost, s));
+        if (a->y) GPAD_CUDA(cudaMemcpyAsync(a->y, h->pi_y, bm_, cudaMemcpyDeviceToHost, s));
+        if (a->w) GPAD_CUDA(cudaMemcpyAsync(a->w, h->pi_w, bm_, cudaMemcpyDeviceToHost, s));
+        if (a->z) GPAD_CUDA(cudaMemcpyAsync(a->z, h->pi_z, bn_, cudaMemcpyDeviceToHost, s));
+        if (a->zhat) GPAD_CUDA(cudaMemcpyAsync(a->zhat, h->pi_zhat, bn_, cudaMemcpyDeviceToHost, s));
+        if (a->iters) GPAD_CUDA(cudaMemcpyAsync(a->iters, h->pi_iters, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+        if (a->status) GPAD_CUDA(cudaMemcpyAsync(a->status, h->pi_status, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+        if (a->max_viol) GPAD_CUDA(cudaMemcpyAsync(a->max_viol, h->pi_viol, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
+        if (a->gap) GPAD_CUDA(cudaMemcpyAsync(a->gap, h->pi_gap, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
         GPAD_CUDA(cudaStreamSynchronize(s));
     }
     return GPAD_OK;
@@ -550,10 +715,6 @@ int gpad_setup(const gpad_config_t* cfg, const float* M_G, const float* G_L, gpa
         set_error("device %d is sm_%d%d; libgpad_b200 contains sm_100a code only", dev, prop.major, prop.minor);
         return GPAD_ERR_UNSUPPORTED;
     }
-    if (cfg->mode == GPAD_MODE_BATCH_PER_INSTANCE) {
-        set_error("GPAD_MODE_BATCH_PER_INSTANCE is not implemented yet");
-        return GPAD_ERR_UNSUPPORTED;
-    }
     gpad_handle_s* h = new gpad_handle_s;
     h->cfg = *cfg; h->cfg.device = dev;
     h->n = cfg->n_u * cfg->N; h->device = dev; h->num_sms = prop.multiProcessorCount;
@@ -562,6 +723,7 @@ int gpad_setup(const gpad_config_t* cfg, const float* M_G, const float* G_L, gpa
     std::vector<float> MG, GL;
     do {
         if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = GPAD_ERR_CUDA; set_error("stream creation failed"); break; }
+        if (cfg->mode == GPAD_MODE_BATCH_PER_INSTANCE) { rc = setup_per_instance(h, M_G, G_L); break; }
         rc = fetch_operators(*cfg, M_G, G_L, (size_t)h->n * cfg->m, 1, MG, GL);
         if (rc != GPAD_OK) break;
         rc = cfg->mode == GPAD_MODE_LATENCY ? setup_latency(h, MG, GL) : setup_batch(h, MG, GL);
@@ -597,6 +759,7 @@ int gpad_solve(gpad_handle_t h, const gpad_solve_args_t* a) {
         return GPAD_ERR_UNSUPPORTED;
     }
     GPAD_CUDA(cudaSetDevice(h->device));
+    if (h->cfg.mode == GPAD_MODE_BATCH_PER_INSTANCE) return solve_per_instance(h, a);
     return h->cfg.mode == GPAD_MODE_LATENCY ? solve_latency(h, a) : solve_batch(h, a);
 }
 

@@ -7,14 +7,18 @@ namespace lat {
 
 enum { SYNC_BLOCK = 0, SYNC_CLUSTER = 1, SYNC_GRID = 2 };
 constexpr int kMaxThreads = 512;
+constexpr int kRegChunks = 8;    // float4 operator fragments per lane and phase in the register-resident variant
 
 struct Params {
     int n, m;
-    int nld, mld;            // n, m rounded up to 4 floats (row strides of G_L / M_G)
+    int nld, mld;            // row strides of G_L / M_G: n, m rounded up to 4 * lanes-per-row floats
     int rows_a, rows_b;      // rows of M_G / G_L per CTA (ceil(n/G), ceil(m/G))
     int rows_a_pad, rows_b_pad;  // rounded up to 4
     int g_pad;               // G rounded up to 4
-    int lpr_a, lpr_b;        // lanes per row in phase A / B
+    int lg_a, lg_b;          // log2(lanes per row) in phase A / B
+    int res_a, res_b;        // own rows of M_G / G_L resident in shared memory (memory variant)
+    int batch;               // SYNC_BLOCK only: independent instances, one CTA each (per-instance operators)
+    size_t op_stride_a, op_stride_b;   // elements between consecutive instances' M_G / G_L (0: shared)
     const float* M_G;        // [n][mld] sequential layout, zero padded
     const float* G_L;        // [m][nld]
     const float* g_P;        // [n]
@@ -38,9 +42,10 @@ struct Params {
     int* nonfinite_flag;     // zeroed before launch
 };
 
-size_t smem_bytes(const Params& p, bool ops_smem);
-int launch(const Params& p, int sync_mode, bool ops_smem, int G, int threads, cudaStream_t stream);
-int max_cluster_size(bool ops_smem, int threads, size_t smem);
+size_t smem_bytes(const Params& p, bool regs);
+int launch(const Params& p, int sync_mode, bool regs, int G, int threads, cudaStream_t stream);
+int launch_convert_ops(float* dst, const float* src, int B, int rows, int cols, int ld, bool flipped, cudaStream_t stream);
+int max_cluster_size(int threads, size_t smem);
 
 }  // namespace lat
 }  // namespace gpad

@@ -201,7 +201,8 @@ class Solver:
             M_G = np.ascontiguousarray(M_G, np.float32)
             G_L = np.ascontiguousarray(G_L, np.float32)
             if n_u > 0 and N > 0 and m > 0:
-                assert M_G.size == n_u * N * m and G_L.size == n_u * N * m
+                copies = max_batch if mode == MODE_BATCH_PER_INSTANCE else 1
+                assert M_G.size == copies * n_u * N * m and G_L.size == copies * n_u * N * m
         self._keep = (M_G, G_L)
         self._h = C.c_void_p()
         check(lib().gpad_setup(C.byref(cfg), _ptr(M_G), _ptr(G_L), C.byref(self._h)), "gpad_setup")

@@ -21,16 +21,19 @@ def shard_seed(base_seed, rank):
     return base_seed + rank
 
 
-def gather_first_moves(z, n_u, dst=0):
-    """gather u0 = z[:, :n_u] of every rank on `dst`; returns [world*B, n_u] there, None elsewhere.
-    All ranks must hold the same shard size (bench) or pass their own; sizes are exchanged first."""
+def gather_first_moves(z, n_u, dst=0, equal_shards=False):
+    """gather u0 = z[:, :n_u] of every rank on `dst`; returns [sum of shard sizes, n_u] there, None
+    elsewhere.  equal_shards=True skips the (host-synchronising) exchange of shard sizes."""
     u0 = z[:, :n_u].contiguous()
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return u0
     world, rank = dist.get_world_size(), dist.get_rank()
-    sizes = [torch.zeros(1, dtype=torch.int64, device=u0.device) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([u0.shape[0]], dtype=torch.int64, device=u0.device))
-    sizes = [int(s.item()) for s in sizes]
+    if equal_shards:
+        sizes = [u0.shape[0]] * world
+    else:
+        sizes = [torch.zeros(1, dtype=torch.int64, device=u0.device) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([u0.shape[0]], dtype=torch.int64, device=u0.device))
+        sizes = [int(s.item()) for s in sizes]
     if len(set(sizes)) == 1:
         out = [torch.empty_like(u0) for _ in range(world)] if rank == dst else None
         dist.gather(u0, out, dst=dst)

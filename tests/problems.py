@@ -44,9 +44,11 @@ class Problem:
         return np.ascontiguousarray(self.G_L.T)   # [n][m]
 
 
-def battery(n_u=3, N=4):
+def battery(n_u=3, N=4, cap_scale=None):
     n, p = n_u, N
     cap = 0.027 * 4.1 * np.ones(n)                         # gpad.m:18
+    if cap_scale is not None:                              # per-instance plants (BASELINE config 5)
+        cap = cap * np.asarray(cap_scale, float)
     A = np.eye(n)                                          # gpad.m:34
     Bm = np.diag(-1.0 / (3600.0 * cap))                    # gpad.m:47-49
     M_ak = np.vstack([np.linalg.matrix_power(A, i) for i in range(1, p + 1)])   # gpad.m:50-52
