@@ -457,7 +457,11 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
     const bool tcp = h->cfg.precision == GPAD_PREC_TF32X3;
     BatchState& st = h->st;
     st.n = n; st.m = m; st.np = round_up(n, 32); st.mp = round_up(m, 32);
-    st.Bp = round_up(h->cfg.max_batch, 128);
+    // cta_group::1 by default: measured on B200 the CTA-pair kernel (GPAD_TC_CG=2) ties on product 2 (HBM-bound
+    // epilogue) and loses on product 1 (cross-CTA hand-off of the in-kernel w split), see DESIGN.md 4.1
+    int cg = 1;
+    if (const char* e = getenv("GPAD_TC_CG")) cg = atoi(e) == 2 ? 2 : 1;
+    st.Bp = round_up(h->cfg.max_batch, 256);
     int bn1 = 0, nt1 = 0, bn2 = 0, nt2 = 0;
     tc::plan_tiles(n, &bn1, &nt1);
     tc::plan_tiles(m, &bn2, &nt2);
@@ -488,22 +492,23 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         if (const char* e = getenv("GPAD_TC_BK")) bk = atoi(e) == 32 ? 32 : 16;
         tc::GemmDesc& g1 = h->g1; tc::GemmDesc& g2 = h->g2;
         g1.bk = g2.bk = bk;
+        g1.cg = g2.cg = cg;
         g1.k_pad = st.mp; g1.bn = bn1; g1.n_tiles = nt1; g1.ncols_valid = n;
         g2.k_pad = st.np; g2.bn = bn2; g2.n_tiles = nt2; g2.ncols_valid = m;
-        g1.stages = tc::pick_stages(bk, bn1, h->smem_optin);
-        g2.stages = tc::pick_stages(bk, bn2, h->smem_optin);
+        g1.stages = cg == 2 ? tc::pick_stages2(bk, bn1, h->smem_optin) : tc::pick_stages(bk, bn1, h->smem_optin);
+        g2.stages = cg == 2 ? tc::pick_stages2(bk, bn2, h->smem_optin) : tc::pick_stages(bk, bn2, h->smem_optin);
         if (const char* e = getenv("GPAD_TC_STAGES")) { g1.stages = std::min(g1.stages, std::max(2, atoi(e))); g2.stages = std::min(g2.stages, std::max(2, atoi(e))); }
         for (int k = 0; k < 3; ++k) GPAD_TRY(tc::make_tmap(&g1.tmY[k], st.yb[k], st.mp, st.Bp, st.mp, bk, 128));
-        GPAD_TRY(tc::make_tmap(&g1.tmB_hi, h->op.M_G, st.mp, h->op.n_rows_pad, st.mp, bk, bn1));
-        GPAD_TRY(tc::make_tmap(&g1.tmB_lo, h->op.M_G_lo, st.mp, h->op.n_rows_pad, st.mp, bk, bn1));
+        GPAD_TRY(tc::make_tmap(&g1.tmB_hi, h->op.M_G, st.mp, h->op.n_rows_pad, st.mp, bk, bn1 / cg));
+        GPAD_TRY(tc::make_tmap(&g1.tmB_lo, h->op.M_G_lo, st.mp, h->op.n_rows_pad, st.mp, bk, bn1 / cg));
         GPAD_TRY(tc::make_tmap(&g2.tmA_hi, st.zh_hi, st.np, st.Bp, st.np, bk, 128));
         GPAD_TRY(tc::make_tmap(&g2.tmA_lo, st.zh_lo, st.np, st.Bp, st.np, bk, 128));
-        GPAD_TRY(tc::make_tmap(&g2.tmB_hi, h->op.G_L, st.np, h->op.m_rows_pad, st.np, bk, bn2));
-        GPAD_TRY(tc::make_tmap(&g2.tmB_lo, h->op.G_L_lo, st.np, h->op.m_rows_pad, st.np, bk, bn2));
+        GPAD_TRY(tc::make_tmap(&g2.tmB_hi, h->op.G_L, st.np, h->op.m_rows_pad, st.np, bk, bn2 / cg));
+        GPAD_TRY(tc::make_tmap(&g2.tmB_lo, h->op.G_L_lo, st.np, h->op.m_rows_pad, st.np, bk, bn2 / cg));
         snprintf(buf, sizeof(buf),
-                 "batch-shared: tcgen05 kind::tf32 x3 (hi/lo split, w built in-kernel), TMA ring bk=%d, product1 tiles 128x%d x%d "
-                 "(%d stages), product2 tiles 128x%d x%d (%d stages), TMEM 2x256 cols, persistent over %d SMs",
-                 bk, bn1, nt1, g1.stages, bn2, nt2, g2.stages, h->num_sms);
+                 "batch-shared: tcgen05 cta_group::%d kind::tf32 x3 (hi/lo split, w built in-kernel), TMA ring bk=%d, product1 tiles "
+                 "%dx%d x%d (%d stages), product2 tiles %dx%d x%d (%d stages), TMEM 2x256 cols, persistent over %d SMs",
+                 cg, bk, 128 * cg, bn1, nt1, g1.stages, 128 * cg, bn2, nt2, g2.stages, h->num_sms);
     } else {
         snprintf(buf, sizeof(buf), "batch-shared: CUDA-core fp32 GEMM 128x128x16 tiles with fused GPAD epilogues");
     }
@@ -555,9 +560,10 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
     k.g_P = st.g_P; k.p_D = st.p_D; k.f = a->f ? st.f : nullptr;
     k.z = st.z; k.zhat = st.zhat; k.zh_hi = st.zh_hi; k.zh_lo = st.zh_lo;
     k.sbar = st.sbar; k.red = st.red; k.done = checking ? st.done : nullptr;
-    const int m_tiles = round_up(B, 128) / 128;
+    const int tile_rows = (tcp && h->g1.cg == 2) ? 256 : 128;
+    const int m_tiles = round_up(B, tile_rows) / tile_rows;
     h->g1.m_tiles = m_tiles; h->g2.m_tiles = m_tiles;
-    const int Bp_call = m_tiles * 128;
+    const int Bp_call = m_tiles * tile_rows;
 
     for (int v = 0; v < a->max_iter; ++v) {
         const bool check = checking && ((v + 1) % a->check_every == 0);
@@ -802,13 +808,15 @@ int gpad_debug_gemm_tf32x3(const float* A, const float* B, float* C, int M, int 
     if (const char* e = getenv("GPAD_TC_BK")) bk = atoi(e) == 32 ? 32 : 16;
     tc::GemmDesc g;
     g.bk = bk;
+    g.cg = 1;
+    if (const char* e = getenv("GPAD_TC_CG")) g.cg = atoi(e) == 2 ? 2 : 1;
     g.k_pad = round_up(K, 32);
     tc::plan_tiles(N, &g.bn, &g.n_tiles);
-    g.m_tiles = round_up(M, 128) / 128;
+    g.m_tiles = round_up(M, 128 * g.cg) / (128 * g.cg);
     g.ncols_valid = N;
-    g.stages = tc::pick_stages(bk, g.bn, prop.sharedMemPerBlockOptin);
+    g.stages = g.cg == 2 ? tc::pick_stages2(bk, g.bn, prop.sharedMemPerBlockOptin) : tc::pick_stages(bk, g.bn, prop.sharedMemPerBlockOptin);
     if (const char* e = getenv("GPAD_TC_STAGES")) g.stages = std::min(g.stages, std::max(2, atoi(e)));
-    const int Mp = g.m_tiles * 128, Np = round_up(g.bn * g.n_tiles, 128);
+    const int Mp = g.m_tiles * 128 * g.cg, Np = round_up(g.bn * g.n_tiles, 128);
     float *Ap, *Al, *Bp, *Bl;
     const size_t ca = (size_t)Mp * g.k_pad, cb = (size_t)Np * g.k_pad;
     GPAD_CUDA(cudaMalloc(&Ap, ca * 4)); GPAD_CUDA(cudaMalloc(&Al, ca * 4));
@@ -821,8 +829,8 @@ int gpad_debug_gemm_tf32x3(const float* A, const float* B, float* C, int M, int 
         if ((rc = tc::launch_split(Bp, Bp, Bl, cb, s)) != GPAD_OK) break;
         if ((rc = tc::make_tmap(&g.tmA_hi, Ap, g.k_pad, Mp, g.k_pad, bk, 128)) != GPAD_OK) break;
         if ((rc = tc::make_tmap(&g.tmA_lo, Al, g.k_pad, Mp, g.k_pad, bk, 128)) != GPAD_OK) break;
-        if ((rc = tc::make_tmap(&g.tmB_hi, Bp, g.k_pad, Np, g.k_pad, bk, g.bn)) != GPAD_OK) break;
-        if ((rc = tc::make_tmap(&g.tmB_lo, Bl, g.k_pad, Np, g.k_pad, bk, g.bn)) != GPAD_OK) break;
+        if ((rc = tc::make_tmap(&g.tmB_hi, Bp, g.k_pad, Np, g.k_pad, bk, g.bn / g.cg)) != GPAD_OK) break;
+        if ((rc = tc::make_tmap(&g.tmB_lo, Bl, g.k_pad, Np, g.k_pad, bk, g.bn / g.cg)) != GPAD_OK) break;
         BatchKernelArgs k{};
         k.B = M;
         rc = tc::launch_gemm(0, g, k, C, N, prop.multiProcessorCount, s);

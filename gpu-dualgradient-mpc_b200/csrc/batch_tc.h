@@ -12,6 +12,7 @@ struct GemmDesc {
     CUtensorMap tmA_hi, tmA_lo;   // A [rows = batch][K] tiles of 128 x bk (product 1: y_v and y_{v-1}, split in-kernel)
     CUtensorMap tmY[3];           // product 1: the three rotating y buffers
     CUtensorMap tmB_hi, tmB_lo;   // B [rows = outputs][K] tiles of bn x bk
+    int cg = 1;                   // 1: one CTA per 128 x bn tile; 2: CTA pair (cta_group::2) per 256 x bn tile
     int bk = 16;                  // K block in floats: 16 (SWIZZLE_64B) or 32 (SWIZZLE_128B)
     int k_pad = 0;                // K rounded up to bk
     int m_tiles = 0, n_tiles = 0, bn = 0, stages = 0;
@@ -23,6 +24,9 @@ void plan_tiles(int ncols, int* bn, int* n_tiles);
 size_t smem_bytes(int bk, int bn, int stages);
 int pick_stages(int bk, int bn, size_t smem_limit);
 int launch_gemm(int phase, const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s);
+size_t smem_bytes2(int bk, int bn, int stages);
+int pick_stages2(int bk, int bn, size_t smem_limit);
+int launch_gemm2(int phase, const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s);
 int launch_split(const float* src, float* hi, float* lo, size_t count, cudaStream_t s);
 
 }  // namespace tc

@@ -1,0 +1,111 @@
+// tc_epilogue.cuh -- the fused GPAD epilogue of one transposed 32x32 accumulator block, shared by the
+// cta_group::1 and cta_group::2 tcgen05 kernels.  `buf` holds the block transposed in shared memory
+// (buf[row * 33 + col]); lane = output column, rows row_base..row_base+31 of the batch.
+#pragma once
+#include "batch_common.cuh"
+
+namespace gpad {
+namespace tc {
+
+template <int PHASE>
+__device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, const float* buf, int lane, int row_base, int blk,
+                                               int n_tile, int bn, int ncols_valid, float* __restrict__ Cdbg, int ldc) {
+    const int cin = blk * 32 + lane;            // column inside the tile
+    const int c = n_tile * bn + cin;       // global output column
+    const bool col_ok = cin < bn && c < ncols_valid;
+    if (PHASE == 0) {
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+            const int b = row_base + rr;
+            if (col_ok && b < args.B) Cdbg[(size_t)b * ldc + c] = buf[rr * 33 + lane];
+        }
+    } else if (!args.it.check && !args.done) {
+        // fast path (fixed-iteration solves): rows in chunks of kChunk with every global
+        // load of the chunk issued before the first use, so each warp keeps
+        // kChunk * (2 or 3) x 128 B in flight; streaming cache hints keep the operators in L2
+        constexpr int kChunk = 16;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += kChunk) {
+            if (PHASE == 1) {
+                float gp[kChunk], zo[kChunk];
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) {
+                    const int b = row_base + r0 + j;
+                    const bool ok = col_ok && b < args.B;
+                    const size_t o = (size_t)b * args.np + c;
+                    gp[j] = ok ? __ldcs(args.g_P + o) : 0.f;
+                    zo[j] = ok ? __ldcs(args.z + o) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) {
+                    const int b = row_base + r0 + j;
+                    if (!(col_ok && b < args.B)) continue;
+                    const size_t o = (size_t)b * args.np + c;
+                    const float zh = buf[(r0 + j) * 33 + lane] - gp[j];
+                    __stcs(args.z + o, __fadd_rn(__fmul_rn(1.0f - args.it.theta, zo[j]), __fmul_rn(args.it.theta, zh)));
+                    __stcs(args.zhat + o, zh);
+                    float hi, lo;
+                    split_tf32(zh, hi, lo);
+                    args.zh_hi[o] = hi;      // re-read by product 2 of this iteration: default caching
+                    args.zh_lo[o] = lo;
+                }
+            } else {
+                float yc[kChunk], yp[kChunk], pd[kChunk];
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) {
+                    const int b = row_base + r0 + j;
+                    const bool ok = col_ok && b < args.B;
+                    const size_t o = (size_t)b * args.mp + c;
+                    yc[j] = ok ? __ldcs(args.y_cur + o) : 0.f;
+                    yp[j] = ok ? __ldcs(args.y_prev + o) : 0.f;
+                    pd[j] = ok ? __ldcs(args.p_D + o) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) {
+                    const int b = row_base + r0 + j;
+                    if (!(col_ok && b < args.B)) continue;
+                    const size_t o = (size_t)b * args.mp + c;
+                    const float wv = momentum(yc[j], yp[j], args.it.beta);
+                    const float sacc = buf[(r0 + j) * 33 + lane] + (wv + pd[j]);
+                    args.y_next[o] = 0.5f * (sacc + fabsf(sacc));   // read back by the next two kernels
+                }
+            }
+        }
+    } else {
+        // general path: termination bookkeeping (per-row reductions, stopped instances)
+#pragma unroll 2
+        for (int rr = 0; rr < 32; ++rr) {
+            const int b = row_base + rr;
+            const float val = buf[rr * 33 + lane];
+            bool ok = col_ok && b < args.B;
+            if (ok && args.done) ok = args.done[b] == 0;
+            if (PHASE == 1) {
+                float f_zhat = 0.f;
+                if (ok) epilogue1<true>(args, b, c, val, f_zhat);
+                if (args.it.check && args.f) {
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) f_zhat += __shfl_xor_sync(0xffffffffu, f_zhat, o);
+                    if (lane == 0 && b < args.B) atomicAdd(args.red + (size_t)b * kRedStride + 5, f_zhat);
+                }
+            } else {
+                Red2 red;
+                if (ok) epilogue2(args, b, c, val, red);
+                if (args.it.check) {
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        red.max_sbar = fmaxf(red.max_sbar, __shfl_xor_sync(0xffffffffu, red.max_sbar, o));
+                        red.max_rhat = fmaxf(red.max_rhat, __shfl_xor_sync(0xffffffffu, red.max_rhat, o));
+                        red.min_w = fminf(red.min_w, __shfl_xor_sync(0xffffffffu, red.min_w, o));
+                        red.w_rhat += __shfl_xor_sync(0xffffffffu, red.w_rhat, o);
+                        red.w_dot += __shfl_xor_sync(0xffffffffu, red.w_dot, o);
+                        red.bad = fmaxf(red.bad, __shfl_xor_sync(0xffffffffu, red.bad, o));
+                    }
+                    if (lane == 0 && b < args.B && !(args.done && args.done[b])) flush_red2(args, b, red);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace tc
+}  // namespace gpad

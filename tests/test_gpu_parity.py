@@ -242,8 +242,11 @@ def test_latency_warm_start_and_device_buffers(torch_cuda, G, oracle):
 
 
 # ------------------------------------------------------------------------------------ tensor-core GEMM hook
+@pytest.mark.parametrize("cta_group", ["1", "2"])
 @pytest.mark.parametrize("shape", [(128, 16, 16), (128, 256, 64), (300, 200, 1000), (1000, 416, 2400), (257, 2400, 400)])
-def test_tf32x3_gemm_reaches_fp32_accuracy(torch_cuda, G, shape):
+def test_tf32x3_gemm_reaches_fp32_accuracy(torch_cuda, G, shape, cta_group, monkeypatch):
+    """both tcgen05 kernels: one CTA per 128-row tile (cta_group::1) and CTA pairs (cta_group::2, M = 256)"""
+    monkeypatch.setenv("GPAD_TC_CG", cta_group)
     t = torch_cuda
     M, N, K = shape
     rng = np.random.default_rng(M + N + K)
@@ -299,8 +302,10 @@ def test_batch_battery_matches_oracle(torch_cuda, G, oracle, prec, dims, B):
     s.close()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
-def test_batch_quadrotor_matches_oracle(torch_cuda, G, oracle, prec):
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32x3-pairs"])
+def test_batch_quadrotor_matches_oracle(torch_cuda, G, oracle, prec, monkeypatch):
+    monkeypatch.setenv("GPAD_TC_CG", "2" if prec.endswith("pairs") else "1")
+    prec = prec.split("-")[0]
     N = 20
     pb = P.quadrotor(N)
     B = 140
