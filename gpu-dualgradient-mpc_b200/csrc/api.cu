@@ -115,7 +115,8 @@ int dev_alloc(gpad_handle_s* h, T** p, size_t count) {
 // operators -> host, sequential layout (M_G [n][m], G_L [m][n])
 int fetch_operators(const gpad_config_t& c, const float* M_G, const float* G_L, size_t count_each, int copies,
                     std::vector<float>& MG, std::vector<float>& GL) {
-    const size_t total = count_each * copies;
+    const size_t flat_each = (size_t)c.N * c.m;
+    const size_t total = (c.layout == GPAD_LAYOUT_FLAT ? flat_each : count_each) * copies;
     std::vector<float> a(total), b(total);
     if (c.operators_mem == GPAD_MEM_DEVICE) {
         GPAD_CUDA(cudaMemcpy(a.data(), M_G, total * sizeof(float), cudaMemcpyDeviceToHost));
@@ -126,6 +127,10 @@ int fetch_operators(const gpad_config_t& c, const float* M_G, const float* G_L, 
     }
     if (c.layout == GPAD_LAYOUT_SEQUENTIAL) { MG.swap(a); GL.swap(b); return GPAD_OK; }
     const int n = c.n_u * c.N, m = c.m;
+    if (c.layout == GPAD_LAYOUT_FLAT) {      // flattened battery operators: expand to dense sequential
+        MG.assign((size_t)n * m, 0.f); GL.assign((size_t)n * m, 0.f);
+        return gpad_expand_operators(c.n_u, c.N, m, a.data(), b.data(), MG.data(), GL.data());
+    }
     MG.resize(total); GL.resize(total);
     for (int k = 0; k < copies; ++k) {
         const float* fa = a.data() + k * count_each; const float* fb = b.data() + k * count_each;
@@ -570,6 +575,7 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
         k.it.theta = a->theta[v];
         k.it.beta = a->beta[v];
         k.it.check = check ? 1 : 0;
+        k.it.store_zhat = (checking || v + 1 == a->max_iter) ? 1 : 0;
         k.y_prev = st.yb[(v + 2) % 3];           // y_{v-1}
         k.y_cur = st.yb[v % 3];                  // y_v
         k.y_next = st.yb[(v + 1) % 3];           // y_{v+1} overwrites y_{v-2}
@@ -697,7 +703,10 @@ int gpad_step_four(const float* G_L, float* y_vp1, const float* w_v, const float
 int gpad_setup(const gpad_config_t* cfg, const float* M_G, const float* G_L, gpad_handle_t* out) {
     GPAD_REQUIRE(cfg && M_G && G_L && out, "gpad_setup: null argument");
     GPAD_REQUIRE(cfg->n_u > 0 && cfg->N > 0 && cfg->m > 0, "gpad_setup: n_u, N, m must be positive");
-    GPAD_REQUIRE(cfg->layout == GPAD_LAYOUT_FLIPPED || cfg->layout == GPAD_LAYOUT_SEQUENTIAL, "gpad_setup: bad layout");
+    GPAD_REQUIRE(cfg->layout == GPAD_LAYOUT_FLIPPED || cfg->layout == GPAD_LAYOUT_SEQUENTIAL || cfg->layout == GPAD_LAYOUT_FLAT,
+                 "gpad_setup: bad layout");
+    GPAD_REQUIRE(cfg->layout != GPAD_LAYOUT_FLAT || (cfg->mode != GPAD_MODE_BATCH_PER_INSTANCE && cfg->m >= 4 * cfg->n_u * cfg->N),
+                 "gpad_setup: GPAD_LAYOUT_FLAT needs m >= 4 n_u N and shared operators");
     GPAD_REQUIRE(cfg->mode >= GPAD_MODE_LATENCY && cfg->mode <= GPAD_MODE_BATCH_PER_INSTANCE, "gpad_setup: bad mode");
     GPAD_REQUIRE(cfg->precision == GPAD_PREC_FP32 || cfg->precision == GPAD_PREC_TF32X3, "gpad_setup: bad precision");
     GPAD_REQUIRE(cfg->max_batch >= 1, "gpad_setup: max_batch must be >= 1");

@@ -38,6 +38,7 @@ struct IterScalars {
     float theta;      // theta_v
     float beta;       // beta_v: w_v = y_v + beta_v (y_v - y_{v-1}) is recomputed wherever it is needed
     int check;        // 1 when the termination quantities are reduced this iteration
+    int store_zhat;   // zhat itself is an output only: written on the last iteration / in tolerance mode
 };
 
 // ---- device state of a batched (shared-operator) solve; all row-major [rows][ld] ----

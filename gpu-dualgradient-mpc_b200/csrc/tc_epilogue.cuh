@@ -43,7 +43,7 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
                     const size_t o = (size_t)b * args.np + c;
                     const float zh = buf[(r0 + j) * 33 + lane] - gp[j];
                     __stcs(args.z + o, __fadd_rn(__fmul_rn(1.0f - args.it.theta, zo[j]), __fmul_rn(args.it.theta, zh)));
-                    __stcs(args.zhat + o, zh);
+                    if (args.it.store_zhat) __stcs(args.zhat + o, zh);
                     float hi, lo;
                     split_tf32(zh, hi, lo);
                     args.zh_hi[o] = hi;      // re-read by product 2 of this iteration: default caching

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgpad_b200.so")
 
 # enums of include/gpad.h
-LAYOUT_FLIPPED, LAYOUT_SEQUENTIAL = 0, 1
+LAYOUT_FLIPPED, LAYOUT_SEQUENTIAL, LAYOUT_FLAT = 0, 1, 2
 MODE_LATENCY, MODE_BATCH_SHARED, MODE_BATCH_PER_INSTANCE = 1, 2, 3
 PREC_FP32, PREC_TF32X3 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -29,6 +29,7 @@ EXPORTS = [
     "gpad_problem_battery", "gpad_problem_quadrotor", "gpad_problem_destroy", "gpad_problem_dims",
     "gpad_problem_operators", "gpad_problem_instances", "gpad_problem_plant", "gpad_schedule",
     "gpad_file_read", "gpad_file_write", "gpad_file_free", "gpad_debug_gemm_tf32x3",
+    "gpad_flatten_operators", "gpad_expand_operators", "gpad_closed_loop",
 ]
 
 _fp = C.POINTER(C.c_float)
@@ -96,6 +97,9 @@ def lib():
         L.gpad_problem_instances.argtypes = [C.c_void_p, C.c_int, _dp, _fp, _fp, _fp]
         L.gpad_problem_plant.argtypes = [C.c_void_p, _ip, _dp, _dp]
         L.gpad_schedule.argtypes = [_fp, _fp, C.c_int, C.c_int]
+        L.gpad_flatten_operators.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp]
+        L.gpad_expand_operators.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]
+        L.gpad_closed_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, C.c_int, _fp, _fp, C.c_int, C.c_int, _dp, _dp]
         L.gpad_file_read.argtypes = [C.c_char_p, C.POINTER(FileData)]
         L.gpad_file_write.argtypes = [C.c_char_p, C.POINTER(FileData)]
         L.gpad_file_free.argtypes = [C.POINTER(FileData)]
@@ -202,7 +206,8 @@ class Solver:
             G_L = np.ascontiguousarray(G_L, np.float32)
             if n_u > 0 and N > 0 and m > 0:
                 copies = max_batch if mode == MODE_BATCH_PER_INSTANCE else 1
-                assert M_G.size == copies * n_u * N * m and G_L.size == copies * n_u * N * m
+                each = N * m if layout == LAYOUT_FLAT else n_u * N * m
+                assert M_G.size == copies * each and G_L.size == copies * each
         self._keep = (M_G, G_L)
         self._h = C.c_void_p()
         check(lib().gpad_setup(C.byref(cfg), _ptr(M_G), _ptr(G_L), C.byref(self._h)), "gpad_setup")
@@ -272,6 +277,36 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+
+def flatten_operators(n_u, N, m, M_G, G_L):
+    """dense sequential -> flat ([N][m], [m][N]); returns (M_G_flat, G_L_flat, max_residual)"""
+    M_G = np.ascontiguousarray(M_G, np.float32); G_L = np.ascontiguousarray(G_L, np.float32)
+    Mf = np.empty((N, m), np.float32); Gf = np.empty((m, N), np.float32)
+    res = C.c_float()
+    check(lib().gpad_flatten_operators(n_u, N, m, _f32p(M_G), _f32p(G_L), _f32p(Mf), _f32p(Gf), C.byref(res)), "gpad_flatten_operators")
+    return Mf, Gf, res.value
+
+
+def expand_operators(n_u, N, m, M_G_flat, G_L_flat):
+    Mf = np.ascontiguousarray(M_G_flat, np.float32); Gf = np.ascontiguousarray(G_L_flat, np.float32)
+    M_G = np.empty((n_u * N, m), np.float32); G_L = np.empty((m, n_u * N), np.float32)
+    check(lib().gpad_expand_operators(n_u, N, m, _f32p(Mf), _f32p(Gf), _f32p(M_G), _f32p(G_L)), "gpad_expand_operators")
+    return M_G, G_L
+
+
+def closed_loop(problem, solver, x0, samples, theta, beta, max_iter=None, xref=None, warm_start=False):
+    """receding-horizon simulation (gpad.m:79-95) -> (x_traj [samples+1][B][nx], u_traj [samples][B][n_u])"""
+    x0 = np.ascontiguousarray(np.atleast_2d(x0), np.float64)
+    B, nx = x0.shape
+    theta = np.ascontiguousarray(theta, np.float32); beta = np.ascontiguousarray(beta, np.float32)
+    max_iter = len(theta) if max_iter is None else max_iter
+    xr = None if xref is None else np.ascontiguousarray(np.atleast_2d(xref), np.float64)
+    xt = np.empty((samples + 1, B, nx)); ut = np.empty((samples, B, problem.n_u))
+    check(lib().gpad_closed_loop(problem._h, solver._h, B, x0.ctypes.data_as(_dp), None if xr is None else xr.ctypes.data_as(_dp),
+                                 samples, _f32p(theta), _f32p(beta), max_iter, 1 if warm_start else 0,
+                                 xt.ctypes.data_as(_dp), ut.ctypes.data_as(_dp)), "gpad_closed_loop")
+    return xt, ut
 
 
 # ---- step shims (device pointers) ----

@@ -355,6 +355,93 @@ int gpad_problem_plant(gpad_problem_t p, int* nx, double* A, double* B) {
     return GPAD_OK;
 }
 
+int gpad_flatten_operators(int n_u, int N, int m, const float* MG, const float* GL, float* MGf, float* GLf, float* max_residual) {
+    if (!MG || !GL || !MGf || !GLf || n_u < 1 || N < 1 || m < 4 * n_u * N) return GPAD_ERR_INVALID_ARG;
+    const int n = n_u * N, box = 4 * n_u * N;
+    float resid = 0.f;
+    // M_G flat [N][m]: row s holds, for column k of the box part, the entry of dense row (s n_u + k % n_u);
+    // the sum-constraint columns are shared by the n_u dense rows of stage s (seq_functions.cpp:5-20)
+    for (int s = 0; s < N; ++s)
+        for (int k = 0; k < m; ++k) {
+            const int u_of_k = k < box ? k % n_u : 0;
+            MGf[(size_t)s * m + k] = MG[(size_t)(s * n_u + u_of_k) * m + k];
+            for (int u = 0; u < n_u; ++u) {
+                const float dense = MG[(size_t)(s * n_u + u) * m + k];
+                const float flat = (k >= box || u == k % n_u) ? MGf[(size_t)s * m + k] : 0.f;
+                resid = std::fmax(resid, std::fabs(dense - flat));
+            }
+        }
+    // G_L flat [m][N]: row i, stage s holds dense G_L[i][s n_u + i % n_u] (box rows) or the common value of
+    // the n_u entries of stage s (sum-constraint rows)  (seq_functions.cpp:23-43)
+    for (int i = 0; i < m; ++i)
+        for (int s = 0; s < N; ++s) {
+            const int u_of_i = i < box ? i % n_u : 0;
+            GLf[(size_t)i * N + s] = GL[(size_t)i * n + s * n_u + u_of_i];
+            for (int u = 0; u < n_u; ++u) {
+                const float dense = GL[(size_t)i * n + s * n_u + u];
+                const float flat = (i >= box || u == i % n_u) ? GLf[(size_t)i * N + s] : 0.f;
+                resid = std::fmax(resid, std::fabs(dense - flat));
+            }
+        }
+    if (max_residual) *max_residual = resid;
+    return GPAD_OK;
+}
+
+int gpad_expand_operators(int n_u, int N, int m, const float* MGf, const float* GLf, float* MG, float* GL) {
+    if (!MG || !GL || !MGf || !GLf || n_u < 1 || N < 1 || m < 4 * n_u * N) return GPAD_ERR_INVALID_ARG;
+    const int n = n_u * N, box = 4 * n_u * N;
+    for (int s = 0; s < N; ++s)
+        for (int u = 0; u < n_u; ++u)
+            for (int k = 0; k < m; ++k)
+                MG[(size_t)(s * n_u + u) * m + k] = (k >= box || u == k % n_u) ? MGf[(size_t)s * m + k] : 0.f;
+    for (int i = 0; i < m; ++i)
+        for (int s = 0; s < N; ++s)
+            for (int u = 0; u < n_u; ++u)
+                GL[(size_t)i * n + s * n_u + u] = (i >= box || u == i % n_u) ? GLf[(size_t)i * N + s] : 0.f;
+    return GPAD_OK;
+}
+
+int gpad_closed_loop(gpad_problem_t p, gpad_handle_t h, int B, const double* x0, const double* xref, int samples,
+                     const float* theta, const float* beta, int max_iter, int warm_start, double* x_traj, double* u_traj) {
+    if (!p || !h || !x0 || !theta || !beta || B < 1 || samples < 1 || max_iter < 1) return GPAD_ERR_INVALID_ARG;
+    const int nx = p->nx, nu = p->n_u, n = p->n, m = p->m, npar = p->n_par, nref = npar - nx;
+    if (nref > 0 && !xref) return GPAD_ERR_INVALID_ARG;
+    std::vector<double> x(x0, x0 + (size_t)B * nx), par((size_t)B * npar), xn(nx);
+    std::vector<float> gP((size_t)B * n), pD((size_t)B * m), z((size_t)B * n), y1((size_t)B * m), y0v((size_t)B * m);
+    std::vector<float> wy1, wy0;
+    if (x_traj) std::memcpy(x_traj, x.data(), sizeof(double) * x.size());
+    for (int k = 0; k < samples; ++k) {
+        for (int b = 0; b < B; ++b) {
+            std::memcpy(&par[(size_t)b * npar], &x[(size_t)b * nx], sizeof(double) * nx);
+            if (nref > 0) std::memcpy(&par[(size_t)b * npar + nx], xref + (size_t)b * nref, sizeof(double) * nref);
+        }
+        int rc = gpad_problem_instances(p, B, par.data(), gP.data(), pD.data(), nullptr);           // gpad.m:81,85
+        if (rc != GPAD_OK) return rc;
+        gpad_solve_args_t a;
+        std::memset(&a, 0, sizeof(a));
+        a.batch = B; a.mem = GPAD_MEM_HOST;
+        a.g_P = gP.data(); a.p_D = pD.data(); a.theta = theta; a.beta = beta; a.max_iter = max_iter;
+        if (warm_start && k > 0) { wy1 = y1; wy0 = y0v; a.y0 = wy1.data(); a.y_prev0 = wy0.data(); }
+        a.z = z.data(); a.y_next = y1.data(); a.y = y0v.data();
+        rc = gpad_solve(h, &a);                                                                       // gpad.m:90
+        if (rc != GPAD_OK) return rc;
+        for (int b = 0; b < B; ++b) {
+            const float* u = &z[(size_t)b * n];                                                       // u = z_v(1:n_u), gpad.m:91
+            double* xb = &x[(size_t)b * nx];
+            for (int i = 0; i < nx; ++i) {
+                double s = 0.0;
+                for (int j = 0; j < nx; ++j) s += p->A(i, j) * xb[j];
+                for (int j = 0; j < nu; ++j) s += p->B(i, j) * (double)u[j];
+                xn[i] = s;                                                                            // gpad.m:93
+            }
+            std::memcpy(xb, xn.data(), sizeof(double) * nx);
+            if (u_traj) for (int j = 0; j < nu; ++j) u_traj[((size_t)k * B + b) * nu + j] = (double)u[j];
+        }
+        if (x_traj) std::memcpy(x_traj + (size_t)(k + 1) * B * nx, x.data(), sizeof(double) * x.size());
+    }
+    return GPAD_OK;
+}
+
 int gpad_schedule(float* theta, float* beta, int count, int variant) {
     if (!theta || !beta || count < 0) return GPAD_ERR_INVALID_ARG;
     double th_prev = 1.0, th = 1.0, lagged = 0.0;      // acceldualgrad.m:17,27

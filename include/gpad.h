@@ -44,7 +44,10 @@ typedef enum {
 typedef enum {
     GPAD_LAYOUT_FLIPPED = 0,    /* M_G [m][n], G_L [n][m]: what the reference kernels read
                                    (ENABLE_FLIPPING, kernel_functions.cu:50,180)            */
-    GPAD_LAYOUT_SEQUENTIAL = 1  /* M_G [n][m], G_L [m][n]: what seq_functions.cpp:61,82 read */
+    GPAD_LAYOUT_SEQUENTIAL = 1, /* M_G [n][m], G_L [m][n]: what seq_functions.cpp:61,82 read */
+    GPAD_LAYOUT_FLAT = 2        /* battery-structured "flattened" operators M_G [N][m], G_L [m][N]
+                                   (ENABLE_FLATTEN_MATRICES, main.cu:39-41,50-52; seq_functions.cpp:5-43,
+                                   kernel_functions.cu:74-109); expanded to dense at gpad_setup          */
 } gpad_layout;
 
 typedef enum {
@@ -193,6 +196,23 @@ int gpad_problem_instances(gpad_problem_t p, int B, const double* params, float*
                            float* f);
 /* plant matrices for closed-loop simulation: A [nx][nx], B [nx][n_u] row-major (double) */
 int gpad_problem_plant(gpad_problem_t p, int* nx, double* A, double* B);
+
+/* Flattened (battery-structured) operators <-> dense sequential operators.  The flat form exists when
+ * M_G[(s n_u + u)][k] is zero unless k >= 4 n_u N or k % n_u == u (and likewise for G_L), i.e. identical
+ * cells (Cookbook 2.2).  gpad_flatten_operators returns in *max_residual the largest |entry| that the flat
+ * form cannot represent (0 for the reference's battery problem). */
+int gpad_flatten_operators(int n_u, int N, int m, const float* M_G_seq, const float* G_L_seq, float* M_G_flat,
+                           float* G_L_flat, float* max_residual);
+int gpad_expand_operators(int n_u, int N, int m, const float* M_G_flat, const float* G_L_flat, float* M_G_seq,
+                          float* G_L_seq);
+
+/* Closed-loop receding-horizon simulation (gpad.m:79-95): every sample builds g_P / p_D from the current
+ * states, solves the batch with h (max_iter iterations, fixed), applies u = z[0:n_u] and advances
+ * x <- A x + B u in double.  warm_start != 0 feeds the previous duals (y_I, y_{I-1}) into the next solve; the
+ * reference cold-starts every sample (acceldualgrad.m:16-18).  x0 [batch][nx]; xref [batch][n_par-nx] or NULL;
+ * x_traj [samples+1][batch][nx]; u_traj [samples][batch][n_u]. */
+int gpad_closed_loop(gpad_problem_t prob, gpad_handle_t h, int batch, const double* x0, const double* xref, int samples,
+                     const float* theta, const float* beta, int max_iter, int warm_start, double* x_traj, double* u_traj);
 
 /* theta_v, beta_v for v = 0..count-1 (paper eq. 8e / acceldualgrad.m:55-56) */
 int gpad_schedule(float* theta, float* beta, int count, int variant);

@@ -410,3 +410,48 @@ def test_per_instance_operators_match_oracle(torch_cuda, G, oracle, dims, B, lay
     for k in VECS:
         assert P.rel_inf(warm[k][b], ora[k]) <= 2e-5, k
     s.close()
+
+
+# ------------------------------------------------------------------------------------ data formats / closed loop
+def test_flat_layout_solves_like_dense(torch_cuda, G):
+    pb = G.Problem("battery", n_u=10, N=15)
+    M_G, G_L = pb.operators()
+    Mf, Gf, resid = G.flatten_operators(10, 15, pb.m, M_G, G_L)
+    assert resid == 0.0
+    g_P, p_D, _ = pb.instances(P.BATTERY_X0_10)
+    theta, beta = schedule(100)
+    dense = G.Solver(10, 15, pb.m, pb.L, M_G, G_L, mode=G.MODE_LATENCY)
+    flat = G.Solver(10, 15, pb.m, pb.L, Mf, Gf, layout=G.LAYOUT_FLAT, mode=G.MODE_LATENCY)
+    a, b = dense.solve_host(g_P, p_D, theta, beta), flat.solve_host(g_P, p_D, theta, beta)
+    for k in VECS:
+        assert np.array_equal(a[k], b[k]), k
+    dense.close(); flat.close()
+
+
+@pytest.mark.parametrize("warm", [False, True])
+def test_closed_loop_battery_matches_oracle_loop(torch_cuda, G, oracle, warm):
+    """gpad.m:79-95 restated in C++ host code (gpad_closed_loop) against the same loop driven by the oracle"""
+    n_u, N, samples = 3, 4, 40
+    pb = G.Problem("battery", n_u=n_u, N=N)
+    ref = P.battery(n_u, N)
+    M_G, G_L = pb.operators()
+    theta, beta = schedule(100)
+    x0 = np.array([[0.41, -0.33, 0.12], [-0.2, 0.05, 0.45]])
+    s = G.Solver(n_u, N, pb.m, pb.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_FP32, max_batch=2)
+    xt, ut = G.closed_loop(pb, s, x0, samples, theta, beta, warm_start=warm)
+    s.close()
+    A, Bm = pb.plant()
+    x = x0.copy()
+    y1 = y0 = None
+    for k in range(samples):
+        g_P, p_D, _ = pb.instances(x, want_f=False)
+        sol = oracle.solve_batch(n_u, N, pb.m, M_G, G_L, g_P, p_D, theta, beta,
+                                 **({"y0": y1, "y_prev0": y0} if (warm and k > 0) else {}))
+        y1, y0 = sol["y_next"], sol["y"]
+        u = sol["z"][:, :n_u].astype(np.float64)
+        assert np.max(np.abs(ut[k] - u)) <= 1e-5 * max(1.0, np.abs(u).max()), k
+        x = x @ A.T + u @ Bm.T
+        assert np.max(np.abs(xt[k + 1] - x)) <= 1e-6
+    assert np.abs(ut).max() <= 0.3 + 1e-3                          # balancing currents respect the input box
+    spread0 = np.ptp(xt[0], axis=1); spread1 = np.ptp(xt[-1], axis=1)
+    assert (spread1 < spread0).all()                               # the cells are being balanced

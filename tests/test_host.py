@@ -119,3 +119,32 @@ def test_no_cpu_fallback_without_a_gpu():
     M = np.zeros((12, 56), np.float32)
     with pytest.raises(G.GpadError, match="no usable CUDA device|no CUDA device"):
         G.Solver(3, 4, 56, 1.0, M, M.T)
+
+
+@pytest.mark.parametrize("dims", [(3, 4), (10, 15)])
+def test_flat_operators_round_trip_and_match_reference_flat_steps(dims):
+    """ENABLE_FLATTEN_MATRICES data format (main.cu:39-41, seq_functions.cpp:5-43): the battery operators
+    flatten without residual, expand back exactly, and the reference-restated flat step functions on the
+    flat operators reproduce the dense step functions."""
+    from oracle import Oracle
+    n_u, N = dims
+    pb = G.Problem("battery", n_u=n_u, N=N)
+    M_G, G_L = pb.operators()
+    Mf, Gf, resid = G.flatten_operators(n_u, N, pb.m, M_G, G_L)
+    assert Mf.shape == (N, pb.m) and Gf.shape == (pb.m, N) and resid == 0.0
+    M2, G2 = G.expand_operators(n_u, N, pb.m, Mf, Gf)
+    assert np.array_equal(M2, M_G) and np.array_equal(G2, G_L)
+    o = Oracle()
+    rng = np.random.default_rng(1)
+    w = rng.standard_normal(pb.m).astype(np.float32)
+    g_P, p_D, _ = pb.instances(rng.random(n_u) - 0.5)
+    z_dense = o.step_two(M_G, w, g_P[0], n_u, N)
+    z_flat = o.step_two(Mf, w, g_P[0], n_u, N, flat=True)
+    assert np.array_equal(z_dense, z_flat)                       # same non-zero terms in the same order
+    y_dense = o.step_four(G_L, w, p_D[0], z_dense, n_u, N)
+    y_flat = o.step_four(Gf, w, p_D[0], z_dense, n_u, N, flat=True)
+    # the flat variant adds (sum + w) + p_D, the dense one sum + (w + p_D) (seq_functions.cpp:37 vs :84)
+    assert np.allclose(y_dense, y_flat, rtol=2e-6, atol=1e-7) and np.array_equal(y_dense > 0, y_flat > 0)
+    # a dense operator without the battery structure does not flatten
+    _, _, r2 = G.flatten_operators(n_u, N, pb.m, rng.standard_normal(M_G.shape).astype(np.float32), G_L)
+    assert r2 > 0.1
