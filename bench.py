@@ -210,6 +210,42 @@ def latency_probe(torch, G):
     return out
 
 
+def per_instance_probe(torch, G, B=262144):
+    """BASELINE config 5 (per-instance plants, batched-GEMV mode): battery (3,4) QPs each with its own
+    M_G / G_L; HBM roofline against the algorithmic minimum bytes per solve (operators stay on chip)"""
+    n_u, N = 3, 4
+    prob = G.Problem("battery", n_u=n_u, N=N)
+    M_G, G_L = prob.operators()
+    n, m = prob.n, prob.m
+    rng = np.random.default_rng(5)
+    scale = (1.0 + 0.1 * (2 * rng.random((B, 1, 1)) - 1)).astype(np.float32)      # +-10 % per-instance operator perturbation
+    dM = torch.from_numpy(M_G[None] * scale).cuda().contiguous(); dG = torch.from_numpy(G_L[None] / scale).cuda().contiguous()
+    g_P, p_D, _ = prob.instances(rng.random((B, n_u)) - 0.5, want_f=False)
+    theta, beta = G.schedule(ITERS)
+    s = G.Solver(n_u, N, m, prob.L, dM, dG, mode=G.MODE_BATCH_PER_INSTANCE, max_batch=B, operators_mem=G.MEM_DEVICE)
+    dg, dp = torch.from_numpy(g_P).cuda(), torch.from_numpy(p_D).cuda()
+    out = {k: torch.empty((B, m if k in ("y_next", "y", "w") else n), device="cuda") for k in ("y_next", "y", "z", "zhat", "w")}
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        s.solve_device(B, dg, dp, theta, beta, ITERS, stream=st, **out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        s.solve_device(B, dg, dp, theta, beta, ITERS, stream=st, **out)
+    e1.record(); e1.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / reps
+    bytes_min = ((2 * n * m + n + m) * 4 + (3 * m + 2 * n) * 4) * B
+    _, hbm, src = measured_peaks()
+    res = {"workload": f"battery(3,4) n={n} m={m}, {B} QPs with per-instance operators, 100 iterations", "solves_per_s": B / sec,
+           "ms_per_batch": sec * 1e3, "algorithmic_bytes_per_solve": bytes_min // B, "achieved_GBps": bytes_min / sec / 1e9,
+           "hbm_peak_GBps": hbm, "frac_of_hbm_roofline": bytes_min / sec / 1e9 / hbm, "path": s.description,
+           "note": "instruction-bound: ~100 warp instructions per QP-iteration vs an HBM floor of 0.83 ms per 1M solves"}
+    s.close()
+    return res
+
+
 def run_ours(args):
     import torch
     import gpad_b200 as G
@@ -333,6 +369,7 @@ def run_ours(args):
 
     cpu_val, cpu_info = cpu_rate(args.cpu_budget)
     lat = latency_probe(torch, G) if not args.no_latency else None
+    per_inst = per_instance_probe(torch, G) if not args.no_latency else None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -348,6 +385,7 @@ def run_ours(args):
         "cpu_baseline": dict(value=cpu_val, unit=UNIT, **cpu_info),
         "clocks": clocks,
         "single_qp_latency": lat,
+        "per_instance_operators": per_inst,
     }
     emit_line(line)
     if dist is not None:

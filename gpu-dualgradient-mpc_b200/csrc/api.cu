@@ -70,6 +70,8 @@ struct gpad_handle_s {
     lat::Params lp{};
     int sync_mode = 0, G = 1, threads = 256;
     bool ops_smem = false;
+    bool small = false;                       // lean one-CTA kernel (latency_small.cu)
+    int cha = 1, chb = 1;
     float *d_gP = nullptr, *d_pD = nullptr, *d_f = nullptr, *d_y0 = nullptr, *d_yprev0 = nullptr;
     float *d_theta = nullptr, *d_beta = nullptr;
     int sched_cap = 0;
@@ -156,6 +158,8 @@ int upload_padded(gpad_handle_s* h, const float* src, int rows, int cols, int ro
 struct LatPlan {
     int sync = -1, G = 1, threads = 64;
     bool regs = false;
+    bool small = false;
+    int cha = 1, chb = 1;
     lat::Params p{};
 };
 
@@ -206,6 +210,34 @@ bool plan_for(int n, int m, int G, bool want_regs, size_t smem_limit, bool no_re
     return lat::smem_bytes(p, out.regs) <= smem_limit;
 }
 
+// lean one-CTA plan (latency_small.cu): every row of both operators gets lanes-per-row = 2^lg lanes with
+// CH in {1,2,4,8} float4 fragments per lane; prefers <= 4 fragments, all rows must fit in 512 threads
+bool plan_small(int n, int m, LatPlan& out) {
+    lat::Params& p = out.p;
+    p = lat::Params{};
+    p.n = n; p.m = m;
+    const int m4 = (m + 3) / 4, n4 = (n + 3) / 4;
+    auto pick = [&](int len4, int rows, int& lg, int& ch) {
+        for (int target : {4, 8})
+            for (lg = 0; lg <= 5; ++lg) {
+                const int chunks = (len4 + (1 << lg) - 1) >> lg;
+                if (chunks <= target && (rows << lg) <= lat::kMaxThreads) {
+                    ch = 1;
+                    while (ch < chunks) ch <<= 1;
+                    return true;
+                }
+            }
+        return false;
+    };
+    if (!pick(m4, n, p.lg_a, out.cha) || !pick(n4, m, p.lg_b, out.chb)) return false;
+    p.mld = (4 << p.lg_a) * out.cha; p.nld = (4 << p.lg_b) * out.chb;
+    out.threads = std::max(32, round_up(std::max(n << p.lg_a, m << p.lg_b), 32));
+    p.rows_a = n; p.rows_b = m; p.rows_a_pad = round_up(n, 4); p.rows_b_pad = round_up(m, 4); p.g_pad = 4;
+    p.res_a = p.res_b = 0;
+    out.G = 1; out.sync = lat::SYNC_BLOCK; out.regs = true; out.small = true;
+    return true;
+}
+
 // ------------------------------------------------------------------ latency mode
 int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vector<float>& GL) {
     const int n = h->n, m = h->cfg.m;
@@ -222,9 +254,9 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
         ok = (!no_res && plan_for(n, m, G, true, limit, no_res, plan)) || plan_for(n, m, G, false, limit, no_res, plan);
         plan.sync = sync;
     } else {
-        // 1. one CTA with register-resident operators; 2. the smallest cluster that allows it;
-        // 3. the whole chip, operators in shared memory as far as they fit
-        if (plan_for(n, m, 1, true, limit, false, plan)) { plan.sync = lat::SYNC_BLOCK; ok = true; }
+        // 1. one CTA with register-resident operators (lean kernel); 2. the smallest cluster that allows
+        // register residency; 3. the whole chip, operators in shared memory as far as they fit
+        if (plan_small(n, m, plan)) ok = true;
         for (int C : {2, 4, 8, 16}) {
             if (ok) break;
             if (!plan_for(n, m, C, true, limit, false, plan)) continue;
@@ -242,6 +274,7 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
     lat::Params& p = h->lp;
     p = plan.p;
     h->sync_mode = plan.sync; h->G = plan.G; h->threads = plan.threads; h->ops_smem = plan.regs;
+    h->small = plan.small; h->cha = plan.cha; h->chb = plan.chb;
     p.L = h->cfg.L;
     p.batch = 1; p.op_stride_a = p.op_stride_b = 0;
     float *dMG, *dGL;
@@ -264,7 +297,8 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
     p.barrier = h->d_flags; p.nonfinite_flag = reinterpret_cast<int*>(h->d_flags + 1);
 
     char where[96];
-    if (plan.regs) snprintf(where, sizeof(where), "in registers");
+    if (plan.small) snprintf(where, sizeof(where), "and per-row state in registers (lean kernel, %dx%d fragments)", plan.cha, plan.chb);
+    else if (plan.regs) snprintf(where, sizeof(where), "in registers");
     else snprintf(where, sizeof(where), "%d/%d + %d/%d rows per CTA in shared memory, rest streamed from L2", p.res_a, p.rows_a, p.res_b, p.rows_b);
     char buf[320];
     snprintf(buf, sizeof(buf), "latency: persistent kernel, %s x%d CTAs, %d threads, lanes/row %d|%d, operators %s, smem %zu B/CTA",
@@ -322,9 +356,14 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
     p.out_status = dev && a->status ? a->status : h->o_status;
     p.out_max_viol = dev && a->max_viol ? a->max_viol : h->o_viol;
     p.out_gap = dev && a->gap ? a->gap : h->o_gap;
-    GPAD_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned), s));
     cudaEvent_t pe = h->prof_begin(s);
-    GPAD_TRY(lat::launch(p, h->sync_mode, h->ops_smem, h->G, h->threads, s));
+    if (h->small) {
+        p.sched_smem = round_up(std::min(a->max_iter, lat::small_sched_capacity()), 4);
+        GPAD_TRY(lat::launch_small(p, h->cha, h->chb, h->threads, s));
+    } else {
+        GPAD_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned), s));
+        GPAD_TRY(lat::launch(p, h->sync_mode, h->ops_smem, h->G, h->threads, s));
+    }
     h->prof_end(0, pe, s);
     h->launches += 1;
     if (host) {
@@ -349,12 +388,14 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
 int setup_per_instance(gpad_handle_s* h, const float* M_G, const float* G_L) {
     const int n = h->n, m = h->cfg.m, B = h->cfg.max_batch;
     LatPlan plan;
-    if (plan_for(n, m, 1, true, h->smem_optin, false, plan)) plan.sync = lat::SYNC_BLOCK;
+    if (plan_small(n, m, plan)) plan.sync = lat::SYNC_BLOCK;
+    else if (plan_for(n, m, 1, true, h->smem_optin, false, plan)) plan.sync = lat::SYNC_BLOCK;
     else if (plan_for(n, m, 1, false, h->smem_optin, false, plan)) plan.sync = lat::SYNC_BLOCK;
     else { set_error("per-instance mode: n=%d, m=%d does not fit one CTA", n, m); return GPAD_ERR_UNSUPPORTED; }
     lat::Params& p = h->lp;
     p = plan.p;
     h->sync_mode = lat::SYNC_BLOCK; h->G = 1; h->threads = plan.threads; h->ops_smem = plan.regs;
+    h->small = plan.small; h->cha = plan.cha; h->chb = plan.chb;
     p.L = h->cfg.L;
     p.batch = B;
     p.op_stride_a = (size_t)n * p.mld; p.op_stride_b = (size_t)m * p.nld;
@@ -400,7 +441,8 @@ int setup_per_instance(gpad_handle_s* h, const float* M_G, const float* G_L) {
     char buf[320];
     snprintf(buf, sizeof(buf), "batch-per-instance: one CTA per QP (batched GEMV), %d threads, lanes/row %d|%d, operators %s, smem %zu B/CTA",
              plan.threads, 1 << p.lg_a, 1 << p.lg_b,
-             plan.regs ? "read once into registers" : "in shared memory / streamed", lat::smem_bytes(p, plan.regs));
+             plan.small ? "and per-row state read once into registers (lean kernel)" : plan.regs ? "read once into registers" : "in shared memory / streamed",
+             plan.small ? lat::small_smem_bytes(p) : lat::smem_bytes(p, plan.regs));
     h->desc = buf;
     return GPAD_OK;
 }
@@ -438,7 +480,12 @@ int solve_per_instance(gpad_handle_s* h, const gpad_solve_args_t* a) {
     p.out_max_viol = dev ? a->max_viol : (a->max_viol ? h->pi_viol : nullptr);
     p.out_gap = dev ? a->gap : (a->gap ? h->pi_gap : nullptr);
     cudaEvent_t pe = h->prof_begin(s);
-    GPAD_TRY(lat::launch(p, lat::SYNC_BLOCK, h->ops_smem, 1, h->threads, s));
+    if (h->small) {
+        p.sched_smem = round_up(std::min(a->max_iter, lat::small_sched_capacity()), 4);
+        GPAD_TRY(lat::launch_small(p, h->cha, h->chb, h->threads, s));
+    } else {
+        GPAD_TRY(lat::launch(p, lat::SYNC_BLOCK, h->ops_smem, 1, h->threads, s));
+    }
     h->prof_end(0, pe, s);
     h->launches += 1;
     if (host) {

@@ -17,6 +17,7 @@ struct Params {
     int g_pad;               // G rounded up to 4
     int lg_a, lg_b;          // log2(lanes per row) in phase A / B
     int res_a, res_b;        // own rows of M_G / G_L resident in shared memory (memory variant)
+    int sched_smem;          // latency_small.cu: theta/beta entries staged in shared memory
     int batch;               // SYNC_BLOCK only: independent instances, one CTA each (per-instance operators)
     size_t op_stride_a, op_stride_b;   // elements between consecutive instances' M_G / G_L (0: shared)
     const float* M_G;        // [n][mld] sequential layout, zero padded
@@ -46,6 +47,10 @@ size_t smem_bytes(const Params& p, bool regs);
 int launch(const Params& p, int sync_mode, bool regs, int G, int threads, cudaStream_t stream);
 int launch_convert_ops(float* dst, const float* src, int B, int rows, int cols, int ld, bool flipped, cudaStream_t stream);
 int max_cluster_size(int threads, size_t smem);
+// latency_small.cu: lean one-CTA-per-QP kernel (operators + per-row state in registers)
+size_t small_smem_bytes(const Params& p);
+int small_sched_capacity();
+int launch_small(const Params& p, int cha, int chb, int threads, cudaStream_t stream);
 
 }  // namespace lat
 }  // namespace gpad
