@@ -212,10 +212,11 @@ bool plan_for(int n, int m, int G, bool want_regs, size_t smem_limit, bool no_re
 
 // lean one-CTA plan (latency_small.cu): every row of both operators gets lanes-per-row = 2^lg lanes with
 // CH in {1,2,4,8} float4 fragments per lane; prefers <= 4 fragments, all rows must fit in 512 threads
-bool plan_small(int n, int m, LatPlan& out) {
+bool plan_small(int n, int m, int C, LatPlan& out) {
     lat::Params& p = out.p;
     p = lat::Params{};
     p.n = n; p.m = m;
+    const int rows_a = (n + C - 1) / C, rows_b = (m + C - 1) / C;
     const int m4 = (m + 3) / 4, n4 = (n + 3) / 4;
     auto pick = [&](int len4, int rows, int& lg, int& ch) {
         for (int target : {4, 8})
@@ -229,12 +230,13 @@ bool plan_small(int n, int m, LatPlan& out) {
             }
         return false;
     };
-    if (!pick(m4, n, p.lg_a, out.cha) || !pick(n4, m, p.lg_b, out.chb)) return false;
+    if (!pick(m4, rows_a, p.lg_a, out.cha) || !pick(n4, rows_b, p.lg_b, out.chb)) return false;
     p.mld = (4 << p.lg_a) * out.cha; p.nld = (4 << p.lg_b) * out.chb;
-    out.threads = std::max(32, round_up(std::max(n << p.lg_a, m << p.lg_b), 32));
-    p.rows_a = n; p.rows_b = m; p.rows_a_pad = round_up(n, 4); p.rows_b_pad = round_up(m, 4); p.g_pad = 4;
+    out.threads = std::max(32, round_up(std::max(rows_a << p.lg_a, rows_b << p.lg_b), 32));
+    p.rows_a = rows_a; p.rows_b = rows_b; p.rows_a_pad = round_up(rows_a, 4); p.rows_b_pad = round_up(rows_b, 4);
+    p.g_pad = round_up(C, 4);
     p.res_a = p.res_b = 0;
-    out.G = 1; out.sync = lat::SYNC_BLOCK; out.regs = true; out.small = true;
+    out.G = C; out.sync = C > 1 ? lat::SYNC_CLUSTER : lat::SYNC_BLOCK; out.regs = true; out.small = true;
     return true;
 }
 
@@ -250,18 +252,22 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
         int sync = lat::SYNC_GRID, G = h->num_sms;
         if (!strncmp(env, "block", 5)) { sync = lat::SYNC_BLOCK; G = 1; }
         else if (!strncmp(env, "cluster:", 8)) { sync = lat::SYNC_CLUSTER; G = std::max(1, std::min(16, atoi(env + 8))); }
+        else if (!strncmp(env, "lean:", 5)) { sync = lat::SYNC_CLUSTER; G = std::max(1, std::min(16, atoi(env + 5))); }
         else if (!strncmp(env, "grid:", 5)) { G = std::max(1, std::min(h->num_sms, atoi(env + 5))); }
-        ok = (!no_res && plan_for(n, m, G, true, limit, no_res, plan)) || plan_for(n, m, G, false, limit, no_res, plan);
-        plan.sync = sync;
+        if (!strncmp(env, "lean:", 5)) {
+            ok = plan_small(n, m, G, plan);
+        } else {
+            ok = (!no_res && plan_for(n, m, G, true, limit, no_res, plan)) || plan_for(n, m, G, false, limit, no_res, plan);
+            plan.sync = sync;
+        }
     } else {
         // 1. one CTA with register-resident operators (lean kernel); 2. the smallest cluster that allows
         // register residency; 3. the whole chip, operators in shared memory as far as they fit
-        if (plan_small(n, m, plan)) ok = true;
+        if (plan_small(n, m, 1, plan)) ok = true;
+        const int max_cluster = ok ? 1 : lat::max_cluster_size(lat::kMaxThreads, 64 * 1024);
         for (int C : {2, 4, 8, 16}) {
-            if (ok) break;
-            if (!plan_for(n, m, C, true, limit, false, plan)) continue;
-            if (C > lat::max_cluster_size(plan.threads, lat::smem_bytes(plan.p, true))) continue;
-            plan.sync = lat::SYNC_CLUSTER; ok = true;
+            if (ok || C > max_cluster) break;
+            if (plan_small(n, m, C, plan)) ok = true;
         }
         if (!ok) { ok = plan_for(n, m, h->num_sms, false, limit, no_res, plan); plan.sync = lat::SYNC_GRID; }
     }
@@ -303,7 +309,7 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
     char buf[320];
     snprintf(buf, sizeof(buf), "latency: persistent kernel, %s x%d CTAs, %d threads, lanes/row %d|%d, operators %s, smem %zu B/CTA",
              plan.sync == lat::SYNC_BLOCK ? "single-CTA" : plan.sync == lat::SYNC_CLUSTER ? "cluster(DSMEM)" : "cooperative-grid",
-             plan.G, plan.threads, 1 << p.lg_a, 1 << p.lg_b, where, lat::smem_bytes(p, plan.regs));
+             plan.G, plan.threads, 1 << p.lg_a, 1 << p.lg_b, where, plan.small ? lat::small_smem_bytes(p) : lat::smem_bytes(p, plan.regs));
     h->desc = buf;
     return GPAD_OK;
 }
@@ -359,7 +365,7 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
     cudaEvent_t pe = h->prof_begin(s);
     if (h->small) {
         p.sched_smem = round_up(std::min(a->max_iter, lat::small_sched_capacity()), 4);
-        GPAD_TRY(lat::launch_small(p, h->cha, h->chb, h->threads, s));
+        GPAD_TRY(lat::launch_small(p, h->cha, h->chb, h->G, h->threads, s));
     } else {
         GPAD_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned), s));
         GPAD_TRY(lat::launch(p, h->sync_mode, h->ops_smem, h->G, h->threads, s));
@@ -388,7 +394,7 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
 int setup_per_instance(gpad_handle_s* h, const float* M_G, const float* G_L) {
     const int n = h->n, m = h->cfg.m, B = h->cfg.max_batch;
     LatPlan plan;
-    if (plan_small(n, m, plan)) plan.sync = lat::SYNC_BLOCK;
+    if (plan_small(n, m, 1, plan)) plan.sync = lat::SYNC_BLOCK;
     else if (plan_for(n, m, 1, true, h->smem_optin, false, plan)) plan.sync = lat::SYNC_BLOCK;
     else if (plan_for(n, m, 1, false, h->smem_optin, false, plan)) plan.sync = lat::SYNC_BLOCK;
     else { set_error("per-instance mode: n=%d, m=%d does not fit one CTA", n, m); return GPAD_ERR_UNSUPPORTED; }
@@ -482,7 +488,7 @@ int solve_per_instance(gpad_handle_s* h, const gpad_solve_args_t* a) {
     cudaEvent_t pe = h->prof_begin(s);
     if (h->small) {
         p.sched_smem = round_up(std::min(a->max_iter, lat::small_sched_capacity()), 4);
-        GPAD_TRY(lat::launch_small(p, h->cha, h->chb, h->threads, s));
+        GPAD_TRY(lat::launch_small(p, h->cha, h->chb, 1, h->threads, s));
     } else {
         GPAD_TRY(lat::launch(p, lat::SYNC_BLOCK, h->ops_smem, 1, h->threads, s));
     }

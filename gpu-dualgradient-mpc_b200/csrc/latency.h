@@ -50,7 +50,7 @@ int max_cluster_size(int threads, size_t smem);
 // latency_small.cu: lean one-CTA-per-QP kernel (operators + per-row state in registers)
 size_t small_smem_bytes(const Params& p);
 int small_sched_capacity();
-int launch_small(const Params& p, int cha, int chb, int threads, cudaStream_t stream);
+int launch_small(const Params& p, int cha, int chb, int cluster, int threads, cudaStream_t stream);
 
 }  // namespace lat
 }  // namespace gpad
