@@ -96,14 +96,18 @@ __device__ __forceinline__ void put(float* loc, int idx, float v) {
 // into each CTA's shared memory that also credits 4 bytes to that CTA's mbarrier (st.async ... complete_tx);
 // the consumer waits on its OWN mbarrier until the whole vector (len * 4 bytes) has landed.
 __device__ __forceinline__ uint32_t smem_addr(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void st_async_all(uint32_t loc_addr, uint32_t bar_addr, float v, int C) {
-    for (int r = 0; r < C; ++r) {
-        uint32_t ra, rb;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(loc_addr), "r"(r));
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(bar_addr), "r"(r));
+// cluster-window addresses are affine in the CTA rank: addr(rank) = addr(0) + rank * stride, so the two mapa
+// per destination are hoisted out of the iteration loop (rank0 addresses + stride computed once)
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_all(uint32_t data0, uint32_t bar0, uint32_t stride, float v, int C) {
+    const uint32_t bits = __float_as_uint(v);
+    for (int r = 0; r < C; ++r, data0 += stride, bar0 += stride)
         asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
-                     ::"r"(ra), "r"(__float_as_uint(v)), "r"(rb) : "memory");
-    }
+                     ::"r"(data0), "r"(bits), "r"(bar0) : "memory");
 }
 __device__ __forceinline__ void mbar_init_s(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -189,6 +193,12 @@ __global__ void __launch_bounds__(kMaxThreads) gpad_small_kernel(const Params p_
         for (int i = tid; i < p.max_iter; i += nthr) { th_s[i] = p.theta[i]; be_s[i] = p.beta[i]; }
     const uint32_t zbar = smem_addr(xbar), wbar = smem_addr(xbar + 1);
     const uint32_t zh_addr = smem_addr(zh_s), w_addr = smem_addr(w_s);
+    uint32_t zbar0 = 0, wbar0 = 0, zh0 = 0, w0 = 0, cstride = 0;      // rank-0 views of the exchange targets
+    if (CLUSTER) {
+        zbar0 = mapa_rank(zbar, 0); wbar0 = mapa_rank(wbar, 0);
+        zh0 = mapa_rank(zh_addr, 0) + 4u * row_a; w0 = mapa_rank(w_addr, 0) + 4u * row_b;
+        cstride = C > 1 ? mapa_rank(zbar, 1) - zbar0 : 0;
+    }
     uint32_t zpar = 0, wpar = 0;             // phase parities of the two exchange barriers
     if (CLUSTER && tid == 0) {
         mbar_init_s(zbar, 1); mbar_init_s(wbar, 1);
@@ -222,7 +232,7 @@ __global__ void __launch_bounds__(kMaxThreads) gpad_small_kernel(const Params p_
             if (own_a) {
                 zh_r = d - gp_r;
                 z_r = __fadd_rn(__fmul_rn(one_minus, z_r), __fmul_rn(theta, zh_r));
-                if (CLUSTER) st_async_all(zh_addr + 4u * row_a, zbar, zh_r, C);
+                if (CLUSTER) st_async_all(zh0, zbar0, cstride, zh_r, C);
                 else zh_s[row_a] = zh_r;
             }
         }
@@ -248,7 +258,7 @@ __global__ void __launch_bounds__(kMaxThreads) gpad_small_kernel(const Params p_
                 if (checking) sb_r = __fadd_rn(__fmul_rn(one_minus, sb_r), __fmul_rn(theta, d + pd_r));
                 if (!check && !last) {      // advance; on check / last iterations w_v, y_v stay (they are outputs)
                     const float wn = __fadd_rn(yn, __fmul_rn(beta_next, __fsub_rn(yn, yv)));
-                    if (CLUSTER) st_async_all(w_addr + 4u * row_b, wbar, wn, C);
+                    if (CLUSTER) st_async_all(w0, wbar0, cstride, wn, C);
                     else w_s[row_b] = wn;
                     w_r = wn;
                     yp = yv; yv = yn;
