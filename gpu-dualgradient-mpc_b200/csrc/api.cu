@@ -71,6 +71,9 @@ struct gpad_handle_s {
     int sync_mode = 0, G = 1, threads = 256;
     bool ops_smem = false;
     bool small = false;                       // lean one-CTA kernel (latency_small.cu)
+    bool grid_lean = false;                   // lean whole-chip kernel (latency_grid.cu)
+    unsigned stamp_next = 16;                 // flag-in-data exchange epochs
+    size_t ll_words = 0;
     int cha = 1, chb = 1;
     float *d_gP = nullptr, *d_pD = nullptr, *d_f = nullptr, *d_y0 = nullptr, *d_yprev0 = nullptr;
     float *d_theta = nullptr, *d_beta = nullptr;
@@ -159,6 +162,7 @@ struct LatPlan {
     int sync = -1, G = 1, threads = 64;
     bool regs = false;
     bool small = false;
+    bool grid_lean = false;
     int cha = 1, chb = 1;
     lat::Params p{};
 };
@@ -240,6 +244,47 @@ bool plan_small(int n, int m, int C, LatPlan& out) {
     return true;
 }
 
+// lean whole-chip plan (latency_grid.cu): per phase the 16 warps form cw column slices x rg row groups with
+// rb <= 4 rows per warp and ch <= 6 float4 chunks per lane; the option with the fewest shared-memory loads wins
+bool plan_grid(int n, int m, int G, size_t smem_limit, bool no_resident, LatPlan& out) {
+    lat::Params& p = out.p;
+    p = lat::Params{};
+    p.n = n; p.m = m;
+    p.rows_a = (n + G - 1) / G; p.rows_b = (m + G - 1) / G;
+    p.rows_a_pad = round_up(p.rows_a, 4); p.rows_b_pad = round_up(p.rows_b, 4);
+    p.g_pad = round_up(G, 4);
+    if (p.rows_a > 512 || p.rows_b > 512) return false;
+    auto pick = [](int len4, int rows, int& cw, int& rg, int& rb, int& ch) {
+        long best = -1;
+        for (int g = 1; g <= 16; g <<= 1) {
+            const int c = 16 / g;
+            const int b = std::min(4, (rows + g - 1) / g);
+            const int h = (len4 + c * 32 - 1) / (c * 32);
+            if (h > 6) continue;
+            const int passes = (rows + g * b - 1) / (g * b);
+            const long cost = (long)passes * h * (b + 1);
+            if (best < 0 || cost < best) { best = cost; cw = c; rg = g; rb = b; ch = h; }
+        }
+        return best >= 0;
+    };
+    if (!pick((m + 3) / 4, p.rows_a, p.cwa, p.rga, p.rba, p.cha) || !pick((n + 3) / 4, p.rows_b, p.cwb, p.rgb, p.rbb, p.chb)) return false;
+    p.mld = p.cwa * 32 * 4 * p.cha; p.nld = p.cwb * 32 * 4 * p.chb;
+    p.lg_a = p.lg_b = 5;
+    p.res_a = p.res_b = 0;
+    const size_t fixed = lat::grid_smem_bytes(p);
+    if (fixed > smem_limit) return false;
+    if (!no_resident) {
+        const size_t budget = smem_limit - fixed;
+        const size_t want = ((size_t)p.rows_a * p.mld + (size_t)p.rows_b * p.nld) * sizeof(float);
+        const double frac = want ? std::min(1.0, (double)budget / (double)want) : 1.0;
+        p.res_a = (int)(p.rows_a * frac);
+        const size_t left = budget - (size_t)p.res_a * p.mld * sizeof(float);
+        p.res_b = (int)std::min<size_t>(p.rows_b, left / ((size_t)p.nld * sizeof(float)));
+    }
+    out.G = G; out.sync = lat::SYNC_GRID; out.regs = false; out.small = false; out.grid_lean = true; out.threads = 512;
+    return lat::grid_smem_bytes(p) <= smem_limit;
+}
+
 // ------------------------------------------------------------------ latency mode
 int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vector<float>& GL) {
     const int n = h->n, m = h->cfg.m;
@@ -254,8 +299,11 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
         else if (!strncmp(env, "cluster:", 8)) { sync = lat::SYNC_CLUSTER; G = std::max(1, std::min(16, atoi(env + 8))); }
         else if (!strncmp(env, "lean:", 5)) { sync = lat::SYNC_CLUSTER; G = std::max(1, std::min(16, atoi(env + 5))); }
         else if (!strncmp(env, "grid:", 5)) { G = std::max(1, std::min(h->num_sms, atoi(env + 5))); }
+        else if (!strncmp(env, "leangrid:", 9)) { G = std::max(1, std::min(h->num_sms, atoi(env + 9))); }
         if (!strncmp(env, "lean:", 5)) {
             ok = plan_small(n, m, G, plan);
+        } else if (!strncmp(env, "leangrid:", 9)) {
+            ok = plan_grid(n, m, G, limit, no_res, plan);
         } else {
             ok = (!no_res && plan_for(n, m, G, true, limit, no_res, plan)) || plan_for(n, m, G, false, limit, no_res, plan);
             plan.sync = sync;
@@ -269,6 +317,8 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
             if (ok || C > max_cluster) break;
             if (plan_small(n, m, C, plan)) ok = true;
         }
+        // (the lean flag-in-data grid kernel, GPAD_LATENCY_PLAN=leangrid:<G>, measured 2x slower than this
+        //  generic grid plan on B200 and is opt-in only: DESIGN.md 4.3)
         if (!ok) { ok = plan_for(n, m, h->num_sms, false, limit, no_res, plan); plan.sync = lat::SYNC_GRID; }
     }
     if (!ok) {
@@ -280,9 +330,16 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
     lat::Params& p = h->lp;
     p = plan.p;
     h->sync_mode = plan.sync; h->G = plan.G; h->threads = plan.threads; h->ops_smem = plan.regs;
-    h->small = plan.small; h->cha = plan.cha; h->chb = plan.chb;
+    h->small = plan.small; h->cha = plan.cha; h->chb = plan.chb; h->grid_lean = plan.grid_lean;
     p.L = h->cfg.L;
     p.batch = 1; p.op_stride_a = p.op_stride_b = 0;
+    if (plan.grid_lean) {
+        h->ll_words = 2 * ((size_t)m + n + (size_t)plan.G * 8);
+        unsigned long long* ll = nullptr;
+        GPAD_TRY(dev_alloc(h, &ll, h->ll_words));
+        GPAD_CUDA(cudaMemset(ll, 0, h->ll_words * sizeof(unsigned long long)));
+        p.ll_w = ll; p.ll_z = ll + 2 * (size_t)m; p.ll_r = p.ll_z + 2 * (size_t)n;
+    }
     float *dMG, *dGL;
     GPAD_TRY(upload_padded(h, MG.data(), n, m, n, p.mld, &dMG));
     GPAD_TRY(upload_padded(h, GL.data(), m, n, m, p.nld, &dGL));
@@ -302,14 +359,17 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
     GPAD_TRY(dev_alloc(h, &h->d_flags, 2));
     p.barrier = h->d_flags; p.nonfinite_flag = reinterpret_cast<int*>(h->d_flags + 1);
 
-    char where[96];
-    if (plan.small) snprintf(where, sizeof(where), "and per-row state in registers (lean kernel, %dx%d fragments)", plan.cha, plan.chb);
+    char where[192];
+    if (plan.grid_lean) snprintf(where, sizeof(where), "%d/%d + %d/%d rows per CTA in shared memory (lean grid kernel: warps %dx%d | %dx%d, flag-in-data exchange)",
+                                 p.res_a, p.rows_a, p.res_b, p.rows_b, p.cwa, p.rga, p.cwb, p.rgb);
+    else if (plan.small) snprintf(where, sizeof(where), "and per-row state in registers (lean kernel, %dx%d fragments)", plan.cha, plan.chb);
     else if (plan.regs) snprintf(where, sizeof(where), "in registers");
     else snprintf(where, sizeof(where), "%d/%d + %d/%d rows per CTA in shared memory, rest streamed from L2", p.res_a, p.rows_a, p.res_b, p.rows_b);
     char buf[320];
     snprintf(buf, sizeof(buf), "latency: persistent kernel, %s x%d CTAs, %d threads, lanes/row %d|%d, operators %s, smem %zu B/CTA",
              plan.sync == lat::SYNC_BLOCK ? "single-CTA" : plan.sync == lat::SYNC_CLUSTER ? "cluster(DSMEM)" : "cooperative-grid",
-             plan.G, plan.threads, 1 << p.lg_a, 1 << p.lg_b, where, plan.small ? lat::small_smem_bytes(p) : lat::smem_bytes(p, plan.regs));
+             plan.G, plan.threads, 1 << p.lg_a, 1 << p.lg_b, where,
+             plan.grid_lean ? lat::grid_smem_bytes(p) : plan.small ? lat::small_smem_bytes(p) : lat::smem_bytes(p, plan.regs));
     h->desc = buf;
     return GPAD_OK;
 }
@@ -366,6 +426,16 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
     if (h->small) {
         p.sched_smem = round_up(std::min(a->max_iter, lat::small_sched_capacity()), 4);
         GPAD_TRY(lat::launch_small(p, h->cha, h->chb, h->G, h->threads, s));
+    } else if (h->grid_lean) {
+        // every solve gets its own stamp range so words of earlier solves never match
+        const unsigned need = 3u * (unsigned)(4 * a->max_iter + 64);
+        if (h->stamp_next > 0xFFFFFFFFu - need - 16u) {
+            GPAD_CUDA(cudaMemsetAsync(p.ll_w, 0, h->ll_words * sizeof(unsigned long long), s));
+            h->stamp_next = 16;
+        }
+        p.stamp_base = h->stamp_next;
+        h->stamp_next += need;
+        GPAD_TRY(lat::launch_grid(p, h->G, s));
     } else {
         GPAD_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned), s));
         GPAD_TRY(lat::launch(p, h->sync_mode, h->ops_smem, h->G, h->threads, s));

@@ -137,7 +137,7 @@ def test_latency_fixed_iterations_match_oracle(torch_cuda, G, oracle, dims):
     s.close()
 
 
-@pytest.mark.parametrize("plan", ["block", "cluster:2", "cluster:8", "grid:16", "grid:148"])
+@pytest.mark.parametrize("plan", ["block", "cluster:2", "cluster:8", "grid:16", "grid:148", "lean:16", "leangrid:148"])
 def test_latency_every_synchronisation_variant(torch_cuda, G, oracle, plan, monkeypatch):
     """the same QP through single-CTA, cluster/DSMEM and cooperative-grid variants, operators in
     shared memory and streamed from L2"""
@@ -146,7 +146,7 @@ def test_latency_every_synchronisation_variant(torch_cuda, G, oracle, plan, monk
     theta, beta = schedule(100)
     ora = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta)
     f64 = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta)
-    for no_smem in ([True] if plan == "block" else [False, True]):
+    for no_smem in ([True] if plan == "block" else [False] if plan.startswith("lean:") else [False, True]):
         monkeypatch.setenv("GPAD_LATENCY_PLAN", plan)
         if no_smem:
             monkeypatch.setenv("GPAD_LATENCY_NO_SMEM_OPS", "1")
