@@ -40,3 +40,10 @@ clean:
 	rm -rf build $(LIBDIR); $(MAKE) -C oracle clean
 
 .PHONY: all oracle clean
+
+# microbenchmarks behind the design decisions (not product code; run on the GPU box)
+ubench: build/ubench_tc
+build/ubench_%: tests/ubench/ubench_%.cu $(wildcard $(CSRC)/*.cuh)
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -ccbin $(HOSTCXX) -I$(CSRC) -Iinclude -cudart static -o $@ $<
+.PHONY: ubench

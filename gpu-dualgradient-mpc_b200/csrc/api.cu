@@ -167,6 +167,13 @@ struct LatPlan {
     lat::Params p{};
 };
 
+// CTAs per cluster that share each operator tile through TMA multicast in the cta_group::1 tcgen05 kernels
+int tc_multicast() {
+    int mc = 1;
+    if (const char* e = getenv("GPAD_TC_MC")) mc = atoi(e) == 2 ? 2 : 1;
+    return mc;
+}
+
 int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 // fills row split, lanes-per-row, strides, residency for G cooperating CTAs; returns false if infeasible
@@ -621,22 +628,24 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         tc::GemmDesc& g1 = h->g1; tc::GemmDesc& g2 = h->g2;
         g1.bk = g2.bk = bk;
         g1.cg = g2.cg = cg;
+        g1.mc = g2.mc = cg == 1 ? tc_multicast() : 1;
+        const int bdiv = cg * g1.mc;                 // operator rows per TMA box = bn / bdiv
         g1.k_pad = st.mp; g1.bn = bn1; g1.n_tiles = nt1; g1.ncols_valid = n;
         g2.k_pad = st.np; g2.bn = bn2; g2.n_tiles = nt2; g2.ncols_valid = m;
         g1.stages = cg == 2 ? tc::pick_stages2(bk, bn1, h->smem_optin) : tc::pick_stages(bk, bn1, h->smem_optin);
         g2.stages = cg == 2 ? tc::pick_stages2(bk, bn2, h->smem_optin) : tc::pick_stages(bk, bn2, h->smem_optin);
         if (const char* e = getenv("GPAD_TC_STAGES")) { g1.stages = std::min(g1.stages, std::max(2, atoi(e))); g2.stages = std::min(g2.stages, std::max(2, atoi(e))); }
         for (int k = 0; k < 3; ++k) GPAD_TRY(tc::make_tmap(&g1.tmY[k], st.yb[k], st.mp, st.Bp, st.mp, bk, 128));
-        GPAD_TRY(tc::make_tmap(&g1.tmB_hi, h->op.M_G, st.mp, h->op.n_rows_pad, st.mp, bk, bn1 / cg));
-        GPAD_TRY(tc::make_tmap(&g1.tmB_lo, h->op.M_G_lo, st.mp, h->op.n_rows_pad, st.mp, bk, bn1 / cg));
+        GPAD_TRY(tc::make_tmap(&g1.tmB_hi, h->op.M_G, st.mp, h->op.n_rows_pad, st.mp, bk, bn1 / bdiv));
+        GPAD_TRY(tc::make_tmap(&g1.tmB_lo, h->op.M_G_lo, st.mp, h->op.n_rows_pad, st.mp, bk, bn1 / bdiv));
         GPAD_TRY(tc::make_tmap(&g2.tmA_hi, st.zh_hi, st.np, st.Bp, st.np, bk, 128));
         GPAD_TRY(tc::make_tmap(&g2.tmA_lo, st.zh_lo, st.np, st.Bp, st.np, bk, 128));
-        GPAD_TRY(tc::make_tmap(&g2.tmB_hi, h->op.G_L, st.np, h->op.m_rows_pad, st.np, bk, bn2 / cg));
-        GPAD_TRY(tc::make_tmap(&g2.tmB_lo, h->op.G_L_lo, st.np, h->op.m_rows_pad, st.np, bk, bn2 / cg));
+        GPAD_TRY(tc::make_tmap(&g2.tmB_hi, h->op.G_L, st.np, h->op.m_rows_pad, st.np, bk, bn2 / bdiv));
+        GPAD_TRY(tc::make_tmap(&g2.tmB_lo, h->op.G_L_lo, st.np, h->op.m_rows_pad, st.np, bk, bn2 / bdiv));
         snprintf(buf, sizeof(buf),
-                 "batch-shared: tcgen05 cta_group::%d kind::tf32 x3 (hi/lo split, w built in-kernel), TMA ring bk=%d, product1 tiles "
+                 "batch-shared: tcgen05 cta_group::%d kind::tf32 x3 (hi/lo split, w built in-kernel), TMA ring bk=%d (operator tiles multicast x%d), product1 tiles "
                  "%dx%d x%d (%d stages), product2 tiles %dx%d x%d (%d stages), TMEM 2x256 cols, persistent over %d SMs",
-                 cg, bk, 128 * cg, bn1, nt1, g1.stages, 128 * cg, bn2, nt2, g2.stages, h->num_sms);
+                 cg, bk, g1.mc, 128 * cg, bn1, nt1, g1.stages, 128 * cg, bn2, nt2, g2.stages, h->num_sms);
     } else {
         snprintf(buf, sizeof(buf), "batch-shared: CUDA-core fp32 GEMM 128x128x16 tiles with fused GPAD epilogues");
     }
@@ -688,6 +697,8 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
     k.g_P = st.g_P; k.p_D = st.p_D; k.f = a->f ? st.f : nullptr;
     k.z = st.z; k.zhat = st.zhat; k.zh_hi = st.zh_hi; k.zh_lo = st.zh_lo;
     k.sbar = st.sbar; k.red = st.red; k.done = checking ? st.done : nullptr;
+    k.prefetch = 1;
+    if (const char* e = getenv("GPAD_TC_PREFETCH")) k.prefetch = atoi(e) != 0;
     const int tile_rows = (tcp && h->g1.cg == 2) ? 256 : 128;
     const int m_tiles = round_up(B, tile_rows) / tile_rows;
     h->g1.m_tiles = m_tiles; h->g2.m_tiles = m_tiles;
@@ -942,13 +953,14 @@ int gpad_debug_gemm_tf32x3(const float* A, const float* B, float* C, int M, int 
     g.bk = bk;
     g.cg = 1;
     if (const char* e = getenv("GPAD_TC_CG")) g.cg = atoi(e) == 2 ? 2 : 1;
+    g.mc = g.cg == 1 ? tc_multicast() : 1;
     g.k_pad = round_up(K, 32);
     tc::plan_tiles(N, &g.bn, &g.n_tiles);
     g.m_tiles = round_up(M, 128 * g.cg) / (128 * g.cg);
     g.ncols_valid = N;
     g.stages = g.cg == 2 ? tc::pick_stages2(bk, g.bn, prop.sharedMemPerBlockOptin) : tc::pick_stages(bk, g.bn, prop.sharedMemPerBlockOptin);
     if (const char* e = getenv("GPAD_TC_STAGES")) g.stages = std::min(g.stages, std::max(2, atoi(e)));
-    const int Mp = g.m_tiles * 128 * g.cg, Np = round_up(g.bn * g.n_tiles, 128);
+    const int Mp = round_up(g.m_tiles, g.mc) * 128 * g.cg, Np = round_up(g.bn * g.n_tiles, 128);
     float *Ap, *Al, *Bp, *Bl;
     const size_t ca = (size_t)Mp * g.k_pad, cb = (size_t)Np * g.k_pad;
     GPAD_CUDA(cudaMalloc(&Ap, ca * 4)); GPAD_CUDA(cudaMalloc(&Al, ca * 4));
@@ -961,8 +973,8 @@ int gpad_debug_gemm_tf32x3(const float* A, const float* B, float* C, int M, int 
         if ((rc = tc::launch_split(Bp, Bp, Bl, cb, s)) != GPAD_OK) break;
         if ((rc = tc::make_tmap(&g.tmA_hi, Ap, g.k_pad, Mp, g.k_pad, bk, 128)) != GPAD_OK) break;
         if ((rc = tc::make_tmap(&g.tmA_lo, Al, g.k_pad, Mp, g.k_pad, bk, 128)) != GPAD_OK) break;
-        if ((rc = tc::make_tmap(&g.tmB_hi, Bp, g.k_pad, Np, g.k_pad, bk, g.bn / g.cg)) != GPAD_OK) break;
-        if ((rc = tc::make_tmap(&g.tmB_lo, Bl, g.k_pad, Np, g.k_pad, bk, g.bn / g.cg)) != GPAD_OK) break;
+        if ((rc = tc::make_tmap(&g.tmB_hi, Bp, g.k_pad, Np, g.k_pad, bk, g.bn / (g.cg * g.mc))) != GPAD_OK) break;
+        if ((rc = tc::make_tmap(&g.tmB_lo, Bl, g.k_pad, Np, g.k_pad, bk, g.bn / (g.cg * g.mc))) != GPAD_OK) break;
         BatchKernelArgs k{};
         k.B = M;
         rc = tc::launch_gemm(0, g, k, C, N, prop.multiProcessorCount, s);

@@ -39,6 +39,7 @@ struct BatchKernelArgs {
     float* sbar;
     float* red;
     const int* done;       // per-instance "stopped" flag (null in fixed-iteration mode)
+    int prefetch;          // tcgen05 path: epilogue warps pull the next tile's operands into L2 (batch_tc.cu)
 };
 
 __device__ __forceinline__ float tf32_rn(float x) {

@@ -23,6 +23,8 @@
 //   overlaps the mainloop of tile t+1.
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "batch_common.cuh"
 #include "gpad_internal.h"
 #include "batch_tc.h"
@@ -34,13 +36,16 @@ namespace tc {
 
 namespace {
 
+// work units are (m_group, n_tile): a cluster of `mc` CTAs takes mc consecutive 128-row batch tiles of the same
+// operator tile, so the operator boxes can be multicast; CTA rank r owns batch tile m_group * mc + r
 struct TileSched {
-    int tile, step, total, n_tiles;
-    __device__ TileSched(int total_, int n_tiles_) : tile(blockIdx.x), step(gridDim.x), total(total_), n_tiles(n_tiles_) {}
-    __device__ bool valid() const { return tile < total; }
-    __device__ void next() { tile += step; }
-    __device__ int m_tile() const { return tile / n_tiles; }
-    __device__ int n_tile() const { return tile % n_tiles; }
+    int unit, step, total, n_tiles, mc, rank;
+    __device__ TileSched(int m_tiles, int n_tiles_, int mc_, int rank_)
+        : unit(blockIdx.x / mc_), step(gridDim.x / mc_), total((m_tiles + mc_ - 1) / mc_ * n_tiles_), n_tiles(n_tiles_), mc(mc_), rank(rank_) {}
+    __device__ bool valid() const { return unit < total; }
+    __device__ void next() { unit += step; }
+    __device__ int m_tile() const { return unit / n_tiles * mc + rank; }
+    __device__ int n_tile() const { return unit % n_tiles; }
 };
 
 // PHASE 0: plain store of C (test hook); 1: GPAD product 1; 2: GPAD product 2
@@ -48,7 +53,7 @@ template <int PHASE, int BK>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-               int num_k_blocks, int m_tiles, int n_tiles, int bn, int stages,
+               int num_k_blocks, int m_tiles, int n_tiles, int bn, int stages, int mc,
                const BatchKernelArgs args, float* __restrict__ Cdbg, int ldc, int ncols_valid) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -67,12 +72,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = m_tiles * n_tiles;
+    const int rank = mc > 1 ? (int)cluster_ctarank() : 0;
+    const uint16_t mc_mask = (uint16_t)((1u << mc) - 1);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
         for (int s = 0; s < stages; ++s) {
-            mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); mbar_init(smem_u32(ready_bar + s), kXformWarps);
+            mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), mc); mbar_init(smem_u32(ready_bar + s), kXformWarps);
         }
         for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), kEpi); }
         fence_barrier_init();
@@ -80,42 +86,53 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
+    if (mc > 1) cluster_sync_all();                           // peers' barriers are initialised before anything is multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ============================ TMA producer ============================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (TileSched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
-                const int row_a = ts.m_tile() * kBM, row_b = ts.n_tile() * bn;
-                for (int kb = 0; kb < num_k_blocks; ++kb) {
-                    mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
-                    const uint32_t fb = smem_u32(full_bar + stage);
+        // warp-uniform loop, one elected lane issues (see elect_one)
+        int stage = 0; uint32_t phase = 0;
+        for (TileSched ts(m_tiles, n_tiles, mc, rank); ts.valid(); ts.next()) {
+            const int row_a = ts.m_tile() * kBM, row_b = ts.n_tile() * bn;
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+                const uint32_t fb = smem_u32(full_bar + stage);
+                const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
+                if (elect_one()) {
                     mbar_expect_tx(fb, stage_bytes);
-                    const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
                     tma_load_2d(base, &tmA_hi, kb * BK, row_a, fb);
                     tma_load_2d(base + a_bytes, &tmA_lo, kb * BK, row_a, fb);
-                    tma_load_2d(base + 2 * a_bytes, &tmB_hi, kb * BK, row_b, fb);
-                    tma_load_2d(base + 2 * a_bytes + b_bytes, &tmB_lo, kb * BK, row_b, fb);
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                    if (mc > 1) {     // this CTA fetches 1/mc of the operator tile for the whole cluster
+                        const int part = bn / mc;
+                        const uint32_t off = (uint32_t)(rank * part) * BK * 4;
+                        tma_load_2d_mc(base + 2 * a_bytes + off, &tmB_hi, kb * BK, row_b + rank * part, fb, mc_mask);
+                        tma_load_2d_mc(base + 2 * a_bytes + b_bytes + off, &tmB_lo, kb * BK, row_b + rank * part, fb, mc_mask);
+                    } else {
+                        tma_load_2d(base + 2 * a_bytes, &tmB_hi, kb * BK, row_b, fb);
+                        tma_load_2d(base + 2 * a_bytes + b_bytes, &tmB_lo, kb * BK, row_b, fb);
+                    }
                 }
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(bn);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (TileSched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
-                mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+        // warp-uniform loop (waits and descriptor arithmetic in uniform registers), one elected lane issues
+        const uint32_t idesc = make_idesc(bn);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (TileSched ts(m_tiles, n_tiles, mc, rank); ts.valid(); ts.next()) {
+            mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                mbar_wait(smem_u32((kXform ? ready_bar : full_bar) + stage), phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
-                for (int kb = 0; kb < num_k_blocks; ++kb) {
-                    mbar_wait(smem_u32((kXform ? ready_bar : full_bar) + stage), phase);
-                    tc_fence_after();
-                    const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
+                if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
                         const uint64_t a_hi = make_smem_desc<BK>(base + ks * 32);
@@ -126,12 +143,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
                         umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
                     }
-                    umma_commit(smem_u32(empty_bar + stage));      // frees the ring slot when these MMAs retire
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                    // frees the ring slot when these MMAs retire (in every CTA that multicasts into it)
+                    if (mc > 1) umma_commit_mc(smem_u32(empty_bar + stage), mc_mask);
+                    else umma_commit(smem_u32(empty_bar + stage));
                 }
-                umma_commit(smem_u32(tfull_bar + acc));            // accumulator complete
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
+            if (elect_one()) umma_commit(smem_u32(tfull_bar + acc));   // accumulator complete
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (kXform && warp < kFirstEpiWarp) {
         // ============================ transform warps (product 1) ============================
@@ -141,7 +162,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const float beta = args.it.beta;
         constexpr int kVec = kBM * BK / 4;                      // float4 per A tile
         int stage = 0; uint32_t phase = 0;
-        for (TileSched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
+        for (TileSched ts(m_tiles, n_tiles, mc, rank); ts.valid(); ts.next()) {
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 mbar_wait(smem_u32(full_bar + stage), phase);
                 float4* t0 = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
@@ -172,7 +193,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         float* buf = epi_buf + (warp - 2) * kEpiBufFloats;
         const int nblk = (bn + 31) / 32;
         int acc = 0; uint32_t acc_phase = 0;
-        for (TileSched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
+        // The epilogue's operand loads do not depend on the accumulator.  Each warp holds only ~6 KB of them in flight,
+        // which against ~2 us of loaded HBM latency made the epilogue (not the MMA pipe) the slower stage.  So every warp
+        // pulls the operand lines of its rows of the NEXT tile into L2 one whole tile period ahead; the loads then hit L2.
+        auto prefetch_operands = [&](const TileSched& t) {
+            if (PHASE == 0) return;
+            const int b = t.m_tile() * kBM + q * 32 + lane;
+            if (b >= args.B) return;
+            const int c0 = t.n_tile() * bn;
+            const int ld = PHASE == 1 ? args.np : args.mp;
+            const size_t row = (size_t)b * ld;
+            const int first = (c0 * 4) >> 7, last = (min(c0 + bn, ncols_valid) * 4 - 1) >> 7;     // 128 B lines of this row
+            for (int l = first + part; l <= last; l += kParts) {
+                const size_t o = row + (size_t)l * 32;
+                if (PHASE == 1) { prefetch_l2(args.g_P + o); prefetch_l2(args.z + o); }
+                else { prefetch_l2(args.y_cur + o); prefetch_l2(args.y_prev + o); prefetch_l2(args.p_D + o); }
+            }
+        };
+        {
+            TileSched first(m_tiles, n_tiles, mc, rank);
+            if (first.valid() && args.prefetch) prefetch_operands(first);
+        }
+        for (TileSched ts(m_tiles, n_tiles, mc, rank); ts.valid(); ts.next()) {
+            if (args.prefetch) {
+                TileSched nxt = ts;
+                nxt.next();
+                if (nxt.valid()) prefetch_operands(nxt);
+            }
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tc_fence_after();
             const int row_base = ts.m_tile() * kBM + q * 32;
@@ -192,8 +239,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
     }
 
+    __syncwarp();
     tc_fence_before();
     __syncthreads();
+    if (mc > 1) cluster_sync_all();                           // nobody leaves while a peer may still multicast into this CTA
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -268,11 +317,17 @@ static int launch_one(const GemmDesc& g, const BatchKernelArgs& args, float* C, 
     auto kern = tc_gemm_kernel<PHASE, BK>;
     const size_t smem = smem_bytes(BK, g.bn, g.stages);
     GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tiles = g.m_tiles * g.n_tiles;
-    const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, kThreads, smem, s>>>(g.tmA_hi, g.tmA_lo, g.tmB_hi, g.tmB_lo, g.k_pad / BK, g.m_tiles, g.n_tiles, g.bn,
-                                      g.stages, args, C, ldc, g.ncols_valid);
-    GPAD_CUDA(cudaGetLastError());
+    const int mc = g.mc > 1 ? g.mc : 1;
+    const int units = (g.m_tiles + mc - 1) / mc * g.n_tiles;
+    const int clusters = std::min(units, num_sms / mc);
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(clusters * mc); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    GPAD_CUDA(cudaLaunchKernelEx(&lc, kern, g.tmA_hi, g.tmA_lo, g.tmB_hi, g.tmB_lo, g.k_pad / BK, g.m_tiles, g.n_tiles, g.bn,
+                                 g.stages, mc, args, C, ldc, g.ncols_valid));
     return GPAD_OK;
 }
 

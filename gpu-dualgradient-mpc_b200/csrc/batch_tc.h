@@ -13,6 +13,7 @@ struct GemmDesc {
     CUtensorMap tmY[3];           // product 1: the three rotating y buffers
     CUtensorMap tmB_hi, tmB_lo;   // B [rows = outputs][K] tiles of bn x bk
     int cg = 1;                   // 1: one CTA per 128 x bn tile; 2: CTA pair (cta_group::2) per 256 x bn tile
+    int mc = 1;                   // cg == 1: CTAs per cluster sharing each operator tile through TMA multicast (1 or 2)
     int bk = 16;                  // K block in floats: 16 (SWIZZLE_64B) or 32 (SWIZZLE_128B)
     int k_pad = 0;                // K rounded up to bk
     int m_tiles = 0, n_tiles = 0, bn = 0, stages = 0;

@@ -85,15 +85,16 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
     if (warp == 0) {
         // ============================ TMA producer (both CTAs) ============================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (PairSched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
-                const int row_a = ts.m_tile() * 256 + (int)rank * kBM;
-                const int row_b = ts.n_tile() * bn + (int)rank * bh;
-                for (int kb = 0; kb < num_k_blocks; ++kb) {
-                    mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
-                    const uint32_t fb = smem_u32(full_bar + stage);
-                    const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
+        // warp-uniform loop, one elected lane issues (see elect_one)
+        int stage = 0; uint32_t phase = 0;
+        for (PairSched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
+            const int row_a = ts.m_tile() * 256 + (int)rank * kBM;
+            const int row_b = ts.n_tile() * bn + (int)rank * bh;
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+                const uint32_t fb = smem_u32(full_bar + stage);
+                const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
+                if (elect_one()) {
                     if (kXform) {
                         // A tiles feed this CTA's transform warps: own barrier; B halves feed the pair's MMA
                         const uint32_t fa = smem_u32(fulla_bar + stage);
@@ -108,39 +109,45 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     }
                     tma_load_2d_2sm(base + 2 * a_bytes, &tmB_hi, kb * BK, row_b, fb);
                     tma_load_2d_2sm(base + 2 * a_bytes + bh_bytes, &tmB_lo, kb * BK, row_b, fb);
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ============================ MMA issuer (leader CTA only) ============================
-        if (rank == 0 && lane == 0) {
+        // warp-uniform loop, one elected lane issues (see elect_one)
+        if (rank == 0) {
             const uint32_t idesc = make_idesc_2sm(bn);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (PairSched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
-                mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                mbar_wait_cluster(smem_u32(tempty_bar + acc), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
                     mbar_wait(smem_u32(full_bar + stage), phase);
-                    if (kXform) mbar_wait(smem_u32(ready_bar + stage), phase);
+                    if (kXform) mbar_wait_cluster(smem_u32(ready_bar + stage), phase);
                     tc_fence_after();
                     const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < BK / 8; ++ks) {
-                        const uint64_t a_hi = make_smem_desc<BK>(base + ks * 32);
-                        const uint64_t a_lo = make_smem_desc<BK>(base + a_bytes + ks * 32);
-                        const uint64_t b_hi = make_smem_desc<BK>(base + 2 * a_bytes + ks * 32);
-                        const uint64_t b_lo = make_smem_desc<BK>(base + 2 * a_bytes + bh_bytes + ks * 32);
-                        umma_tf32_2sm(d_tmem, a_hi, b_lo, idesc, (kb | ks) != 0 ? 1u : 0u);
-                        umma_tf32_2sm(d_tmem, a_lo, b_hi, idesc, 1u);
-                        umma_tf32_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+                        for (int ks = 0; ks < BK / 8; ++ks) {
+                            const uint64_t a_hi = make_smem_desc<BK>(base + ks * 32);
+                            const uint64_t a_lo = make_smem_desc<BK>(base + a_bytes + ks * 32);
+                            const uint64_t b_hi = make_smem_desc<BK>(base + 2 * a_bytes + ks * 32);
+                            const uint64_t b_lo = make_smem_desc<BK>(base + 2 * a_bytes + bh_bytes + ks * 32);
+                            umma_tf32_2sm(d_tmem, a_hi, b_lo, idesc, (kb | ks) != 0 ? 1u : 0u);
+                            umma_tf32_2sm(d_tmem, a_lo, b_hi, idesc, 1u);
+                            umma_tf32_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+                        }
+                        umma_commit_2sm(smem_u32(empty_bar + stage));     // frees the slot in both CTAs
                     }
-                    umma_commit_2sm(smem_u32(empty_bar + stage));     // frees the slot in both CTAs
+                    __syncwarp();
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_2sm(smem_u32(tfull_bar + acc));           // accumulator complete, both CTAs
+                if (elect_one()) umma_commit_2sm(smem_u32(tfull_bar + acc));   // accumulator complete, both CTAs
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -201,6 +208,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
     }
 
+    __syncwarp();
     tc_fence_before();
     cluster_sync_all();                 // nobody leaves (or frees TMEM) while the peer may still use this CTA
     if (warp == 1) {

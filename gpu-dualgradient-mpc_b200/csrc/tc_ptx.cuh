@@ -18,6 +18,16 @@ constexpr int kEpiBufFloats = 32 * 33;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one elected lane of a fully converged warp (always the same lane while all 32 are active).  The single-thread
+// tcgen05 / TMA instructions are issued under this predicate from warp-UNIFORM loops: a role loop that runs
+// entirely under `if (lane == 0)` makes ptxas serialise every descriptor through a per-thread R2UR loop, which
+// measured ~145 clk per tcgen05.mma (tests/ubench/ubench_tc.cu) -- above the 104-128 clk the MMA itself needs.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -52,6 +62,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -134,6 +147,18 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait_cluster(bar, parity)) {}
+}
+// multicast TMA load: the box lands at the same shared-memory offset in every CTA of `mask`, each
+// destination CTA's mbarrier (same offset) is credited with the bytes; the L2 -> SM fabric carries it once
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+// commit of this CTA's MMAs that arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
 }
 // 2-SM TMA load: executed by both CTAs of the pair, data lands in the executing CTA's shared memory,
 // the transaction bytes are credited to the LEADER's mbarrier (peer bit of the address cleared)
