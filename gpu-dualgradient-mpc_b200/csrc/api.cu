@@ -600,6 +600,11 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
     int bn1 = 0, nt1 = 0, bn2 = 0, nt2 = 0;
     tc::plan_tiles(n, &bn1, &nt1);
     tc::plan_tiles(m, &bn2, &nt2);
+    // product 1: second-generation kernel (P-formulation, A operand through TMEM) unless disabled / CTA pairs requested
+    bool p1 = tcp && cg == 1;
+    if (const char* e = getenv("GPAD_TC_P1")) p1 = p1 && atoi(e) != 0;
+    if (const char* e = getenv("GPAD_TC_PFORM")) p1 = p1 && atoi(e) != 0;
+    if (p1) tc::plan_tiles_p1(n, &bn1, &nt1);
     h->op.n_rows_pad = round_up(std::max(bn1 * nt1, n), 128);
     h->op.m_rows_pad = round_up(std::max(bn2 * nt2, m), 128);
     GPAD_TRY(upload_padded(h, MG.data(), n, m, h->op.n_rows_pad, st.mp, &h->op.M_G));
@@ -614,9 +619,10 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
     GPAD_TRY(dev_alloc(h, &st.active_count, 1));
     GPAD_TRY(dev_alloc(h, &h->stage_in, (size_t)h->cfg.max_batch * std::max(n, m)));
     GPAD_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_active), sizeof(int)));
-    char buf[320];
+    char buf[640];
     if (tcp) {
         GPAD_TRY(dev_alloc(h, &st.zh_hi, bnn)); GPAD_TRY(dev_alloc(h, &st.zh_lo, bnn));
+        GPAD_TRY(dev_alloc(h, &st.Pb[0], bnn)); GPAD_TRY(dev_alloc(h, &st.Pb[1], bnn));
         GPAD_CUDA(cudaMemset(st.zh_hi, 0, bnn * sizeof(float))); GPAD_CUDA(cudaMemset(st.zh_lo, 0, bnn * sizeof(float)));
         const size_t c1 = (size_t)h->op.n_rows_pad * st.mp, c2 = (size_t)h->op.m_rows_pad * st.np;
         GPAD_TRY(dev_alloc(h, &h->op.M_G_lo, c1)); GPAD_TRY(dev_alloc(h, &h->op.G_L_lo, c2));
@@ -634,14 +640,25 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         g2.k_pad = st.np; g2.bn = bn2; g2.n_tiles = nt2; g2.ncols_valid = m;
         g1.stages = cg == 2 ? tc::pick_stages2(bk, bn1, h->smem_optin) : tc::pick_stages(bk, bn1, h->smem_optin);
         g2.stages = cg == 2 ? tc::pick_stages2(bk, bn2, h->smem_optin) : tc::pick_stages(bk, bn2, h->smem_optin);
+        if (p1) {
+            g1.p1 = 1; g1.bk = 16; g1.mc = 1;
+            GPAD_TRY(tc::plan_rings_p1(bn1, h->smem_optin, &g1.a_stages, &g1.stages));
+        }
         if (const char* e = getenv("GPAD_TC_STAGES")) { g1.stages = std::min(g1.stages, std::max(2, atoi(e))); g2.stages = std::min(g2.stages, std::max(2, atoi(e))); }
-        for (int k = 0; k < 3; ++k) GPAD_TRY(tc::make_tmap(&g1.tmY[k], st.yb[k], st.mp, st.Bp, st.mp, bk, 128));
-        GPAD_TRY(tc::make_tmap(&g1.tmB_hi, h->op.M_G, st.mp, h->op.n_rows_pad, st.mp, bk, bn1 / bdiv));
-        GPAD_TRY(tc::make_tmap(&g1.tmB_lo, h->op.M_G_lo, st.mp, h->op.n_rows_pad, st.mp, bk, bn1 / bdiv));
+        for (int k = 0; k < 3; ++k) GPAD_TRY(tc::make_tmap(&g1.tmY[k], st.yb[k], st.mp, st.Bp, st.mp, g1.bk, 128));
+        GPAD_TRY(tc::make_tmap(&g1.tmB_hi, h->op.M_G, st.mp, h->op.n_rows_pad, st.mp, g1.bk, p1 ? bn1 : bn1 / bdiv));
+        GPAD_TRY(tc::make_tmap(&g1.tmB_lo, h->op.M_G_lo, st.mp, h->op.n_rows_pad, st.mp, g1.bk, p1 ? bn1 : bn1 / bdiv));
         GPAD_TRY(tc::make_tmap(&g2.tmA_hi, st.zh_hi, st.np, st.Bp, st.np, bk, 128));
         GPAD_TRY(tc::make_tmap(&g2.tmA_lo, st.zh_lo, st.np, st.Bp, st.np, bk, 128));
         GPAD_TRY(tc::make_tmap(&g2.tmB_hi, h->op.G_L, st.np, h->op.m_rows_pad, st.np, bk, bn2 / bdiv));
         GPAD_TRY(tc::make_tmap(&g2.tmB_lo, h->op.G_L_lo, st.np, h->op.m_rows_pad, st.np, bk, bn2 / bdiv));
+        if (p1)
+            snprintf(buf, sizeof(buf),
+                     "batch-shared: tcgen05 cta_group::1 kind::tf32 x3; product1 = P-formulation (A = y_v only, split in registers, A operand "
+                     "through a TMEM ring, state ring %d x 8 KB + operator ring %d stages), tiles 128x%d x%d; product2 tiles 128x%d x%d "
+                     "(%d stages, TMA ring bk=%d, operator multicast x%d), TMEM 512 cols, persistent over %d SMs",
+                     g1.a_stages, g1.stages, bn1, nt1, bn2, nt2, g2.stages, bk, g2.mc, h->num_sms);
+        else
         snprintf(buf, sizeof(buf),
                  "batch-shared: tcgen05 cta_group::%d kind::tf32 x3 (hi/lo split, w built in-kernel), TMA ring bk=%d (operator tiles multicast x%d), product1 tiles "
                  "%dx%d x%d (%d stages), product2 tiles %dx%d x%d (%d stages), TMEM 2x256 cols, persistent over %d SMs",
@@ -697,12 +714,27 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
     k.g_P = st.g_P; k.p_D = st.p_D; k.f = a->f ? st.f : nullptr;
     k.z = st.z; k.zhat = st.zhat; k.zh_hi = st.zh_hi; k.zh_lo = st.zh_lo;
     k.sbar = st.sbar; k.red = st.red; k.done = checking ? st.done : nullptr;
-    k.prefetch = 1;
+    k.prefetch = 0;   // measured slower on B200 (product 2: 0.71 -> 0.90 ms): the SM ingest path is the bound, extra requests cost
     if (const char* e = getenv("GPAD_TC_PREFETCH")) k.prefetch = atoi(e) != 0;
     const int tile_rows = (tcp && h->g1.cg == 2) ? 256 : 128;
     const int m_tiles = round_up(B, tile_rows) / tile_rows;
     h->g1.m_tiles = m_tiles; h->g2.m_tiles = m_tiles;
     const int Bp_call = m_tiles * tile_rows;
+    // P-formulation of product 1 (cta_group::1 tcgen05 kernel): P_v = M_G y_v, M_G w_v = P_v + beta_v (P_v - P_{v-1})
+    k.pform = (tcp && h->g1.cg == 1) ? 1 : 0;
+    if (const char* e = getenv("GPAD_TC_PFORM")) k.pform = k.pform && atoi(e) != 0;
+    if (h->g1.p1) k.pform = 1;
+    if (k.pform && a->max_iter > 0) {
+        if (a->y_prev0) {          // warm start: P_{-1} = M_G y_{-1} (one extra product-1 launch)
+            BatchKernelArgs kp = k;
+            kp.p_only = 1; kp.P_cur = st.Pb[1]; kp.P_prev = st.Pb[0];
+            h->g1.tmA_hi = h->g1.tmY[2]; h->g1.tmA_lo = h->g1.tmY[2];
+            GPAD_TRY(h->g1.p1 ? tc::launch_p1(h->g1, kp, h->num_sms, s) : tc::launch_gemm(1, h->g1, kp, nullptr, 0, h->num_sms, s));
+            h->launches += 1;
+        } else {
+            GPAD_CUDA(cudaMemsetAsync(st.Pb[1], 0, sizeof(float) * (size_t)st.Bp * st.np, s));
+        }
+    }
 
     for (int v = 0; v < a->max_iter; ++v) {
         const bool check = checking && ((v + 1) % a->check_every == 0);
@@ -713,10 +745,11 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
         k.y_prev = st.yb[(v + 2) % 3];           // y_{v-1}
         k.y_cur = st.yb[v % 3];                  // y_v
         k.y_next = st.yb[(v + 1) % 3];           // y_{v+1} overwrites y_{v-2}
+        k.P_cur = st.Pb[v & 1]; k.P_prev = st.Pb[(v + 1) & 1];
         if (tcp) { h->g1.tmA_hi = h->g1.tmY[v % 3]; h->g1.tmA_lo = h->g1.tmY[(v + 2) % 3]; }
         if (tcp) {
             cudaEvent_t pe = h->prof_begin(s);
-            GPAD_TRY(tc::launch_gemm(1, h->g1, k, nullptr, 0, h->num_sms, s));
+            GPAD_TRY(h->g1.p1 ? tc::launch_p1(h->g1, k, h->num_sms, s) : tc::launch_gemm(1, h->g1, k, nullptr, 0, h->num_sms, s));
             h->prof_end(1, pe, s);
             pe = h->prof_begin(s);
             GPAD_TRY(tc::launch_gemm(2, h->g2, k, nullptr, 0, h->num_sms, s));

@@ -39,6 +39,12 @@ struct BatchKernelArgs {
     float* sbar;
     float* red;
     const int* done;       // per-instance "stopped" flag (null in fixed-iteration mode)
+    // P-formulation of product 1 (tcgen05 cta_group::1 path): the GEMM computes P_v = M_G y_v and the epilogue forms
+    // M_G w_v = P_v + beta (P_v - P_{v-1}) -- linear in y, so y_{v-1} never has to be staged as an MMA operand
+    int pform;
+    int p_only;            // warm start: this launch only produces P_{-1} = M_G y_{-1}
+    const float* P_prev;   // [Bp][np] P_{v-1}
+    float* P_cur;          // [Bp][np] P_v
     int prefetch;          // tcgen05 path: epilogue warps pull the next tile's operands into L2 (batch_tc.cu)
 };
 

@@ -101,9 +101,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const uint32_t fb = smem_u32(full_bar + stage);
                 const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
                 if (elect_one()) {
-                    mbar_expect_tx(fb, stage_bytes);
+                    const bool one_a = kXform && args.pform;        // P-formulation: only y_v is staged
+                    mbar_expect_tx(fb, one_a ? stage_bytes - a_bytes : stage_bytes);
                     tma_load_2d(base, &tmA_hi, kb * BK, row_a, fb);
-                    tma_load_2d(base + a_bytes, &tmA_lo, kb * BK, row_a, fb);
+                    if (!one_a) tma_load_2d(base + a_bytes, &tmA_lo, kb * BK, row_a, fb);
                     if (mc > 1) {     // this CTA fetches 1/mc of the operator tile for the whole cluster
                         const int part = bn / mc;
                         const uint32_t off = (uint32_t)(rank * part) * BK * 4;
@@ -167,16 +168,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 mbar_wait(smem_u32(full_bar + stage), phase);
                 float4* t0 = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
                 float4* t1 = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + a_bytes);
+                if (args.pform) {
+                    // A = y_v itself: tile0 <- RN_tf32(y), tile1 <- RN_tf32(y - tile0) (tile1 is not TMA-filled)
 #pragma unroll
-                for (int i = xt; i < kVec; i += 32 * kXformWarps) {
-                    const float4 y = t0[i], yp = t1[i];
-                    float4 hi, lo;
-                    split_tf32(momentum(y.x, yp.x, beta), hi.x, lo.x);
-                    split_tf32(momentum(y.y, yp.y, beta), hi.y, lo.y);
-                    split_tf32(momentum(y.z, yp.z, beta), hi.z, lo.z);
-                    split_tf32(momentum(y.w, yp.w, beta), hi.w, lo.w);
-                    t0[i] = hi;
-                    t1[i] = lo;
+                    for (int i = xt; i < kVec; i += 32 * kXformWarps) {
+                        const float4 y = t0[i];
+                        float4 hi, lo;
+                        split_tf32(y.x, hi.x, lo.x);
+                        split_tf32(y.y, hi.y, lo.y);
+                        split_tf32(y.z, hi.z, lo.z);
+                        split_tf32(y.w, hi.w, lo.w);
+                        t0[i] = hi;
+                        t1[i] = lo;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = xt; i < kVec; i += 32 * kXformWarps) {
+                        const float4 y = t0[i], yp = t1[i];
+                        float4 hi, lo;
+                        split_tf32(momentum(y.x, yp.x, beta), hi.x, lo.x);
+                        split_tf32(momentum(y.y, yp.y, beta), hi.y, lo.y);
+                        split_tf32(momentum(y.z, yp.z, beta), hi.z, lo.z);
+                        split_tf32(momentum(y.w, yp.w, beta), hi.w, lo.w);
+                        t0[i] = hi;
+                        t1[i] = lo;
+                    }
                 }
                 fence_proxy_async_smem();                       // generic-proxy writes -> visible to the MMA (async proxy)
                 __syncwarp();

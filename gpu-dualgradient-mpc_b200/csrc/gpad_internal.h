@@ -55,6 +55,7 @@ struct BatchState {
     float* zhat = nullptr;  // [Bp][np]
     float* zh_hi = nullptr; // TF32X3 only
     float* zh_lo = nullptr;
+    float* Pb[2] = {nullptr, nullptr};  // TF32X3 only: P_v = M_G y_v lives in Pb[v & 1] (P-formulation of product 1)
     float* sbar = nullptr;  // [Bp][mp] averaged residual (termination only)
     float* red = nullptr;   // [Bp][8] per-instance reductions (termination only)
     int* done = nullptr;    // [Bp] instance stopped (termination mode)

@@ -19,7 +19,7 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
             const int b = row_base + rr;
             if (col_ok && b < args.B) Cdbg[(size_t)b * ldc + c] = buf[rr * 33 + lane];
         }
-    } else if (!args.it.check && !args.done) {
+    } else if ((!args.it.check && !args.done) || (PHASE == 1 && args.p_only)) {
         // fast path (fixed-iteration solves): rows in chunks of kChunk with every global
         // load of the chunk issued before the first use, so each warp keeps
         // kChunk * (2 or 3) x 128 B in flight; streaming cache hints keep the operators in L2
@@ -27,7 +27,15 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
 #pragma unroll 1
         for (int r0 = 0; r0 < 32; r0 += kChunk) {
             if (PHASE == 1) {
-                float gp[kChunk], zo[kChunk];
+                if (args.p_only) {       // warm start: P_{-1} = M_G y_{-1}, nothing else
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j) {
+                        const int b = row_base + r0 + j;
+                        if (col_ok && b < args.B) args.P_cur[(size_t)b * args.np + c] = buf[(r0 + j) * 33 + lane];
+                    }
+                    continue;
+                }
+                float gp[kChunk], zo[kChunk], pp[kChunk];
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j) {
                     const int b = row_base + r0 + j;
@@ -35,13 +43,19 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
                     const size_t o = (size_t)b * args.np + c;
                     gp[j] = ok ? __ldcs(args.g_P + o) : 0.f;
                     zo[j] = ok ? __ldcs(args.z + o) : 0.f;
+                    pp[j] = (ok && args.pform) ? __ldcs(args.P_prev + o) : 0.f;
                 }
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j) {
                     const int b = row_base + r0 + j;
                     if (!(col_ok && b < args.B)) continue;
                     const size_t o = (size_t)b * args.np + c;
-                    const float zh = buf[(r0 + j) * 33 + lane] - gp[j];
+                    float acc = buf[(r0 + j) * 33 + lane];
+                    if (args.pform) {
+                        __stcs(args.P_cur + o, acc);
+                        acc = momentum(acc, pp[j], args.it.beta);          // M_G w_v from P_v, P_{v-1}
+                    }
+                    const float zh = acc - gp[j];
                     __stcs(args.z + o, __fadd_rn(__fmul_rn(1.0f - args.it.theta, zo[j]), __fmul_rn(args.it.theta, zh)));
                     if (args.it.store_zhat) __stcs(args.zhat + o, zh);
                     float hi, lo;
@@ -81,7 +95,15 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
             if (ok && args.done) ok = args.done[b] == 0;
             if (PHASE == 1) {
                 float f_zhat = 0.f;
-                if (ok) epilogue1<true>(args, b, c, val, f_zhat);
+                if (ok) {
+                    float acc = val;
+                    if (args.pform) {
+                        const size_t o = (size_t)b * args.np + c;
+                        args.P_cur[o] = val;
+                        acc = momentum(val, args.P_prev[o], args.it.beta);
+                    }
+                    epilogue1<true>(args, b, c, acc, f_zhat);
+                }
                 if (args.it.check && args.f) {
 #pragma unroll
                     for (int o = 16; o; o >>= 1) f_zhat += __shfl_xor_sync(0xffffffffu, f_zhat, o);

@@ -38,16 +38,6 @@ struct Cfg {
     int warp_issue;  // 0: the whole issue loop runs under `if (lane == 0)`; 1: warp-uniform loop, elect.sync around each MMA
 };
 
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
-
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -647,6 +637,10 @@ int main(int argc, char** argv) {
     //                                         bn  box  a_st b_st t_st kb  tiles cl m_tiles
     run2("split bn=208 a4 b3 t3",         Cfg2{208, 104, 4, 3, 3, KB, T, 1, 512});
     run2("split bn=208 a8 b3 t3",         Cfg2{208, 104, 8, 3, 3, KB, T, 1, 512});
+    run2("split bn=208 a8 b4 t3",         Cfg2{208, 104, 8, 4, 3, KB, T, 1, 512});
+    run2("split bn=208 a8 b5 t3",         Cfg2{208, 104, 8, 5, 3, KB, T, 1, 512});
+    run2("split bn=208 a6 b5 t3",         Cfg2{208, 104, 6, 5, 3, KB, T, 1, 512});
+    run2("split bn=208 a8 b3 t4",         Cfg2{208, 104, 8, 3, 4, KB, T, 1, 512});
     run2("split bn=208 a8 b4 t4",         Cfg2{208, 104, 8, 4, 4, KB, T, 1, 512});
     run2("split bn=208 a12 b4 t6",        Cfg2{208, 104, 12, 4, 6, KB, T, 1, 512});
     run2("split bn=208 a12 b4 t6 cluster2", Cfg2{208, 104, 12, 4, 6, KB, T, 2, 512});
