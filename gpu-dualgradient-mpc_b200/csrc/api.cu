@@ -605,6 +605,9 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
     if (const char* e = getenv("GPAD_TC_P1")) p1 = p1 && atoi(e) != 0;
     if (const char* e = getenv("GPAD_TC_PFORM")) p1 = p1 && atoi(e) != 0;
     if (p1) tc::plan_tiles_p1(n, &bn1, &nt1);
+    bool p2ts = false;                           // product 2 through the same TMEM-A kernel (GPAD_TC_P2TS=1)
+    if (const char* e = getenv("GPAD_TC_P2TS")) p2ts = p1 && atoi(e) != 0;
+    if (p2ts) tc::plan_tiles_p1(m, &bn2, &nt2);
     h->op.n_rows_pad = round_up(std::max(bn1 * nt1, n), 128);
     h->op.m_rows_pad = round_up(std::max(bn2 * nt2, m), 128);
     GPAD_TRY(upload_padded(h, MG.data(), n, m, h->op.n_rows_pad, st.mp, &h->op.M_G));
@@ -624,6 +627,7 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         GPAD_TRY(dev_alloc(h, &st.zh_hi, bnn)); GPAD_TRY(dev_alloc(h, &st.zh_lo, bnn));
         GPAD_TRY(dev_alloc(h, &st.Pb[0], bnn)); GPAD_TRY(dev_alloc(h, &st.Pb[1], bnn));
         GPAD_CUDA(cudaMemset(st.zh_hi, 0, bnn * sizeof(float))); GPAD_CUDA(cudaMemset(st.zh_lo, 0, bnn * sizeof(float)));
+        GPAD_CUDA(cudaMemset(st.zhat, 0, bnn * sizeof(float)));    // its K-padding columns feed product 2 when it stages zhat itself
         const size_t c1 = (size_t)h->op.n_rows_pad * st.mp, c2 = (size_t)h->op.m_rows_pad * st.np;
         GPAD_TRY(dev_alloc(h, &h->op.M_G_lo, c1)); GPAD_TRY(dev_alloc(h, &h->op.G_L_lo, c2));
         GPAD_TRY(tc::launch_split(h->op.M_G, h->op.M_G, h->op.M_G_lo, c1, nullptr));
@@ -642,16 +646,23 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         g2.stages = cg == 2 ? tc::pick_stages2(bk, bn2, h->smem_optin) : tc::pick_stages(bk, bn2, h->smem_optin);
         if (p1) {
             g1.p1 = 1; g1.bk = 16; g1.mc = 1;
-            GPAD_TRY(tc::plan_rings_p1(bn1, h->smem_optin, &g1.a_stages, &g1.stages));
+            GPAD_TRY(tc::plan_rings_p1(1, bn1, h->smem_optin, &g1.a_stages, &g1.stages));
+        }
+        if (p2ts) {
+            g2.p1 = 1; g2.bk = 16; g2.mc = 1;
+            GPAD_TRY(tc::plan_rings_p1(2, bn2, h->smem_optin, &g2.a_stages, &g2.stages));
         }
         if (const char* e = getenv("GPAD_TC_STAGES")) { g1.stages = std::min(g1.stages, std::max(2, atoi(e))); g2.stages = std::min(g2.stages, std::max(2, atoi(e))); }
         for (int k = 0; k < 3; ++k) GPAD_TRY(tc::make_tmap(&g1.tmY[k], st.yb[k], st.mp, st.Bp, st.mp, g1.bk, 128));
         GPAD_TRY(tc::make_tmap(&g1.tmB_hi, h->op.M_G, st.mp, h->op.n_rows_pad, st.mp, g1.bk, p1 ? bn1 : bn1 / bdiv));
         GPAD_TRY(tc::make_tmap(&g1.tmB_lo, h->op.M_G_lo, st.mp, h->op.n_rows_pad, st.mp, g1.bk, p1 ? bn1 : bn1 / bdiv));
-        GPAD_TRY(tc::make_tmap(&g2.tmA_hi, st.zh_hi, st.np, st.Bp, st.np, bk, 128));
+        g2.xf2 = 0;      // measured slower (0.72 -> 0.81 ms): the in-place split adds shared-memory traffic to a kernel bound by it
+        if (const char* e = getenv("GPAD_TC_XF2")) g2.xf2 = cg == 1 && atoi(e) != 0;
+        if (p2ts) g2.xf2 = 1;                        // zhat is staged as one fp32 tile and split in registers
+        GPAD_TRY(tc::make_tmap(&g2.tmA_hi, g2.xf2 ? st.zhat : st.zh_hi, st.np, st.Bp, st.np, g2.bk, 128));
         GPAD_TRY(tc::make_tmap(&g2.tmA_lo, st.zh_lo, st.np, st.Bp, st.np, bk, 128));
-        GPAD_TRY(tc::make_tmap(&g2.tmB_hi, h->op.G_L, st.np, h->op.m_rows_pad, st.np, bk, bn2 / bdiv));
-        GPAD_TRY(tc::make_tmap(&g2.tmB_lo, h->op.G_L_lo, st.np, h->op.m_rows_pad, st.np, bk, bn2 / bdiv));
+        GPAD_TRY(tc::make_tmap(&g2.tmB_hi, h->op.G_L, st.np, h->op.m_rows_pad, st.np, g2.bk, p2ts ? bn2 : bn2 / bdiv));
+        GPAD_TRY(tc::make_tmap(&g2.tmB_lo, h->op.G_L_lo, st.np, h->op.m_rows_pad, st.np, g2.bk, p2ts ? bn2 : bn2 / bdiv));
         if (p1)
             snprintf(buf, sizeof(buf),
                      "batch-shared: tcgen05 cta_group::1 kind::tf32 x3; product1 = P-formulation (A = y_v only, split in registers, A operand "
@@ -724,12 +735,13 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
     k.pform = (tcp && h->g1.cg == 1) ? 1 : 0;
     if (const char* e = getenv("GPAD_TC_PFORM")) k.pform = k.pform && atoi(e) != 0;
     if (h->g1.p1) k.pform = 1;
+    k.zh_single = (tcp && h->g2.xf2) ? 1 : 0;
     if (k.pform && a->max_iter > 0) {
         if (a->y_prev0) {          // warm start: P_{-1} = M_G y_{-1} (one extra product-1 launch)
             BatchKernelArgs kp = k;
             kp.p_only = 1; kp.P_cur = st.Pb[1]; kp.P_prev = st.Pb[0];
             h->g1.tmA_hi = h->g1.tmY[2]; h->g1.tmA_lo = h->g1.tmY[2];
-            GPAD_TRY(h->g1.p1 ? tc::launch_p1(h->g1, kp, h->num_sms, s) : tc::launch_gemm(1, h->g1, kp, nullptr, 0, h->num_sms, s));
+            GPAD_TRY(h->g1.p1 ? tc::launch_p1(1, h->g1, kp, h->num_sms, s) : tc::launch_gemm(1, h->g1, kp, nullptr, 0, h->num_sms, s));
             h->launches += 1;
         } else {
             GPAD_CUDA(cudaMemsetAsync(st.Pb[1], 0, sizeof(float) * (size_t)st.Bp * st.np, s));
@@ -749,10 +761,10 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
         if (tcp) { h->g1.tmA_hi = h->g1.tmY[v % 3]; h->g1.tmA_lo = h->g1.tmY[(v + 2) % 3]; }
         if (tcp) {
             cudaEvent_t pe = h->prof_begin(s);
-            GPAD_TRY(h->g1.p1 ? tc::launch_p1(h->g1, k, h->num_sms, s) : tc::launch_gemm(1, h->g1, k, nullptr, 0, h->num_sms, s));
+            GPAD_TRY(h->g1.p1 ? tc::launch_p1(1, h->g1, k, h->num_sms, s) : tc::launch_gemm(1, h->g1, k, nullptr, 0, h->num_sms, s));
             h->prof_end(1, pe, s);
             pe = h->prof_begin(s);
-            GPAD_TRY(tc::launch_gemm(2, h->g2, k, nullptr, 0, h->num_sms, s));
+            GPAD_TRY(h->g2.p1 ? tc::launch_p1(2, h->g2, k, h->num_sms, s) : tc::launch_gemm(2, h->g2, k, nullptr, 0, h->num_sms, s));
             h->prof_end(2, pe, s);
         } else {
             cudaEvent_t pe = h->prof_begin(s);

@@ -45,6 +45,7 @@ struct BatchKernelArgs {
     int p_only;            // warm start: this launch only produces P_{-1} = M_G y_{-1}
     const float* P_prev;   // [Bp][np] P_{v-1}
     float* P_cur;          // [Bp][np] P_v
+    int zh_single;         // product 2 splits zhat itself: product 1 stores zhat (fp32) only, not zh_hi / zh_lo
     int prefetch;          // tcgen05 path: epilogue warps pull the next tile's operands into L2 (batch_tc.cu)
 };
 
@@ -76,7 +77,7 @@ __device__ __forceinline__ void epilogue1(const BatchKernelArgs& a, int b, int i
     const float zh = acc - a.g_P[o];
     a.z[o] = __fadd_rn(__fmul_rn(1.0f - a.it.theta, a.z[o]), __fmul_rn(a.it.theta, zh));   // unfused like the CPU build
     a.zhat[o] = zh;
-    if (SPLIT) {
+    if (SPLIT && !a.zh_single) {
         float hi, lo;
         split_tf32(zh, hi, lo);
         a.zh_hi[o] = hi;

@@ -48,9 +48,16 @@ struct TileSched {
     __device__ int n_tile() const { return unit % n_tiles; }
 };
 
+// warp roles per instantiation: warps 0/1 producer + MMA, then transform warps, then epilogue warps
+//   product 1 (first generation): 4 transform + 8 epilogue; product 2 / test hook: 12 epilogue;
+//   product 2 staging zhat itself: 2 transform + 12 epilogue (16 warps, 128 registers per thread)
+__host__ __device__ constexpr int xform_warps(int phase, bool xf) { return xf ? (phase == 2 ? 2 : kXformWarps) : 0; }
+__host__ __device__ constexpr int epi_warps(int phase, bool xf) { return (xf && phase != 2) ? kWorkWarps - kXformWarps : kWorkWarps; }
+__host__ __device__ constexpr int cta_threads(int phase, bool xf) { return 32 * (2 + xform_warps(phase, xf) + epi_warps(phase, xf)); }
+
 // PHASE 0: plain store of C (test hook); 1: GPAD product 1; 2: GPAD product 2
-template <int PHASE, int BK>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int PHASE, int BK, bool XF>
+__global__ void __launch_bounds__(cta_threads(PHASE, XF), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                int num_k_blocks, int m_tiles, int n_tiles, int bn, int stages, int mc,
@@ -59,9 +66,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t a_bytes = kBM * BK * 4, b_bytes = (uint32_t)bn * BK * 4;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-    constexpr bool kXform = PHASE == 1;                       // A tiles are y_v / y_{v-1}: build w hi/lo in place
-    constexpr int kEpi = kXform ? kWorkWarps - kXformWarps : kWorkWarps;
-    constexpr int kFirstEpiWarp = 2 + (kXform ? kXformWarps : 0);
+    constexpr bool kXform = XF;            // transform warps: product 1: A tiles are y_v (/ y_{v-1}) -> hi/lo of y (w) in place;
+                                           // product 2: the A tile is zhat (fp32) -> hi/lo in place
+    constexpr bool kSplitOnly = PHASE == 2;
+    constexpr int kXW = xform_warps(PHASE, XF);
+    constexpr int kEpi = epi_warps(PHASE, XF);
+    constexpr int kFirstEpiWarp = 2 + kXW;
     float* epi_buf = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kWorkWarps * kEpiBufFloats);
     uint64_t* full_bar = bars;
@@ -78,7 +88,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
         for (int s = 0; s < stages; ++s) {
-            mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), mc); mbar_init(smem_u32(ready_bar + s), kXformWarps);
+            mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), mc); mbar_init(smem_u32(ready_bar + s), kXW > 0 ? kXW : 1);
         }
         for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), kEpi); }
         fence_barrier_init();
@@ -101,7 +111,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const uint32_t fb = smem_u32(full_bar + stage);
                 const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
                 if (elect_one()) {
-                    const bool one_a = kXform && args.pform;        // P-formulation: only y_v is staged
+                    const bool one_a = kXform && (kSplitOnly || args.pform);   // only one fp32 tile is staged, tile 1 is produced in place
                     mbar_expect_tx(fb, one_a ? stage_bytes - a_bytes : stage_bytes);
                     tma_load_2d(base, &tmA_hi, kb * BK, row_a, fb);
                     if (!one_a) tma_load_2d(base + a_bytes, &tmA_lo, kb * BK, row_a, fb);
@@ -168,10 +178,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 mbar_wait(smem_u32(full_bar + stage), phase);
                 float4* t0 = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
                 float4* t1 = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + a_bytes);
-                if (args.pform) {
-                    // A = y_v itself: tile0 <- RN_tf32(y), tile1 <- RN_tf32(y - tile0) (tile1 is not TMA-filled)
+                if (kSplitOnly || args.pform) {
+                    // A = the staged vector itself: tile0 <- RN_tf32(y), tile1 <- RN_tf32(y - tile0) (tile1 is not TMA-filled)
 #pragma unroll
-                    for (int i = xt; i < kVec; i += 32 * kXformWarps) {
+                    for (int i = xt; i < kVec; i += 32 * kXW) {
                         const float4 y = t0[i];
                         float4 hi, lo;
                         split_tf32(y.x, hi.x, lo.x);
@@ -183,7 +193,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     }
                 } else {
 #pragma unroll
-                    for (int i = xt; i < kVec; i += 32 * kXformWarps) {
+                    for (int i = xt; i < kVec; i += 32 * kXW) {
                         const float4 y = t0[i], yp = t1[i];
                         float4 hi, lo;
                         split_tf32(momentum(y.x, yp.x, beta), hi.x, lo.x);
@@ -206,7 +216,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int part = ew >> 2;               // warps sharing a quarter alternate over column blocks
         constexpr int kParts = kEpi / 4;
-        float* buf = epi_buf + (warp - 2) * kEpiBufFloats;
+        float* buf = epi_buf + ew * kEpiBufFloats;
         const int nblk = (bn + 31) / 32;
         int acc = 0; uint32_t acc_phase = 0;
         // The epilogue's operand loads do not depend on the accumulator.  Each warp holds only ~6 KB of them in flight,
@@ -328,16 +338,16 @@ int pick_stages(int bk, int bn, size_t smem_limit) {
     return s;
 }
 
-template <int PHASE, int BK>
+template <int PHASE, int BK, bool XF = (PHASE == 1)>
 static int launch_one(const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s) {
-    auto kern = tc_gemm_kernel<PHASE, BK>;
+    auto kern = tc_gemm_kernel<PHASE, BK, XF>;
     const size_t smem = smem_bytes(BK, g.bn, g.stages);
     GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int mc = g.mc > 1 ? g.mc : 1;
     const int units = (g.m_tiles + mc - 1) / mc * g.n_tiles;
     const int clusters = std::min(units, num_sms / mc);
     cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(clusters * mc); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = smem; lc.stream = s;
+    lc.gridDim = dim3(clusters * mc); lc.blockDim = dim3(cta_threads(PHASE, XF)); lc.dynamicSmemBytes = smem; lc.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -352,10 +362,12 @@ int launch_gemm(int phase, const GemmDesc& g, const BatchKernelArgs& args, float
     if (g.bk == 16) {
         if (phase == 0) return launch_one<0, 16>(g, args, C, ldc, num_sms, s);
         if (phase == 1) return launch_one<1, 16>(g, args, C, ldc, num_sms, s);
+        if (g.xf2) return launch_one<2, 16, true>(g, args, C, ldc, num_sms, s);
         return launch_one<2, 16>(g, args, C, ldc, num_sms, s);
     }
     if (phase == 0) return launch_one<0, 32>(g, args, C, ldc, num_sms, s);
     if (phase == 1) return launch_one<1, 32>(g, args, C, ldc, num_sms, s);
+    if (g.xf2) return launch_one<2, 32, true>(g, args, C, ldc, num_sms, s);
     return launch_one<2, 32>(g, args, C, ldc, num_sms, s);
 }
 

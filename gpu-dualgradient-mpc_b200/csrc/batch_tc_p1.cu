@@ -14,8 +14,8 @@
 //     row), split it into tf32 hi | lo in registers and tcgen05.st it into a 3-slot TMEM ring; the MMAs take A from
 //     TMEM (tcgen05.mma [d], [a_tmem], b_desc), so only B is read from shared memory.
 // TMEM: 2 accumulator stages x bn (<= 208) columns + 3 x 32 columns of A ring = 512.
-// Warps: 0 operator producer, 1 TMEM allocator + MMA issuer, 2 state producer, 3 idle, 4..7 transform (TMEM lane
-// quarter = warp % 4), 8..15 epilogue.  All single-thread instructions are issued from warp-uniform loops (elect.sync).
+// Warps: 0 operator producer, 1 TMEM allocator + MMA issuer, 2 state producer, 3..6 transform (TMEM lane
+// quarter = warp % 4), 7.. epilogue (8 warps for product 1).  All single-thread instructions are issued from warp-uniform loops (elect.sync).
 #include <cuda.h>
 
 #include <algorithm>
@@ -31,8 +31,8 @@ namespace tc {
 
 namespace {
 
-constexpr int kP1Threads = 512;
-constexpr int kP1EpiWarps = 8;
+constexpr int kP1FirstXform = 3;       // warps 3..6 transform (any 4 consecutive warps cover the 4 TMEM lane quarters)
+constexpr int kP1FirstEpi = 7;
 constexpr int kP1TStages = 3;          // TMEM A ring slots (32 columns each: hi 16 | lo 16)
 constexpr int kP1BK = 16;
 
@@ -64,7 +64,8 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kP1Threads, 1)
+template <int PHASE, int EPI>
+__global__ void __launch_bounds__(32 * (kP1FirstEpi + EPI), 1)
 tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmB_hi,
              const __grid_constant__ CUtensorMap tmB_lo, int num_k_blocks, int m_tiles, int n_tiles, int bn,
              int a_stages, int b_stages, const BatchKernelArgs args, int ncols_valid) {
@@ -76,7 +77,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + (size_t)a_stages * a_bytes;
     float* epi_buf = reinterpret_cast<float*>(b_ring + (size_t)b_stages * 2 * b_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kP1EpiWarps * kEpiBufFloats);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + EPI * kEpiBufFloats);
     uint64_t* afull = bars;
     uint64_t* aempty = afull + a_stages;
     uint64_t* bfull = aempty + a_stages;
@@ -97,7 +98,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         for (int s = 0; s < a_stages; ++s) { mbar_init(smem_u32(afull + s), 1); mbar_init(smem_u32(aempty + s), 4); }
         for (int s = 0; s < b_stages; ++s) { mbar_init(smem_u32(bfull + s), 1); mbar_init(smem_u32(bempty + s), 1); }
         for (int s = 0; s < kP1TStages; ++s) { mbar_init(smem_u32(ready + s), 4); mbar_init(smem_u32(tfree + s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), kP1EpiWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), EPI); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -176,7 +177,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
             __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= kP1FirstXform && warp < kP1FirstEpi) {
         // ============================ transform warps: y tile -> tf32 hi | lo -> TMEM A ring ============================
         // TMA wrote the tile with SWIZZLE_64B: 16-byte chunk c of row r sits at r * 64 + ((c ^ ((r >> 1) & 3)) << 4)
         const int q = warp & 3, row = q * 32 + lane;
@@ -214,12 +215,12 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
                 if (++t == kP1TStages) { t = 0; tph ^= 1; }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= kP1FirstEpi) {
         // ============================ epilogue warps ============================
-        const int ew = warp - 8;
+        const int ew = warp - kP1FirstEpi;
         const int q = warp & 3;
         const int part = ew >> 2;
-        constexpr int kParts = kP1EpiWarps / 4;
+        constexpr int kParts = EPI / 4;
         float* buf = epi_buf + ew * kEpiBufFloats;
         const int nblk = (bn + 31) / 32;
         int acc = 0; uint32_t acc_phase = 0;
@@ -233,7 +234,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
 #pragma unroll
                 for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = __uint_as_float(v[j]);
                 __syncwarp();
-                epilogue_block<1>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, nullptr, 0);
+                epilogue_block<PHASE>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, nullptr, 0);
                 __syncwarp();
             }
             tc_fence_before();
@@ -252,9 +253,9 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     }
 }
 
-size_t p1_smem_bytes(int bn, int a_stages, int b_stages) {
+size_t p1_smem_bytes(int bn, int a_stages, int b_stages, int epi) {
     return 1024 + (size_t)a_stages * kBM * kP1BK * 4 + (size_t)b_stages * 2 * bn * kP1BK * 4 +
-           (size_t)kP1EpiWarps * kEpiBufFloats * 4 + (2 * a_stages + 2 * b_stages + 2 * kP1TStages + 4) * 8 + 16;
+           (size_t)epi * kEpiBufFloats * 4 + (2 * a_stages + 2 * b_stages + 2 * kP1TStages + 4) * 8 + 16;
 }
 
 }  // namespace
@@ -268,23 +269,31 @@ void plan_tiles_p1(int ncols, int* bn, int* n_tiles) {
     *n_tiles = nt;
 }
 
-int plan_rings_p1(int bn, size_t smem_limit, int* a_stages, int* b_stages) {
+int plan_rings_p1(int phase, int bn, size_t smem_limit, int* a_stages, int* b_stages) {
+    const int epi = phase == 1 ? 8 : 12;
     int b = 5, a = 8;
-    while (b > 2 && p1_smem_bytes(bn, a, b) > smem_limit) --b;
-    while (a > 2 && p1_smem_bytes(bn, a, b) > smem_limit) --a;
-    if (p1_smem_bytes(bn, a, b) > smem_limit) return GPAD_ERR_UNSUPPORTED;
-    while (a < 12 && p1_smem_bytes(bn, a + 1, b) <= smem_limit) ++a;     // spare shared memory deepens the HBM-facing ring
+    while (b > 2 && p1_smem_bytes(bn, a, b, epi) > smem_limit) --b;
+    while (a > 2 && p1_smem_bytes(bn, a, b, epi) > smem_limit) --a;
+    if (p1_smem_bytes(bn, a, b, epi) > smem_limit) return GPAD_ERR_UNSUPPORTED;
+    while (a < 12 && p1_smem_bytes(bn, a + 1, b, epi) <= smem_limit) ++a;     // spare shared memory deepens the HBM-facing ring
     *a_stages = a; *b_stages = b;
     return GPAD_OK;
 }
 
-int launch_p1(const GemmDesc& g, const BatchKernelArgs& args, int num_sms, cudaStream_t s) {
-    const size_t smem = p1_smem_bytes(g.bn, g.a_stages, g.stages);
-    GPAD_CUDA(cudaFuncSetAttribute(tc_p1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+// phase 1: P_v = Y_v M_G^T (A = y_v); phase 2: Y+ = Zhat G_L^T (A = zhat_v, fp32, split in registers like y)
+int launch_p1(int phase, const GemmDesc& g, const BatchKernelArgs& args, int num_sms, cudaStream_t s) {
+    const size_t smem = p1_smem_bytes(g.bn, g.a_stages, g.stages, phase == 1 ? 8 : 12);
     const int tiles = g.m_tiles * g.n_tiles;
     const int grid = std::min(tiles, num_sms);
-    tc_p1_kernel<<<grid, kP1Threads, smem, s>>>(g.tmA_hi, g.tmB_hi, g.tmB_lo, g.k_pad / kP1BK, g.m_tiles, g.n_tiles, g.bn,
-                                                g.a_stages, g.stages, args, g.ncols_valid);
+    if (phase == 1) {
+        GPAD_CUDA(cudaFuncSetAttribute(tc_p1_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_p1_kernel<1, 8><<<grid, 32 * (kP1FirstEpi + 8), smem, s>>>(g.tmA_hi, g.tmB_hi, g.tmB_lo, g.k_pad / kP1BK, g.m_tiles, g.n_tiles, g.bn,
+                                                       g.a_stages, g.stages, args, g.ncols_valid);
+    } else {
+        GPAD_CUDA(cudaFuncSetAttribute(tc_p1_kernel<2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_p1_kernel<2, 12><<<grid, 32 * (kP1FirstEpi + 12), smem, s>>>(g.tmA_hi, g.tmB_hi, g.tmB_lo, g.k_pad / kP1BK, g.m_tiles, g.n_tiles, g.bn,
+                                                       g.a_stages, g.stages, args, g.ncols_valid);
+    }
     GPAD_CUDA(cudaGetLastError());
     return GPAD_OK;
 }

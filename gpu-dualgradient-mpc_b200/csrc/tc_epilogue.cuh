@@ -57,11 +57,15 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
                     }
                     const float zh = acc - gp[j];
                     __stcs(args.z + o, __fadd_rn(__fmul_rn(1.0f - args.it.theta, zo[j]), __fmul_rn(args.it.theta, zh)));
-                    if (args.it.store_zhat) __stcs(args.zhat + o, zh);
-                    float hi, lo;
-                    split_tf32(zh, hi, lo);
-                    args.zh_hi[o] = hi;      // re-read by product 2 of this iteration: default caching
-                    args.zh_lo[o] = lo;
+                    if (args.zh_single) {
+                        args.zhat[o] = zh;       // product 2's A operand (split there) and the zhat output
+                    } else {
+                        if (args.it.store_zhat) __stcs(args.zhat + o, zh);
+                        float hi, lo;
+                        split_tf32(zh, hi, lo);
+                        args.zh_hi[o] = hi;      // re-read by product 2 of this iteration: default caching
+                        args.zh_lo[o] = lo;
+                    }
                 }
             } else {
                 float yc[kChunk], yp[kChunk], pd[kChunk];
