@@ -358,9 +358,12 @@ def run_ours(args):
     if prec == G.PREC_TF32X3:
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "kernel": "tc_gemm_kernel (tcgen05 kind::tf32 x3)", "algorithmic_flops_per_launch": flops_per_launch,
+                "kernel": "tc_p1_kernel<1> (product 1) + tc_gemm_kernel<2> (product 2), tcgen05 kind::tf32 x3", "algorithmic_flops_per_launch": flops_per_launch,
                 "mean_launch_ms": k_ms, "launches_timed": int(c1 + c2), "product1_ms": ms1 / max(c1, 1), "product2_ms": ms2 / max(c2, 1),
                 "kernel_share_of_step": (ms1 + ms2) / elapsed_ms,
+                # the tensor pipe itself, measured on this pool's B200 with MMAs only (tests/ubench/ubench_tc.cu,
+                # profiles/r1_ubench_tc_issue_and_shapes.log): 2048 tf32 MAC/clk/SM -> 366 TF/s of 3xTF32-effective at ~1.81 GHz
+                "tcgen05_tf32x3_peak_measured": 366.0, "frac_of_tcgen05_peak": (achieved / 366.0) if achieved else None,
                 "peak_basis": f"{peak_src}: bf16 sustained {bf16_sus} TF/s / 2 (tf32) / 3 (hi*lo + lo*hi + hi*hi MMAs per product), of measured"}
     else:
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12

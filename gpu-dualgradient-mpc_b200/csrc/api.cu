@@ -72,6 +72,7 @@ struct gpad_handle_s {
     bool ops_smem = false;
     bool small = false;                       // lean one-CTA kernel (latency_small.cu)
     bool grid_lean = false;                   // lean whole-chip kernel (latency_grid.cu)
+    bool grid2 = false;                       // fixed-iteration solves run latency_grid2.cu (whole chip, vectors in registers)
     unsigned stamp_next = 16;                 // flag-in-data exchange epochs
     size_t ll_words = 0;
     int cha = 1, chb = 1;
@@ -372,12 +373,22 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
     else if (plan.small) snprintf(where, sizeof(where), "and per-row state in registers (lean kernel, %dx%d fragments)", plan.cha, plan.chb);
     else if (plan.regs) snprintf(where, sizeof(where), "in registers");
     else snprintf(where, sizeof(where), "%d/%d + %d/%d rows per CTA in shared memory, rest streamed from L2", p.res_a, p.rows_a, p.res_b, p.rows_b);
-    char buf[320];
+    char buf[448];
     snprintf(buf, sizeof(buf), "latency: persistent kernel, %s x%d CTAs, %d threads, lanes/row %d|%d, operators %s, smem %zu B/CTA",
              plan.sync == lat::SYNC_BLOCK ? "single-CTA" : plan.sync == lat::SYNC_CLUSTER ? "cluster(DSMEM)" : "cooperative-grid",
              plan.G, plan.threads, 1 << p.lg_a, 1 << p.lg_b, where,
              plan.grid_lean ? lat::grid_smem_bytes(p) : plan.small ? lat::small_smem_bytes(p) : lat::smem_bytes(p, plan.regs));
     h->desc = buf;
+    // fixed-iteration solves of a whole-chip plan run the second-generation kernel when it covers the problem
+    h->grid2 = plan.sync == lat::SYNC_GRID && !plan.small && !plan.grid_lean && !plan.regs && plan.G == h->num_sms &&
+               lat::grid2_supported(p, limit);
+    if (const char* e = getenv("GPAD_LATENCY_GRID2")) h->grid2 = h->grid2 && atoi(e) != 0;
+    if (h->grid2) {
+        snprintf(buf, sizeof(buf), "latency: persistent kernel, cooperative-grid x%d CTAs, 512 threads, column-partitioned GEMV: exchanged "
+                 "vectors in registers, M_G rows in shared memory (%zu B/CTA), G_L fragments in registers, counter barrier "
+                 "[tolerance-based solves: generic grid kernel]", plan.G, lat::grid2_smem_bytes(p));
+        h->desc = buf;
+    }
     return GPAD_OK;
 }
 
@@ -443,6 +454,10 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
         p.stamp_base = h->stamp_next;
         h->stamp_next += need;
         GPAD_TRY(lat::launch_grid(p, h->G, s));
+    } else if (h->grid2 && p.check_every == 0 && p.max_iter >= 1) {
+        GPAD_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned), s));
+        p.sched_smem = getenv("GPAD_G2_RELAXED") ? atoi(getenv("GPAD_G2_RELAXED")) : 0;
+        GPAD_TRY(lat::launch_grid2(p, h->G, s));
     } else {
         GPAD_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned), s));
         GPAD_TRY(lat::launch(p, h->sync_mode, h->ops_smem, h->G, h->threads, s));

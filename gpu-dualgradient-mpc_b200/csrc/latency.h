@@ -62,5 +62,10 @@ int launch_small(const Params& p, int cha, int chb, int cluster, int threads, cu
 size_t grid_smem_bytes(const Params& p);
 int launch_grid(const Params& p, int G, cudaStream_t stream);
 
+// latency_grid2.cu: second-generation whole-chip kernel (column partition, vectors in registers, fixed-iteration solves)
+size_t grid2_smem_bytes(const Params& p);
+int grid2_supported(const Params& p, size_t smem_limit);
+int launch_grid2(const Params& p, int G, cudaStream_t stream);
+
 }  // namespace lat
 }  // namespace gpad
