@@ -241,6 +241,33 @@ def test_latency_warm_start_and_device_buffers(torch_cuda, G, oracle):
     s.close()
 
 
+@pytest.mark.parametrize("dims", [(30, 30), (10, 100)])
+def test_latency_grid2_matches_generic_grid_kernel(torch_cuda, G, oracle, dims, monkeypatch):
+    """fixed-iteration solves of the whole-chip plans run latency_grid2.cu; the generic grid kernel (latency.cu) is the
+    cross-check on the same problem, cold and warm started, and both sit within the parity tolerance of the oracle"""
+    n_u, N = dims
+    pb, g_P, p_D, _ = battery_case(n_u, N, seed=9)
+    theta, beta = schedule(50)
+    res = {}
+    for name, env in (("grid2", "1"), ("generic", "0")):
+        monkeypatch.setenv("GPAD_LATENCY_GRID2", env)
+        s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_LATENCY)
+        assert ("column-partitioned" in s.description) == (name == "grid2"), s.description
+        cold = s.solve_host(g_P, p_D, theta, beta)
+        warm = s.solve_host(g_P, p_D, theta, beta, y0=cold["y_next"], y_prev0=cold["y"])
+        res[name] = (cold, warm)
+        s.close()
+    for k in VECS:
+        assert P.rel_inf(res["grid2"][0][k], res["generic"][0][k]) <= TOL, k
+        assert P.rel_inf(res["grid2"][1][k], res["generic"][1][k]) <= TOL, k
+    cold = res["grid2"][0]
+    ora = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, y0=cold["y_next"], y_prev0=cold["y"])
+    f64 = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, y0=cold["y_next"], y_prev0=cold["y"])
+    check_parity({k: res["grid2"][1][k] for k in VECS}, ora, f64, f"grid2 warm start {dims}")
+    assert int(res["grid2"][1]["iters"]) == 50 and int(res["grid2"][1]["status"]) == 0
+
+
+
 # ------------------------------------------------------------------------------------ tensor-core GEMM hook
 @pytest.mark.parametrize("cta_group", ["1", "2"])
 @pytest.mark.parametrize("shape", [(128, 16, 16), (128, 256, 64), (300, 200, 1000), (1000, 416, 2400), (257, 2400, 400)])
@@ -319,6 +346,54 @@ def test_batch_quadrotor_matches_oracle(torch_cuda, G, oracle, prec, monkeypatch
     worst = check_parity(gpu, ora, f64, f"batch {prec} quadrotor N={N}")
     print(f"\n quadrotor N={N} {prec}: worst GPU-vs-oracle rel_inf {worst:.2e}")
     s.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_batch_warm_start_matches_oracle(torch_cuda, G, oracle, prec):
+    """y_0 / y_{-1} handed in (receding-horizon warm start): the tcgen05 path needs P_{-1} = M_G y_{-1} first
+    (one extra product-1 launch, batch_tc_p1.cu), the result must match the oracle started from the same pair"""
+    n_u, N, B = 10, 15, 70
+    pb = P.battery(n_u, N)
+    X0 = np.random.default_rng(5).random((B, n_u)) - 0.5
+    g_P, p_D, _ = pb.instance(X0)
+    theta, beta = schedule(40)
+    s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED,
+                 precision=G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32, max_batch=B)
+    cold = s.solve_host(g_P, p_D, theta, beta)
+    warm = s.solve_host(g_P, p_D, theta, beta, y0=cold["y_next"], y_prev0=cold["y"])
+    worst = 0.0
+    for b in range(0, B, 9):
+        ora = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P[b], p_D[b], theta, beta, y0=cold["y_next"][b], y_prev0=cold["y"][b])
+        f64 = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P[b], p_D[b], theta, beta, y0=cold["y_next"][b], y_prev0=cold["y"][b])
+        worst = max(worst, check_parity({k: warm[k][b] for k in VECS}, ora, f64, f"batch warm start {prec} [{b}]"))
+    print(f"\n batch warm start {prec}: worst GPU-vs-oracle rel_inf {worst:.2e}")
+    s.close()
+
+
+@pytest.mark.parametrize("knobs", [{"GPAD_TC_P1": "0"}, {"GPAD_TC_P1": "0", "GPAD_TC_PFORM": "0"}, {"GPAD_TC_MC": "2"},
+                                   {"GPAD_TC_XF2": "1"}, {"GPAD_TC_P2TS": "1"}])
+def test_batch_tc_kernel_variants_match_default(torch_cuda, G, knobs, monkeypatch):
+    """the opt-in / first-generation tcgen05 kernels (legacy product 1 with and without the P-formulation, cluster
+    multicast of the operator tiles, product 2 staging zhat itself, product 2 through the TMEM-A kernel) against the
+    default plan on the same batch: same active sets, iterates within the parity tolerance"""
+    N, B = 20, 300
+    pb = P.quadrotor(N)
+    par = P.quadrotor_params(B, np.random.default_rng(11))
+    g_P, p_D, _ = pb.instance(par)
+    theta, beta = schedule(60)
+    s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
+    ref = s.solve_host(g_P, p_D, theta, beta)
+    s.close()
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
+    print("\n", s.description)
+    alt = s.solve_host(g_P, p_D, theta, beta)
+    s.close()
+    for k in VECS:
+        assert P.rel_inf(alt[k], ref[k]) <= 2e-5, (knobs, k, P.rel_inf(alt[k], ref[k]))
+    assert np.array_equal(alt["y_next"] > 0, ref["y_next"] > 0)
+
 
 
 @pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
