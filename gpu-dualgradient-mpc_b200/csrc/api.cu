@@ -386,7 +386,7 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
     if (h->grid2) {
         snprintf(buf, sizeof(buf), "latency: persistent kernel, cooperative-grid x%d CTAs, 512 threads, column-partitioned GEMV: exchanged "
                  "vectors in registers, M_G rows in shared memory (%zu B/CTA), G_L fragments in registers, counter barrier "
-                 "[tolerance-based solves: generic grid kernel]", plan.G, lat::grid2_smem_bytes(p));
+                 "[solves with a cost vector f and termination: generic grid kernel]", plan.G, lat::grid2_smem_bytes(p));
         h->desc = buf;
     }
     return GPAD_OK;
@@ -454,7 +454,7 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
         p.stamp_base = h->stamp_next;
         h->stamp_next += need;
         GPAD_TRY(lat::launch_grid(p, h->G, s));
-    } else if (h->grid2 && p.check_every == 0 && p.max_iter >= 1) {
+    } else if (h->grid2 && (p.check_every == 0 || p.f == nullptr) && p.max_iter >= 1) {
         GPAD_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned), s));
         p.sched_smem = getenv("GPAD_G2_RELAXED") ? atoi(getenv("GPAD_G2_RELAXED")) : 0;
         GPAD_TRY(lat::launch_grid2(p, h->G, s));

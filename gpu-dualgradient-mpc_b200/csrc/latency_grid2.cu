@@ -16,7 +16,8 @@
 //     which also owns that row's state (z, g_P / y_v, y_{v-1}, p_D, w_i) in registers;
 //   * exchange: plain stores to a global vector + the red.release / ld.acquire counter barrier of latency.cu
 //     (flag-per-CTA and multi-counter barriers measured slower, see GridBarrier).
-// Termination checking (check_every > 0) stays on the generic kernel; gpad_solve picks per call.
+// Termination: the z / zhat feasibility tests and the absolute duality-gap test (every solve without the cost vector f);
+// solves that hand in f (relative gap and dual-gap branch, two more operator products) stay on the generic kernel.
 #include <cuda_runtime.h>
 
 #include "gpad_internal.h"
@@ -86,7 +87,7 @@ struct GridBarrier {
 };
 
 // KA: float4 chunks of w per thread (ceil(mld / 4 / 512)); RBH: own rows of G_L per thread group
-template <int KA, int RBH>
+template <int KA, int RBH, bool CHECK>
 __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -103,7 +104,9 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
     float* scr_a = ops_a + (size_t)kRA * mld;         // [kRA][16]
     float* scr_b = scr_a + kRA * 16;                  // [H * RBH][wph]
     float* st_a = scr_b + H * RBH * wph;              // [3][kRA]   z, zhat, g_P of the own phase-A rows
-    float* st_b = st_a + 3 * kRA;                     // [5][64]    y_v, y_{v-1}, p_D, w_i, y_{v+1} of the own phase-B rows
+    float* st_b = st_a + 3 * kRA;                     // [6][64]    y_v, y_{v-1}, p_D, w_i, y_{v+1}, sbar of the own phase-B rows
+    float* red_l = st_b + 6 * 64;                     // [2][8]     termination partials of the two finalising warps
+    float* red_g = red_l + 16;                        // [8]        grid-wide termination quantities
 
     // ---- prologue: operators on chip, initial state ----
     for (int i = tid; i < kRA * CA; i += kT) {
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
     // threads 0..nb-1): keeping it in registers of all 512 threads pushed the kernel into local-memory spills
     float* z_r = st_a + tid; float* zh_r = st_a + kRA + tid; float* gp_r = st_a + 2 * kRA + tid;
     float* yv_r = st_b + tid; float* yp_r = st_b + 64 + tid; float* pd_r = st_b + 128 + tid;
-    float* w_r = st_b + 192 + tid; float* yn_r = st_b + 256 + tid;
+    float* w_r = st_b + 192 + tid; float* yn_r = st_b + 256 + tid; float* sb_r = st_b + 320 + tid;
     if (tid < kRA) { *z_r = 0.f; *zh_r = 0.f; *gp_r = (tid < na) ? p.g_P[a0 + tid] : 0.f; }
     if (tid < 64) {
         const bool ok = tid < nb;
@@ -149,8 +152,12 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
         *yv_r = yv; *yp_r = yp; *pd_r = ok ? p.p_D[b0 + tid] : 0.f;
         *w_r = __fadd_rn(yv, __fmul_rn(p.beta[0], __fsub_rn(yv, yp)));
         *yn_r = yv;
+        *sb_r = 0.f;
     }
     GridBarrier bar;
+    int iters = 0, status = GPAD_STATUS_MAX_ITER;
+    float out_viol = __int_as_float(0x7fc00000), out_gap = __int_as_float(0x7fc00000);
+    int until_check = CHECK ? p.check_every : 0x7fffffff, check_count = 0;
     __syncthreads();
 
     float theta_pf = p.theta[0];
@@ -163,6 +170,8 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
             theta_pf = __ldg(p.theta + v + 1);
             beta_pf = (v + 2 < p.max_iter) ? __ldg(p.beta + v + 2) : 0.f;
         }
+        const bool check = CHECK && (--until_check == 0);
+        if (check) { until_check = p.check_every; ++check_count; }
 
         // ---------------- phase A: zhat rows (step 2), z average (step 3) ----------------
         {
@@ -205,15 +214,93 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
             constexpr int kSh = RBH == 8 ? 2 : 1;
             if ((lane & ((1 << kSh) - 1)) == 0) scr_b[(h * RBH + (lane >> kSh)) * wph + wih] = tot;
             __syncthreads();
+            // termination partials of this row (acceldualgrad.m:66-79; same quantities as latency.cu)
+            float r_max_sbar = -INFINITY, r_max_rhat = -INFINITY, r_min_w = INFINITY, r_w_rhat = 0.f, r_w_dot = 0.f, r_bad = 0.f;
             if (tid < nb) {
                 float d = 0.f;
                 for (int k = 0; k < wph; ++k) d += scr_b[tid * wph + k];
-                const float s = d + (*w_r + *pd_r);
+                const float wi = *w_r, pd = *pd_r;
+                const float s = d + (wi + pd);
                 const float yn = 0.5f * (s + fabsf(s));
                 *yn_r = yn;
-                if (!last) {
+                if (CHECK) {
+                    const float rhat = d + pd;
+                    const float sb = __fadd_rn(__fmul_rn(one_minus, *sb_r), __fmul_rn(theta, rhat));
+                    *sb_r = sb;
+                    if (check) {
+                        r_max_sbar = sb; r_max_rhat = rhat; r_min_w = wi;
+                        r_w_rhat = wi * rhat; r_w_dot = wi * d;
+                        r_bad = isfinite(yn) ? 0.f : 1.f;
+                    }
+                }
+                if (!check && !last) {
                     // advance: w_{v+1}, y_{v-1} <- y_v <- y_{v+1}; not on the last iteration: w_v / y_v are outputs
                     const float yv = *yv_r;
+                    const float wn = __fadd_rn(yn, __fmul_rn(beta_next, __fsub_rn(yn, yv)));
+                    *w_r = wn;
+                    p.x_w[b0 + tid] = wn;
+                    *yp_r = yv;
+                    *yv_r = yn;
+                }
+            }
+            iters = v + 1;
+            if (check) {
+                // ---- termination test: every CTA reduces the same numbers in the same order and takes the same decision ----
+                float* xred = p.x_red + (check_count & 1) * 8 * p.g_pad;
+                if (warp < 2) {
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        r_max_sbar = fmaxf(r_max_sbar, __shfl_xor_sync(0xffffffffu, r_max_sbar, o));
+                        r_max_rhat = fmaxf(r_max_rhat, __shfl_xor_sync(0xffffffffu, r_max_rhat, o));
+                        r_min_w = fminf(r_min_w, __shfl_xor_sync(0xffffffffu, r_min_w, o));
+                        r_w_rhat += __shfl_xor_sync(0xffffffffu, r_w_rhat, o);
+                        r_w_dot += __shfl_xor_sync(0xffffffffu, r_w_dot, o);
+                        r_bad = fmaxf(r_bad, __shfl_xor_sync(0xffffffffu, r_bad, o));
+                    }
+                    if (lane == 0) {
+                        float* r = red_l + warp * 8;
+                        r[0] = r_max_sbar; r[1] = r_max_rhat; r[2] = r_min_w; r[3] = r_w_rhat; r[4] = r_w_dot; r[5] = r_bad;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    xred[0 * p.g_pad + c] = fmaxf(red_l[0], red_l[8]);
+                    xred[1 * p.g_pad + c] = fmaxf(red_l[1], red_l[9]);
+                    xred[2 * p.g_pad + c] = fminf(red_l[2], red_l[10]);
+                    xred[3 * p.g_pad + c] = red_l[3] + red_l[11];
+                    xred[4 * p.g_pad + c] = red_l[4] + red_l[12];
+                    xred[5 * p.g_pad + c] = fmaxf(red_l[5], red_l[13]);
+                }
+                bar.sync(p.barrier, p.sched_smem);
+                if (warp == 0) {
+                    float a = -INFINITY, b = -INFINITY, cm = INFINITY, d = 0.f, e = 0.f, g = 0.f;
+                    for (int k = lane; k < (int)gridDim.x; k += 32) {
+                        a = fmaxf(a, __ldcg(xred + 0 * p.g_pad + k)); b = fmaxf(b, __ldcg(xred + 1 * p.g_pad + k));
+                        cm = fminf(cm, __ldcg(xred + 2 * p.g_pad + k)); d += __ldcg(xred + 3 * p.g_pad + k);
+                        e += __ldcg(xred + 4 * p.g_pad + k); g = fmaxf(g, __ldcg(xred + 5 * p.g_pad + k));
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+                        cm = fminf(cm, __shfl_xor_sync(0xffffffffu, cm, o)); d += __shfl_xor_sync(0xffffffffu, d, o);
+                        e += __shfl_xor_sync(0xffffffffu, e, o); g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, o));
+                    }
+                    if (lane == 0) { red_g[0] = a; red_g[1] = b; red_g[2] = cm; red_g[3] = d; red_g[4] = e; red_g[5] = g; }
+                }
+                __syncthreads();
+                const float viol_z = p.L * red_g[0], viol_zhat = p.L * red_g[1];
+                out_viol = viol_z;
+                bool stop = false;
+                if (red_g[5] > 0.f) { status = GPAD_STATUS_NONFINITE; stop = true; }
+                else if (viol_z <= p.eps_g) { status = GPAD_STATUS_CONVERGED_Z; stop = true; }
+                else if (viol_zhat <= p.eps_g && red_g[2] >= 0.f) {      // f == NULL on this kernel: absolute gap only
+                    const float gapv = -p.L * red_g[3];
+                    out_gap = gapv;
+                    if (gapv <= p.eps_V) { status = GPAD_STATUS_CONVERGED_ZHAT; out_viol = viol_zhat; stop = true; }
+                }
+                if (stop) break;
+                if (!last && tid < nb) {
+                    const float yn = *yn_r, yv = *yv_r;
                     const float wn = __fadd_rn(yn, __fmul_rn(beta_next, __fsub_rn(yn, yv)));
                     *w_r = wn;
                     p.x_w[b0 + tid] = wn;
@@ -245,16 +332,17 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
     }
     bar.sync(p.barrier, p.sched_smem);
     if (c == 0 && tid == 0) {
-        *p.out_iters = p.max_iter;
-        *p.out_status = (*reinterpret_cast<volatile int*>(p.nonfinite_flag)) ? GPAD_STATUS_NONFINITE : GPAD_STATUS_MAX_ITER;
-        *p.out_max_viol = __int_as_float(0x7fc00000);
-        *p.out_gap = __int_as_float(0x7fc00000);
+        if (status == GPAD_STATUS_MAX_ITER && *reinterpret_cast<volatile int*>(p.nonfinite_flag)) status = GPAD_STATUS_NONFINITE;
+        *p.out_iters = iters;
+        *p.out_status = status;
+        *p.out_max_viol = out_viol;
+        *p.out_gap = out_gap;
     }
 }
 
 template <int KA, int RBH>
 int launch_t(const Params& p, int G, int H, size_t smem, cudaStream_t s) {
-    auto kern = gpad_grid2_kernel<KA, RBH>;
+    auto kern = p.check_every > 0 ? gpad_grid2_kernel<KA, RBH, true> : gpad_grid2_kernel<KA, RBH, false>;
     GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     Params pc = p;
     void* args[] = {&pc, &H};
@@ -273,7 +361,7 @@ static int groups_for(int nld) {
 size_t grid2_smem_bytes(const Params& p) {
     const int H = groups_for(p.nld);
     const int rbh = H ? (p.rows_b + H - 1) / H : 0;
-    return ((size_t)kRA * p.mld + kRA * 16 + (size_t)H * (rbh <= 8 ? 8 : 16) * (kT / (H ? H : 1) / 32) + 3 * kRA + 5 * 64) * sizeof(float);
+    return ((size_t)kRA * p.mld + kRA * 16 + (size_t)H * (rbh <= 8 ? 8 : 16) * (kT / (H ? H : 1) / 32) + 3 * kRA + 6 * 64 + 16 + 8) * sizeof(float);
 }
 
 // 1 when this plan covers the problem (p.rows_a / rows_b / mld / nld of the generic grid plan with G CTAs)

@@ -172,7 +172,8 @@ def test_latency_against_reference_golden(torch_cuda, G, golden_dir, case):
 
 
 @pytest.mark.parametrize("dims,eps", [((3, 4), 1e-2), ((3, 4), 1e-3), ((3, 4), 1e-4), ((10, 15), 1e-2),
-                                      ((10, 15), 1e-3), ((15, 10), 1e-3), ((10, 15), 1e-4)])
+                                      ((10, 15), 1e-3), ((15, 10), 1e-3), ((10, 15), 1e-4),
+                                      ((30, 30), 1e-2), ((10, 100), 1e-2)])   # whole-chip plans: grid2 without f, generic grid kernel with f
 @pytest.mark.parametrize("with_f", [False, True])
 def test_latency_termination_matches_oracle(torch_cuda, G, oracle, dims, eps, with_f):
     n_u, N = dims
@@ -186,14 +187,21 @@ def test_latency_termination_matches_oracle(torch_cuda, G, oracle, dims, eps, wi
     assert gpu["status"] == ora["status"], (gpu["status"], ora["status"])
     assert abs(gpu["iters"] - ora["iters"]) <= slack, (gpu["iters"], ora["iters"])
     if gpu["iters"] == ora["iters"]:
+        # long solves drift: the bound is relative to the reference's own distance from exact arithmetic after the
+        # same number of iterations (the fp64 arbiter run for exactly that many iterations, no termination test)
+        it = int(ora["iters"])
+        f64 = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta[:it], beta[:it])
         for k in VECS:
-            assert P.rel_inf(gpu[k], ora[k]) <= 3e-5, k
-        assert abs(gpu["max_viol"] - ora["max_viol"]) <= 1e-5 + 1e-3 * abs(ora["max_viol"])
+            noise = P.rel_inf(ora[k], f64[k])
+            assert P.rel_inf(gpu[k], ora[k]) <= max(3e-5, 1.5 * noise), (k, P.rel_inf(gpu[k], ora[k]), noise)
+        # max_viol = L * max(sbar): an fp32 rounding of the (cancelling) residual is scaled by L (1131 for (10,100))
+        assert abs(gpu["max_viol"] - ora["max_viol"]) <= max(1e-5, 1e-7 * pb.L) + 1e-3 * abs(ora["max_viol"])
     # check_every = 7 stops on a multiple of 7 and agrees with the oracle under the same setting
     gpu7 = s.solve_host(g_P, p_D, theta, beta, f=f if with_f else None, check_every=7, eps_g=eps, eps_V=eps)
     ora7 = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, f=f if with_f else None,
                         check_every=7, eps_g=eps, eps_V=eps)
-    assert gpu7["iters"] % 7 == 0 and abs(gpu7["iters"] - ora7["iters"]) <= 7 * slack
+    assert gpu7["status"] == ora7["status"]
+    assert (gpu7["iters"] % 7 == 0 or gpu7["status"] == 0) and abs(gpu7["iters"] - ora7["iters"]) <= 7 * slack
     s.close()
 
 
