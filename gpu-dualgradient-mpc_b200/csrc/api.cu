@@ -634,9 +634,11 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
     GPAD_TRY(dev_alloc(h, &st.red, (size_t)st.Bp * kRedStride));
     GPAD_TRY(dev_alloc(h, &st.done, st.Bp)); GPAD_TRY(dev_alloc(h, &st.iters, st.Bp)); GPAD_TRY(dev_alloc(h, &st.status, st.Bp));
     GPAD_TRY(dev_alloc(h, &st.max_viol, st.Bp)); GPAD_TRY(dev_alloc(h, &st.gap, st.Bp));
-    GPAD_TRY(dev_alloc(h, &st.active_count, 1));
+    GPAD_TRY(dev_alloc(h, &st.active_count, 2));
+    GPAD_TRY(dev_alloc(h, &st.need, st.Bp)); GPAD_TRY(dev_alloc(h, &st.zy, bnn));
+    GPAD_CUDA(cudaMemset(st.zy, 0, bnn * sizeof(float)));
     GPAD_TRY(dev_alloc(h, &h->stage_in, (size_t)h->cfg.max_batch * std::max(n, m)));
-    GPAD_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_active), sizeof(int)));
+    GPAD_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_active), 2 * sizeof(int)));
     char buf[640];
     if (tcp) {
         GPAD_TRY(dev_alloc(h, &st.zh_hi, bnn)); GPAD_TRY(dev_alloc(h, &st.zh_lo, bnn));
@@ -793,8 +795,27 @@ int solve_batch(gpad_handle_s* h, const gpad_solve_args_t* a) {
         if (check) {
             GPAD_TRY(launch_batch_decide(st, v + 1, h->cfg.L, a->eps_g, a->eps_V, a->f != nullptr, s));
             h->launches += 1;
-            GPAD_CUDA(cudaMemcpyAsync(h->h_active, st.active_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+            GPAD_CUDA(cudaMemcpyAsync(h->h_active, st.active_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
             GPAD_CUDA(cudaStreamSynchronize(s));
+            if (a->f && h->h_active[1] > 0) {
+                // dual-gap branch: z_y = M_G y_{v+1} - g_P and G_L z_y for the flagged instances (two more products)
+                BatchKernelArgs kd = k;
+                kd.dual = 1; kd.need = st.need; kd.zy = st.zy; kd.p_only = 0;
+                kd.it.check = 1; kd.it.beta = 0.f; kd.it.theta = 0.f; kd.it.store_zhat = 0;
+                kd.y_cur = k.y_next; kd.y_prev = k.y_next;      // beta = 0: w = y_{v+1}
+                if (tcp) { h->g1.tmA_hi = h->g1.tmY[(v + 1) % 3]; h->g1.tmA_lo = h->g1.tmY[(v + 1) % 3]; }
+                if (tcp) {
+                    GPAD_TRY(h->g1.p1 ? tc::launch_p1(1, h->g1, kd, h->num_sms, s) : tc::launch_gemm(1, h->g1, kd, nullptr, 0, h->num_sms, s));
+                    GPAD_TRY(tc::launch_gemm(2, h->g2, kd, nullptr, 0, h->num_sms, s));
+                } else {
+                    GPAD_TRY(launch_simt_product(1, h->op, kd, Bp_call, s));
+                    GPAD_TRY(launch_simt_product(2, h->op, kd, Bp_call, s));
+                }
+                GPAD_TRY(launch_batch_decide_dual(st, v + 1, h->cfg.L, a->eps_V, s));
+                h->launches += 3;
+                GPAD_CUDA(cudaMemcpyAsync(h->h_active, st.active_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+                GPAD_CUDA(cudaStreamSynchronize(s));
+            }
             if (*h->h_active <= 0) break;
         }
     }
@@ -963,8 +984,8 @@ int gpad_solve(gpad_handle_t h, const gpad_solve_args_t* a) {
     GPAD_REQUIRE(a->g_P && a->p_D, "gpad_solve: g_P and p_D are required");
     GPAD_REQUIRE(a->max_iter >= 1 && a->theta && a->beta, "gpad_solve: max_iter >= 1 and theta/beta are required");
     GPAD_REQUIRE(a->check_every <= 0 || (a->eps_g >= 0.f && a->eps_V >= 0.f), "gpad_solve: negative tolerance");
-    if (h->cfg.mode == GPAD_MODE_BATCH_SHARED && a->check_every > 0 && a->f) {
-        set_error("gpad_solve: the relative / dual gap tests (f != NULL) are evaluated in latency mode only");
+    if (h->cfg.mode == GPAD_MODE_BATCH_SHARED && a->check_every > 0 && a->f && (h->g2.xf2 || h->g2.p1)) {
+        set_error("gpad_solve: the dual-gap branch (f != NULL) is not available with the experimental product-2 kernels (GPAD_TC_XF2 / GPAD_TC_P2TS)");
         return GPAD_ERR_UNSUPPORTED;
     }
     GPAD_CUDA(cudaSetDevice(h->device));

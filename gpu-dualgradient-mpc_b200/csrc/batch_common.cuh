@@ -45,6 +45,11 @@ struct BatchKernelArgs {
     int p_only;            // warm start: this launch only produces P_{-1} = M_G y_{-1}
     const float* P_prev;   // [Bp][np] P_{v-1}
     float* P_cur;          // [Bp][np] P_v
+    // dual-gap evaluation launches (termination branch 3): product 1 forms z_y = M_G y_{v+1} - g_P for the
+    // flagged instances (need[b]) and f'z_y, product 2 reduces y'(G_L z_y) and y'p_D; nothing else is updated
+    int dual;
+    const int* need;       // [Bp] instance takes the dual-gap branch at this check
+    float* zy;             // [Bp][np] z_y (CUDA-core path; the tcgen05 path reuses zh_hi / zh_lo)
     int zh_single;         // product 2 splits zhat itself: product 1 stores zhat (fp32) only, not zh_hi / zh_lo
     int prefetch;          // tcgen05 path: epilogue warps pull the next tile's operands into L2 (batch_tc.cu)
 };
@@ -74,6 +79,20 @@ __device__ __forceinline__ void atomic_min_float(float* addr, float v) {
 template <bool SPLIT>
 __device__ __forceinline__ void epilogue1(const BatchKernelArgs& a, int b, int i, float acc, float& f_zhat) {
     const size_t o = (size_t)b * a.np + i;
+    if (a.dual) {
+        if (!a.need[b]) return;
+        const float zy = acc - a.g_P[o];
+        if (SPLIT) {
+            float hi, lo;
+            split_tf32(zy, hi, lo);
+            a.zh_hi[o] = hi;
+            a.zh_lo[o] = lo;
+        } else {
+            a.zy[o] = zy;
+        }
+        f_zhat = fmaf(a.f[o], zy, f_zhat);
+        return;
+    }
     const float zh = acc - a.g_P[o];
     a.z[o] = __fadd_rn(__fmul_rn(1.0f - a.it.theta, a.z[o]), __fmul_rn(a.it.theta, zh));   // unfused like the CPU build
     a.zhat[o] = zh;
@@ -97,6 +116,14 @@ __device__ __forceinline__ float momentum(float y, float y_prev, float beta) {
 // ---- product 2 epilogue for one element (instance b, row i of G_L) ----
 __device__ __forceinline__ void epilogue2(const BatchKernelArgs& a, int b, int i, float acc, Red2& r) {
     const size_t o = (size_t)b * a.mp + i;
+    if (a.dual) {           // y = y_{v+1} is an input here; red slots 3 / 4 collect y'(G_L z_y) and y'p_D
+        if (a.need[b]) {
+            const float y = a.y_next[o];
+            r.w_rhat = fmaf(y, acc, r.w_rhat);
+            r.w_dot = fmaf(y, a.p_D[o], r.w_dot);
+        }
+        return;
+    }
     const float wv = momentum(a.y_cur[o], a.y_prev[o], a.it.beta), pd = a.p_D[o];
     const float s = acc + (wv + pd);
     const float yn = 0.5f * (s + fabsf(s));

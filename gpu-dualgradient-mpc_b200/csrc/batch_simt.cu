@@ -146,38 +146,46 @@ __global__ void batch_init_kernel(int Bp, int np, int mp, float* __restrict__ z,
 
 __global__ void batch_reset_term_kernel(int Bp, float* __restrict__ red, int* __restrict__ done, int* __restrict__ iters,
                                         int* __restrict__ status, float* __restrict__ max_viol, float* __restrict__ gap,
-                                        int* __restrict__ active, int B, int max_iter) {
+                                        int* __restrict__ active, int* __restrict__ need, int B, int max_iter) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b == 0) *active = B;
+    if (b == 0) { active[0] = B; active[1] = 0; }
     if (b >= Bp) return;
     float* r = red + (size_t)b * kRedStride;
     r[0] = -INFINITY; r[1] = -INFINITY; r[2] = INFINITY; r[3] = 0.f; r[4] = 0.f; r[5] = 0.f; r[6] = 0.f; r[7] = 0.f;
     done[b] = 0;
+    need[b] = 0;
     iters[b] = max_iter;
     status[b] = GPAD_STATUS_MAX_ITER;
     max_viol[b] = __int_as_float(0x7fc00000);
     gap[b] = __int_as_float(0x7fc00000);
 }
 
-// termination decision per instance after a check iteration.  The dual-gap
-// branch (w has a negative entry) needs two more operator products and is only evaluated in
-// latency mode; here such instances keep iterating.
+// termination decision per instance after a check iteration (same tests as oracle_solve).
+// Instances whose zhat is feasible but whose w has a negative entry take the dual-gap branch when f is given: they
+// are flagged in need[] (V(zhat) and the violation parked in red[7] / red[6]) and decided by
+// batch_decide_dual_kernel after the two extra operator products.
 __global__ void batch_decide_kernel(int B, int iter_done, float L, float eps_g, float eps_V, int have_f,
                                     float* __restrict__ red, int* __restrict__ done, int* __restrict__ iters,
                                     int* __restrict__ status, float* __restrict__ max_viol, float* __restrict__ gap,
-                                    int* __restrict__ active) {
+                                    int* __restrict__ active, int* __restrict__ need) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B || done[b]) return;
     float* r = red + (size_t)b * kRedStride;
     const float viol_z = L * r[0], viol_zhat = L * r[1];
     int st = -1;
     float mv = viol_z, gp = gap[b];
+    bool dual = false;
+    float V = 0.f;
     if (r[6] > 0.f) st = GPAD_STATUS_NONFINITE;
     else if (viol_z <= eps_g) st = GPAD_STATUS_CONVERGED_Z;
-    else if (viol_zhat <= eps_g && r[2] >= 0.f) {
-        gp = -L * r[3];
-        const float V = 0.5f * (r[5] - L * r[4]);
-        if (gp <= eps_V || (have_f && gp <= V * eps_V / (1.0f + eps_V))) { st = GPAD_STATUS_CONVERGED_ZHAT; mv = viol_zhat; }
+    else if (viol_zhat <= eps_g) {
+        V = 0.5f * (r[5] - L * r[4]);
+        if (r[2] >= 0.f) {
+            gp = -L * r[3];
+            if (gp <= eps_V || (have_f && gp <= V * eps_V / (1.0f + eps_V))) { st = GPAD_STATUS_CONVERGED_ZHAT; mv = viol_zhat; }
+        } else if (have_f) {
+            dual = true;
+        }
     }
     max_viol[b] = mv;
     gap[b] = gp;
@@ -188,6 +196,36 @@ __global__ void batch_decide_kernel(int B, int iter_done, float L, float eps_g, 
         atomicSub(active, 1);
     }
     r[0] = -INFINITY; r[1] = -INFINITY; r[2] = INFINITY; r[3] = 0.f; r[4] = 0.f; r[5] = 0.f; r[6] = 0.f;
+    if (dual) {
+        need[b] = 1;
+        r[6] = viol_zhat;
+        r[7] = V;
+        atomicAdd(active + 1, 1);
+    }
+}
+
+// second half of the dual-gap branch: red[5] = f'z_y, red[3] = y'(G_L z_y), red[4] = y'p_D with y = y_{v+1}
+//   Phi(y) = f'z_y / 2 + (L/2) y'(G_L z_y) + L y'p_D;   stop when V(zhat) - Phi <= eps_V max(Phi, 1)
+__global__ void batch_decide_dual_kernel(int B, int iter_done, float L, float eps_V, float* __restrict__ red,
+                                         int* __restrict__ done, int* __restrict__ iters, int* __restrict__ status,
+                                         float* __restrict__ max_viol, float* __restrict__ gap, int* __restrict__ active,
+                                         int* __restrict__ need) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) active[1] = 0;
+    if (b >= B || !need[b]) return;
+    float* r = red + (size_t)b * kRedStride;
+    const float Phi = 0.5f * r[5] + 0.5f * L * r[3] + L * r[4];
+    const float gapv = r[7] - Phi;
+    gap[b] = gapv;
+    if (gapv <= eps_V * fmaxf(Phi, 1.0f)) {
+        status[b] = GPAD_STATUS_CONVERGED_DUAL;
+        iters[b] = iter_done;
+        max_viol[b] = r[6];
+        done[b] = 1;
+        atomicSub(active, 1);
+    }
+    need[b] = 0;
+    r[3] = 0.f; r[4] = 0.f; r[5] = 0.f; r[6] = 0.f; r[7] = 0.f;
 }
 
 // outputs of instance b after I_b iterations: y_I in yb[I % 3], y_{I-1} in yb[(I-1) % 3], and
@@ -246,14 +284,21 @@ int launch_batch_init(const BatchState& st, bool checking, cudaStream_t s) {
 
 int launch_batch_reset_term(const BatchState& st, int max_iter, cudaStream_t s) {
     batch_reset_term_kernel<<<(st.Bp + 255) / 256, 256, 0, s>>>(st.Bp, st.red, st.done, st.iters, st.status, st.max_viol,
-                                                              st.gap, st.active_count, st.B, max_iter);
+                                                              st.gap, st.active_count, st.need, st.B, max_iter);
     GPAD_CUDA(cudaGetLastError());
     return GPAD_OK;
 }
 
 int launch_batch_decide(const BatchState& st, int iter_done, float L, float eps_g, float eps_V, bool have_f, cudaStream_t s) {
     batch_decide_kernel<<<(st.B + 255) / 256, 256, 0, s>>>(st.B, iter_done, L, eps_g, eps_V, have_f ? 1 : 0, st.red, st.done,
-                                                          st.iters, st.status, st.max_viol, st.gap, st.active_count);
+                                                          st.iters, st.status, st.max_viol, st.gap, st.active_count, st.need);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+int launch_batch_decide_dual(const BatchState& st, int iter_done, float L, float eps_V, cudaStream_t s) {
+    batch_decide_dual_kernel<<<(st.B + 255) / 256, 256, 0, s>>>(st.B, iter_done, L, eps_V, st.red, st.done, st.iters, st.status,
+                                                               st.max_viol, st.gap, st.active_count, st.need);
     GPAD_CUDA(cudaGetLastError());
     return GPAD_OK;
 }
@@ -278,7 +323,7 @@ int launch_simt_product(int phase, const Operators& op, const BatchKernelArgs& a
         simt_gemm_kernel<1><<<g1, 256, 0, s>>>(args.y_cur, args.y_prev, args.mp, op.M_G, args.mp, args.mp, args);
     } else {
         dim3 g2((args.m + BN - 1) / BN, Bp / BM);
-        simt_gemm_kernel<2><<<g2, 256, 0, s>>>(args.zhat, nullptr, args.np, op.G_L, args.np, args.np, args);
+        simt_gemm_kernel<2><<<g2, 256, 0, s>>>(args.dual ? args.zy : args.zhat, nullptr, args.np, op.G_L, args.np, args.np, args);
     }
     GPAD_CUDA(cudaGetLastError());
     return GPAD_OK;

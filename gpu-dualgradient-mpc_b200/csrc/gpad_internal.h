@@ -63,7 +63,9 @@ struct BatchState {
     int* status = nullptr;  // [Bp]
     float* max_viol = nullptr;
     float* gap = nullptr;
-    int* active_count = nullptr;  // [1] instances still iterating
+    int* active_count = nullptr;  // [2] instances still iterating, instances waiting for the dual-gap evaluation
+    int* need = nullptr;          // [Bp] instance takes the dual-gap branch at this check
+    float* zy = nullptr;          // [Bp][np] z_y scratch of the dual-gap evaluation (CUDA-core path)
 };
 
 struct Operators {
@@ -85,6 +87,7 @@ int launch_unpad_y(float* dst_next, float* dst_cur, float* dst_w, int m, int B, 
 int launch_batch_init(const BatchState& st, bool checking, cudaStream_t s);
 int launch_batch_reset_term(const BatchState& st, int max_iter, cudaStream_t s);
 int launch_batch_decide(const BatchState& st, int iter_done, float L, float eps_g, float eps_V, bool have_f, cudaStream_t s);
+int launch_batch_decide_dual(const BatchState& st, int iter_done, float L, float eps_V, cudaStream_t s);
 int launch_batch_finite(const BatchState& st, const float* y_next, cudaStream_t s);
 int launch_simt_product(int phase, const Operators& op, const BatchKernelArgs& args, int Bp, cudaStream_t s);
 int launch_step_one(const float* y, const float* y_prev, float* w, float beta, int m, cudaStream_t s);

@@ -101,7 +101,7 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
                 float f_zhat = 0.f;
                 if (ok) {
                     float acc = val;
-                    if (args.pform) {
+                    if (args.pform && !args.dual) {
                         const size_t o = (size_t)b * args.np + c;
                         args.P_cur[o] = val;
                         acc = momentum(val, args.P_prev[o], args.it.beta);

@@ -404,14 +404,15 @@ def test_batch_tc_kernel_variants_match_default(torch_cuda, G, knobs, monkeypatc
 
 
 
+@pytest.mark.parametrize("with_f", [False, True])
 @pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
-def test_batch_termination_matches_oracle(torch_cuda, G, oracle, prec):
+def test_batch_termination_matches_oracle(torch_cuda, G, oracle, prec, with_f):
     n_u, N, B = 3, 4, 200
     pb = P.battery(n_u, N)
     X0 = np.random.default_rng(11).random((B, n_u)) - 0.5
-    g_P, p_D, _ = pb.instance(X0)
+    g_P, p_D, f = pb.instance(X0)
     theta, beta = schedule(400)
-    kw = dict(check_every=2, eps_g=1e-3, eps_V=1e-3)
+    kw = dict(check_every=2, eps_g=1e-3, eps_V=1e-3, f=f if with_f else None)
     s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED,
                  precision=G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32, max_batch=B)
     gpu = s.solve_host(g_P, p_D, theta, beta, **kw)
@@ -422,6 +423,31 @@ def test_batch_termination_matches_oracle(torch_cuda, G, oracle, prec):
     for k in VECS:
         assert P.rel_inf(gpu[k], ora[k]) <= 3e-5, k
     s.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_batch_dual_gap_branch(torch_cuda, G, oracle, prec):
+    """shared-operator batch with the cost vector f: instances that reach a check with a feasible zhat and a negative
+    entry in w take the V(zhat) - Phi(y) branch (two extra operator products for the flagged instances); statuses and
+    iteration counts follow the oracle instance by instance"""
+    n_u, N, B = 4, 6, 96
+    pb = P.battery(n_u, N)
+    X0 = np.random.default_rng(100).random((B, n_u)) - 0.5
+    g_P, p_D, f = pb.instance(X0)
+    theta, beta = schedule(3000)
+    kw = dict(check_every=1, eps_g=5e-2, eps_V=5e-2, f=f)
+    ora = oracle.solve_batch(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, **kw)
+    s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED,
+                 precision=G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32, max_batch=B)
+    gpu = s.solve_host(g_P, p_D, theta, beta, **kw)
+    s.close()
+    print("\n statuses (oracle):", {int(k): int((ora["status"] == k).sum()) for k in np.unique(ora["status"])})
+    assert (ora["status"] == 3).sum() > 0, "no instance exercised the dual-gap branch"
+    assert np.array_equal(gpu["status"], ora["status"]), np.flatnonzero(gpu["status"] != ora["status"])
+    assert np.array_equal(gpu["iters"], ora["iters"]), np.flatnonzero(gpu["iters"] != ora["iters"])
+    for k in VECS:
+        assert P.rel_inf(gpu[k], ora[k]) <= 3e-5, k
+
 
 
 def test_full_size_quadrotor_properties(torch_cuda, G, oracle):
