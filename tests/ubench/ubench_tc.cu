@@ -34,6 +34,7 @@ struct Cfg {
     int cluster;     // 1, 2 or 4: operator boxes are multicast to the whole cluster
     int m_tiles;     // distinct state tiles in the buffer
     int order;       // 0: the three MMAs of one accumulator back to back; 1: accumulators interleaved
+    int bulk_b;      // 1: operator k-blocks are contiguous pre-packed images fetched with ONE cp.async.bulk (no per-row TMA requests)
     int bk;          // K floats per k-block: 16 (64 B rows, SWIZZLE_64B) or 32 (128 B rows, SWIZZLE_128B)
     int warp_issue;  // 0: the whole issue loop runs under `if (lane == 0)`; 1: warp-uniform loop, elect.sync around each MMA
 };
@@ -61,7 +62,7 @@ template <int BK>
 __global__ void __launch_bounds__(192, 1)
 ub_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
           const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const Cfg c,
-          unsigned long long* __restrict__ cycles) {
+          unsigned long long* __restrict__ cycles, const float* __restrict__ bsrc) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t a_bytes = 128 * BK * 4, b_bytes = (uint32_t)c.bn * BK * 4, box_bytes = (uint32_t)c.box_rows * BK * 4;
@@ -107,6 +108,11 @@ ub_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                     tma_load_2d(base, &tmA0, kb * BK, m_tile * 128, fb);
                     if (c.a_tiles > 1) tma_load_2d(base + a_bytes, &tmA1, kb * BK, m_tile * 128, fb);
                     const uint32_t bb = base + c.a_tiles * a_bytes;
+                    if (c.bulk_b) {
+                        const char* src = reinterpret_cast<const char*>(bsrc) + (size_t)(kb % 64) * 2 * b_bytes;
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(bb), "l"(src), "r"(2 * b_bytes), "r"(fb) : "memory");
+                    } else
                     for (int bx = (int)rank; bx < nboxes; bx += c.cluster) {
                         if (c.cluster > 1) {
                             tma_load_2d_mc(bb + bx * box_bytes, &tmB0, kb * BK, bx * c.box_rows, fb, mask);
@@ -464,7 +470,7 @@ static CUtensorMap make_map(const float* ptr, int k_elems, int rows, int ld, int
     cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { printf("tensor map encode failed %d\n", (int)r); exit(1); }
     return m;
@@ -478,7 +484,7 @@ static void run(const char* name, Cfg c) {
     CUtensorMap a0 = make_map(dA0, K, ROWS_A, K, 128, c.bk), a1 = make_map(dA1, K, ROWS_A, K, 128, c.bk);
     CUtensorMap b0 = make_map(dB0, K, ROWS_B, K, c.box_rows, c.bk), b1 = make_map(dB1, K, ROWS_B, K, c.box_rows, c.bk);
     const size_t stage_bytes = (size_t)c.a_tiles * 128 * c.bk * 4 + 2 * (size_t)c.bn * c.bk * 4;
-    auto kern = c.bk == 32 ? ub_kernel<32> : ub_kernel<16>;
+    auto kern = c.bk == 32 ? ub_kernel<32> : c.bk == 8 ? ub_kernel<8> : ub_kernel<16>;
     const size_t smem = 1024 + c.stages * stage_bytes + (3 * c.stages + 2) * 8 + 16;
     if (smem > 232448) { printf("%-44s skipped (smem %zu)\n", name, smem); return; }
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -504,7 +510,7 @@ static void run(const char* name, Cfg c) {
     for (int rep = 0; rep < 4; ++rep) {
         CK(cudaMemsetAsync(dCyc, 0, 1024 * 8));
         CK(cudaEventRecord(e0));
-        CK(cudaLaunchKernelEx(&lc, kern, a0, a1, b0, b1, c, dCyc));
+        CK(cudaLaunchKernelEx(&lc, kern, a0, a1, b0, b1, c, dCyc, (const float*)dB0));
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -586,7 +592,7 @@ int main(int argc, char** argv) {
         for (int i = 1; i + 13 < argc; i += 14) {
             Cfg c{atoi(argv[i + 1]), atoi(argv[i + 2]), atoi(argv[i + 3]), atoi(argv[i + 4]), atoi(argv[i + 5]), atoi(argv[i + 6]),
                   atoi(argv[i + 7]), atoi(argv[i + 8]), atoi(argv[i + 9]), atoi(argv[i + 10]), atoi(argv[i + 11]), 512, atoi(argv[i + 12]),
-                  16, atoi(argv[i + 13])};
+                  0, 16, atoi(argv[i + 13])};
             run(argv[i], c);
         }
         return 0;
@@ -597,42 +603,42 @@ int main(int argc, char** argv) {
         const int ns[] = {64, 128, 208, 240, 256};
         for (int n : ns) {
             char nm[64]; snprintf(nm, sizeof nm, "mma only 128x%d", n);
-            run(nm, Cfg{n, n, n / 2, 2, 2, KB, T, 0, 1, 0, 1, 512, 0, 16, wi});
+            run(nm, Cfg{n, n, n / 2, 2, 2, KB, T, 0, 1, 0, 1, 512, 0, 0, 16, wi});
         }
-        run("mma only 2x128",                 Cfg{256, 128, 128, 2, 2, KB, T, 0, 1, 0, 1, 512, 0, 16, wi});
-        run("mma only 2x208",                 Cfg{416, 208, 104, 2, 2, KB, T, 0, 1, 0, 1, 512, 0, 16, wi});
-        run("mma only 2x256",                 Cfg{512, 256, 128, 2, 2, KB, T, 0, 1, 0, 1, 512, 0, 16, wi});
-        run("mma only 4x104",                 Cfg{416, 104, 104, 2, 2, KB, T, 0, 1, 0, 1, 512, 0, 16, wi});
-        run("tma+mma bn=208 (today, no xform)", Cfg{208, 208, 104, 2, 4, KB, T, 1, 1, 0, 1, 512, 0, 16, wi});
-        run("tma+mma+xform bn=208 (today)",   Cfg{208, 208, 104, 2, 4, KB, T, 1, 1, 1, 1, 512, 0, 16, wi});
-        run("tma+mma bn=416",                 Cfg{416, 208, 104, 2, 3, KB, T, 1, 1, 0, 1, 512, 0, 16, wi});
-        run("tma+mma+xform bn=416",           Cfg{416, 208, 104, 2, 3, KB, T, 1, 1, 1, 1, 512, 0, 16, wi});
-        run("tma+mma bn=416 cluster2",        Cfg{416, 208, 104, 2, 3, KB, T, 1, 1, 0, 2, 512, 0, 16, wi});
-        run("tma+mma+xform bn=416 cluster2",  Cfg{416, 208, 104, 2, 3, KB, T, 1, 1, 1, 2, 512, 0, 16, wi});
-        run("tma+mma bn=416 cluster4",        Cfg{416, 208, 104, 2, 3, KB, T, 1, 1, 0, 4, 512, 0, 16, wi});
+        run("mma only 2x128",                 Cfg{256, 128, 128, 2, 2, KB, T, 0, 1, 0, 1, 512, 0, 0, 16, wi});
+        run("mma only 2x208",                 Cfg{416, 208, 104, 2, 2, KB, T, 0, 1, 0, 1, 512, 0, 0, 16, wi});
+        run("mma only 2x256",                 Cfg{512, 256, 128, 2, 2, KB, T, 0, 1, 0, 1, 512, 0, 0, 16, wi});
+        run("mma only 4x104",                 Cfg{416, 104, 104, 2, 2, KB, T, 0, 1, 0, 1, 512, 0, 0, 16, wi});
+        run("tma+mma bn=208 (today, no xform)", Cfg{208, 208, 104, 2, 4, KB, T, 1, 1, 0, 1, 512, 0, 0, 16, wi});
+        run("tma+mma+xform bn=208 (today)",   Cfg{208, 208, 104, 2, 4, KB, T, 1, 1, 1, 1, 512, 0, 0, 16, wi});
+        run("tma+mma bn=416",                 Cfg{416, 208, 104, 2, 3, KB, T, 1, 1, 0, 1, 512, 0, 0, 16, wi});
+        run("tma+mma+xform bn=416",           Cfg{416, 208, 104, 2, 3, KB, T, 1, 1, 1, 1, 512, 0, 0, 16, wi});
+        run("tma+mma bn=416 cluster2",        Cfg{416, 208, 104, 2, 3, KB, T, 1, 1, 0, 2, 512, 0, 0, 16, wi});
+        run("tma+mma+xform bn=416 cluster2",  Cfg{416, 208, 104, 2, 3, KB, T, 1, 1, 1, 2, 512, 0, 0, 16, wi});
+        run("tma+mma bn=416 cluster4",        Cfg{416, 208, 104, 2, 3, KB, T, 1, 1, 0, 4, 512, 0, 0, 16, wi});
         // product 2 shapes: K = 416 (26 k-blocks), ten operator tiles of 240 per state tile
-        run("p2: mma only bn=240",            Cfg{240, 240, 120, 2, 3, 26, 40, 0, 1, 0, 1, 512, 0, 16, wi});
-        run("p2: tma+mma bn=240",             Cfg{240, 240, 120, 2, 3, 26, 40, 1, 1, 0, 1, 512, 0, 16, wi});
-        run("p2: tma+mma bn=240 cluster2",    Cfg{240, 240, 120, 2, 3, 26, 40, 1, 1, 0, 2, 512, 0, 16, wi});
-        run("p2: tma+mma bn=480",             Cfg{480, 240, 120, 2, 2, 26, 20, 1, 1, 0, 1, 512, 0, 16, wi});
-        run("p2: tma+mma bn=480 cluster2",    Cfg{480, 240, 120, 2, 2, 26, 20, 1, 1, 0, 2, 512, 0, 16, wi});
+        run("p2: mma only bn=240",            Cfg{240, 240, 120, 2, 3, 26, 40, 0, 1, 0, 1, 512, 0, 0, 16, wi});
+        run("p2: tma+mma bn=240",             Cfg{240, 240, 120, 2, 3, 26, 40, 1, 1, 0, 1, 512, 0, 0, 16, wi});
+        run("p2: tma+mma bn=240 cluster2",    Cfg{240, 240, 120, 2, 3, 26, 40, 1, 1, 0, 2, 512, 0, 0, 16, wi});
+        run("p2: tma+mma bn=480",             Cfg{480, 240, 120, 2, 2, 26, 20, 1, 1, 0, 1, 512, 0, 0, 16, wi});
+        run("p2: tma+mma bn=480 cluster2",    Cfg{480, 240, 120, 2, 2, 26, 20, 1, 1, 0, 2, 512, 0, 0, 16, wi});
     }
     printf("---- product 1 candidates: A = y only (one state tile), hi/lo built by transform warps into a TMEM A ring (TS MMAs)\n");
-    run("y-only smem-xform bn=208 (A2 layout)", Cfg{208, 208, 104, 2, 3, KB, T, 1, 1, 1, 1, 512, 0, 16, 1});
-    run("y-only tmem-A bn=208",            Cfg{208, 208, 104, 1, 3, KB, T, 1, 1, 2, 1, 512, 0, 16, 1});
-    run("y-only tmem-A bn=208 cluster2",   Cfg{208, 208, 104, 1, 3, KB, T, 1, 1, 2, 2, 512, 0, 16, 1});
-    run("mma only TS 128x208",             Cfg{208, 208, 104, 1, 3, KB, T, 0, 1, 2, 1, 512, 0, 16, 1});
-    run("mma only TS 2x208",               Cfg{416, 208, 104, 1, 3, KB, T, 0, 1, 2, 1, 512, 0, 16, 1});
-    run("y-only tmem-A bn=208 4 stages",   Cfg{208, 208, 104, 1, 4, KB, T, 1, 1, 2, 1, 512, 0, 16, 1});
-    run("y-only tmem-A bn=208 5 stages",   Cfg{208, 208, 104, 1, 5, KB, T, 1, 1, 2, 1, 512, 0, 16, 1});
-    run("y-only tmem-A bn=208 5 st cluster2", Cfg{208, 208, 104, 1, 5, KB, T, 1, 1, 2, 2, 512, 0, 16, 1});
-    run("y-only tmem-A bn=240 5 stages",   Cfg{240, 240, 120, 1, 5, KB, T, 1, 1, 2, 1, 512, 0, 16, 1});
-    run("y-only tmem-A bn=240 5 st cluster2", Cfg{240, 240, 120, 1, 5, KB, T, 1, 1, 2, 2, 512, 0, 16, 1});
-    run("tma+mma (no xform) bn=208 a1 5 st", Cfg{208, 208, 104, 1, 5, KB, T, 1, 1, 0, 1, 512, 0, 16, 1});
-    run("tma+mma (no xform) bn=208 a1 5 st cl2", Cfg{208, 208, 104, 1, 5, KB, T, 1, 1, 0, 2, 512, 0, 16, 1});
-    run("y-only tmem-A bn=416 (2x208)",    Cfg{416, 208, 104, 1, 3, KB, T, 1, 1, 2, 1, 512, 0, 16, 1});
-    run("y-only tmem-A bn=416 cluster2",   Cfg{416, 208, 104, 1, 3, KB, T, 1, 1, 2, 2, 512, 0, 16, 1});
-    run("y-only tmem-A bn=416 cluster4",   Cfg{416, 208, 104, 1, 3, KB, T, 1, 1, 2, 4, 512, 0, 16, 1});
+    run("y-only smem-xform bn=208 (A2 layout)", Cfg{208, 208, 104, 2, 3, KB, T, 1, 1, 1, 1, 512, 0, 0, 16, 1});
+    run("y-only tmem-A bn=208",            Cfg{208, 208, 104, 1, 3, KB, T, 1, 1, 2, 1, 512, 0, 0, 16, 1});
+    run("y-only tmem-A bn=208 cluster2",   Cfg{208, 208, 104, 1, 3, KB, T, 1, 1, 2, 2, 512, 0, 0, 16, 1});
+    run("mma only TS 128x208",             Cfg{208, 208, 104, 1, 3, KB, T, 0, 1, 2, 1, 512, 0, 0, 16, 1});
+    run("mma only TS 2x208",               Cfg{416, 208, 104, 1, 3, KB, T, 0, 1, 2, 1, 512, 0, 0, 16, 1});
+    run("y-only tmem-A bn=208 4 stages",   Cfg{208, 208, 104, 1, 4, KB, T, 1, 1, 2, 1, 512, 0, 0, 16, 1});
+    run("y-only tmem-A bn=208 5 stages",   Cfg{208, 208, 104, 1, 5, KB, T, 1, 1, 2, 1, 512, 0, 0, 16, 1});
+    run("y-only tmem-A bn=208 5 st cluster2", Cfg{208, 208, 104, 1, 5, KB, T, 1, 1, 2, 2, 512, 0, 0, 16, 1});
+    run("y-only tmem-A bn=240 5 stages",   Cfg{240, 240, 120, 1, 5, KB, T, 1, 1, 2, 1, 512, 0, 0, 16, 1});
+    run("y-only tmem-A bn=240 5 st cluster2", Cfg{240, 240, 120, 1, 5, KB, T, 1, 1, 2, 2, 512, 0, 0, 16, 1});
+    run("tma+mma (no xform) bn=208 a1 5 st", Cfg{208, 208, 104, 1, 5, KB, T, 1, 1, 0, 1, 512, 0, 0, 16, 1});
+    run("tma+mma (no xform) bn=208 a1 5 st cl2", Cfg{208, 208, 104, 1, 5, KB, T, 1, 1, 0, 2, 512, 0, 0, 16, 1});
+    run("y-only tmem-A bn=416 (2x208)",    Cfg{416, 208, 104, 1, 3, KB, T, 1, 1, 2, 1, 512, 0, 0, 16, 1});
+    run("y-only tmem-A bn=416 cluster2",   Cfg{416, 208, 104, 1, 3, KB, T, 1, 1, 2, 2, 512, 0, 0, 16, 1});
+    run("y-only tmem-A bn=416 cluster4",   Cfg{416, 208, 104, 1, 3, KB, T, 1, 1, 2, 4, 512, 0, 0, 16, 1});
     printf("---- split rings: deep state ring (HBM), shallow operator ring (L2), TMEM A ring\n");
     //                                         bn  box  a_st b_st t_st kb  tiles cl m_tiles
     run2("split bn=208 a4 b3 t3",         Cfg2{208, 104, 4, 3, 3, KB, T, 1, 512});
@@ -650,16 +656,36 @@ int main(int argc, char** argv) {
     run2("split bn=256 a8 b4 t6",         Cfg2{256, 128, 8, 4, 6, KB, T, 1, 512});
     run2("split bn=256 a8 b4 t6 cluster2", Cfg2{256, 128, 8, 4, 6, KB, T, 2, 512});
     printf("---- 128 B rows (BK = 32, SWIZZLE_128B) against 64 B rows (BK = 16)\n");
-    run("bk32 tma only bn=208 A2",          Cfg{208, 208, 104, 2, 2, K / 32, T, 1, 0, 0, 1, 512, 0, 32, 1});
-    run("bk32 tma only bn=416 A2 (2 st)",   Cfg{416, 208, 104, 2, 1, K / 32, T, 1, 0, 0, 1, 512, 0, 32, 1});
-    run("bk32 tma+mma bn=208 A2 2 st",      Cfg{208, 208, 104, 2, 2, K / 32, T, 1, 1, 0, 1, 512, 0, 32, 1});
-    run("bk32 tma+mma+xform bn=208 A2 2 st", Cfg{208, 208, 104, 2, 2, K / 32, T, 1, 1, 1, 1, 512, 0, 32, 1});
-    run("bk32 tma+mma bn=208 a1 3 st",      Cfg{208, 208, 104, 1, 3, K / 32, T, 1, 1, 0, 1, 512, 0, 32, 1});
-    run("bk32 tma+mma bn=240 A2 2 st (p2)", Cfg{240, 240, 120, 2, 2, 13, 40, 1, 1, 0, 1, 512, 0, 32, 1});
-    run("bk16 tma+mma bn=208 A2 2 st",      Cfg{208, 208, 104, 2, 2, K / 16, T, 1, 1, 0, 1, 512, 0, 16, 1});
-    run("bk16 tma+mma bn=208 A2 4 st",      Cfg{208, 208, 104, 2, 4, K / 16, T, 1, 1, 0, 1, 512, 0, 16, 1});
-    run("tma only A only (bn=16)",        Cfg{16, 16, 16, 2, 8, KB, T, 1, 0, 0, 1, 512, 0, 16, 0});
-    run("tma only bn=208 A2",             Cfg{208, 208, 104, 2, 4, KB, T, 1, 0, 0, 1, 512, 0, 16, 0});
-    run("tma only bn=416 A2",             Cfg{416, 208, 104, 2, 3, KB, T, 1, 0, 0, 1, 512, 0, 16, 0});
+    run("bk32 tma only bn=208 A2",          Cfg{208, 208, 104, 2, 2, K / 32, T, 1, 0, 0, 1, 512, 0, 0, 32, 1});
+    run("bk32 tma only bn=416 A2 (2 st)",   Cfg{416, 208, 104, 2, 1, K / 32, T, 1, 0, 0, 1, 512, 0, 0, 32, 1});
+    run("bk32 tma+mma bn=208 A2 2 st",      Cfg{208, 208, 104, 2, 2, K / 32, T, 1, 1, 0, 1, 512, 0, 0, 32, 1});
+    run("bk32 tma+mma+xform bn=208 A2 2 st", Cfg{208, 208, 104, 2, 2, K / 32, T, 1, 1, 1, 1, 512, 0, 0, 32, 1});
+    run("bk32 tma+mma bn=208 a1 3 st",      Cfg{208, 208, 104, 1, 3, K / 32, T, 1, 1, 0, 1, 512, 0, 0, 32, 1});
+    printf("---- operator k-blocks as contiguous pre-packed images, one cp.async.bulk each (no per-row TMA requests)\n");
+    run("p2 bn=240 A2 3 st, tensor-map B",  Cfg{240, 240, 120, 2, 3, 26, 40, 1, 1, 0, 1, 512, 0, 0, 16, 1});
+    run("p2 bn=240 A2 3 st, bulk B",        Cfg{240, 240, 120, 2, 3, 26, 40, 1, 1, 0, 1, 512, 0, 1, 16, 1});
+    run("p2 bn=240 A2 3 st, bulk B, tma only", Cfg{240, 240, 120, 2, 3, 26, 40, 1, 0, 0, 1, 512, 0, 1, 16, 1});
+    run("p2 bn=240 A2 3 st, tensor-map B, tma only", Cfg{240, 240, 120, 2, 3, 26, 40, 1, 0, 0, 1, 512, 0, 0, 16, 1});
+    run("p1 bn=208 A2 4 st, tensor-map B",  Cfg{208, 208, 104, 2, 4, KB, T, 1, 1, 0, 1, 512, 0, 0, 16, 1});
+    run("p1 bn=208 A2 4 st, bulk B",        Cfg{208, 208, 104, 2, 4, KB, T, 1, 1, 0, 1, 512, 0, 1, 16, 1});
+    printf("---- same with the state tiles L2 resident (8 distinct batch tiles), as zhat is in product 2\n");
+    run("p2 L2-A bn=240 3 st, tensor-map B",  Cfg{240, 240, 120, 2, 3, 26, 40, 1, 1, 0, 1, 8, 0, 0, 16, 1});
+    run("p2 L2-A bn=240 3 st, bulk B",        Cfg{240, 240, 120, 2, 3, 26, 40, 1, 1, 0, 1, 8, 0, 1, 16, 1});
+    run("p2 L2-A bn=240 3 st, tensor-map B, tma only", Cfg{240, 240, 120, 2, 3, 26, 40, 1, 0, 0, 1, 8, 0, 0, 16, 1});
+    run("p2 L2-A bn=240 3 st, bulk B, tma only", Cfg{240, 240, 120, 2, 3, 26, 40, 1, 0, 0, 1, 8, 0, 1, 16, 1});
+    run("p2 L2-A bn=240 mma only",            Cfg{240, 240, 120, 2, 3, 26, 40, 0, 1, 0, 1, 8, 0, 0, 16, 1});
+    printf("---- 32 B rows (BK = 8, SWIZZLE_32B): does the MMA read whole 128 B shared-memory lines?\n");
+    run("bk8  tma+mma bn=240 A2 6 st (p2)", Cfg{240, 240, 120, 2, 6, 52, 40, 1, 1, 0, 1, 512, 0, 0, 8, 1});
+    run("bk8  tma+mma bn=240 A2 8 st (p2)", Cfg{240, 240, 120, 2, 8, 52, 40, 1, 1, 0, 1, 512, 0, 0, 8, 1});
+    run("bk8  tma only bn=240 A2 8 st",     Cfg{240, 240, 120, 2, 8, 52, 40, 1, 0, 0, 1, 512, 0, 0, 8, 1});
+    run("bk16 tma+mma bn=240 A2 3 st (p2)", Cfg{240, 240, 120, 2, 3, 26, 40, 1, 1, 0, 1, 512, 0, 0, 16, 1});
+    run("bk16 tma+mma bn=240 A2 4 st (p2)", Cfg{240, 240, 120, 2, 4, 26, 40, 1, 1, 0, 1, 512, 0, 0, 16, 1});
+    run("bk8  tma+mma bn=208 A2 8 st",      Cfg{208, 208, 104, 2, 8, K / 8, T, 1, 1, 0, 1, 512, 0, 0, 8, 1});
+    run("bk32 tma+mma bn=240 A2 2 st (p2)", Cfg{240, 240, 120, 2, 2, 13, 40, 1, 1, 0, 1, 512, 0, 0, 32, 1});
+    run("bk16 tma+mma bn=208 A2 2 st",      Cfg{208, 208, 104, 2, 2, K / 16, T, 1, 1, 0, 1, 512, 0, 0, 16, 1});
+    run("bk16 tma+mma bn=208 A2 4 st",      Cfg{208, 208, 104, 2, 4, K / 16, T, 1, 1, 0, 1, 512, 0, 0, 16, 1});
+    run("tma only A only (bn=16)",        Cfg{16, 16, 16, 2, 8, KB, T, 1, 0, 0, 1, 512, 0, 0, 16, 0});
+    run("tma only bn=208 A2",             Cfg{208, 208, 104, 2, 4, KB, T, 1, 0, 0, 1, 512, 0, 0, 16, 0});
+    run("tma only bn=416 A2",             Cfg{416, 208, 104, 2, 3, KB, T, 1, 0, 0, 1, 512, 0, 0, 16, 0});
     return 0;
 }
