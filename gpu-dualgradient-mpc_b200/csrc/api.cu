@@ -456,7 +456,6 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
         GPAD_TRY(lat::launch_grid(p, h->G, s));
     } else if (h->grid2 && (p.check_every == 0 || p.f == nullptr) && p.max_iter >= 1) {
         GPAD_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned), s));
-        p.sched_smem = getenv("GPAD_G2_RELAXED") ? atoi(getenv("GPAD_G2_RELAXED")) : 0;
         GPAD_TRY(lat::launch_grid2(p, h->G, s));
     } else {
         GPAD_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned), s));

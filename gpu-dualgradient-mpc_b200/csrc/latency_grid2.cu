@@ -70,16 +70,15 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
 
 // Grid-wide barrier: one release-add per CTA on a single counter, thread 0 spins with ld.acquire.  Measured on B200
 // (battery (10,100), 100 iterations): this counter 578 us; arrivals spread over 4 counters polled with relaxed loads
-// + one fence 703 us; one epoch flag per CTA polled by 148 threads 917 us, by one warp 1125 us.
+// + one fence 703 us; one epoch flag per CTA polled by 148 threads 917 us, by one warp 1125 us; {value, tag} records
+// validated by the consumers + relaxed arrive (no fence) 610 us after the shuffle rework (this barrier: 514 us).
 struct GridBarrier {
     unsigned epoch = 0;
-    __device__ __forceinline__ void sync(unsigned* counter, int mode = 0) {
-        const bool p_relaxed = mode == 1;
+    __device__ __forceinline__ void sync(unsigned* counter) {
         __syncthreads();                      // this CTA's published stores precede thread 0's release
-        if (threadIdx.x == 0 && mode != 2) {
+        if (threadIdx.x == 0) {
             epoch += gridDim.x;
-            if (p_relaxed) asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
-            else red_release_add(counter, 1u);
+            red_release_add(counter, 1u);
             while (ld_acquire(counter) < epoch) {}
         }
         __syncthreads();
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
                 p.x_zhat[a0 + tid] = zh;
             }
         }
-        bar.sync(p.barrier, p.sched_smem);
+        bar.sync(p.barrier);
         float4 zc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tc < CB) zc = ld_cg4(p.x_zhat + 4 * tc);
 
@@ -271,7 +270,7 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
                     xred[4 * p.g_pad + c] = red_l[4] + red_l[12];
                     xred[5 * p.g_pad + c] = fmaxf(red_l[5], red_l[13]);
                 }
-                bar.sync(p.barrier, p.sched_smem);
+                bar.sync(p.barrier);
                 if (warp == 0) {
                     float a = -INFINITY, b = -INFINITY, cm = INFINITY, d = 0.f, e = 0.f, g = 0.f;
                     for (int k = lane; k < (int)gridDim.x; k += 32) {
@@ -310,7 +309,7 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
             }
         }
         if (!last) {
-            bar.sync(p.barrier, p.sched_smem);
+            bar.sync(p.barrier);
 #pragma unroll
             for (int k = 0; k < KA; ++k) {
                 const int ch = tid + k * kT;
@@ -330,7 +329,7 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
         p.out_z[a0 + tid] = *z_r;
         p.out_zhat[a0 + tid] = *zh_r;
     }
-    bar.sync(p.barrier, p.sched_smem);
+    bar.sync(p.barrier);
     if (c == 0 && tid == 0) {
         if (status == GPAD_STATUS_MAX_ITER && *reinterpret_cast<volatile int*>(p.nonfinite_flag)) status = GPAD_STATUS_NONFINITE;
         *p.out_iters = iters;
