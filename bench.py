@@ -246,6 +246,37 @@ def per_instance_probe(torch, G, B=262144):
     return res
 
 
+def battery_batch_probe(torch, G, B=4096):
+    """BASELINE config 3: 4096 battery-balancing QPs (10,100) sharing M_G / G_L, random initial states, fixed 100
+    iterations, tensor-core GEMM mode; algorithmic flops 4 n m per instance-iteration"""
+    n_u, N = 10, 100
+    prob = G.Problem("battery", n_u=n_u, N=N)
+    M_G, G_L = prob.operators()
+    n, m = prob.n, prob.m
+    rng = np.random.default_rng(3)
+    g_P, p_D, _ = prob.instances(rng.random((B, n_u)) - 0.5, want_f=False)
+    theta, beta = G.schedule(ITERS)
+    s = G.Solver(n_u, N, m, prob.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
+    dg, dp = torch.from_numpy(g_P).cuda(), torch.from_numpy(p_D).cuda()
+    dz = torch.empty((B, n), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        s.solve_device(B, dg, dp, theta, beta, ITERS, stream=st, z=dz)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        s.solve_device(B, dg, dp, theta, beta, ITERS, stream=st, z=dz)
+    e1.record(); e1.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / reps
+    res = {"workload": f"battery(10,100) n={n} m={m}, {B} QPs sharing M_G/G_L, 100 iterations", "solves_per_s": B / sec,
+           "ms_per_batch": sec * 1e3, "achieved_TFLOPs": 4.0 * n * m * B * ITERS / sec / 1e12,
+           "z_finite": bool(torch.isfinite(dz).all()), "path": s.description}
+    s.close()
+    return res
+
+
 def run_ours(args):
     import torch
     import gpad_b200 as G
@@ -373,6 +404,7 @@ def run_ours(args):
     cpu_val, cpu_info = cpu_rate(args.cpu_budget)
     lat = latency_probe(torch, G) if not args.no_latency else None
     per_inst = per_instance_probe(torch, G) if not args.no_latency else None
+    bat3 = battery_batch_probe(torch, G) if not args.no_latency else None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -389,6 +421,7 @@ def run_ours(args):
         "clocks": clocks,
         "single_qp_latency": lat,
         "per_instance_operators": per_inst,
+        "battery_batch_4096": bat3,
     }
     emit_line(line)
     if dist is not None:

@@ -450,6 +450,29 @@ def test_batch_dual_gap_branch(torch_cuda, G, oracle, prec):
 
 
 
+def test_batch_battery_main_size_matches_oracle(torch_cuda, G, oracle):
+    """BASELINE config 3 shapes: battery (10,100), n = 1000, m = 4200 (5 product-1 tiles of 208 columns, 17 product-2
+    tiles), a batch that is not a multiple of the 128-row tile; a few instances against the oracle, and the
+    tensor-core path against the CUDA-core path on all of them"""
+    n_u, N, B = 10, 100, 300
+    pb = P.battery(n_u, N)
+    X0 = np.random.default_rng(21).random((B, n_u)) - 0.5
+    g_P, p_D, _ = pb.instance(X0)
+    theta, beta = schedule(25)
+    res = {}
+    for prec, code in (("fp32", G.PREC_FP32), ("tf32x3", G.PREC_TF32X3)):
+        s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=code, max_batch=B)
+        res[prec] = s.solve_host(g_P, p_D, theta, beta)
+        s.close()
+    for k in VECS:
+        assert P.rel_inf(res["tf32x3"][k], res["fp32"][k]) <= (2 * TOL if k == "zhat" else TOL), k
+    for b in (0, 131, 299):
+        d = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P[b], p_D[b], theta, beta)
+        o32 = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P[b], p_D[b], theta, beta)
+        check_parity({k: res["tf32x3"][k][b] for k in VECS}, o32, d, f"battery (10,100) batch instance {b}")
+
+
+
 def test_full_size_quadrotor_properties(torch_cuda, G, oracle):
     """BASELINE config 4 shapes (n=400, m=2400) at a batch the oracle cannot follow: size-independent
     properties instead -- the tensor-core path agrees with the CUDA-core path, duplicate instances
