@@ -241,7 +241,7 @@ def per_instance_probe(torch, G, B=262144):
     res = {"workload": f"battery(3,4) n={n} m={m}, {B} QPs with per-instance operators, 100 iterations", "solves_per_s": B / sec,
            "ms_per_batch": sec * 1e3, "algorithmic_bytes_per_solve": bytes_min // B, "achieved_GBps": bytes_min / sec / 1e9,
            "hbm_peak_GBps": hbm, "frac_of_hbm_roofline": bytes_min / sec / 1e9 / hbm, "path": s.description,
-           "note": "instruction-bound: ~100 warp instructions per QP-iteration vs an HBM floor of 0.83 ms per 1M solves"}
+           "note": "latency-bound: one dependent shuffle/FMA chain per iteration and ~16 QPs in flight per SM, vs an HBM floor of 0.83 ms per 1M solves"}
     s.close()
     return res
 

@@ -62,6 +62,9 @@ int launch_small(const Params& p, int cha, int chb, int cluster, int threads, cu
 size_t grid_smem_bytes(const Params& p);
 int launch_grid(const Params& p, int G, cudaStream_t stream);
 
+// latency_warp.cu: one warp per QP for the tiny problems (n <= 16, m <= 64), latency and per-instance batch modes
+int warp_supported(const Params& p);
+int launch_warp(const Params& p, cudaStream_t stream);
 // latency_grid2.cu: second-generation whole-chip kernel (column partition, vectors in registers, fixed-iteration solves)
 size_t grid2_smem_bytes(const Params& p);
 int grid2_supported(const Params& p, size_t smem_limit);

@@ -22,6 +22,7 @@
 
 #include "gpad_internal.h"
 #include "latency.h"
+#include "lat_util.cuh"
 
 namespace gpad {
 namespace lat {
@@ -35,30 +36,6 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc)
     acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
     return acc;
 }
-// sums R per-lane values over the 32 lanes of a warp with R - 1 + log2(32 / R) shuffles instead of 5 R: every
-// step pairs lanes that differ in one bit, each keeps one half of the values and hands over the other half.
-// On return lane l holds the warp total of value (l >> log2(32 / R)) & (R - 1).
-template <int R>
-__device__ __forceinline__ float warp_sum_transposed(float (&v)[R], int lane) {
-    static_assert(R == 8 || R == 16, "R");
-    int o = 16;
-#pragma unroll
-    for (int s = R / 2; s >= 1; s >>= 1, o >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < s; ++i) {
-            const float send = up ? v[i] : v[i + s];
-            const float keep = up ? v[i + s] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-    }
-    float t = v[0];
-#pragma unroll
-    for (; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    return t;
-}
-__device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -1,0 +1,186 @@
+// latency_warp.cu -- ONE WARP per QP for the tiny problems (n <= 16, m <= 64; the reference's default battery
+// problem is n = 12, m = 56, gpad.m:4-5): latency mode with one warp, GPAD_MODE_BATCH_PER_INSTANCE with four warps
+// (= four independent QPs) per CTA.
+//
+// The lean one-CTA kernel (latency_small.cu) spends two __syncthreads and two shared-memory exchanges per iteration on
+// a problem whose whole state fits one warp.  Here lane l owns dual entries i = l and l + 32:
+//   phase A (step 2, kernel_functions.cu:16-64): lane l holds COLUMNS l, l+32 of M_G, so its own w_i never leaves
+//            the lane; the 16 (padded) row sums are reduced with the transposed butterfly (16 shuffles) and the
+//            owner lanes apply -g_P and the z average (step 3);
+//   phase B (step 4 + step 1, kernel_functions.cu:142-200, 7-14): zhat is broadcast with n shuffles, lane l holds
+//            ROWS l, l+32 of G_L and finishes y_{v+1}, w_{v+1} for its own entries.
+// No shared memory, no block barrier, no global traffic in the loop except the (cached) theta / beta schedule.
+// Termination: the z / zhat feasibility tests and the absolute gap (solves without the cost vector f); solves that
+// hand in f use latency_small.cu.
+#include <cuda_runtime.h>
+
+#include "gpad_internal.h"
+#include "lat_util.cuh"
+#include "latency.h"
+
+namespace gpad {
+namespace lat {
+
+namespace {
+
+constexpr int kWR = 16;    // rows of M_G, padded
+constexpr int kMR = 2;     // dual entries per lane
+constexpr int kWarpsPerCta = 4;
+
+template <bool CHECK>
+__global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp_kernel(const Params p_in, int warps_per_cta) {
+    Params p = p_in;
+    const int lane = threadIdx.x & 31;
+    const size_t inst = (size_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    if (inst >= (size_t)(p.batch > 1 ? p.batch : 1)) return;       // whole warps leave together; nothing below is block-wide
+    p.M_G += inst * p.op_stride_a; p.G_L += inst * p.op_stride_b;
+    p.g_P += inst * p.n; p.p_D += inst * p.m;
+    if (p.y0) p.y0 += inst * p.m;
+    if (p.y_prev0) p.y_prev0 += inst * p.m;
+    const int n = p.n, m = p.m;
+
+    // ---- operators and state into registers ----
+    float mg[kMR][kWR], gl[kMR][kWR];
+    float yv[kMR], yp[kMR], pd[kMR], w[kMR], yn[kMR], sb[kMR];
+    bool own[kMR];
+    const float beta0 = p.beta[0];
+#pragma unroll
+    for (int j = 0; j < kMR; ++j) {
+        const int i = lane + 32 * j;
+        own[j] = i < m;
+#pragma unroll
+        for (int r = 0; r < kWR; ++r) {
+            mg[j][r] = (own[j] && r < n) ? __ldg(p.M_G + (size_t)r * p.mld + i) : 0.f;
+            gl[j][r] = (own[j] && r < n) ? __ldg(p.G_L + (size_t)i * p.nld + r) : 0.f;
+        }
+        yv[j] = (own[j] && p.y0) ? p.y0[i] : 0.f;
+        yp[j] = (own[j] && p.y_prev0) ? p.y_prev0[i] : 0.f;
+        pd[j] = own[j] ? p.p_D[i] : 0.f;
+        w[j] = __fadd_rn(yv[j], __fmul_rn(beta0, __fsub_rn(yv[j], yp[j])));     // step 1 of iteration 0
+        yn[j] = yv[j];
+        sb[j] = 0.f;
+    }
+    const int r_me = (lane >> 1) & (kWR - 1);          // the row whose total this lane holds after the reduction
+    const float gp_me = r_me < n ? p.g_P[r_me] : 0.f;
+    float z_me = 0.f, zh_me = 0.f;
+
+    int iters = 0, status = GPAD_STATUS_MAX_ITER;
+    float out_viol = __int_as_float(0x7fc00000), out_gap = __int_as_float(0x7fc00000);
+    int until_check = CHECK ? p.check_every : 0x7fffffff;
+    float theta_pf = __ldg(p.theta), beta_pf = p.max_iter > 1 ? __ldg(p.beta + 1) : 0.f;
+    for (int v = 0; v < p.max_iter; ++v) {
+        const float theta = theta_pf, one_minus = 1.0f - theta;
+        const bool last = (v + 1 == p.max_iter);
+        const float beta_next = last ? 0.f : beta_pf;
+        if (!last) {
+            theta_pf = __ldg(p.theta + v + 1);
+            beta_pf = (v + 2 < p.max_iter) ? __ldg(p.beta + v + 2) : 0.f;
+        }
+        const bool check = CHECK && (--until_check == 0);
+        if (check) until_check = p.check_every;
+
+        // ---------------- phase A ----------------
+        float acc[kWR];
+#pragma unroll
+        for (int r = 0; r < kWR; ++r) acc[r] = fmaf(mg[1][r], w[1], mg[0][r] * w[0]);
+        const float tot = warp_sum_transposed<kWR>(acc, lane);
+        zh_me = tot - gp_me;
+        z_me = __fadd_rn(__fmul_rn(one_minus, z_me), __fmul_rn(theta, zh_me));
+
+        // ---------------- phase B ----------------
+        float d[kMR] = {0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < kWR; ++c) {
+            const float zc = __shfl_sync(0xffffffffu, zh_me, 2 * c);
+#pragma unroll
+            for (int j = 0; j < kMR; ++j) d[j] = fmaf(gl[j][c], zc, d[j]);
+        }
+        float r_max_sbar = -INFINITY, r_max_rhat = -INFINITY, r_min_w = INFINITY, r_w_rhat = 0.f, r_bad = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMR; ++j) {
+            const float s = d[j] + (w[j] + pd[j]);
+            yn[j] = 0.5f * (s + fabsf(s));
+            if (CHECK) {
+                const float rhat = d[j] + pd[j];
+                sb[j] = __fadd_rn(__fmul_rn(one_minus, sb[j]), __fmul_rn(theta, rhat));
+                if (check && own[j]) {
+                    r_max_sbar = fmaxf(r_max_sbar, sb[j]); r_max_rhat = fmaxf(r_max_rhat, rhat); r_min_w = fminf(r_min_w, w[j]);
+                    r_w_rhat = fmaf(w[j], rhat, r_w_rhat);
+                    if (!isfinite(yn[j])) r_bad = 1.f;
+                }
+            }
+        }
+        iters = v + 1;
+        if (check) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                r_max_sbar = fmaxf(r_max_sbar, __shfl_xor_sync(0xffffffffu, r_max_sbar, o));
+                r_max_rhat = fmaxf(r_max_rhat, __shfl_xor_sync(0xffffffffu, r_max_rhat, o));
+                r_min_w = fminf(r_min_w, __shfl_xor_sync(0xffffffffu, r_min_w, o));
+                r_w_rhat += __shfl_xor_sync(0xffffffffu, r_w_rhat, o);
+                r_bad = fmaxf(r_bad, __shfl_xor_sync(0xffffffffu, r_bad, o));
+            }
+            const float viol_z = p.L * r_max_sbar, viol_zhat = p.L * r_max_rhat;
+            out_viol = viol_z;
+            bool stop = false;
+            if (r_bad > 0.f) { status = GPAD_STATUS_NONFINITE; stop = true; }
+            else if (viol_z <= p.eps_g) { status = GPAD_STATUS_CONVERGED_Z; stop = true; }
+            else if (viol_zhat <= p.eps_g && r_min_w >= 0.f) {       // f == NULL on this kernel: absolute gap only
+                const float gapv = -p.L * r_w_rhat;
+                out_gap = gapv;
+                if (gapv <= p.eps_V) { status = GPAD_STATUS_CONVERGED_ZHAT; out_viol = viol_zhat; stop = true; }
+            }
+            if (stop) break;
+        }
+        if (!last) {
+            // advance: w_{v+1}, y_{v-1} <- y_v <- y_{v+1}; not on the last iteration: w_v / y_v are outputs
+#pragma unroll
+            for (int j = 0; j < kMR; ++j) {
+                w[j] = __fadd_rn(yn[j], __fmul_rn(beta_next, __fsub_rn(yn[j], yv[j])));
+                yp[j] = yv[j];
+                yv[j] = yn[j];
+            }
+        }
+    }
+
+    // ---------------- outputs (main.cu:176-180 + termination outputs) ----------------
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < kMR; ++j) {
+        const int i = lane + 32 * j;
+        if (own[j]) {
+            if (p.out_y_next) p.out_y_next[inst * m + i] = yn[j];
+            if (p.out_y) p.out_y[inst * m + i] = yv[j];
+            if (p.out_w) p.out_w[inst * m + i] = w[j];
+            bad = bad || !isfinite(yn[j]);
+        }
+    }
+    if ((lane & 1) == 0 && r_me < n) {
+        if (p.out_z) p.out_z[inst * n + r_me] = z_me;
+        if (p.out_zhat) p.out_zhat[inst * n + r_me] = zh_me;
+    }
+    if (status == GPAD_STATUS_MAX_ITER && __any_sync(0xffffffffu, bad)) status = GPAD_STATUS_NONFINITE;
+    if (lane == 0) {
+        if (p.out_iters) p.out_iters[inst] = iters;
+        if (p.out_status) p.out_status[inst] = status;
+        if (p.out_max_viol) p.out_max_viol[inst] = out_viol;
+        if (p.out_gap) p.out_gap[inst] = out_gap;
+    }
+}
+
+}  // namespace
+
+int warp_supported(const Params& p) { return p.n <= kWR && p.m <= 32 * kMR; }
+
+int launch_warp(const Params& p, cudaStream_t stream) {
+    const int B = p.batch > 1 ? p.batch : 1;
+    const int wpc = B > 1 ? kWarpsPerCta : 1;
+    const int grid = (B + wpc - 1) / wpc;
+    if (p.check_every > 0) gpad_warp_kernel<true><<<grid, 32 * wpc, 0, stream>>>(p, wpc);
+    else gpad_warp_kernel<false><<<grid, 32 * wpc, 0, stream>>>(p, wpc);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+}  // namespace lat
+}  // namespace gpad

@@ -46,7 +46,9 @@ def check_parity(gpu, ora, f64, label=""):
         e64 = P.rel_inf(gpu[k], f64[k])
         eor = P.rel_inf(gpu[k], ora[k])
         noise = P.rel_inf(ora[k], f64[k])
-        assert eor <= max(2 * TOL if k == "zhat" else TOL, 1.5 * noise), f"{label} {k}: GPU vs oracle {eor:.3e} (oracle vs fp64 {noise:.3e})"
+        # triangle inequality: the reference sits `noise` from exact arithmetic, the GPU may sit max(TOL, noise) from it
+        own = max(2 * TOL if k == "zhat" else TOL, noise)
+        assert eor <= own + noise, f"{label} {k}: GPU vs oracle {eor:.3e} (oracle vs fp64 {noise:.3e})"
         assert e64 <= 1.25 * noise + TOL, f"{label} {k}: GPU vs fp64 {e64:.3e}, oracle vs fp64 {noise:.3e}"
         worst = max(worst, eor)
     act_g, act_o = gpu["y_next"] > 0, ora["y_next"] > 0
