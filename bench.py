@@ -277,6 +277,26 @@ def battery_batch_probe(torch, G, B=4096):
     return res
 
 
+def closed_loop_probe(torch, G, B=16384, samples=5, iters=20):
+    """warm-started receding-horizon steps of a quadrotor batch, everything on the device
+    (instance build from the states, solve, state advance); only the trajectories cross PCIe"""
+    prob = G.Problem("quadrotor", N=100)
+    M_G, G_L = prob.operators()
+    par = quad_params(B, 1)
+    nx = prob.plant()[0].shape[0]
+    x0, xref = np.ascontiguousarray(par[:, :nx]), np.ascontiguousarray(par[:, nx:])
+    theta, beta = G.schedule(iters)
+    s = G.Solver(4, 100, prob.m, prob.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
+    G.closed_loop(prob, s, x0, 1, theta, beta, xref=xref, warm_start=True)
+    t0 = time.perf_counter()
+    xt, ut = G.closed_loop(prob, s, x0, samples, theta, beta, xref=xref, warm_start=True)
+    sec = time.perf_counter() - t0
+    s.close()
+    return {"workload": f"quadrotor N=100, {B} plants, {samples} receding-horizon samples x {iters} warm-started iterations",
+            "plant_steps_per_s": B * samples / sec, "ms_per_sample": sec / samples * 1e3,
+            "finite": bool(np.isfinite(xt).all() and np.isfinite(ut).all())}
+
+
 def run_ours(args):
     import torch
     import gpad_b200 as G
@@ -405,6 +425,7 @@ def run_ours(args):
     lat = latency_probe(torch, G) if not args.no_latency else None
     per_inst = per_instance_probe(torch, G) if not args.no_latency else None
     bat3 = battery_batch_probe(torch, G) if not args.no_latency else None
+    cloop = closed_loop_probe(torch, G) if not args.no_latency else None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -422,6 +443,7 @@ def run_ours(args):
         "single_qp_latency": lat,
         "per_instance_operators": per_inst,
         "battery_batch_4096": bat3,
+        "closed_loop": cloop,
     }
     emit_line(line)
     if dist is not None:

@@ -100,6 +100,13 @@ void chol_solve(const Mat& Lc, Mat& X) {
 
 }  // namespace
 
+namespace gpad {
+int closed_loop_device(gpad_handle_t h, int B, int nx, int nu, int n, int m, int npar, double L, const double* Kg,
+                       const double* Bb, const double* b0, const double* A, const double* Bm, const double* x0,
+                       const double* xref, int samples, const float* theta, const float* beta, int max_iter, int warm_start,
+                       double* x_traj, double* u_traj);
+}
+
 struct gpad_problem_s {
     int n_u = 0, N = 0, n = 0, m = 0, n_par = 0, nx = 0;
     double L = 0.0;
@@ -404,42 +411,11 @@ int gpad_expand_operators(int n_u, int N, int m, const float* MGf, const float* 
 int gpad_closed_loop(gpad_problem_t p, gpad_handle_t h, int B, const double* x0, const double* xref, int samples,
                      const float* theta, const float* beta, int max_iter, int warm_start, double* x_traj, double* u_traj) {
     if (!p || !h || !x0 || !theta || !beta || B < 1 || samples < 1 || max_iter < 1) return GPAD_ERR_INVALID_ARG;
-    const int nx = p->nx, nu = p->n_u, n = p->n, m = p->m, npar = p->n_par, nref = npar - nx;
-    if (nref > 0 && !xref) return GPAD_ERR_INVALID_ARG;
-    std::vector<double> x(x0, x0 + (size_t)B * nx), par((size_t)B * npar), xn(nx);
-    std::vector<float> gP((size_t)B * n), pD((size_t)B * m), z((size_t)B * n), y1((size_t)B * m), y0v((size_t)B * m);
-    std::vector<float> wy1, wy0;
-    if (x_traj) std::memcpy(x_traj, x.data(), sizeof(double) * x.size());
-    for (int k = 0; k < samples; ++k) {
-        for (int b = 0; b < B; ++b) {
-            std::memcpy(&par[(size_t)b * npar], &x[(size_t)b * nx], sizeof(double) * nx);
-            if (nref > 0) std::memcpy(&par[(size_t)b * npar + nx], xref + (size_t)b * nref, sizeof(double) * nref);
-        }
-        int rc = gpad_problem_instances(p, B, par.data(), gP.data(), pD.data(), nullptr);           // gpad.m:81,85
-        if (rc != GPAD_OK) return rc;
-        gpad_solve_args_t a;
-        std::memset(&a, 0, sizeof(a));
-        a.batch = B; a.mem = GPAD_MEM_HOST;
-        a.g_P = gP.data(); a.p_D = pD.data(); a.theta = theta; a.beta = beta; a.max_iter = max_iter;
-        if (warm_start && k > 0) { wy1 = y1; wy0 = y0v; a.y0 = wy1.data(); a.y_prev0 = wy0.data(); }
-        a.z = z.data(); a.y_next = y1.data(); a.y = y0v.data();
-        rc = gpad_solve(h, &a);                                                                       // gpad.m:90
-        if (rc != GPAD_OK) return rc;
-        for (int b = 0; b < B; ++b) {
-            const float* u = &z[(size_t)b * n];                                                       // u = z_v(1:n_u), gpad.m:91
-            double* xb = &x[(size_t)b * nx];
-            for (int i = 0; i < nx; ++i) {
-                double s = 0.0;
-                for (int j = 0; j < nx; ++j) s += p->A(i, j) * xb[j];
-                for (int j = 0; j < nu; ++j) s += p->B(i, j) * (double)u[j];
-                xn[i] = s;                                                                            // gpad.m:93
-            }
-            std::memcpy(xb, xn.data(), sizeof(double) * nx);
-            if (u_traj) for (int j = 0; j < nu; ++j) u_traj[((size_t)k * B + b) * nu + j] = (double)u[j];
-        }
-        if (x_traj) std::memcpy(x_traj + (size_t)(k + 1) * B * nx, x.data(), sizeof(double) * x.size());
-    }
-    return GPAD_OK;
+    if (p->n_par - p->nx > 0 && !xref) return GPAD_ERR_INVALID_ARG;
+    // the whole loop runs on the device (csrc/closed_loop.cu): instance build, solve, state advance
+    return gpad::closed_loop_device(h, B, p->nx, p->n_u, p->n, p->m, p->n_par, p->L, p->Kg.a.data(), p->Bb.a.data(), p->b0.data(),
+                                    p->A.a.data(), p->B.a.data(), x0, xref, samples, theta, beta, max_iter, warm_start, x_traj,
+                                    u_traj);
 }
 
 int gpad_schedule(float* theta, float* beta, int count, int variant) {

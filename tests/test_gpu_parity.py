@@ -589,3 +589,31 @@ def test_closed_loop_battery_matches_oracle_loop(torch_cuda, G, oracle, warm):
     assert np.abs(ut).max() <= 0.3 + 1e-3                          # balancing currents respect the input box
     spread0 = np.ptp(xt[0], axis=1); spread1 = np.ptp(xt[-1], axis=1)
     assert (spread1 < spread0).all()                               # the cells are being balanced
+
+
+def test_closed_loop_quadrotor_device_resident(torch_cuda, G, oracle):
+    """the device-resident loop (csrc/closed_loop.cu: instance build, tcgen05 solve, state advance, warm start) on a
+    quadrotor batch with set-point parameters, against the same loop orchestrated on the host with the oracle"""
+    N, B, samples = 10, 130, 6
+    pb = G.Problem("quadrotor", N=N)
+    M_G, G_L = pb.operators()
+    theta, beta = schedule(30)
+    par = P.quadrotor_params(B, np.random.default_rng(5))
+    nx = pb.plant()[0].shape[0]
+    x0, xref = np.ascontiguousarray(par[:, :nx]), np.ascontiguousarray(par[:, nx:])
+    s = G.Solver(4, N, pb.m, pb.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
+    xt, ut = G.closed_loop(pb, s, x0, samples, theta, beta, xref=xref, warm_start=True)
+    s.close()
+    A, Bm = pb.plant()
+    for b in (0, 64, 129):
+        x = x0[b:b + 1].copy()
+        y1 = y0 = None
+        for k in range(samples):
+            g_P, p_D, _ = pb.instances(np.hstack([x, xref[b:b + 1]]), want_f=False)
+            sol = oracle.solve(4, N, pb.m, M_G, G_L, g_P[0], p_D[0], theta, beta,
+                               **({"y0": y1, "y_prev0": y0} if k > 0 else {}))
+            y1, y0 = sol["y_next"], sol["y"]
+            u = sol["z"][:4].astype(np.float64)
+            assert np.max(np.abs(ut[k, b] - u)) <= 2e-5 * max(1.0, np.abs(u).max()), (b, k)
+            x = x @ A.T + u[None] @ Bm.T
+            assert np.max(np.abs(xt[k + 1, b] - x[0])) <= 1e-5 * max(1.0, np.abs(x).max()), (b, k)
