@@ -381,7 +381,7 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
              plan.grid_lean ? lat::grid_smem_bytes(p) : plan.small ? lat::small_smem_bytes(p) : lat::smem_bytes(p, plan.regs));
     h->desc = buf;
     // fixed-iteration solves of a whole-chip plan run the second-generation kernel when it covers the problem
-    h->grid2 = plan.sync == lat::SYNC_GRID && !plan.small && !plan.grid_lean && !plan.regs && plan.G == h->num_sms &&
+    h->grid2 = plan.sync == lat::SYNC_GRID && !plan.small && !plan.grid_lean && plan.G == h->num_sms &&
                lat::grid2_supported(p, limit);
     if (const char* e = getenv("GPAD_LATENCY_GRID2")) h->grid2 = h->grid2 && atoi(e) != 0;
     h->warp = plan.small && plan.G == 1 && lat::warp_supported(p);
@@ -461,7 +461,7 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
         p.stamp_base = h->stamp_next;
         h->stamp_next += need;
         GPAD_TRY(lat::launch_grid(p, h->G, s));
-    } else if (h->grid2 && (p.check_every == 0 || p.f == nullptr) && p.max_iter >= 1) {
+    } else if (h->grid2 && p.max_iter >= 1) {
         GPAD_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned), s));
         GPAD_TRY(lat::launch_grid2(p, h->G, s));
     } else {

@@ -16,8 +16,8 @@
 //     which also owns that row's state (z, g_P / y_v, y_{v-1}, p_D, w_i) in registers;
 //   * exchange: plain stores to a global vector + the red.release / ld.acquire counter barrier of latency.cu
 //     (flag-per-CTA and multi-counter barriers measured slower, see GridBarrier).
-// Termination: the z / zhat feasibility tests and the absolute duality-gap test (every solve without the cost vector f);
-// solves that hand in f (relative gap and dual-gap branch, two more operator products) stay on the generic kernel.
+// Termination: all three branches of SURVEY row T (z / zhat feasibility, absolute and relative gap, and the dual-gap branch,
+// which runs the two phases once more on y_{v+1}).
 #include <cuda_runtime.h>
 
 #include "gpad_internal.h"
@@ -79,10 +79,10 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
     float* ops_a = smem;                              // [kRA][mld] own rows of M_G (zero rows beyond na)
     float* scr_a = ops_a + (size_t)kRA * mld;         // [kRA][16]
     float* scr_b = scr_a + kRA * 16;                  // [H * RBH][wph]
-    float* st_a = scr_b + H * RBH * wph;              // [3][kRA]   z, zhat, g_P of the own phase-A rows
-    float* st_b = st_a + 3 * kRA;                     // [6][64]    y_v, y_{v-1}, p_D, w_i, y_{v+1}, sbar of the own phase-B rows
-    float* red_l = st_b + 6 * 64;                     // [2][8]     termination partials of the two finalising warps
-    float* red_g = red_l + 16;                        // [8]        grid-wide termination quantities
+    float* st_a = scr_b + H * RBH * wph;              // [4][kRA]   z, zhat, g_P, f of the own phase-A rows
+    float* st_b = st_a + 4 * kRA;                     // [6][64]    y_v, y_{v-1}, p_D, w_i, y_{v+1}, sbar of the own phase-B rows
+    float* red_l = st_b + 6 * 64;                     // [3][8]     termination partials: two phase-B finalising warps, phase A
+    float* red_g = red_l + 24;                        // [8]        grid-wide termination quantities
 
     // ---- prologue: operators on chip, initial state ----
     for (int i = tid; i < kRA * CA; i += kT) {
@@ -118,10 +118,10 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
     }
     // row state lives in shared memory, touched only by the finalising threads (phase A: threads 0..na-1, phase B:
     // threads 0..nb-1): keeping it in registers of all 512 threads pushed the kernel into local-memory spills
-    float* z_r = st_a + tid; float* zh_r = st_a + kRA + tid; float* gp_r = st_a + 2 * kRA + tid;
+    float* z_r = st_a + tid; float* zh_r = st_a + kRA + tid; float* gp_r = st_a + 2 * kRA + tid; float* f_r = st_a + 3 * kRA + tid;
     float* yv_r = st_b + tid; float* yp_r = st_b + 64 + tid; float* pd_r = st_b + 128 + tid;
     float* w_r = st_b + 192 + tid; float* yn_r = st_b + 256 + tid; float* sb_r = st_b + 320 + tid;
-    if (tid < kRA) { *z_r = 0.f; *zh_r = 0.f; *gp_r = (tid < na) ? p.g_P[a0 + tid] : 0.f; }
+    if (tid < kRA) { *z_r = 0.f; *zh_r = 0.f; *gp_r = (tid < na) ? p.g_P[a0 + tid] : 0.f; *f_r = (tid < na && p.f) ? p.f[a0 + tid] : 0.f; }
     if (tid < 64) {
         const bool ok = tid < nb;
         const float yv = (ok && p.y0) ? p.y0[b0 + tid] : 0.f, yp = (ok && p.y_prev0) ? p.y_prev0[b0 + tid] : 0.f;
@@ -135,6 +135,63 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
     float out_viol = __int_as_float(0x7fc00000), out_gap = __int_as_float(0x7fc00000);
     int until_check = CHECK ? p.check_every : 0x7fffffff, check_count = 0;
     __syncthreads();
+
+    // own rows of M_G times a full m-vector held as register chunks: row sums land in scr_a[r][0..15]
+    auto rows_a = [&](const float4 (&vec)[KA]) {
+        float acc[kRA];
+#pragma unroll
+        for (int r = 0; r < kRA; ++r) acc[r] = 0.f;
+#pragma unroll
+        for (int k = 0; k < KA; ++k) {
+            const int ch = tid + k * kT;
+            if (ch < CA) {
+#pragma unroll
+                for (int r = 0; r < kRA; ++r)
+                    acc[r] = dot4(reinterpret_cast<const float4*>(ops_a + (size_t)r * mld)[ch], vec[k], acc[r]);
+            }
+        }
+        const float tot = warp_sum_transposed<kRA>(acc, lane);       // lanes 4r .. 4r+3 hold row r
+        if ((lane & 3) == 0) scr_a[(lane >> 2) * 16 + warp] = tot;
+        __syncthreads();
+    };
+    auto sum_a = [&]() -> float {       // finalising thread tid < na
+        const float4* s4 = reinterpret_cast<const float4*>(scr_a + tid * 16);
+        const float4 s0 = s4[0], s1 = s4[1], s2 = s4[2], s3 = s4[3];
+        return ((s0.x + s0.y) + (s0.z + s0.w)) + ((s1.x + s1.y) + (s1.z + s1.w)) +
+               ((s2.x + s2.y) + (s2.z + s2.w)) + ((s3.x + s3.y) + (s3.z + s3.w));
+    };
+    // own rows of G_L (register fragments) times the n-vector chunk zc: row sums land in scr_b[row][0..wph-1]
+    auto rows_b = [&](const float4 zc) {
+        float acc[RBH];
+#pragma unroll
+        for (int j = 0; j < RBH; ++j) acc[j] = dot4(gl[j], zc, 0.f);
+        const float tot = warp_sum_transposed<RBH>(acc, lane);       // lanes (32 / RBH) j .. hold row j of the group
+        constexpr int kSh = RBH == 8 ? 2 : 1;
+        if ((lane & ((1 << kSh) - 1)) == 0) scr_b[(h * RBH + (lane >> kSh)) * wph + wih] = tot;
+        __syncthreads();
+    };
+    auto sum_b = [&]() -> float {       // finalising thread tid < nb
+        float d = 0.f;
+        for (int k = 0; k < wph; ++k) d += scr_b[tid * wph + k];
+        return d;
+    };
+    // sum over all CTAs of up to 3 per-CTA partials published in xr[k * g_pad + c]; every CTA gets the same totals
+    auto grid_sum3 = [&](float* xr, float a, float b, float c3) {      // a, b, c3 valid in thread 0
+        if (tid == 0) { xr[0 * p.g_pad + c] = a; xr[1 * p.g_pad + c] = b; xr[2 * p.g_pad + c] = c3; }
+        bar.sync(p.barrier);
+        if (warp == 0) {
+            float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+            for (int k = lane; k < (int)gridDim.x; k += 32) {
+                x0 += __ldcg(xr + 0 * p.g_pad + k); x1 += __ldcg(xr + 1 * p.g_pad + k); x2 += __ldcg(xr + 2 * p.g_pad + k);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                x0 += __shfl_xor_sync(0xffffffffu, x0, o); x1 += __shfl_xor_sync(0xffffffffu, x1, o); x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+            }
+            if (lane == 0) { red_g[0] = x0; red_g[1] = x1; red_g[2] = x2; }
+        }
+        __syncthreads();
+    };
 
     float theta_pf = p.theta[0];
     float beta_pf = p.max_iter > 1 ? p.beta[1] : 0.f;
@@ -150,31 +207,19 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
         if (check) { until_check = p.check_every; ++check_count; }
 
         // ---------------- phase A: zhat rows (step 2), z average (step 3) ----------------
-        {
-            float acc[kRA];
-#pragma unroll
-            for (int r = 0; r < kRA; ++r) acc[r] = 0.f;
-#pragma unroll
-            for (int k = 0; k < KA; ++k) {
-                const int ch = tid + k * kT;
-                if (ch < CA) {
-#pragma unroll
-                    for (int r = 0; r < kRA; ++r)
-                        acc[r] = dot4(reinterpret_cast<const float4*>(ops_a + (size_t)r * mld)[ch], wv[k], acc[r]);
-                }
-            }
-            const float tot = warp_sum_transposed<kRA>(acc, lane);       // lanes 4r .. 4r+3 hold row r
-            if ((lane & 3) == 0) scr_a[(lane >> 2) * 16 + warp] = tot;
-            __syncthreads();
+        rows_a(wv);
+        if (tid < 32) {
+            float fz = 0.f;
             if (tid < na) {
-                const float4* s4 = reinterpret_cast<const float4*>(scr_a + tid * 16);
-                const float4 s0 = s4[0], s1 = s4[1], s2 = s4[2], s3 = s4[3];
-                const float d = ((s0.x + s0.y) + (s0.z + s0.w)) + ((s1.x + s1.y) + (s1.z + s1.w)) +
-                                ((s2.x + s2.y) + (s2.z + s2.w)) + ((s3.x + s3.y) + (s3.z + s3.w));
-                const float zh = d - *gp_r;
+                const float zh = sum_a() - *gp_r;
                 *zh_r = zh;
                 *z_r = __fadd_rn(__fmul_rn(one_minus, *z_r), __fmul_rn(theta, zh));
                 p.x_zhat[a0 + tid] = zh;
+                fz = *f_r * zh;
+            }
+            if (check && p.f) {       // f'zhat partial of this CTA (rows live in lanes 0..7 of warp 0)
+                fz += __shfl_xor_sync(0xffffffffu, fz, 4); fz += __shfl_xor_sync(0xffffffffu, fz, 2); fz += __shfl_xor_sync(0xffffffffu, fz, 1);
+                if (tid == 0) red_l[16] = fz;
             }
         }
         bar.sync(p.barrier);
@@ -183,18 +228,11 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
 
         // ---------------- phase B: dual step + projection (step 4), momentum (step 1 of v+1) ----------------
         {
-            float acc[RBH];
-#pragma unroll
-            for (int j = 0; j < RBH; ++j) acc[j] = dot4(gl[j], zc, 0.f);
-            const float tot = warp_sum_transposed<RBH>(acc, lane);       // lanes (32 / RBH) j .. hold row j of the group
-            constexpr int kSh = RBH == 8 ? 2 : 1;
-            if ((lane & ((1 << kSh) - 1)) == 0) scr_b[(h * RBH + (lane >> kSh)) * wph + wih] = tot;
-            __syncthreads();
+            rows_b(zc);
             // termination partials of this row (acceldualgrad.m:66-79; same quantities as latency.cu)
             float r_max_sbar = -INFINITY, r_max_rhat = -INFINITY, r_min_w = INFINITY, r_w_rhat = 0.f, r_w_dot = 0.f, r_bad = 0.f;
             if (tid < nb) {
-                float d = 0.f;
-                for (int k = 0; k < wph; ++k) d += scr_b[tid * wph + k];
+                const float d = sum_b();
                 const float wi = *w_r, pd = *pd_r;
                 const float s = d + (wi + pd);
                 const float yn = 0.5f * (s + fabsf(s));
@@ -246,11 +284,13 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
                     xred[3 * p.g_pad + c] = red_l[3] + red_l[11];
                     xred[4 * p.g_pad + c] = red_l[4] + red_l[12];
                     xred[5 * p.g_pad + c] = fmaxf(red_l[5], red_l[13]);
+                    xred[6 * p.g_pad + c] = p.f ? red_l[16] : 0.f;
                 }
                 bar.sync(p.barrier);
                 if (warp == 0) {
-                    float a = -INFINITY, b = -INFINITY, cm = INFINITY, d = 0.f, e = 0.f, g = 0.f;
+                    float a = -INFINITY, b = -INFINITY, cm = INFINITY, d = 0.f, e = 0.f, g = 0.f, fzs = 0.f;
                     for (int k = lane; k < (int)gridDim.x; k += 32) {
+                        fzs += __ldcg(xred + 6 * p.g_pad + k);
                         a = fmaxf(a, __ldcg(xred + 0 * p.g_pad + k)); b = fmaxf(b, __ldcg(xred + 1 * p.g_pad + k));
                         cm = fminf(cm, __ldcg(xred + 2 * p.g_pad + k)); d += __ldcg(xred + 3 * p.g_pad + k);
                         e += __ldcg(xred + 4 * p.g_pad + k); g = fmaxf(g, __ldcg(xred + 5 * p.g_pad + k));
@@ -260,19 +300,68 @@ __global__ void __launch_bounds__(kT, 1) gpad_grid2_kernel(const Params p, int H
                         a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
                         cm = fminf(cm, __shfl_xor_sync(0xffffffffu, cm, o)); d += __shfl_xor_sync(0xffffffffu, d, o);
                         e += __shfl_xor_sync(0xffffffffu, e, o); g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, o));
+                        fzs += __shfl_xor_sync(0xffffffffu, fzs, o);
                     }
-                    if (lane == 0) { red_g[0] = a; red_g[1] = b; red_g[2] = cm; red_g[3] = d; red_g[4] = e; red_g[5] = g; }
+                    if (lane == 0) { red_g[3] = d; red_g[4] = e; red_g[5] = g; red_g[6] = fzs; red_g[7] = cm; red_g[0] = a; red_g[1] = b; }
                 }
                 __syncthreads();
                 const float viol_z = p.L * red_g[0], viol_zhat = p.L * red_g[1];
+                const float min_w = red_g[7], w_rhat = red_g[3], w_dot = red_g[4], bad = red_g[5], fzhat = red_g[6];
                 out_viol = viol_z;
                 bool stop = false;
-                if (red_g[5] > 0.f) { status = GPAD_STATUS_NONFINITE; stop = true; }
+                if (bad > 0.f) { status = GPAD_STATUS_NONFINITE; stop = true; }
                 else if (viol_z <= p.eps_g) { status = GPAD_STATUS_CONVERGED_Z; stop = true; }
-                else if (viol_zhat <= p.eps_g && red_g[2] >= 0.f) {      // f == NULL on this kernel: absolute gap only
-                    const float gapv = -p.L * red_g[3];
-                    out_gap = gapv;
-                    if (gapv <= p.eps_V) { status = GPAD_STATUS_CONVERGED_ZHAT; out_viol = viol_zhat; stop = true; }
+                else if (viol_zhat <= p.eps_g) {
+                    const float V = 0.5f * (fzhat - p.L * w_dot);
+                    if (min_w >= 0.f) {
+                        const float gapv = -p.L * w_rhat;
+                        out_gap = gapv;
+                        if (gapv <= p.eps_V || (p.f && gapv <= V * p.eps_V / (1.0f + p.eps_V))) {
+                            status = GPAD_STATUS_CONVERGED_ZHAT; out_viol = viol_zhat; stop = true;
+                        }
+                    } else if (p.f) {
+                        // dual branch: Phi(y_{v+1}) needs z_y = M_G y+ - g_P and G_L z_y: the two phases once more on y+,
+                        // through the same exchange buffers (nothing of iteration v is still read from them)
+                        if (tid < nb) p.x_w[b0 + tid] = *yn_r;
+                        bar.sync(p.barrier);
+                        float4 yv4[KA];
+#pragma unroll
+                        for (int k = 0; k < KA; ++k) {
+                            const int ch = tid + k * kT;
+                            yv4[k] = ch < CA ? ld_cg4(p.x_w + 4 * ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        rows_a(yv4);
+                        if (tid < 32) {
+                            float fzy = 0.f;
+                            if (tid < na) {
+                                const float zy = sum_a() - *gp_r;
+                                p.x_zhat[a0 + tid] = zy;
+                                fzy = *f_r * zy;
+                            }
+                            fzy += __shfl_xor_sync(0xffffffffu, fzy, 4); fzy += __shfl_xor_sync(0xffffffffu, fzy, 2); fzy += __shfl_xor_sync(0xffffffffu, fzy, 1);
+                            if (tid == 0) red_l[16] = fzy;
+                        }
+                        bar.sync(p.barrier);
+                        float4 zy4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (tc < CB) zy4 = ld_cg4(p.x_zhat + 4 * tc);
+                        rows_b(zy4);
+                        float y_gz = 0.f, y_pd = 0.f;
+                        if (tid < nb) {
+                            const float dd = sum_b(), yn = *yn_r;
+                            y_gz = yn * dd; y_pd = yn * *pd_r;
+                        }
+                        if (warp < 2) {
+#pragma unroll
+                            for (int o = 16; o; o >>= 1) { y_gz += __shfl_xor_sync(0xffffffffu, y_gz, o); y_pd += __shfl_xor_sync(0xffffffffu, y_pd, o); }
+                            if (lane == 0) { red_l[warp * 8 + 0] = y_gz; red_l[warp * 8 + 1] = y_pd; }
+                        }
+                        __syncthreads();
+                        grid_sum3(p.x_red + 2 * 8 * p.g_pad, red_l[16], red_l[0] + red_l[8], red_l[1] + red_l[9]);
+                        const float Phi = 0.5f * red_g[0] + 0.5f * p.L * red_g[1] + p.L * red_g[2];
+                        const float gapv = V - Phi;
+                        out_gap = gapv;
+                        if (gapv <= p.eps_V * fmaxf(Phi, 1.0f)) { status = GPAD_STATUS_CONVERGED_DUAL; out_viol = viol_zhat; stop = true; }
+                    }
                 }
                 if (stop) break;
                 if (!last && tid < nb) {
@@ -337,7 +426,7 @@ static int groups_for(int nld) {
 size_t grid2_smem_bytes(const Params& p) {
     const int H = groups_for(p.nld);
     const int rbh = H ? (p.rows_b + H - 1) / H : 0;
-    return ((size_t)kRA * p.mld + kRA * 16 + (size_t)H * (rbh <= 8 ? 8 : 16) * (kT / (H ? H : 1) / 32) + 3 * kRA + 6 * 64 + 16 + 8) * sizeof(float);
+    return ((size_t)kRA * p.mld + kRA * 16 + (size_t)H * (rbh <= 8 ? 8 : 16) * (kT / (H ? H : 1) / 32) + 4 * kRA + 6 * 64 + 24 + 8) * sizeof(float);
 }
 
 // 1 when this plan covers the problem (p.rows_a / rows_b / mld / nld of the generic grid plan with G CTAs)

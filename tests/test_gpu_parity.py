@@ -207,8 +207,12 @@ def test_latency_termination_matches_oracle(torch_cuda, G, oracle, dims, eps, wi
     s.close()
 
 
-def test_latency_dual_gap_branch(torch_cuda, G, oracle):
-    """instances that reach a check with a negative entry in w take the V(zhat) - Phi(y) branch"""
+@pytest.mark.parametrize("plan", ["default", "grid:148"])
+def test_latency_dual_gap_branch(torch_cuda, G, oracle, plan, monkeypatch):
+    """instances that reach a check with a negative entry in w take the V(zhat) - Phi(y) branch; on the default plan
+    (one CTA, latency_small.cu, because f is given) and forced onto the whole chip (latency_grid2.cu)"""
+    if plan != "default":
+        monkeypatch.setenv("GPAD_LATENCY_PLAN", plan)
     hit = 0
     theta, beta = schedule(3000)
     for seed in range(12):
@@ -219,6 +223,7 @@ def test_latency_dual_gap_branch(torch_cuda, G, oracle):
         kw = dict(check_every=1, eps_g=5e-2, eps_V=5e-2)
         ora = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, f=f, **kw)
         s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_LATENCY)
+        assert plan == "default" or "column-partitioned" in s.description, s.description
         gpu = s.solve_host(g_P, p_D, theta, beta, f=f, **kw)
         s.close()
         assert gpu["status"] == ora["status"] and gpu["iters"] == ora["iters"], (seed, gpu["status"], ora["status"], gpu["iters"], ora["iters"])
