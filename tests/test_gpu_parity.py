@@ -622,3 +622,28 @@ def test_closed_loop_quadrotor_device_resident(torch_cuda, G, oracle):
             assert np.max(np.abs(ut[k, b] - u)) <= 2e-5 * max(1.0, np.abs(u).max()), (b, k)
             x = x @ A.T + u[None] @ Bm.T
             assert np.max(np.abs(xt[k + 1, b] - x[0])) <= 1e-5 * max(1.0, np.abs(x).max()), (b, k)
+
+
+def test_gpad_main_driver_on_reference_format_file(torch_cuda, G, oracle, tmp_path):
+    """the main.cu-equivalent driver binary (host/gpad_main.cpp -> C ABI): reads a reference-format data file
+    (main.cu:29-67, flipped operators), solves, prints what main.cu prints plus the norms of the five vectors it
+    copies back; the norms must be those of the oracle on the same file"""
+    import re, subprocess
+    n_u, N = 10, 15
+    pb, g_P, p_D, _ = battery_case(n_u, N, seed=2)
+    theta, beta = schedule(100)
+    path = str(tmp_path / "problem.txt")
+    G.file_write(path, n_u, N, pb.m, pb.L, pb.M_G_flipped(), g_P, pb.G_L_flipped(), p_D, theta, beta)
+    exe = os.path.join(os.path.dirname(G.LIB_PATH), "gpad_main")
+    out = subprocess.run([exe, path], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert f"n_u = {n_u}, N = {N}, m = {pb.m}" in out.stdout
+    back = G.file_read(path)                                 # the text round trip (%f-style decimals) is what both sides solve
+    ora = oracle.solve(n_u, N, pb.m, back["M_G"].reshape(pb.m, pb.n).T.copy(), back["G_L"].reshape(pb.n, pb.m).T.copy(),
+                       back["g_P"], back["p_D"], back["theta"], back["beta"])
+    norms = dict(re.findall(r"\|(\w+)\| = ([0-9.eE+-]+)", out.stdout))
+    for key, vec in (("y_vp1", "y_next"), ("y_v", "y"), ("z_v", "z"), ("zhat_v", "zhat"), ("w_v", "w")):
+        ref = float(np.abs(ora[vec]).max())
+        assert abs(float(norms[key]) - ref) <= 2e-5 * max(ref, 1e-3), (key, norms[key], ref)
+    m_it = re.search(r"status = (\d+), iterations = (\d+)", out.stdout)
+    assert m_it and int(m_it.group(1)) == 0 and int(m_it.group(2)) == 100
