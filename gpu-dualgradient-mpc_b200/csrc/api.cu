@@ -389,8 +389,8 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
     if (h->warp) h->desc += " [solves without f: one warp, operators and state in registers, no block barrier (latency_warp.cu)]";
     if (h->grid2) {
         snprintf(buf, sizeof(buf), "latency: persistent kernel, cooperative-grid x%d CTAs, 512 threads, column-partitioned GEMV: exchanged "
-                 "vectors in registers, M_G rows in shared memory (%zu B/CTA), G_L fragments in registers, counter barrier "
-                 "[solves with a cost vector f and termination: generic grid kernel]", plan.G, lat::grid2_smem_bytes(p));
+                 "vectors in registers, M_G rows in shared memory (%zu B/CTA), G_L fragments in registers, counter barrier, "
+                 "all termination branches in-kernel", plan.G, lat::grid2_smem_bytes(p));
         h->desc = buf;
     }
     return GPAD_OK;
