@@ -204,8 +204,17 @@ def latency_probe(torch, G):
             e0.record(); s.solve_device(1, dg, dp, theta, beta, ITERS, stream=st, z=dz, y_next=dy); e1.record()
             e1.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
-        out[f"battery({n_u},{N}) n={prob.n} m={prob.m}"] = {"p50_us": float(np.median(ts)), "p99_us": float(np.percentile(ts, 99)),
-                                                            "iterations": ITERS, "path": s.description}
+        entry = {"p50_us": float(np.median(ts)), "p99_us": float(np.percentile(ts, 99)), "iterations": ITERS, "path": s.description}
+        if "cooperative-grid" in s.description:
+            # SM-cycle model of SURVEY 8(d) for a whole-chip plan: operator bytes through the SMs' shared-memory ports
+            # (phase B reads registers in latency_grid2.cu: only M_G counts) + two grid exchanges of ~1.1 us each
+            sms, clk_ghz, t_exchange_us = 148, 1.9, 1.1
+            t_ops_us = 4.0 * prob.n * prob.m / (sms * 128.0) / (clk_ghz * 1e3)
+            model = t_ops_us + 2 * t_exchange_us
+            entry.update({"us_per_iteration": entry["p50_us"] / ITERS, "model_us_per_iteration": model,
+                          "frac_of_model": model / (entry["p50_us"] / ITERS),
+                          "model": "4nm B / (148 SMs x 128 B/clk) at 1.9 GHz + 2 grid exchanges x 1.1 us"})
+        out[f"battery({n_u},{N}) n={prob.n} m={prob.m}"] = entry
         s.close()
     return out
 
