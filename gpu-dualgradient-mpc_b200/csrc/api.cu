@@ -386,7 +386,7 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
     if (const char* e = getenv("GPAD_LATENCY_GRID2")) h->grid2 = h->grid2 && atoi(e) != 0;
     h->warp = plan.small && plan.G == 1 && lat::warp_supported(p);
     if (const char* e = getenv("GPAD_LATENCY_WARP")) h->warp = h->warp && atoi(e) != 0;
-    if (h->warp) h->desc += " [solves without f: one warp, operators and state in registers, no block barrier (latency_warp.cu)]";
+    if (h->warp) h->desc = "latency: one warp, operators and state in registers, no shared memory or block barrier in the loop (latency_warp.cu)";
     if (h->grid2) {
         snprintf(buf, sizeof(buf), "latency: persistent kernel, cooperative-grid x%d CTAs, 512 threads, column-partitioned GEMV: exchanged "
                  "vectors in registers, M_G rows in shared memory (%zu B/CTA), G_L fragments in registers, counter barrier, "
@@ -445,7 +445,7 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
     p.out_max_viol = dev && a->max_viol ? a->max_viol : h->o_viol;
     p.out_gap = dev && a->gap ? a->gap : h->o_gap;
     cudaEvent_t pe = h->prof_begin(s);
-    if (h->warp && (p.check_every == 0 || p.f == nullptr) && p.max_iter >= 1) {
+    if (h->warp && p.max_iter >= 1) {
         p.batch = 1; p.op_stride_a = 0; p.op_stride_b = 0;
         GPAD_TRY(lat::launch_warp(p, s));
     } else if (h->small) {
@@ -551,7 +551,7 @@ int setup_per_instance(gpad_handle_s* h, const float* M_G, const float* G_L) {
     h->warp = lat::warp_supported(p);
     if (const char* e = getenv("GPAD_LATENCY_WARP")) h->warp = h->warp && atoi(e) != 0;
     if (h->warp) h->desc = "batch-per-instance: one WARP per QP (batched GEMV), 4 QPs per CTA, operators and state read once into registers, "
-                           "no shared memory or block barrier in the loop (latency_warp.cu) [solves with f: " + h->desc + "]";
+                           "no shared memory or block barrier in the loop (latency_warp.cu)";
     return GPAD_OK;
 }
 
@@ -588,7 +588,7 @@ int solve_per_instance(gpad_handle_s* h, const gpad_solve_args_t* a) {
     p.out_max_viol = dev ? a->max_viol : (a->max_viol ? h->pi_viol : nullptr);
     p.out_gap = dev ? a->gap : (a->gap ? h->pi_gap : nullptr);
     cudaEvent_t pe = h->prof_begin(s);
-    if (h->warp && (p.check_every == 0 || p.f == nullptr) && p.max_iter >= 1) {
+    if (h->warp && p.max_iter >= 1) {
         GPAD_TRY(lat::launch_warp(p, s));
     } else if (h->small) {
         p.sched_smem = round_up(std::min(a->max_iter, lat::small_sched_capacity()), 4);

@@ -10,8 +10,7 @@
 //   phase B (step 4 + step 1, kernel_functions.cu:142-200, 7-14): zhat is broadcast with n shuffles, lane l holds
 //            ROWS l, l+32 of G_L and finishes y_{v+1}, w_{v+1} for its own entries.
 // No shared memory, no block barrier, no global traffic in the loop except the (cached) theta / beta schedule.
-// Termination: the z / zhat feasibility tests and the absolute gap (solves without the cost vector f); solves that
-// hand in f use latency_small.cu.
+// Termination: all three branches of SURVEY row T; the dual-gap branch runs the two phases once more on y_{v+1}.
 #include <cuda_runtime.h>
 
 #include "gpad_internal.h"
@@ -37,6 +36,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp_kernel(const Para
     p.g_P += inst * p.n; p.p_D += inst * p.m;
     if (p.y0) p.y0 += inst * p.m;
     if (p.y_prev0) p.y_prev0 += inst * p.m;
+    if (p.f) p.f += inst * p.n;
     const int n = p.n, m = p.m;
 
     // ---- operators and state into registers ----
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp_kernel(const Para
     }
     const int r_me = (lane >> 1) & (kWR - 1);          // the row whose total this lane holds after the reduction
     const float gp_me = r_me < n ? p.g_P[r_me] : 0.f;
+    const float f_me = (p.f && r_me < n && (lane & 1) == 0) ? p.f[r_me] : 0.f;      // one lane per row carries f_r
     float z_me = 0.f, zh_me = 0.f;
 
     int iters = 0, status = GPAD_STATUS_MAX_ITER;
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp_kernel(const Para
 #pragma unroll
             for (int j = 0; j < kMR; ++j) d[j] = fmaf(gl[j][c], zc, d[j]);
         }
-        float r_max_sbar = -INFINITY, r_max_rhat = -INFINITY, r_min_w = INFINITY, r_w_rhat = 0.f, r_bad = 0.f;
+        float r_max_sbar = -INFINITY, r_max_rhat = -INFINITY, r_min_w = INFINITY, r_w_rhat = 0.f, r_w_dot = 0.f, r_bad = 0.f;
 #pragma unroll
         for (int j = 0; j < kMR; ++j) {
             const float s = d[j] + (w[j] + pd[j]);
@@ -106,29 +107,63 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp_kernel(const Para
                 if (check && own[j]) {
                     r_max_sbar = fmaxf(r_max_sbar, sb[j]); r_max_rhat = fmaxf(r_max_rhat, rhat); r_min_w = fminf(r_min_w, w[j]);
                     r_w_rhat = fmaf(w[j], rhat, r_w_rhat);
+                    r_w_dot = fmaf(w[j], d[j], r_w_dot);
                     if (!isfinite(yn[j])) r_bad = 1.f;
                 }
             }
         }
         iters = v + 1;
         if (check) {
+            float fz = f_me * zh_me;
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
                 r_max_sbar = fmaxf(r_max_sbar, __shfl_xor_sync(0xffffffffu, r_max_sbar, o));
                 r_max_rhat = fmaxf(r_max_rhat, __shfl_xor_sync(0xffffffffu, r_max_rhat, o));
                 r_min_w = fminf(r_min_w, __shfl_xor_sync(0xffffffffu, r_min_w, o));
                 r_w_rhat += __shfl_xor_sync(0xffffffffu, r_w_rhat, o);
+                r_w_dot += __shfl_xor_sync(0xffffffffu, r_w_dot, o);
                 r_bad = fmaxf(r_bad, __shfl_xor_sync(0xffffffffu, r_bad, o));
+                fz += __shfl_xor_sync(0xffffffffu, fz, o);
             }
             const float viol_z = p.L * r_max_sbar, viol_zhat = p.L * r_max_rhat;
             out_viol = viol_z;
             bool stop = false;
             if (r_bad > 0.f) { status = GPAD_STATUS_NONFINITE; stop = true; }
             else if (viol_z <= p.eps_g) { status = GPAD_STATUS_CONVERGED_Z; stop = true; }
-            else if (viol_zhat <= p.eps_g && r_min_w >= 0.f) {       // f == NULL on this kernel: absolute gap only
-                const float gapv = -p.L * r_w_rhat;
-                out_gap = gapv;
-                if (gapv <= p.eps_V) { status = GPAD_STATUS_CONVERGED_ZHAT; out_viol = viol_zhat; stop = true; }
+            else if (viol_zhat <= p.eps_g) {
+                const float V = 0.5f * (fz - p.L * r_w_dot);
+                if (r_min_w >= 0.f) {
+                    const float gapv = -p.L * r_w_rhat;
+                    out_gap = gapv;
+                    if (gapv <= p.eps_V || (p.f && gapv <= V * p.eps_V / (1.0f + p.eps_V))) {
+                        status = GPAD_STATUS_CONVERGED_ZHAT; out_viol = viol_zhat; stop = true;
+                    }
+                } else if (p.f) {
+                    // dual branch: Phi(y_{v+1}) with z_y = M_G y+ - g_P and G_L z_y -- the two phases once more, on y+
+                    float a2[kWR];
+#pragma unroll
+                    for (int r = 0; r < kWR; ++r) a2[r] = fmaf(mg[1][r], yn[1], mg[0][r] * yn[0]);
+                    const float zy_me = warp_sum_transposed<kWR>(a2, lane) - gp_me;
+                    float fzy = f_me * zy_me, y_gz = 0.f, y_pd = 0.f;
+                    float d2[kMR] = {0.f, 0.f};
+#pragma unroll
+                    for (int c = 0; c < kWR; ++c) {
+                        const float zc = __shfl_sync(0xffffffffu, zy_me, 2 * c);
+#pragma unroll
+                        for (int j = 0; j < kMR; ++j) d2[j] = fmaf(gl[j][c], zc, d2[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kMR; ++j)
+                        if (own[j]) { y_gz = fmaf(yn[j], d2[j], y_gz); y_pd = fmaf(yn[j], pd[j], y_pd); }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        fzy += __shfl_xor_sync(0xffffffffu, fzy, o); y_gz += __shfl_xor_sync(0xffffffffu, y_gz, o); y_pd += __shfl_xor_sync(0xffffffffu, y_pd, o);
+                    }
+                    const float Phi = 0.5f * fzy + 0.5f * p.L * y_gz + p.L * y_pd;
+                    const float gapv = V - Phi;
+                    out_gap = gapv;
+                    if (gapv <= p.eps_V * fmaxf(Phi, 1.0f)) { status = GPAD_STATUS_CONVERGED_DUAL; out_viol = viol_zhat; stop = true; }
+                }
             }
             if (stop) break;
         }

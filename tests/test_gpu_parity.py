@@ -209,8 +209,9 @@ def test_latency_termination_matches_oracle(torch_cuda, G, oracle, dims, eps, wi
 
 @pytest.mark.parametrize("plan", ["default", "grid:148"])
 def test_latency_dual_gap_branch(torch_cuda, G, oracle, plan, monkeypatch):
-    """instances that reach a check with a negative entry in w take the V(zhat) - Phi(y) branch; on the default plan
-    (one CTA, latency_small.cu, because f is given) and forced onto the whole chip (latency_grid2.cu)"""
+    """instances that reach a check with a negative entry in w take the V(zhat) - Phi(y) branch; battery (4,6) on the
+    default plan (one CTA, latency_small.cu; n = 24 is beyond the one-warp kernel) and forced onto the whole chip
+    (latency_grid2.cu)"""
     if plan != "default":
         monkeypatch.setenv("GPAD_LATENCY_PLAN", plan)
     hit = 0
@@ -223,7 +224,7 @@ def test_latency_dual_gap_branch(torch_cuda, G, oracle, plan, monkeypatch):
         kw = dict(check_every=1, eps_g=5e-2, eps_V=5e-2)
         ora = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, f=f, **kw)
         s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_LATENCY)
-        assert plan == "default" or "column-partitioned" in s.description, s.description
+        assert {"default": "lean kernel", "one-cta": "lean kernel", "grid:148": "column-partitioned"}[plan] in s.description, s.description
         gpu = s.solve_host(g_P, p_D, theta, beta, f=f, **kw)
         s.close()
         assert gpu["status"] == ora["status"] and gpu["iters"] == ora["iters"], (seed, gpu["status"], ora["status"], gpu["iters"], ora["iters"])
@@ -647,3 +648,29 @@ def test_gpad_main_driver_on_reference_format_file(torch_cuda, G, oracle, tmp_pa
         assert abs(float(norms[key]) - ref) <= 2e-5 * max(ref, 1e-3), (key, norms[key], ref)
     m_it = re.search(r"status = (\d+), iterations = (\d+)", out.stdout)
     assert m_it and int(m_it.group(1)) == 0 and int(m_it.group(2)) == 100
+
+
+@pytest.mark.parametrize("warp", ["1", "0"])
+def test_tiny_latency_termination_with_cost_vector(torch_cuda, G, oracle, warp, monkeypatch):
+    """battery (3,4) / (4,3) with f: relative-gap and dual-gap branches on the one-warp kernel (latency_warp.cu) and,
+    with GPAD_LATENCY_WARP=0, on the one-CTA kernel (latency_small.cu); status and iteration count follow the oracle"""
+    monkeypatch.setenv("GPAD_LATENCY_WARP", warp)
+    theta, beta = schedule(3000)
+    seen = {}
+    for dims in ((3, 4), (4, 3)):
+        n_u, N = dims
+        pb = P.battery(n_u, N)
+        s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_LATENCY)
+        assert ("one warp" in s.description) == (warp == "1"), s.description
+        for seed in range(10):
+            g_P, p_D, f = pb.instance(np.random.default_rng(300 + seed).random(n_u) - 0.5)
+            for eps in (5e-2, 1e-2):
+                kw = dict(check_every=1, eps_g=eps, eps_V=eps)
+                ora = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, f=f, **kw)
+                gpu = s.solve_host(g_P, p_D, theta, beta, f=f, **kw)
+                assert gpu["status"] == ora["status"] and gpu["iters"] == ora["iters"], (dims, seed, eps, gpu["status"], ora["status"], gpu["iters"], ora["iters"])
+                for k in VECS:
+                    assert P.rel_inf(gpu[k], ora[k]) <= 3e-5, (dims, seed, k)
+                seen[int(ora["status"])] = seen.get(int(ora["status"]), 0) + 1
+        s.close()
+    print("\n statuses:", seen)
