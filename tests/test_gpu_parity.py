@@ -674,3 +674,28 @@ def test_tiny_latency_termination_with_cost_vector(torch_cuda, G, oracle, warp, 
                 seen[int(ora["status"])] = seen.get(int(ora["status"]), 0) + 1
         s.close()
     print("\n statuses:", seen)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_batch_host_pipeline_equals_single_pass(torch_cuda, G, prec, monkeypatch):
+    """opt-in (GPAD_HOST_CHUNK): host-memory fixed-iteration solves cut into ranges whose PCIe copies overlap the iterations
+    of their neighbours (solve_batch_pipelined); an instance's result must not depend on the range it rides in:
+    bit-identical to the single-pass solve, cold and warm started, including a ragged last range"""
+    N, B = 20, 1000
+    pb = P.quadrotor(N)
+    par = P.quadrotor_params(B, np.random.default_rng(13))
+    g_P, p_D, _ = pb.instance(par)
+    theta, beta = schedule(30)
+    code = G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32
+    monkeypatch.delenv("GPAD_HOST_CHUNK", raising=False)
+    s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=code, max_batch=B)
+    one = s.solve_host(g_P, p_D, theta, beta)
+    one_w = s.solve_host(g_P, p_D, theta, beta, y0=one["y_next"], y_prev0=one["y"])
+    monkeypatch.setenv("GPAD_HOST_CHUNK", "256")
+    piped = s.solve_host(g_P, p_D, theta, beta)
+    piped_w = s.solve_host(g_P, p_D, theta, beta, y0=one["y_next"], y_prev0=one["y"])
+    s.close()
+    for k in VECS:
+        assert np.array_equal(piped[k], one[k]), k
+        assert np.array_equal(piped_w[k], one_w[k]), k
+    assert (piped["iters"] == 30).all() and (piped["status"] == 0).all()
