@@ -297,9 +297,11 @@ def closed_loop_probe(torch, G, B=16384, samples=5, iters=20):
     theta, beta = G.schedule(iters)
     s = G.Solver(4, 100, prob.m, prob.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
     G.closed_loop(prob, s, x0, 1, theta, beta, xref=xref, warm_start=True)
-    t0 = time.perf_counter()
-    xt, ut = G.closed_loop(prob, s, x0, samples, theta, beta, xref=xref, warm_start=True)
-    sec = time.perf_counter() - t0
+    sec = float("inf")
+    for _ in range(2):                       # best of two (each call also allocates and frees its device buffers)
+        t0 = time.perf_counter()
+        xt, ut = G.closed_loop(prob, s, x0, samples, theta, beta, xref=xref, warm_start=True)
+        sec = min(sec, time.perf_counter() - t0)
     s.close()
     return {"workload": f"quadrotor N=100, {B} plants, {samples} receding-horizon samples x {iters} warm-started iterations",
             "plant_steps_per_s": B * samples / sec, "ms_per_sample": sec / samples * 1e3,
