@@ -633,6 +633,18 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
     bool p1 = tcp && cg == 1;
     if (const char* e = getenv("GPAD_TC_P1")) p1 = p1 && atoi(e) != 0;
     if (const char* e = getenv("GPAD_TC_PFORM")) p1 = p1 && atoi(e) != 0;
+    if (p1 && !getenv("GPAD_TC_P1")) {
+        // the TMEM-fed kernel costs ~824 clk per 128-row tile and k-block whatever the tile width (<= 208 columns); the
+        // first-generation kernel ~940 clk at 208 columns, growing with the width (<= 256) -- but it may need fewer tiles.
+        // With few tiles the number of waves over the SMs decides (battery (10,100), 4096 QPs: 160 tiles = 2 waves against
+        // 128 tiles = 1 wave: measured 98.7 k against 112 k solves/s), with many tiles the per-tile cost does.
+        int bn_ts = 0, nt_ts = 0;
+        tc::plan_tiles_p1(n, &bn_ts, &nt_ts);
+        const int mt = (h->cfg.max_batch + 127) / 128;
+        const double cost_ts = std::ceil((double)mt * nt_ts / h->num_sms) * 824.0;
+        const double cost_ss = std::ceil((double)mt * nt1 / h->num_sms) * 940.0 * bn1 / 208.0;
+        p1 = cost_ts <= cost_ss;
+    }
     if (p1) tc::plan_tiles_p1(n, &bn1, &nt1);
     bool p2ts = false;                           // product 2 through the same TMEM-A kernel (GPAD_TC_P2TS=1)
     if (const char* e = getenv("GPAD_TC_P2TS")) p2ts = p1 && atoi(e) != 0;
