@@ -650,7 +650,7 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
     if (const char* e = getenv("GPAD_TC_P2TS")) p2ts = p1 && atoi(e) != 0;
     if (p2ts) tc::plan_tiles_p1(m, &bn2, &nt2);
     h->op.n_rows_pad = round_up(std::max(bn1 * nt1, n), 128);
-    h->op.m_rows_pad = round_up(std::max(bn2 * nt2, m), 128);
+    h->op.m_rows_pad = round_up(m + 256, 128);      // any product-2 tiling of width <= 256 stays inside (setup-time autotuning)
     GPAD_TRY(upload_padded(h, MG.data(), n, m, h->op.n_rows_pad, st.mp, &h->op.M_G));
     GPAD_TRY(upload_padded(h, GL.data(), m, n, h->op.m_rows_pad, st.np, &h->op.G_L));
     const size_t bm = (size_t)st.Bp * st.mp, bnn = (size_t)st.Bp * st.np;
@@ -711,6 +711,56 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         GPAD_TRY(tc::make_tmap(&g2.tmA_lo, st.zh_lo, st.np, st.Bp, st.np, bk, 128));
         GPAD_TRY(tc::make_tmap(&g2.tmB_hi, h->op.G_L, st.np, h->op.m_rows_pad, st.np, g2.bk, p2ts ? bn2 : bn2 / bdiv));
         GPAD_TRY(tc::make_tmap(&g2.tmB_lo, h->op.G_L_lo, st.np, h->op.m_rows_pad, st.np, g2.bk, p2ts ? bn2 : bn2 / bdiv));
+        // ---- product 2 tile width: measured, not modelled.  The landscape is irregular (64K quadrotor batch, ms per launch:
+        // 240 -> 0.73, 208 -> 1.04, 192 -> 0.69, 160 -> 0.66, 128 -> 0.81), so a few widths are timed on this handle's own
+        // buffers (3 launches each on the zeroed state) and the fastest is kept.  Results do not depend on the width: every
+        // output element sums over K in the same order.
+        auto config_g2 = [&](int b) -> int {
+            bn2 = b; nt2 = (m + b - 1) / b;
+            g2.bn = bn2; g2.n_tiles = nt2;
+            g2.stages = tc::pick_stages(bk, bn2, h->smem_optin);
+            if (const char* e = getenv("GPAD_TC_STAGES")) g2.stages = std::min(g2.stages, std::max(2, atoi(e)));
+            GPAD_TRY(tc::make_tmap(&g2.tmB_hi, h->op.G_L, st.np, h->op.m_rows_pad, st.np, g2.bk, bn2 / bdiv));
+            GPAD_TRY(tc::make_tmap(&g2.tmB_lo, h->op.G_L_lo, st.np, h->op.m_rows_pad, st.np, g2.bk, bn2 / bdiv));
+            return GPAD_OK;
+        };
+        bool tune = cg == 1 && !p2ts && !g2.xf2 && h->cfg.max_batch >= 1024;
+        if (const char* e = getenv("GPAD_TC_AUTOTUNE")) tune = tune && atoi(e) != 0;
+        if (const char* e = getenv("GPAD_TC_BN2")) {       // explicit width (multiple of 16, <= 256)
+            if (cg == 1 && !p2ts) GPAD_TRY(config_g2(std::max(16, std::min(256, atoi(e) / 16 * 16))));
+            tune = false;
+        }
+        if (tune) {
+            const int bn_default = bn2;
+            BatchKernelArgs k{};
+            k.n = n; k.m = m; k.np = st.np; k.mp = st.mp; k.B = h->cfg.max_batch; k.L = h->cfg.L;
+            k.g_P = st.g_P; k.p_D = st.p_D; k.z = st.z; k.zhat = st.zhat; k.zh_hi = st.zh_hi; k.zh_lo = st.zh_lo;
+            k.sbar = st.sbar; k.red = st.red;
+            k.y_prev = st.yb[2]; k.y_cur = st.yb[0]; k.y_next = st.yb[1];
+            k.it.theta = 1.f; k.it.beta = 0.f;
+            cudaEvent_t e0, e1;
+            GPAD_CUDA(cudaEventCreate(&e0)); GPAD_CUDA(cudaEventCreate(&e1));
+            float best_ms = 1e30f; int best_bn = bn_default;
+            std::vector<int> cand = {bn_default};
+            for (int b : {224, 192, 176, 160, 144, 128}) if (b < bn_default && b * 2 >= 96 && (m + b - 1) / b <= 64) cand.push_back(b);
+            for (int b : cand) {
+                if (config_g2(b) != GPAD_OK) continue;
+                g2.m_tiles = (h->cfg.max_batch + 127) / 128;
+                float ms = 1e30f;
+                bool ok = true;
+                for (int rep = 0; rep < 4 && ok; ++rep) {          // first launch untimed
+                    if (rep == 1) cudaEventRecord(e0, nullptr);
+                    ok = tc::launch_gemm(2, g2, k, nullptr, 0, h->num_sms, nullptr) == GPAD_OK;
+                }
+                cudaEventRecord(e1, nullptr);
+                if (cudaEventSynchronize(e1) != cudaSuccess || !ok) { cudaGetLastError(); continue; }
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (ms < best_ms) { best_ms = ms; best_bn = b; }
+            }
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            GPAD_TRY(config_g2(best_bn));
+            GPAD_CUDA(cudaMemset(st.yb[1], 0, bm * sizeof(float)));      // the timed launches wrote y_next
+        }
         if (p1)
             snprintf(buf, sizeof(buf),
                      "batch-shared: tcgen05 cta_group::1 kind::tf32 x3; product1 = P-formulation (A = y_v only, split in registers, A operand "
