@@ -711,8 +711,8 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         GPAD_TRY(tc::make_tmap(&g2.tmA_lo, st.zh_lo, st.np, st.Bp, st.np, bk, 128));
         GPAD_TRY(tc::make_tmap(&g2.tmB_hi, h->op.G_L, st.np, h->op.m_rows_pad, st.np, g2.bk, p2ts ? bn2 : bn2 / bdiv));
         GPAD_TRY(tc::make_tmap(&g2.tmB_lo, h->op.G_L_lo, st.np, h->op.m_rows_pad, st.np, g2.bk, p2ts ? bn2 : bn2 / bdiv));
-        // ---- product 2 tile width: measured, not modelled.  The landscape is irregular (64K quadrotor batch, ms per launch:
-        // 240 -> 0.73, 208 -> 1.04, 192 -> 0.69, 160 -> 0.66, 128 -> 0.81), so a few widths are timed on this handle's own
+        // ---- product 2 tile width: measured, not modelled (64K quadrotor batch, ms per launch: 240 -> 0.73, 208 -> 1.04,
+        // 192 -> 0.69, 160 -> 0.66, 128 -> 0.81), so a few widths are timed on this handle's own
         // buffers (3 launches each on the zeroed state) and the fastest is kept.  Results do not depend on the width: every
         // output element sums over K in the same order.
         auto config_g2 = [&](int b) -> int {
@@ -742,7 +742,9 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
             GPAD_CUDA(cudaEventCreate(&e0)); GPAD_CUDA(cudaEventCreate(&e1));
             float best_ms = 1e30f; int best_bn = bn_default;
             std::vector<int> cand = {bn_default};
-            for (int b : {224, 192, 176, 160, 144, 128}) if (b < bn_default && b * 2 >= 96 && (m + b - 1) / b <= 64) cand.push_back(b);
+            // multiples of 32 columns: every 32-column block of the epilogue then starts on a 128-byte line (widths that
+            // are only multiples of 16 -- 144, 176, 208, 240 -- measured 0.73 .. 1.04 ms against 0.66 .. 0.69 for 160 / 192)
+            for (int b : {256, 224, 192, 160, 128}) if (b != bn_default && (m + b - 1) / b <= 64) cand.push_back(b);
             for (int b : cand) {
                 if (config_g2(b) != GPAD_OK) continue;
                 g2.m_tiles = (h->cfg.max_batch + 127) / 128;
