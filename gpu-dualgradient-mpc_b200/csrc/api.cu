@@ -645,7 +645,8 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         const double cost_ss = std::ceil((double)mt * nt1 / h->num_sms) * 940.0 * bn1 / 208.0;
         p1 = cost_ts <= cost_ss;
     }
-    if (p1) tc::plan_tiles_p1(n, &bn1, &nt1);
+    int step1 = 0;
+    if (p1) tc::plan_tiles_p1(n, &bn1, &nt1, &step1);
     bool p2ts = false;                           // product 2 through the same TMEM-A kernel (GPAD_TC_P2TS=1)
     if (const char* e = getenv("GPAD_TC_P2TS")) p2ts = p1 && atoi(e) != 0;
     if (p2ts) tc::plan_tiles_p1(m, &bn2, &nt2);
@@ -693,7 +694,7 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         g1.stages = cg == 2 ? tc::pick_stages2(bk, bn1, h->smem_optin) : tc::pick_stages(bk, bn1, h->smem_optin);
         g2.stages = cg == 2 ? tc::pick_stages2(bk, bn2, h->smem_optin) : tc::pick_stages(bk, bn2, h->smem_optin);
         if (p1) {
-            g1.p1 = 1; g1.bk = 16; g1.mc = 1;
+            g1.p1 = 1; g1.bk = 16; g1.mc = 1; g1.step = step1;
             GPAD_TRY(tc::plan_rings_p1(1, bn1, h->smem_optin, &g1.a_stages, &g1.stages));
         }
         if (p2ts) {

@@ -20,6 +20,7 @@ struct GemmDesc {
     int xf2 = 0;                  // product 2 stages zhat as ONE fp32 tile and splits it in shared memory (transform warps)
     int p1 = 0;                   // product 1 runs the second-generation kernel (batch_tc_p1.cu): stages = operator ring,
     int a_stages = 0;             // a_stages = state ring
+    int step = 0;                 // p1: column distance between tile starts (<= bn, see plan_tiles_p1); 0 = bn
     int ncols_valid = 0;          // output columns that exist (n or m)
 };
 
@@ -31,7 +32,7 @@ int launch_gemm(int phase, const GemmDesc& g, const BatchKernelArgs& args, float
 size_t smem_bytes2(int bk, int bn, int stages);
 int pick_stages2(int bk, int bn, size_t smem_limit);
 int launch_gemm2(int phase, const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s);
-void plan_tiles_p1(int ncols, int* bn, int* n_tiles);
+void plan_tiles_p1(int ncols, int* bn, int* n_tiles, int* step = nullptr);
 int plan_rings_p1(int phase, int bn, size_t smem_limit, int* a_stages, int* b_stages);
 int launch_p1(int phase, const GemmDesc& g, const BatchKernelArgs& args, int num_sms, cudaStream_t s);
 int launch_split(const float* src, float* hi, float* lo, size_t count, cudaStream_t s);

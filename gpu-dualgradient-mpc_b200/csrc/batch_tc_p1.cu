@@ -68,7 +68,7 @@ template <int PHASE, int EPI>
 __global__ void __launch_bounds__(32 * (kP1FirstEpi + EPI), 1)
 tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmB_hi,
              const __grid_constant__ CUtensorMap tmB_lo, int num_k_blocks, int m_tiles, int n_tiles, int bn,
-             int a_stages, int b_stages, const BatchKernelArgs args, int ncols_valid) {
+             int a_stages, int b_stages, const BatchKernelArgs args, int ncols_valid, int step) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int BK = kP1BK;
@@ -111,7 +111,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         // ============================ operator producer (M_G hi / lo, L2 resident) ============================
         int s = 0; uint32_t ph = 0;
         for (P1Sched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
-            const int row_b = ts.n_tile() * bn;
+            const int row_b = ts.n_tile() * step;
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 mbar_wait(smem_u32(bempty + s), ph ^ 1);
                 if (elect_one()) {
@@ -234,7 +234,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
 #pragma unroll
                 for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = __uint_as_float(v[j]);
                 __syncwarp();
-                epilogue_block<PHASE>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, nullptr, 0);
+                epilogue_block<PHASE>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, nullptr, 0, step);
                 __syncwarp();
             }
             tc_fence_before();
@@ -261,12 +261,15 @@ size_t p1_smem_bytes(int bn, int a_stages, int b_stages, int epi) {
 }  // namespace
 
 // tiles of at most 208 columns: 2 x 208 accumulator columns + 96 columns of A ring fill the 512 TMEM columns
-void plan_tiles_p1(int ncols, int* bn, int* n_tiles) {
+void plan_tiles_p1(int ncols, int* bn, int* n_tiles, int* step) {
     const int nt = (ncols + 207) / 208;
     int b = ((ncols + nt - 1) / nt + 15) / 16 * 16;
     if (b < 16) b = 16;
     *bn = b;
     *n_tiles = nt;
+    // start the tiles on 128-byte lines when the same number of tiles still covers all columns that way
+    const int s32 = b / 32 * 32;
+    if (step) *step = (nt > 1 && s32 > 0 && (nt - 1) * s32 + b >= ncols) ? s32 : b;
 }
 
 int plan_rings_p1(int phase, int bn, size_t smem_limit, int* a_stages, int* b_stages) {
@@ -288,11 +291,11 @@ int launch_p1(int phase, const GemmDesc& g, const BatchKernelArgs& args, int num
     if (phase == 1) {
         GPAD_CUDA(cudaFuncSetAttribute(tc_p1_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_p1_kernel<1, 8><<<grid, 32 * (kP1FirstEpi + 8), smem, s>>>(g.tmA_hi, g.tmB_hi, g.tmB_lo, g.k_pad / kP1BK, g.m_tiles, g.n_tiles, g.bn,
-                                                       g.a_stages, g.stages, args, g.ncols_valid);
+                                                       g.a_stages, g.stages, args, g.ncols_valid, g.step > 0 ? g.step : g.bn);
     } else {
         GPAD_CUDA(cudaFuncSetAttribute(tc_p1_kernel<2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_p1_kernel<2, 12><<<grid, 32 * (kP1FirstEpi + 12), smem, s>>>(g.tmA_hi, g.tmB_hi, g.tmB_lo, g.k_pad / kP1BK, g.m_tiles, g.n_tiles, g.bn,
-                                                       g.a_stages, g.stages, args, g.ncols_valid);
+                                                       g.a_stages, g.stages, args, g.ncols_valid, g.step > 0 ? g.step : g.bn);
     }
     GPAD_CUDA(cudaGetLastError());
     return GPAD_OK;

@@ -9,10 +9,14 @@ namespace tc {
 
 template <int PHASE>
 __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, const float* buf, int lane, int row_base, int blk,
-                                               int n_tile, int bn, int ncols_valid, float* __restrict__ Cdbg, int ldc) {
+                                               int n_tile, int bn, int ncols_valid, float* __restrict__ Cdbg, int ldc,
+                                               int step = 0) {
+    // tiles start every `step` columns (default: bn).  step < bn (a multiple of 32) keeps every 32-column block on a
+    // 128-byte line; the bn - step columns a tile shares with its predecessor belong to the predecessor
     const int cin = blk * 32 + lane;            // column inside the tile
-    const int c = n_tile * bn + cin;       // global output column
-    const bool col_ok = cin < bn && c < ncols_valid;
+    const int stp = step > 0 ? step : bn;
+    const int c = n_tile * stp + cin;      // global output column
+    const bool col_ok = cin < bn && c < ncols_valid && (n_tile == 0 || cin >= bn - stp);
     if (PHASE == 0) {
 #pragma unroll 8
         for (int rr = 0; rr < 32; ++rr) {
