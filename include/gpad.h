@@ -209,8 +209,9 @@ int gpad_expand_operators(int n_u, int N, int m, const float* M_G_flat, const fl
 /* Closed-loop receding-horizon simulation (gpad.m:79-95): every sample builds g_P / p_D from the current
  * states, solves the batch with h (max_iter iterations, fixed), applies u = z[0:n_u] and advances
  * x <- A x + B u in double.  warm_start != 0 feeds the previous duals (y_I, y_{I-1}) into the next solve; the
- * reference cold-starts every sample (acceldualgrad.m:16-18).  x0 [batch][nx]; xref [batch][n_par-nx] or NULL;
- * x_traj [samples+1][batch][nx]; u_traj [samples][batch][n_u]. */
+ * reference cold-starts every sample (acceldualgrad.m:16-18).  The whole loop runs on the device (instance build, solve,
+ * state advance; nx <= 32); only the trajectories are copied back.  x0 [batch][nx]; xref [batch][n_par-nx] or NULL;
+ * x_traj [samples+1][batch][nx]; u_traj [samples][batch][n_u] (host, either may be NULL). */
 int gpad_closed_loop(gpad_problem_t prob, gpad_handle_t h, int batch, const double* x0, const double* xref, int samples,
                      const float* theta, const float* beta, int max_iter, int warm_start, double* x_traj, double* u_traj);
 
