@@ -28,7 +28,7 @@ EXPORTS = [
     "gpad_profile_enable", "gpad_profile_read",
     "gpad_problem_battery", "gpad_problem_quadrotor", "gpad_problem_destroy", "gpad_problem_dims",
     "gpad_problem_operators", "gpad_problem_instances", "gpad_problem_plant", "gpad_schedule",
-    "gpad_file_read", "gpad_file_write", "gpad_file_free", "gpad_debug_gemm_tf32x3",
+    "gpad_file_read", "gpad_file_write", "gpad_file_free", "gpad_debug_gemm_tf32x3", "gpad_debug_plan_tiles",
     "gpad_flatten_operators", "gpad_expand_operators", "gpad_closed_loop",
 ]
 
@@ -104,6 +104,7 @@ def lib():
         L.gpad_file_write.argtypes = [C.c_char_p, C.POINTER(FileData)]
         L.gpad_file_free.argtypes = [C.POINTER(FileData)]
         L.gpad_debug_gemm_tf32x3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.gpad_debug_plan_tiles.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4
         _lib = L
     return _lib
 
@@ -333,6 +334,13 @@ def step_four(G_L, y_vp1, w, p_D, zhat, N, n_u, m, max_threads=0, stream=None):
 
 def debug_gemm_tf32x3(A, B, Cout, M, N, K, stream=None):
     check(lib().gpad_debug_gemm_tf32x3(_ptr(A), _ptr(B), _ptr(Cout), M, N, K, stream), "gpad_debug_gemm_tf32x3")
+
+
+def debug_plan_tiles(kernel, ncols):
+    """(bn, n_tiles, step, tmem_cols) of the batch kernels' column tiling; host only."""
+    v = [C.c_int() for _ in range(4)]
+    check(lib().gpad_debug_plan_tiles(kernel, ncols, *[C.byref(x) for x in v]), "gpad_debug_plan_tiles")
+    return tuple(x.value for x in v)
 
 
 # ---- reference data file (main.cu:29-67) ----

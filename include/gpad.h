@@ -239,6 +239,12 @@ void gpad_file_free(gpad_file_t* f);
 int gpad_debug_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int K,
                            void* stream);
 
+/* Test hook, host only (no device call): the column tiling the batch kernels use for an operator with
+ * `ncols` output columns. kernel 0 = shared-memory-operand kernel (tiles <= 256 columns), 1 = the
+ * TMEM-operand kernel (tiles <= 208 columns, 96 TMEM columns kept for the state ring).
+ * Tile t covers columns [t*step, t*step + bn); tmem_cols = TMEM columns the plan occupies (<= 512). */
+int gpad_debug_plan_tiles(int kernel, int ncols, int* bn, int* n_tiles, int* step, int* tmem_cols);
+
 #ifdef __cplusplus
 }
 #endif

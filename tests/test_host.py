@@ -148,3 +148,21 @@ def test_flat_operators_round_trip_and_match_reference_flat_steps(dims):
     # a dense operator without the battery structure does not flatten
     _, _, r2 = G.flatten_operators(n_u, N, pb.m, rng.standard_normal(M_G.shape).astype(np.float32), G_L)
     assert r2 > 0.1
+
+
+@pytest.mark.parametrize("kernel,max_bn", [(0, 256), (1, 208)])
+def test_batch_column_tiling_covers_every_width(kernel, max_bn):
+    """Host-side tile planner of the batch kernels (batch_tc.cu plan_tiles, batch_tc_p1.cu plan_tiles_p1):
+    every operator width from 1 to 4800 columns (2x the quadrotor's m = 2400) is covered by the planned tiles,
+    tiles are UMMA-legal (N multiple of 16, <= 256), start on 128-byte lines whenever the stride differs from
+    the width, and the accumulators plus the state ring fit the 512 TMEM columns of one SM."""
+    for ncols in list(range(1, 1200)) + [2399, 2400, 2401, 4799, 4800]:
+        bn, nt, step, tmem = G.debug_plan_tiles(kernel, ncols)
+        assert bn % 16 == 0 and 16 <= bn <= max_bn, (ncols, bn)
+        assert 1 <= step <= bn and (step == bn or step % 32 == 0), (ncols, bn, step)
+        assert (nt - 1) * step + bn >= ncols, (ncols, bn, nt, step)          # last tile reaches the last column
+        assert nt == 1 or (nt - 1) * step < ncols, (ncols, bn, nt, step)     # no tile entirely past the end
+        assert tmem <= 512, (ncols, bn, tmem)
+    assert G.debug_plan_tiles(1, 400)[:3] == (208, 2, 192)                  # quadrotor product 1: aligned second tile
+    with pytest.raises(G.GpadError):
+        G.debug_plan_tiles(2, 400)
