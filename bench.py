@@ -250,7 +250,12 @@ def per_instance_probe(torch, G, B=262144):
     res = {"workload": f"battery(3,4) n={n} m={m}, {B} QPs with per-instance operators, 100 iterations", "solves_per_s": B / sec,
            "ms_per_batch": sec * 1e3, "algorithmic_bytes_per_solve": bytes_min // B, "achieved_GBps": bytes_min / sec / 1e9,
            "hbm_peak_GBps": hbm, "frac_of_hbm_roofline": bytes_min / sec / 1e9 / hbm, "path": s.description,
-           "note": "latency-bound: one dependent shuffle/FMA chain per iteration and ~16 QPs in flight per SM, vs an HBM floor of 0.83 ms per 1M solves"}
+           # the bound that applies: instruction issue. profiles/r1_ncu_per_instance_warp.csv: 174.4 warp instructions per QP-iteration
+           # (smsp__inst_executed / (B x 100)), issue slots 82 % busy, shuffle (LSU) pipe 58 %, FMA 44 %, DRAM 5 %
+           "warp_instructions_per_iteration": 174.4, "issue_roofline_solves_per_s": 148 * 4 * 1.965e9 / (174.4 * ITERS),
+           "frac_of_issue_roofline": (B / sec) / (148 * 4 * 1.965e9 / (174.4 * ITERS)),
+           "note": "operators stay in registers for all 100 iterations, so HBM carries 5 % of its peak and the SM issue slots are the bound: "
+                   "148 SMs x 4 schedulers x 1.965 GHz / 174.4 instructions per QP-iteration"}
     s.close()
     return res
 

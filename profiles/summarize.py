@@ -14,6 +14,10 @@ METRICS = [
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__cluster_size",
     "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "sm__cycles_elapsed.max", "smsp__inst_executed.sum",
+    "sm__inst_issued.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
 ]
 
 def main(rep, out):

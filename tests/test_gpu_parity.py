@@ -116,7 +116,8 @@ def test_step_shim_loop_equals_oracle_solve(torch_cuda, G, oracle):
 
 
 # ------------------------------------------------------------------------------------ latency mode
-LADDER = [(3, 4), (4, 3), (10, 15), (15, 10), (30, 30), (10, 100)]
+# (5,2): n = 10 and (7,2): n = 14 exercise the row-count instantiations of the one-warp kernel (n < 12, 12 < n <= 16)
+LADDER = [(3, 4), (4, 3), (5, 2), (7, 2), (10, 15), (15, 10), (30, 30), (10, 100)]
 
 
 @pytest.mark.parametrize("dims", LADDER)
