@@ -27,6 +27,37 @@ __device__ __forceinline__ float warp_sum_transposed(float (&v)[R], int lane) {
     for (; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     return t;
 }
+// the same reduction with the shuffles as volatile asm: ptxas keeps volatile statements in program order, so every
+// shuffle of one level is issued before the first of the next (breadth-first).  Left to itself ptxas sometimes walks
+// the tree depth-first to save registers, which puts ~4 R dependent shuffles on the critical path of a lone warp.
+__device__ __forceinline__ float shfl_bfly_v(float x, int o) {
+    float r;
+    asm volatile("shfl.sync.bfly.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=f"(r) : "f"(x), "r"(o));
+    return r;
+}
+__device__ __forceinline__ float shfl_idx_v(float x, int src) {
+    float r;
+    asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=f"(r) : "f"(x), "r"(src));
+    return r;
+}
+template <int R>
+__device__ __forceinline__ float warp_sum_transposed_v(float (&v)[R], int lane) {
+    static_assert(R == 8 || R == 16 || R == 32, "R");
+    int o = 16;
+#pragma unroll
+    for (int s = R / 2; s >= 1; s >>= 1, o >>= 1) {
+        const bool up = (lane & o) != 0;
+        float got[R / 2];
+#pragma unroll
+        for (int i = 0; i < s; ++i) got[i] = shfl_bfly_v(up ? v[i] : v[i + s], o);
+#pragma unroll
+        for (int i = 0; i < s; ++i) v[i] = (up ? v[i + s] : v[i]) + got[i];
+    }
+    float t = v[0];
+#pragma unroll
+    for (; o >= 1; o >>= 1) t += shfl_bfly_v(t, o);
+    return t;
+}
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 

@@ -13,6 +13,9 @@
 // Termination: all three branches of SURVEY row T; the dual-gap branch runs the two phases once more on y_{v+1}.
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "gpad_internal.h"
 #include "lat_util.cuh"
 #include "latency.h"
@@ -27,7 +30,8 @@ constexpr int kMR = 2;     // dual entries per lane
 constexpr int kWarpsPerCta = 4;
 
 // NR = rows of M_G that can be non-zero (n <= NR <= kWR): rows beyond it skip their products and their zhat broadcast
-template <bool CHECK, int NR>
+// ORD: shuffles issued in program order (lat_util.cuh warp_sum_transposed_v) -- see launch_warp for which mode uses what
+template <bool CHECK, int NR, bool ORD>
 __global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp_kernel(const Params p_in, int warps_per_cta) {
     Params p = p_in;
     const int lane = threadIdx.x & 31;
@@ -85,17 +89,19 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp_kernel(const Para
         float acc[kWR];
 #pragma unroll
         for (int r = 0; r < kWR; ++r) acc[r] = r < NR ? fmaf(mg[1][r], w[1], mg[0][r] * w[0]) : 0.f;
-        const float tot = warp_sum_transposed<kWR>(acc, lane);
+        const float tot = ORD ? warp_sum_transposed_v<kWR>(acc, lane) : warp_sum_transposed<kWR>(acc, lane);
         zh_me = tot - gp_me;
         z_me = __fadd_rn(__fmul_rn(one_minus, z_me), __fmul_rn(theta, zh_me));
 
         // ---------------- phase B ----------------
         float d[kMR] = {0.f, 0.f};
+        float zc[NR];
+#pragma unroll
+        for (int c = 0; c < NR; ++c) zc[c] = ORD ? shfl_idx_v(zh_me, 2 * c) : __shfl_sync(0xffffffffu, zh_me, 2 * c);
 #pragma unroll
         for (int c = 0; c < NR; ++c) {
-            const float zc = __shfl_sync(0xffffffffu, zh_me, 2 * c);
 #pragma unroll
-            for (int j = 0; j < kMR; ++j) d[j] = fmaf(gl[j][c], zc, d[j]);
+            for (int j = 0; j < kMR; ++j) d[j] = fmaf(gl[j][c], zc[c], d[j]);
         }
         float r_max_sbar = -INFINITY, r_max_rhat = -INFINITY, r_min_w = INFINITY, r_w_rhat = 0.f, r_w_dot = 0.f, r_bad = 0.f;
 #pragma unroll
@@ -213,17 +219,25 @@ int launch_warp(const Params& p, cudaStream_t stream) {
     const int wpc = B > 1 ? kWarpsPerCta : 1;
     const int grid = (B + wpc - 1) / wpc;
     const bool chk = p.check_every > 0;
-    // NR = 12 covers the reference's default battery problem (n = 12): 10 % fewer instructions and 72 instead of 116
-    // registers, +7 % solves/s for batches (issue-bound).  For ONE QP the same instantiation is 60 % slower: with the
-    // smaller register budget ptxas walks the reduction tree depth-first (every shuffle result consumed at once), so
-    // the single warp waits on ~20 dependent shuffles per iteration instead of 5 levels -- latency mode keeps NR = 16.
-    if (p.n <= 12 && B > 1) {
-        if (chk) gpad_warp_kernel<true, 12><<<grid, 32 * wpc, 0, stream>>>(p, wpc);
-        else gpad_warp_kernel<false, 12><<<grid, 32 * wpc, 0, stream>>>(p, wpc);
-    } else {
-        if (chk) gpad_warp_kernel<true, kWR><<<grid, 32 * wpc, 0, stream>>>(p, wpc);
-        else gpad_warp_kernel<false, kWR><<<grid, 32 * wpc, 0, stream>>>(p, wpc);
+    // Batches are issue-bound: NR = 12 covers the reference's default battery problem (n = 12) with 10 % fewer
+    // instructions, and program-ordered shuffles keep the reduction breadth-first at 79 registers (50.6 -> 56.4 M solves/s).
+    // ONE QP is bound by the dependent chain of a lone warp, and there ptxas' own schedule of the 16-row kernel is the
+    // best measured (37 us per 100 iterations; 12 rows: 61 us unordered -- ptxas walks the tree depth-first -- 45 us ordered).
+    int nr = (p.n <= 12 && B > 1) ? 12 : kWR;
+    bool ord = B > 1;
+    if (const char* e = getenv("GPAD_WARP_PLAN")) {          // experiments: "<rows>,<ordered>"
+        int a = 0, b = 0;
+        if (sscanf(e, "%d,%d", &a, &b) == 2 && (a == 12 || a == kWR) && a >= p.n) { nr = a; ord = b != 0; }
     }
+#define GPAD_WARP_LAUNCH(C, N, O) gpad_warp_kernel<C, N, O><<<grid, 32 * wpc, 0, stream>>>(p, wpc)
+    if (nr == 12) {
+        if (ord) { if (chk) GPAD_WARP_LAUNCH(true, 12, true); else GPAD_WARP_LAUNCH(false, 12, true); }
+        else     { if (chk) GPAD_WARP_LAUNCH(true, 12, false); else GPAD_WARP_LAUNCH(false, 12, false); }
+    } else {
+        if (ord) { if (chk) GPAD_WARP_LAUNCH(true, kWR, true); else GPAD_WARP_LAUNCH(false, kWR, true); }
+        else     { if (chk) GPAD_WARP_LAUNCH(true, kWR, false); else GPAD_WARP_LAUNCH(false, kWR, false); }
+    }
+#undef GPAD_WARP_LAUNCH
     GPAD_CUDA(cudaGetLastError());
     return GPAD_OK;
 }

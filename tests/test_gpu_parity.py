@@ -700,3 +700,36 @@ def test_batch_host_pipeline_equals_single_pass(torch_cuda, G, prec, monkeypatch
         assert np.array_equal(piped[k], one[k]), k
         assert np.array_equal(piped_w[k], one_w[k]), k
     assert (piped["iters"] == 30).all() and (piped["status"] == 0).all()
+
+
+@pytest.mark.parametrize("plan", ["16,0", "16,1", "12,0", "12,1"])
+def test_warp_kernel_plans_are_bit_identical(torch_cuda, G, plan, monkeypatch):
+    """latency_warp.cu instantiations (16 or 12 live rows, shuffles scheduled by ptxas or in program order) change the
+    instruction schedule, never the arithmetic: one QP (latency mode) and a per-instance batch, fixed iterations and
+    tolerance mode with the cost vector, must reproduce the default plans bit for bit"""
+    n_u, N, B = 3, 4, 37
+    pb = P.battery(n_u, N)
+    theta, beta = schedule(100)
+    rng = np.random.default_rng(77)
+    g_P = np.empty((B, pb.n), np.float32); p_D = np.empty((B, pb.m), np.float32); f = np.empty((B, pb.n), np.float32)
+    for b in range(B):
+        g_P[b], p_D[b], f[b] = pb.instance(rng.random(n_u) - 0.5)
+    M = np.repeat(pb.M_G[None], B, 0).copy(); Gl = np.repeat(pb.G_L[None], B, 0).copy()
+
+    def run():
+        one = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_LATENCY)
+        many = G.Solver(n_u, N, pb.m, pb.L, M, Gl, mode=G.MODE_BATCH_PER_INSTANCE, max_batch=B)
+        assert "one warp" in one.description.lower() and "warp" in many.description.lower()
+        out = [one.solve_host(g_P[0], p_D[0], theta, beta),
+               one.solve_host(g_P[0], p_D[0], theta, beta, f=f[0], check_every=1, eps_g=1e-2, eps_V=1e-2),
+               many.solve_host(g_P, p_D, theta, beta),
+               many.solve_host(g_P, p_D, theta, beta, f=f, check_every=2, eps_g=1e-2, eps_V=1e-2)]
+        one.close(); many.close()
+        return out
+
+    monkeypatch.delenv("GPAD_WARP_PLAN", raising=False)
+    base = run()
+    monkeypatch.setenv("GPAD_WARP_PLAN", plan)
+    for a, b in zip(base, run()):
+        for k in list(VECS) + ["iters", "status"]:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (plan, k)
