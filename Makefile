@@ -13,7 +13,7 @@ NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -ccbin $(HOSTCXX) -Xcompiler -fPIC,-
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Iinclude -I$(HOST)
 
 CU_SRCS  := $(wildcard $(CSRC)/*.cu)
-CPP_SRCS := $(HOST)/problem.cpp $(HOST)/io.cpp
+CPP_SRCS := $(HOST)/problem.cpp $(HOST)/plants.cpp $(HOST)/io.cpp
 OBJS := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU_SRCS)) $(patsubst $(HOST)/%.cpp,build/host_%.o,$(CPP_SRCS))
 
 all: $(LIBDIR)/libgpad_b200.so $(LIBDIR)/gpad_main oracle

@@ -39,9 +39,8 @@ struct BatchKernelArgs {
     float* sbar;
     float* red;
     const int* done;       // per-instance "stopped" flag (null in fixed-iteration mode)
-    // P-formulation of product 1 (tcgen05 cta_group::1 path): the GEMM computes P_v = M_G y_v and the epilogue forms
+    // P-formulation of product 1 (tcgen05 path): the GEMM computes P_v = M_G y_v and the epilogue forms
     // M_G w_v = P_v + beta (P_v - P_{v-1}) -- linear in y, so y_{v-1} never has to be staged as an MMA operand
-    int pform;
     int p_only;            // warm start: this launch only produces P_{-1} = M_G y_{-1}
     const float* P_prev;   // [Bp][np] P_{v-1}
     float* P_cur;          // [Bp][np] P_v
@@ -50,8 +49,11 @@ struct BatchKernelArgs {
     int dual;
     const int* need;       // [Bp] instance takes the dual-gap branch at this check
     float* zy;             // [Bp][np] z_y (CUDA-core path; the tcgen05 path reuses zh_hi / zh_lo)
-    int zh_single;         // product 2 splits zhat itself: product 1 stores zhat (fp32) only, not zh_hi / zh_lo
-    int prefetch;          // tcgen05 path: epilogue warps pull the next tile's operands into L2 (batch_tc.cu)
+    // tolerance mode, tile retirement: the 128-row batch tiles that still hold a running instance, as a dense list
+    // (batch_simt.cu:batch_tiles_*); null in fixed-iteration solves (every tile runs)
+    const int* tile_list;
+    const int* tile_count;
+    const int* dual_count; // dual-gap launches return at once when no instance waits for the evaluation
 };
 
 __device__ __forceinline__ float tf32_rn(float x) {
@@ -96,7 +98,7 @@ __device__ __forceinline__ void epilogue1(const BatchKernelArgs& a, int b, int i
     const float zh = acc - a.g_P[o];
     a.z[o] = __fadd_rn(__fmul_rn(1.0f - a.it.theta, a.z[o]), __fmul_rn(a.it.theta, zh));   // unfused like the CPU build
     a.zhat[o] = zh;
-    if (SPLIT && !a.zh_single) {
+    if (SPLIT) {
         float hi, lo;
         split_tf32(zh, hi, lo);
         a.zh_hi[o] = hi;

@@ -8,6 +8,8 @@
 // Both operands are K-contiguous (instance-major state, sequential-layout operators), all
 // buffers are zero padded to the tile sizes, so the mainloop has no bounds checks.
 // Tile 128x128x16, 256 threads, 8x8 outputs per thread, double-buffered shared memory.
+#include <algorithm>
+
 #include "batch_common.cuh"
 #include "gpad_internal.h"
 
@@ -27,7 +29,9 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const float* __restrict_
     __shared__ __align__(16) float Bs[2][BK][BN + PAD];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 thread grid, 8x8 outputs each
-    const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+    if (args.dual && args.dual_count && *args.dual_count == 0) return;     // nobody waits for the dual-gap evaluation
+    if (args.tile_count && (int)blockIdx.y >= *args.tile_count) return;     // tolerance mode: retired batch tiles
+    const int row0 = (args.tile_list ? args.tile_list[blockIdx.y] : (int)blockIdx.y) * BM, col0 = blockIdx.x * BN;
 
     float acc[8][8];
 #pragma unroll
@@ -146,9 +150,12 @@ __global__ void batch_init_kernel(int Bp, int np, int mp, float* __restrict__ z,
 
 __global__ void batch_reset_term_kernel(int Bp, float* __restrict__ red, int* __restrict__ done, int* __restrict__ iters,
                                         int* __restrict__ status, float* __restrict__ max_viol, float* __restrict__ gap,
-                                        int* __restrict__ active, int* __restrict__ need, int B, int max_iter) {
+                                        int* __restrict__ active, int* __restrict__ need, int B, int max_iter,
+                                        int* __restrict__ tile_list, int* __restrict__ tile_count,
+                                        unsigned long long* __restrict__ stat) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b == 0) { active[0] = B; active[1] = 0; }
+    if (b == 0) { active[0] = B; active[1] = 0; *tile_count = (B + 127) / 128; stat[0] = 0; stat[1] = 0; }
+    if (b < (B + 127) / 128) tile_list[b] = b;        // every batch tile runs until the first decision
     if (b >= Bp) return;
     float* r = red + (size_t)b * kRedStride;
     r[0] = -INFINITY; r[1] = -INFINITY; r[2] = INFINITY; r[3] = 0.f; r[4] = 0.f; r[5] = 0.f; r[6] = 0.f; r[7] = 0.f;
@@ -228,6 +235,60 @@ __global__ void batch_decide_dual_kernel(int B, int iter_done, float L, float ep
     r[3] = 0.f; r[4] = 0.f; r[5] = 0.f; r[6] = 0.f; r[7] = 0.f;
 }
 
+// ---- tile retirement (tolerance mode): after every decision the 128-row batch tiles that still hold a running
+// instance are listed densely, in ascending order; the GEMM kernels then schedule only those ----
+__global__ void batch_tile_flags_kernel(int B, const int* __restrict__ done, int* __restrict__ flags) {
+    const int b = blockIdx.x * 128 + threadIdx.x;
+    const int run = __syncthreads_or(b < B && !done[b]);
+    if (threadIdx.x == 0) flags[blockIdx.x] = run;
+}
+
+// one block: stat[0] += (tiles that ran since the last decision) x 128 x iterations, then the new list
+__global__ void __launch_bounds__(1024)
+batch_tile_list_kernel(int m_tiles, const int* __restrict__ flags, int* __restrict__ list, int* __restrict__ count,
+                       unsigned long long* __restrict__ stat, int iterations, int rebuild) {
+    __shared__ int warp_sum[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) {
+        stat[0] += (unsigned long long)*count * 128ull * (unsigned long long)iterations;
+        base = 0;
+    }
+    __syncthreads();
+    if (!rebuild) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t0 = 0; t0 < m_tiles; t0 += 1024) {
+        const int t = t0 + threadIdx.x;
+        const int f = (t < m_tiles && flags[t]) ? 1 : 0;
+        int incl = f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int ws = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += v; }
+            warp_sum[lane] = ws;                   // inclusive over warps
+        }
+        __syncthreads();
+        const int before = base + (warp ? warp_sum[warp - 1] : 0) + incl - f;
+        if (f) list[before] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) base += warp_sum[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
+// stat[1] = sum over instances of the iterations they needed
+__global__ void batch_iter_sum_kernel(int B, const int* __restrict__ iters, unsigned long long* __restrict__ stat) {
+    unsigned long long s = 0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) s += (unsigned long long)iters[b];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(stat + 1, s);
+}
+
 // outputs of instance b after I_b iterations: y_I in yb[I % 3], y_{I-1} in yb[(I-1) % 3], and
 // w_{I-1} = y_{I-1} + beta_{I-1} (y_{I-1} - y_{I-2}) with y_{I-2} in yb[(I+1) % 3]
 __global__ void unpad_y_kernel(float* __restrict__ dst_next, float* __restrict__ dst_cur, float* __restrict__ dst_w, int m, int B,
@@ -284,7 +345,23 @@ int launch_batch_init(const BatchState& st, bool checking, cudaStream_t s) {
 
 int launch_batch_reset_term(const BatchState& st, int max_iter, cudaStream_t s) {
     batch_reset_term_kernel<<<(st.Bp + 255) / 256, 256, 0, s>>>(st.Bp, st.red, st.done, st.iters, st.status, st.max_viol,
-                                                              st.gap, st.active_count, st.need, st.B, max_iter);
+                                                              st.gap, st.active_count, st.need, st.B, max_iter, st.tile_list,
+                                                              st.tile_count, st.stat);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+// accounts `iterations` for the tiles that ran since the last decision and (rebuild) lists the tiles still running
+int launch_batch_tiles(const BatchState& st, int iterations, bool rebuild, cudaStream_t s) {
+    const int m_tiles = (st.B + 127) / 128;
+    if (rebuild) batch_tile_flags_kernel<<<m_tiles, 128, 0, s>>>(st.B, st.done, st.tile_flags);
+    batch_tile_list_kernel<<<1, 1024, 0, s>>>(m_tiles, st.tile_flags, st.tile_list, st.tile_count, st.stat, iterations, rebuild ? 1 : 0);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+int launch_batch_iter_sum(const BatchState& st, cudaStream_t s) {
+    batch_iter_sum_kernel<<<std::min(148, (st.B + 255) / 256), 256, 0, s>>>(st.B, st.iters, st.stat);
     GPAD_CUDA(cudaGetLastError());
     return GPAD_OK;
 }

@@ -15,12 +15,16 @@
 //               tcgen05.commit releases ring slots and publishes finished accumulators
 //   warps 2..13 product 2 / test hook: 12 epilogue warps: tcgen05.ld 32x32b -> registers -> per-warp
 //               smem transpose -> coalesced global reads/writes of the fused GPAD epilogue
-//               product 1: warps 2..5 are TRANSFORM warps -- the two A tiles that arrive are y_v and
-//               y_{v-1}; they rewrite them in place as hi/lo of w = y + beta (y - y_prev) (step 1 and
-//               the tf32 split fused into operand staging, so w never exists in HBM), fence the
-//               generic->async proxy and hand the slot to the MMA warp; warps 6..13 are the epilogue
+//               product 1: warps 2..5 are TRANSFORM warps -- the A tile that arrives is y_v (fp32); they
+//               rewrite it in place as tf32 hi and write lo next to it (the momentum is applied to the
+//               product in the epilogue, P-formulation), fence the generic->async proxy and hand the slot
+//               to the MMA warp; warps 6..13 are the epilogue
 //   TMEM: 512 columns = 2 accumulator stages x 256 fp32 columns, so the epilogue of tile t
 //   overlaps the mainloop of tile t+1.
+// Launch boundaries: every kernel is launched with programmatic stream serialization (PDL): its CTAs start as soon
+// as an SM frees up, set up barriers / TMEM / descriptors, and only then wait for the previous kernel's memory
+// (griddepcontrol.wait), so the tail of one product overlaps the prologue of the next.
+// Tolerance mode: the batch tiles that still hold a running instance arrive as a dense list (tile retirement).
 #include <cuda.h>
 
 #include <algorithm>
@@ -36,41 +40,42 @@ namespace tc {
 
 namespace {
 
-// work units are (m_group, n_tile): a cluster of `mc` CTAs takes mc consecutive 128-row batch tiles of the same
-// operator tile, so the operator boxes can be multicast; CTA rank r owns batch tile m_group * mc + r
+// work units are (batch tile, operator tile), operator tile fastest so that the tiles of one batch tile run on
+// neighbouring CTAs at the same time (DRAM locality of the m-sized epilogue rows).  With a tile
+// list (tolerance mode) only the listed batch tiles exist.
 struct TileSched {
-    int unit, step, total, n_tiles, mc, rank;
-    __device__ TileSched(int m_tiles, int n_tiles_, int mc_, int rank_)
-        : unit(blockIdx.x / mc_), step(gridDim.x / mc_), total((m_tiles + mc_ - 1) / mc_ * n_tiles_), n_tiles(n_tiles_), mc(mc_), rank(rank_) {}
+    int unit, step, total, n_tiles;
+    const int* list;
+    __device__ TileSched(int m_tiles, int n_tiles_, const BatchKernelArgs& a)
+        : unit(blockIdx.x), step(gridDim.x), total((a.tile_count ? *a.tile_count : m_tiles) * n_tiles_), n_tiles(n_tiles_), list(a.tile_list) {
+        if (a.dual && a.dual_count && *a.dual_count == 0) total = 0;      // nobody waits for the dual-gap evaluation
+    }
     __device__ bool valid() const { return unit < total; }
     __device__ void next() { unit += step; }
-    __device__ int m_tile() const { return unit / n_tiles * mc + rank; }
+    __device__ int m_tile() const { return list ? list[unit / n_tiles] : unit / n_tiles; }
     __device__ int n_tile() const { return unit % n_tiles; }
 };
 
 // warp roles per instantiation: warps 0/1 producer + MMA, then transform warps, then epilogue warps
-//   product 1 (first generation): 4 transform + 8 epilogue; product 2 / test hook: 12 epilogue;
-//   product 2 staging zhat itself: 2 transform + 12 epilogue (16 warps, 128 registers per thread)
-__host__ __device__ constexpr int xform_warps(int phase, bool xf) { return xf ? (phase == 2 ? 2 : kXformWarps) : 0; }
-__host__ __device__ constexpr int epi_warps(int phase, bool xf) { return (xf && phase != 2) ? kWorkWarps - kXformWarps : kWorkWarps; }
-__host__ __device__ constexpr int cta_threads(int phase, bool xf) { return 32 * (2 + xform_warps(phase, xf) + epi_warps(phase, xf)); }
+//   product 1 (first generation): 4 transform + 8 epilogue; product 2 / test hook: 12 epilogue
+__host__ __device__ constexpr int xform_warps(int phase) { return phase == 1 ? kXformWarps : 0; }
+__host__ __device__ constexpr int epi_warps(int phase) { return kWorkWarps - xform_warps(phase); }
+__host__ __device__ constexpr int cta_threads(int phase) { return 32 * (2 + kWorkWarps); }
 
 // PHASE 0: plain store of C (test hook); 1: GPAD product 1; 2: GPAD product 2
-template <int PHASE, int BK, bool XF>
-__global__ void __launch_bounds__(cta_threads(PHASE, XF), 1)
+template <int PHASE, int BK>
+__global__ void __launch_bounds__(cta_threads(PHASE), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-               int num_k_blocks, int m_tiles, int n_tiles, int bn, int stages, int mc,
+               int num_k_blocks, int m_tiles, int n_tiles, int bn, int stages,
                const BatchKernelArgs args, float* __restrict__ Cdbg, int ldc, int ncols_valid) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t a_bytes = kBM * BK * 4, b_bytes = (uint32_t)bn * BK * 4;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-    constexpr bool kXform = XF;            // transform warps: product 1: A tiles are y_v (/ y_{v-1}) -> hi/lo of y (w) in place;
-                                           // product 2: the A tile is zhat (fp32) -> hi/lo in place
-    constexpr bool kSplitOnly = PHASE == 2;
-    constexpr int kXW = xform_warps(PHASE, XF);
-    constexpr int kEpi = epi_warps(PHASE, XF);
+    constexpr bool kXform = PHASE == 1;    // transform warps: the A tile is y_v (fp32) -> tf32 hi in place, lo next to it
+    constexpr int kXW = xform_warps(PHASE);
+    constexpr int kEpi = epi_warps(PHASE);
     constexpr int kFirstEpiWarp = 2 + kXW;
     float* epi_buf = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kWorkWarps * kEpiBufFloats);
@@ -82,13 +87,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rank = mc > 1 ? (int)cluster_ctarank() : 0;
-    const uint16_t mc_mask = (uint16_t)((1u << mc) - 1);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
         for (int s = 0; s < stages; ++s) {
-            mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), mc); mbar_init(smem_u32(ready_bar + s), kXW > 0 ? kXW : 1);
+            mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); mbar_init(smem_u32(ready_bar + s), kXW > 0 ? kXW : 1);
         }
         for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), kEpi); }
         fence_barrier_init();
@@ -96,34 +99,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
-    if (mc > 1) cluster_sync_all();                           // peers' barriers are initialised before anything is multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: everything above touched no global memory; from here on the previous kernel's writes are needed
+    grid_dependency_wait();
+    grid_launch_dependents();
 
     if (warp == 0) {
         // ============================ TMA producer ============================
         // warp-uniform loop, one elected lane issues (see elect_one)
         int stage = 0; uint32_t phase = 0;
-        for (TileSched ts(m_tiles, n_tiles, mc, rank); ts.valid(); ts.next()) {
+        for (TileSched ts(m_tiles, n_tiles, args); ts.valid(); ts.next()) {
             const int row_a = ts.m_tile() * kBM, row_b = ts.n_tile() * bn;
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
                 const uint32_t fb = smem_u32(full_bar + stage);
                 const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
                 if (elect_one()) {
-                    const bool one_a = kXform && (kSplitOnly || args.pform);   // only one fp32 tile is staged, tile 1 is produced in place
-                    mbar_expect_tx(fb, one_a ? stage_bytes - a_bytes : stage_bytes);
+                    // product 1 stages one fp32 tile (y_v); its lo half is produced in place by the transform warps
+                    mbar_expect_tx(fb, kXform ? stage_bytes - a_bytes : stage_bytes);
                     tma_load_2d(base, &tmA_hi, kb * BK, row_a, fb);
-                    if (!one_a) tma_load_2d(base + a_bytes, &tmA_lo, kb * BK, row_a, fb);
-                    if (mc > 1) {     // this CTA fetches 1/mc of the operator tile for the whole cluster
-                        const int part = bn / mc;
-                        const uint32_t off = (uint32_t)(rank * part) * BK * 4;
-                        tma_load_2d_mc(base + 2 * a_bytes + off, &tmB_hi, kb * BK, row_b + rank * part, fb, mc_mask);
-                        tma_load_2d_mc(base + 2 * a_bytes + b_bytes + off, &tmB_lo, kb * BK, row_b + rank * part, fb, mc_mask);
-                    } else {
-                        tma_load_2d(base + 2 * a_bytes, &tmB_hi, kb * BK, row_b, fb);
-                        tma_load_2d(base + 2 * a_bytes + b_bytes, &tmB_lo, kb * BK, row_b, fb);
-                    }
+                    if (!kXform) tma_load_2d(base + a_bytes, &tmA_lo, kb * BK, row_a, fb);
+                    tma_load_2d(base + 2 * a_bytes, &tmB_hi, kb * BK, row_b, fb);
+                    tma_load_2d(base + 2 * a_bytes + b_bytes, &tmB_lo, kb * BK, row_b, fb);
                 }
                 __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -135,7 +133,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const uint32_t idesc = make_idesc(bn);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (TileSched ts(m_tiles, n_tiles, mc, rank); ts.valid(); ts.next()) {
+        for (TileSched ts(m_tiles, n_tiles, args); ts.valid(); ts.next()) {
             mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
@@ -154,9 +152,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
                         umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
                     }
-                    // frees the ring slot when these MMAs retire (in every CTA that multicasts into it)
-                    if (mc > 1) umma_commit_mc(smem_u32(empty_bar + stage), mc_mask);
-                    else umma_commit(smem_u32(empty_bar + stage));
+                    umma_commit(smem_u32(empty_bar + stage));     // frees the ring slot when these MMAs retire
                 }
                 __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -167,42 +163,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
     } else if (kXform && warp < kFirstEpiWarp) {
         // ============================ transform warps (product 1) ============================
-        // slot layout: [y_v tile | y_{v-1} tile | B_hi | B_lo]; both A tiles carry the same swizzle, so
-        // the rewrite is purely elementwise: tile0 <- RN_tf32(w), tile1 <- RN_tf32(w - tile0)
+        // slot layout: [y_v tile | (lo) | B_hi | B_lo]; tile0 <- RN_tf32(y), tile1 <- RN_tf32(y - tile0): same swizzle,
+        // so the rewrite is purely elementwise
         const int xt = threadIdx.x - 64;                        // 0..127
-        const float beta = args.it.beta;
         constexpr int kVec = kBM * BK / 4;                      // float4 per A tile
         int stage = 0; uint32_t phase = 0;
-        for (TileSched ts(m_tiles, n_tiles, mc, rank); ts.valid(); ts.next()) {
+        for (TileSched ts(m_tiles, n_tiles, args); ts.valid(); ts.next()) {
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 mbar_wait(smem_u32(full_bar + stage), phase);
                 float4* t0 = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
                 float4* t1 = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + a_bytes);
-                if (kSplitOnly || args.pform) {
-                    // A = the staged vector itself: tile0 <- RN_tf32(y), tile1 <- RN_tf32(y - tile0) (tile1 is not TMA-filled)
 #pragma unroll
-                    for (int i = xt; i < kVec; i += 32 * kXW) {
-                        const float4 y = t0[i];
-                        float4 hi, lo;
-                        split_tf32(y.x, hi.x, lo.x);
-                        split_tf32(y.y, hi.y, lo.y);
-                        split_tf32(y.z, hi.z, lo.z);
-                        split_tf32(y.w, hi.w, lo.w);
-                        t0[i] = hi;
-                        t1[i] = lo;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = xt; i < kVec; i += 32 * kXW) {
-                        const float4 y = t0[i], yp = t1[i];
-                        float4 hi, lo;
-                        split_tf32(momentum(y.x, yp.x, beta), hi.x, lo.x);
-                        split_tf32(momentum(y.y, yp.y, beta), hi.y, lo.y);
-                        split_tf32(momentum(y.z, yp.z, beta), hi.z, lo.z);
-                        split_tf32(momentum(y.w, yp.w, beta), hi.w, lo.w);
-                        t0[i] = hi;
-                        t1[i] = lo;
-                    }
+                for (int i = xt; i < kVec; i += 32 * kXW) {
+                    const float4 y = t0[i];
+                    float4 hi, lo;
+                    split_tf32(y.x, hi.x, lo.x);
+                    split_tf32(y.y, hi.y, lo.y);
+                    split_tf32(y.z, hi.z, lo.z);
+                    split_tf32(y.w, hi.w, lo.w);
+                    t0[i] = hi;
+                    t1[i] = lo;
                 }
                 fence_proxy_async_smem();                       // generic-proxy writes -> visible to the MMA (async proxy)
                 __syncwarp();
@@ -219,33 +199,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         float* buf = epi_buf + ew * kEpiBufFloats;
         const int nblk = (bn + 31) / 32;
         int acc = 0; uint32_t acc_phase = 0;
-        // The epilogue's operand loads do not depend on the accumulator.  Each warp holds only ~6 KB of them in flight,
-        // which against ~2 us of loaded HBM latency made the epilogue (not the MMA pipe) the slower stage.  So every warp
-        // pulls the operand lines of its rows of the NEXT tile into L2 one whole tile period ahead; the loads then hit L2.
-        auto prefetch_operands = [&](const TileSched& t) {
-            if (PHASE == 0) return;
-            const int b = t.m_tile() * kBM + q * 32 + lane;
-            if (b >= args.B) return;
-            const int c0 = t.n_tile() * bn;
-            const int ld = PHASE == 1 ? args.np : args.mp;
-            const size_t row = (size_t)b * ld;
-            const int first = (c0 * 4) >> 7, last = (min(c0 + bn, ncols_valid) * 4 - 1) >> 7;     // 128 B lines of this row
-            for (int l = first + part; l <= last; l += kParts) {
-                const size_t o = row + (size_t)l * 32;
-                if (PHASE == 1) { prefetch_l2(args.g_P + o); prefetch_l2(args.z + o); }
-                else { prefetch_l2(args.y_cur + o); prefetch_l2(args.y_prev + o); prefetch_l2(args.p_D + o); }
-            }
-        };
-        {
-            TileSched first(m_tiles, n_tiles, mc, rank);
-            if (first.valid() && args.prefetch) prefetch_operands(first);
-        }
-        for (TileSched ts(m_tiles, n_tiles, mc, rank); ts.valid(); ts.next()) {
-            if (args.prefetch) {
-                TileSched nxt = ts;
-                nxt.next();
-                if (nxt.valid()) prefetch_operands(nxt);
-            }
+        for (TileSched ts(m_tiles, n_tiles, args); ts.valid(); ts.next()) {
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tc_fence_after();
             const int row_base = ts.m_tile() * kBM + q * 32;
@@ -268,7 +222,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (mc > 1) cluster_sync_all();                           // nobody leaves while a peer may still multicast into this CTA
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -338,36 +291,31 @@ int pick_stages(int bk, int bn, size_t smem_limit) {
     return s;
 }
 
-template <int PHASE, int BK, bool XF = (PHASE == 1)>
+template <int PHASE, int BK>
 static int launch_one(const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s) {
-    auto kern = tc_gemm_kernel<PHASE, BK, XF>;
+    auto kern = tc_gemm_kernel<PHASE, BK>;
     const size_t smem = smem_bytes(BK, g.bn, g.stages);
     GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int mc = g.mc > 1 ? g.mc : 1;
-    const int units = (g.m_tiles + mc - 1) / mc * g.n_tiles;
-    const int clusters = std::min(units, num_sms / mc);
+    const int units = g.m_tiles * g.n_tiles;
     cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(clusters * mc); lc.blockDim = dim3(cta_threads(PHASE, XF)); lc.dynamicSmemBytes = smem; lc.stream = s;
+    lc.gridDim = dim3(std::min(units, num_sms)); lc.blockDim = dim3(cta_threads(PHASE)); lc.dynamicSmemBytes = smem; lc.stream = s;
     cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    lc.attrs = at; lc.numAttrs = 1;
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = g.pdl ? 1 : 0;
     GPAD_CUDA(cudaLaunchKernelEx(&lc, kern, g.tmA_hi, g.tmA_lo, g.tmB_hi, g.tmB_lo, g.k_pad / BK, g.m_tiles, g.n_tiles, g.bn,
-                                 g.stages, mc, args, C, ldc, g.ncols_valid));
+                                 g.stages, args, C, ldc, g.ncols_valid));
     return GPAD_OK;
 }
 
 int launch_gemm(int phase, const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s) {
-    if (g.cg == 2) return launch_gemm2(phase, g, args, C, ldc, num_sms, s);
     if (g.bk == 16) {
         if (phase == 0) return launch_one<0, 16>(g, args, C, ldc, num_sms, s);
         if (phase == 1) return launch_one<1, 16>(g, args, C, ldc, num_sms, s);
-        if (g.xf2) return launch_one<2, 16, true>(g, args, C, ldc, num_sms, s);
         return launch_one<2, 16>(g, args, C, ldc, num_sms, s);
     }
     if (phase == 0) return launch_one<0, 32>(g, args, C, ldc, num_sms, s);
     if (phase == 1) return launch_one<1, 32>(g, args, C, ldc, num_sms, s);
-    if (g.xf2) return launch_one<2, 32, true>(g, args, C, ldc, num_sms, s);
     return launch_one<2, 32>(g, args, C, ldc, num_sms, s);
 }
 

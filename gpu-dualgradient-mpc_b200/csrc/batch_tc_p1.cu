@@ -36,12 +36,17 @@ constexpr int kP1FirstEpi = 7;
 constexpr int kP1TStages = 3;          // TMEM A ring slots (32 columns each: hi 16 | lo 16)
 constexpr int kP1BK = 16;
 
+// tiles in (batch tile, operator tile) order; with a tile list (tolerance mode) only the listed batch tiles exist
 struct P1Sched {
     int tile, step, total, n_tiles;
-    __device__ P1Sched(int total_, int n_tiles_) : tile(blockIdx.x), step(gridDim.x), total(total_), n_tiles(n_tiles_) {}
+    const int* list;
+    __device__ P1Sched(int m_tiles, int n_tiles_, const BatchKernelArgs& a)
+        : tile(blockIdx.x), step(gridDim.x), total((a.tile_count ? *a.tile_count : m_tiles) * n_tiles_), n_tiles(n_tiles_), list(a.tile_list) {
+        if (a.dual && a.dual_count && *a.dual_count == 0) total = 0;      // nobody waits for the dual-gap evaluation
+    }
     __device__ bool valid() const { return tile < total; }
     __device__ void next() { tile += step; }
-    __device__ int m_tile() const { return tile / n_tiles; }
+    __device__ int m_tile() const { return list ? list[tile / n_tiles] : tile / n_tiles; }
     __device__ int n_tile() const { return tile % n_tiles; }
 };
 
@@ -64,7 +69,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-template <int PHASE, int EPI>
+template <int EPI>
 __global__ void __launch_bounds__(32 * (kP1FirstEpi + EPI), 1)
 tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmB_hi,
              const __grid_constant__ CUtensorMap tmB_lo, int num_k_blocks, int m_tiles, int n_tiles, int bn,
@@ -89,7 +94,6 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = m_tiles * n_tiles;
     const uint32_t acc_stride = (uint32_t)bn;                      // bn <= 208 is a multiple of 16: 2 * 208 + 96 = 512
     const uint32_t a_col0 = 2 * acc_stride;
 
@@ -106,11 +110,13 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    grid_dependency_wait();          // PDL: the previous kernel's memory is needed from here on
+    grid_launch_dependents();
 
     if (warp == 0) {
         // ============================ operator producer (M_G hi / lo, L2 resident) ============================
         int s = 0; uint32_t ph = 0;
-        for (P1Sched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
+        for (P1Sched ts(m_tiles, n_tiles, args); ts.valid(); ts.next()) {
             const int row_b = ts.n_tile() * step;
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 mbar_wait(smem_u32(bempty + s), ph ^ 1);
@@ -128,7 +134,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     } else if (warp == 2) {
         // ============================ state producer (y_v tiles, HBM) ============================
         int s = 0; uint32_t ph = 0;
-        for (P1Sched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
+        for (P1Sched ts(m_tiles, n_tiles, args); ts.valid(); ts.next()) {
             const int row_a = ts.m_tile() * kBM;
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 mbar_wait(smem_u32(aempty + s), ph ^ 1);
@@ -147,7 +153,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         int s = 0; uint32_t ph = 0;
         int t = 0; uint32_t tph = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (P1Sched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
+        for (P1Sched ts(m_tiles, n_tiles, args); ts.valid(); ts.next()) {
             mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
@@ -184,7 +190,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         int s = 0; uint32_t ph = 0;
         int t = 0; uint32_t tph = 0;
-        for (P1Sched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
+        for (P1Sched ts(m_tiles, n_tiles, args); ts.valid(); ts.next()) {
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 mbar_wait(smem_u32(afull + s), ph);
                 const uint8_t* tile = a_ring + (size_t)s * a_bytes + row * 64;
@@ -224,7 +230,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         float* buf = epi_buf + ew * kEpiBufFloats;
         const int nblk = (bn + 31) / 32;
         int acc = 0; uint32_t acc_phase = 0;
-        for (P1Sched ts(total_tiles, n_tiles); ts.valid(); ts.next()) {
+        for (P1Sched ts(m_tiles, n_tiles, args); ts.valid(); ts.next()) {
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tc_fence_after();
             const int row_base = ts.m_tile() * kBM + q * 32;
@@ -234,7 +240,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
 #pragma unroll
                 for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = __uint_as_float(v[j]);
                 __syncwarp();
-                epilogue_block<PHASE>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, nullptr, 0, step);
+                epilogue_block<1>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, nullptr, 0, step);
                 __syncwarp();
             }
             tc_fence_before();
@@ -272,8 +278,8 @@ void plan_tiles_p1(int ncols, int* bn, int* n_tiles, int* step) {
     if (step) *step = (nt > 1 && s32 > 0 && (nt - 1) * s32 + b >= ncols) ? s32 : b;
 }
 
-int plan_rings_p1(int phase, int bn, size_t smem_limit, int* a_stages, int* b_stages) {
-    const int epi = phase == 1 ? 8 : 12;
+int plan_rings_p1(int bn, size_t smem_limit, int* a_stages, int* b_stages) {
+    const int epi = 8;
     int b = 5, a = 8;
     while (b > 2 && p1_smem_bytes(bn, a, b, epi) > smem_limit) --b;
     while (a > 2 && p1_smem_bytes(bn, a, b, epi) > smem_limit) --a;
@@ -283,21 +289,20 @@ int plan_rings_p1(int phase, int bn, size_t smem_limit, int* a_stages, int* b_st
     return GPAD_OK;
 }
 
-// phase 1: P_v = Y_v M_G^T (A = y_v); phase 2: Y+ = Zhat G_L^T (A = zhat_v, fp32, split in registers like y)
-int launch_p1(int phase, const GemmDesc& g, const BatchKernelArgs& args, int num_sms, cudaStream_t s) {
-    const size_t smem = p1_smem_bytes(g.bn, g.a_stages, g.stages, phase == 1 ? 8 : 12);
+// P_v = Y_v M_G^T (A = y_v)
+int launch_p1(const GemmDesc& g, const BatchKernelArgs& args, int num_sms, cudaStream_t s) {
+    const size_t smem = p1_smem_bytes(g.bn, g.a_stages, g.stages, 8);
     const int tiles = g.m_tiles * g.n_tiles;
-    const int grid = std::min(tiles, num_sms);
-    if (phase == 1) {
-        GPAD_CUDA(cudaFuncSetAttribute(tc_p1_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_p1_kernel<1, 8><<<grid, 32 * (kP1FirstEpi + 8), smem, s>>>(g.tmA_hi, g.tmB_hi, g.tmB_lo, g.k_pad / kP1BK, g.m_tiles, g.n_tiles, g.bn,
-                                                       g.a_stages, g.stages, args, g.ncols_valid, g.step > 0 ? g.step : g.bn);
-    } else {
-        GPAD_CUDA(cudaFuncSetAttribute(tc_p1_kernel<2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_p1_kernel<2, 12><<<grid, 32 * (kP1FirstEpi + 12), smem, s>>>(g.tmA_hi, g.tmB_hi, g.tmB_lo, g.k_pad / kP1BK, g.m_tiles, g.n_tiles, g.bn,
-                                                       g.a_stages, g.stages, args, g.ncols_valid, g.step > 0 ? g.step : g.bn);
-    }
-    GPAD_CUDA(cudaGetLastError());
+    auto kern = tc_p1_kernel<8>;
+    GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(std::min(tiles, num_sms)); lc.blockDim = dim3(32 * (kP1FirstEpi + 8)); lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = g.pdl ? 1 : 0;
+    GPAD_CUDA(cudaLaunchKernelEx(&lc, kern, g.tmA_hi, g.tmB_hi, g.tmB_lo, g.k_pad / kP1BK, g.m_tiles, g.n_tiles, g.bn, g.a_stages,
+                                 g.stages, args, g.ncols_valid, g.step > 0 ? g.step : g.bn));
     return GPAD_OK;
 }
 

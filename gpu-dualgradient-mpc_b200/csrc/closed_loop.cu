@@ -1,53 +1,81 @@
-// closed_loop.cu -- device-resident receding-horizon simulation (gpad.m:79-95), SURVEY 8(f) rows 1 and 2.
+// closed_loop.cu -- on-device instance build and device-resident receding-horizon simulation (gpad.m:79-95),
+// SURVEY 8(f) rows 1 and 2.
 //
-// Per sample, for a whole batch of plants: (1) the per-instance affine maps  g_P = Kg p,  p_D = -(b0 + Bb p) / L  with
-// p = [x; x_ref] are evaluated on the device (acceldualgrad.m:21,23; one thread per output entry, fp64 like the host
-// path, unfused so both paths round identically), (2) gpad_solve runs on device buffers, warm-started from the
-// previous duals if asked, (3) u = z[0:n_u] is applied and x <- A x + B u advanced on the device.  Nothing but the
-// state / input trajectories crosses PCIe.  Called by gpad_closed_loop (host/problem.cpp), which owns the problem data.
+// Instance build: the per-instance affine maps  g_P = Kg p,  f = Ff p,  p_D = -(b0 + Bb p) / L  with p = [x; x_ref]
+// (acceldualgrad.m:21,23; gpad.m:81,85), one thread per output entry, fp64 and unfused like the host path
+// (host/problem.cpp:gpad_problem_instances) so both round identically.  The problem's matrices are uploaded once per
+// device and cached in the problem.
+// Closed loop, per sample and for a whole batch of plants: (1) instance build from the current states, (2) gpad_solve on
+// device buffers, warm-started from the previous duals (as they are, or shifted one stage) if asked, (3) u = z[0:n_u]
+// is applied and x <- A x + B u advanced on the device.  Nothing but the trajectories crosses PCIe.  The plants may be
+// one shared problem (gpad_closed_loop) or one plant per instance (gpad_closed_loop_plants, BASELINE config 5).
 #include <cuda_runtime.h>
 
 #include <vector>
 
+#include "../host/plants_internal.h"
 #include "gpad_internal.h"
 
 namespace gpad {
 
 namespace {
 
-// out[b][i] = (float) sum_c M[i][c] * par[b][c]      (rows = n)
-// out[b][i] = (float) (-(b0[i] + sum_c M[i][c] * par[b][c]) * invL)      (b0 != nullptr)
-__global__ void affine_kernel(float* __restrict__ out, const double* __restrict__ M, const double* __restrict__ b0, double invL,
+// out[b][i] = (float) sum_c M[i][c] * par[b][c]                               (b0 == nullptr)
+// out[b][i] = (float) (-(b0[i] + sum_c M[i][c] * par[b][c]) * invL)           (b0 != nullptr)
+// mat_stride / invL_b: one matrix (and one 1/L) per instance when non-zero / non-null
+__global__ void affine_kernel(float* __restrict__ out, int ld, const double* __restrict__ M, size_t mat_stride,
+                              const double* __restrict__ b0, double invL, const double* __restrict__ invL_b,
                               const double* __restrict__ x, int nx, const double* __restrict__ xref, int nref, int rows, int B) {
     const size_t total = (size_t)B * rows;
     const int np = nx + nref;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(idx / rows), i = (int)(idx % rows);
-        const double* Mi = M + (size_t)i * np;
+        const double* Mi = M + (size_t)b * mat_stride + (size_t)i * np;
         double s = b0 ? b0[i] : 0.0;
         for (int c = 0; c < nx; ++c) s = __dadd_rn(s, __dmul_rn(Mi[c], x[(size_t)b * nx + c]));
         for (int c = 0; c < nref; ++c) s = __dadd_rn(s, __dmul_rn(Mi[nx + c], xref[(size_t)b * nref + c]));
-        out[idx] = b0 ? (float)(-s * invL) : (float)s;
+        out[(size_t)b * ld + i] = b0 ? (float)(-s * (invL_b ? invL_b[b] : invL)) : (float)s;
     }
 }
 
-// x <- A x + B u with u = z[b][0:nu]; records u and the new state
+// x <- A x + B u with u = z[b][0:nu]; records u and the new state; b_stride != 0: one input matrix per instance
 __global__ void advance_kernel(double* __restrict__ x, const float* __restrict__ z, int n, const double* __restrict__ A,
-                               const double* __restrict__ Bm, int nx, int nu, int B, double* __restrict__ u_out,
+                               const double* __restrict__ Bm, size_t b_stride, int nx, int nu, int B, double* __restrict__ u_out,
                                double* __restrict__ x_out) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     double xn[32];
     const double* xb = x + (size_t)b * nx;
+    const double* Bb = Bm + (size_t)b * b_stride;
     const float* u = z + (size_t)b * n;
     for (int i = 0; i < nx; ++i) {
         double s = 0.0;
         for (int j = 0; j < nx; ++j) s = __dadd_rn(s, __dmul_rn(A[i * nx + j], xb[j]));
-        for (int j = 0; j < nu; ++j) s = __dadd_rn(s, __dmul_rn(Bm[i * nu + j], (double)u[j]));
+        for (int j = 0; j < nu; ++j) s = __dadd_rn(s, __dmul_rn(Bb[i * nu + j], (double)u[j]));
         xn[i] = s;
     }
     for (int i = 0; i < nx; ++i) { x[(size_t)b * nx + i] = xn[i]; if (x_out) x_out[(size_t)b * nx + i] = xn[i]; }
     if (u_out) for (int j = 0; j < nu; ++j) u_out[(size_t)b * nu + j] = (double)u[j];
+}
+
+// receding-horizon shift of a dual vector: inside every constraint block {offset, rows per stage} stage s takes the
+// multipliers of stage s + 1, the last stage keeps its own
+__global__ void shift_duals_kernel(float* __restrict__ dst, const float* __restrict__ src, int m, int B, const int* __restrict__ blocks,
+                                   int nblocks, int N) {
+    const size_t total = (size_t)B * m;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / m), i = (int)(idx % m);
+        int from = i;
+        for (int k = 0; k < nblocks; ++k) {
+            const int off = blocks[2 * k], r = blocks[2 * k + 1];
+            if (i >= off && i < off + r * N) {
+                const int s = (i - off) / r, j = (i - off) % r;
+                from = off + min(s + 1, N - 1) * r + j;
+                break;
+            }
+        }
+        dst[idx] = src[(size_t)b * m + from];
+    }
 }
 
 struct DevBufs {
@@ -57,52 +85,109 @@ struct DevBufs {
         if (cudaMalloc(&q, (count ? count : 1) * sizeof(T)) != cudaSuccess) { cudaGetLastError(); set_error("closed loop: cudaMalloc failed"); return GPAD_ERR_ALLOC; }
         p.push_back(q); *out = static_cast<T*>(q); return GPAD_OK;
     }
+    template <typename T> int upload(T** out, const T* src, size_t count, cudaStream_t s) {
+        int rc = alloc(out, count);
+        if (rc != GPAD_OK) return rc;
+        GPAD_CUDA(cudaMemcpyAsync(*out, src, sizeof(T) * count, cudaMemcpyHostToDevice, s));
+        return GPAD_OK;
+    }
     ~DevBufs() { for (void* q : p) cudaFree(q); }
 };
 
-}  // namespace
+struct DeviceScope {             // the handle's device for the duration of the loop, the caller's afterwards
+    int prev = -1;
+    cudaError_t status = cudaSuccess;
+    explicit DeviceScope(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != dev) status = cudaSetDevice(dev);
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
-int closed_loop_device(gpad_handle_t h, int B, int nx, int nu, int n, int m, int npar, double L, const double* Kg,
-                       const double* Bb, const double* b0, const double* A, const double* Bm, const double* x0,
-                       const double* xref, int samples, const float* theta, const float* beta, int max_iter, int warm_start,
-                       double* x_traj, double* u_traj) {
+struct StreamScope {
+    cudaStream_t s = nullptr;
+    cudaError_t status;
+    StreamScope() { status = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); }
+    ~StreamScope() { if (s) cudaStreamDestroy(s); }
+};
+
+// device copies of a problem's instance maps and plant, one per device
+struct ProblemDev {
+    int device = -1;
+    DevBufs mem;
+    double *Kg = nullptr, *Ff = nullptr, *Bb = nullptr, *b0 = nullptr, *A = nullptr, *B = nullptr;
+    int* blocks = nullptr;
+};
+
+int problem_dev_get(gpad_problem_t p, int device, ProblemDev** out) {
+    std::lock_guard<std::mutex> lock(p->dev_mutex);
+    for (void* c : p->dev_cache)
+        if (static_cast<ProblemDev*>(c)->device == device) { *out = static_cast<ProblemDev*>(c); return GPAD_OK; }
+    ProblemDev* d = new ProblemDev;
+    d->device = device;
+    std::vector<int> blk;
+    for (auto& b : p->blocks) { blk.push_back(b.first); blk.push_back(b.second); }
+    int rc = GPAD_OK;
+    do {
+        if ((rc = d->mem.upload(&d->Kg, p->Kg.a.data(), p->Kg.a.size(), nullptr)) != GPAD_OK) break;
+        if ((rc = d->mem.upload(&d->Ff, p->Ff.a.data(), p->Ff.a.size(), nullptr)) != GPAD_OK) break;
+        if ((rc = d->mem.upload(&d->Bb, p->Bb.a.data(), p->Bb.a.size(), nullptr)) != GPAD_OK) break;
+        if ((rc = d->mem.upload(&d->b0, p->b0.data(), p->b0.size(), nullptr)) != GPAD_OK) break;
+        if ((rc = d->mem.upload(&d->A, p->A.a.data(), p->A.a.size(), nullptr)) != GPAD_OK) break;
+        if ((rc = d->mem.upload(&d->B, p->B.a.data(), p->B.a.size(), nullptr)) != GPAD_OK) break;
+        if ((rc = d->mem.upload(&d->blocks, blk.data(), blk.size(), nullptr)) != GPAD_OK) break;
+        if (cudaStreamSynchronize(nullptr) != cudaSuccess) { cudaGetLastError(); rc = GPAD_ERR_CUDA; }
+    } while (0);
+    if (rc != GPAD_OK) { delete d; return rc; }
+    p->dev_cache.push_back(d);
+    *out = d;
+    return GPAD_OK;
+}
+
+inline int grid_for(size_t total) { return (int)std::min<size_t>((total + 255) / 256, 148 * 32); }
+
+// the loop both entry points share; `pl` != nullptr: one plant per instance (plants [first, first + B))
+int run_loop(gpad_handle_t h, int B, int nx, int nu, int n, int m, int npar, int N, const double* dKg, size_t kg_stride,
+             const double* dBb, size_t bb_stride, const double* db0, double invL, const double* dinvL, const double* dA,
+             const double* dBm, size_t bm_stride, const int* dblocks, int nblocks, const double* x0, const double* xref,
+             int samples, const float* theta, const float* beta, int max_iter, int warm_start, double* x_traj, double* u_traj,
+             cudaStream_t s) {
     if (nx > 32) { set_error("closed loop: nx = %d > 32 is not supported", nx); return GPAD_ERR_UNSUPPORTED; }
     const int nref = npar - nx;
     DevBufs d;
-    double *dKg, *dBb, *db0, *dA, *dB, *dx, *dxref = nullptr, *dut, *dxt;
-    float *gP, *pD, *z, *ya[2], *yb[2];
+    double *dx, *dxref = nullptr, *dut, *dxt;
+    float *gP, *pD, *z, *ya[2], *yb[2], *sa = nullptr, *sb = nullptr;
 #define TRYA(e) do { int rc_ = (e); if (rc_ != GPAD_OK) return rc_; } while (0)
-    TRYA(d.alloc(&dKg, (size_t)n * npar)); TRYA(d.alloc(&dBb, (size_t)m * npar)); TRYA(d.alloc(&db0, m));
-    TRYA(d.alloc(&dA, (size_t)nx * nx)); TRYA(d.alloc(&dB, (size_t)nx * nu)); TRYA(d.alloc(&dx, (size_t)B * nx));
-    if (nref > 0) TRYA(d.alloc(&dxref, (size_t)B * nref));
+    TRYA(d.upload(&dx, x0, (size_t)B * nx, s));
+    if (nref > 0) TRYA(d.upload(&dxref, xref, (size_t)B * nref, s));
     TRYA(d.alloc(&dut, u_traj ? (size_t)samples * B * nu : 0)); TRYA(d.alloc(&dxt, x_traj ? (size_t)(samples + 1) * B * nx : 0));
     TRYA(d.alloc(&gP, (size_t)B * n)); TRYA(d.alloc(&pD, (size_t)B * m)); TRYA(d.alloc(&z, (size_t)B * n));
     for (int k = 0; k < 2; ++k) { TRYA(d.alloc(&ya[k], (size_t)B * m)); TRYA(d.alloc(&yb[k], (size_t)B * m)); }
+    if (warm_start == GPAD_WARM_SHIFTED) { TRYA(d.alloc(&sa, (size_t)B * m)); TRYA(d.alloc(&sb, (size_t)B * m)); }
 #undef TRYA
-    cudaStream_t s = nullptr;
-    GPAD_CUDA(cudaMemcpyAsync(dKg, Kg, sizeof(double) * n * npar, cudaMemcpyHostToDevice, s));
-    GPAD_CUDA(cudaMemcpyAsync(dBb, Bb, sizeof(double) * m * npar, cudaMemcpyHostToDevice, s));
-    GPAD_CUDA(cudaMemcpyAsync(db0, b0, sizeof(double) * m, cudaMemcpyHostToDevice, s));
-    GPAD_CUDA(cudaMemcpyAsync(dA, A, sizeof(double) * nx * nx, cudaMemcpyHostToDevice, s));
-    GPAD_CUDA(cudaMemcpyAsync(dB, Bm, sizeof(double) * nx * nu, cudaMemcpyHostToDevice, s));
-    GPAD_CUDA(cudaMemcpyAsync(dx, x0, sizeof(double) * B * nx, cudaMemcpyHostToDevice, s));
-    if (nref > 0) GPAD_CUDA(cudaMemcpyAsync(dxref, xref, sizeof(double) * B * nref, cudaMemcpyHostToDevice, s));
     if (x_traj) GPAD_CUDA(cudaMemcpyAsync(dxt, dx, sizeof(double) * B * nx, cudaMemcpyDeviceToDevice, s));
-    const int grid_n = (int)std::min<size_t>(((size_t)B * n + 255) / 256, 148 * 32);
-    const int grid_m = (int)std::min<size_t>(((size_t)B * m + 255) / 256, 148 * 32);
     for (int k = 0; k < samples; ++k) {
-        affine_kernel<<<grid_n, 256, 0, s>>>(gP, dKg, nullptr, 0.0, dx, nx, dxref, nref, n, B);                 // gpad.m:81
-        affine_kernel<<<grid_m, 256, 0, s>>>(pD, dBb, db0, 1.0 / L, dx, nx, dxref, nref, m, B);                 // gpad.m:85
+        affine_kernel<<<grid_for((size_t)B * n), 256, 0, s>>>(gP, n, dKg, kg_stride, nullptr, 0.0, nullptr, dx, nx, dxref, nref, n, B);       // gpad.m:81
+        affine_kernel<<<grid_for((size_t)B * m), 256, 0, s>>>(pD, m, dBb, bb_stride, db0, invL, dinvL, dx, nx, dxref, nref, m, B);            // gpad.m:85
         GPAD_CUDA(cudaGetLastError());
         gpad_solve_args_t a{};
         a.batch = B; a.mem = GPAD_MEM_DEVICE; a.stream = s;
         a.g_P = gP; a.p_D = pD; a.theta = theta; a.beta = beta; a.max_iter = max_iter;
         const int cur = k & 1, prev = cur ^ 1;
-        if (warm_start && k > 0) { a.y0 = ya[prev]; a.y_prev0 = yb[prev]; }
+        if (warm_start != GPAD_WARM_COLD && k > 0) {
+            if (warm_start == GPAD_WARM_SHIFTED) {
+                shift_duals_kernel<<<grid_for((size_t)B * m), 256, 0, s>>>(sa, ya[prev], m, B, dblocks, nblocks, N);
+                shift_duals_kernel<<<grid_for((size_t)B * m), 256, 0, s>>>(sb, yb[prev], m, B, dblocks, nblocks, N);
+                GPAD_CUDA(cudaGetLastError());
+                a.y0 = sa; a.y_prev0 = sb;
+            } else {
+                a.y0 = ya[prev]; a.y_prev0 = yb[prev];
+            }
+        }
         a.z = z; a.y_next = ya[cur]; a.y = yb[cur];
         const int rc = gpad_solve(h, &a);                                                                       // gpad.m:90
         if (rc != GPAD_OK) return rc;
-        advance_kernel<<<(B + 127) / 128, 128, 0, s>>>(dx, z, n, dA, dB, nx, nu, B, u_traj ? dut + (size_t)k * B * nu : nullptr,
+        advance_kernel<<<(B + 127) / 128, 128, 0, s>>>(dx, z, n, dA, dBm, bm_stride, nx, nu, B, u_traj ? dut + (size_t)k * B * nu : nullptr,
                                                        x_traj ? dxt + (size_t)(k + 1) * B * nx : nullptr);      // gpad.m:91-93
         GPAD_CUDA(cudaGetLastError());
     }
@@ -112,4 +197,82 @@ int closed_loop_device(gpad_handle_t h, int B, int nx, int nu, int n, int m, int
     return GPAD_OK;
 }
 
+}  // namespace
+
+void problem_dev_free(void* cache) {
+    ProblemDev* d = static_cast<ProblemDev*>(cache);
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    cudaSetDevice(d->device);
+    delete d;
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+}
+
+int instances_device(gpad_problem_t p, int device, int B, const double* params_dev, float* g_P, int ld_g, float* p_D, int ld_p,
+                     float* f, int ld_f, cudaStream_t s) {
+    ProblemDev* d = nullptr;
+    int rc = problem_dev_get(p, device, &d);
+    if (rc != GPAD_OK) return rc;
+    const int n = p->n, m = p->m, np = p->n_par;
+    // the whole parameter row plays the role of x (nref = 0): the maps are [rows][n_par]
+    if (g_P) affine_kernel<<<grid_for((size_t)B * n), 256, 0, s>>>(g_P, ld_g, d->Kg, 0, nullptr, 0.0, nullptr, params_dev, np, nullptr, 0, n, B);
+    if (p_D) affine_kernel<<<grid_for((size_t)B * m), 256, 0, s>>>(p_D, ld_p, d->Bb, 0, d->b0, 1.0 / p->L, nullptr, params_dev, np, nullptr, 0, m, B);
+    if (f) affine_kernel<<<grid_for((size_t)B * n), 256, 0, s>>>(f, ld_f, d->Ff, 0, nullptr, 0.0, nullptr, params_dev, np, nullptr, 0, n, B);
+    GPAD_CUDA(cudaGetLastError());
+    return GPAD_OK;
+}
+
+int closed_loop_device(gpad_problem_t p, gpad_handle_t h, int B, const double* x0, const double* xref, int samples,
+                       const float* theta, const float* beta, int max_iter, int warm_start, double* x_traj, double* u_traj) {
+    int device = 0;
+    GPAD_TRY_RC(gpad_handle_dims(h, nullptr, nullptr, nullptr, nullptr, nullptr, &device));
+    DeviceScope dev(device);
+    GPAD_CUDA(dev.status);
+    StreamScope st;
+    GPAD_CUDA(st.status);
+    ProblemDev* d = nullptr;
+    GPAD_TRY_RC(problem_dev_get(p, device, &d));
+    return run_loop(h, B, p->nx, p->n_u, p->n, p->m, p->n_par, p->N, d->Kg, 0, d->Bb, 0, d->b0, 1.0 / p->L, nullptr, d->A, d->B, 0,
+                    d->blocks, (int)p->blocks.size(), x0, xref, samples, theta, beta, max_iter, warm_start, x_traj, u_traj, st.s);
+}
+
+int closed_loop_plants_device(gpad_plants_t p, gpad_handle_t h, int first, int count, const double* x0, int samples,
+                              const float* theta, const float* beta, int max_iter, int warm_start, double* x_traj,
+                              double* u_traj) {
+    int device = 0;
+    GPAD_TRY_RC(gpad_handle_dims(h, nullptr, nullptr, nullptr, nullptr, nullptr, &device));
+    DeviceScope dev(device);
+    GPAD_CUDA(dev.status);
+    StreamScope st;
+    GPAD_CUDA(st.status);
+    const int n = p->n, m = p->m, np = p->n_par, nx = p->nx, nu = p->n_u;
+    DevBufs d;
+    double *dKg, *dBb, *db0, *dA, *dBm, *dinvL;
+    int* dblk;
+    std::vector<double> invL(count);
+    for (int b = 0; b < count; ++b) invL[b] = 1.0 / p->L[first + b];
+    std::vector<int> blk;
+    for (auto& b : p->blocks) { blk.push_back(b.first); blk.push_back(b.second); }
+    GPAD_TRY_RC(d.upload(&dKg, &p->Kg[(size_t)first * n * np], (size_t)count * n * np, st.s));
+    GPAD_TRY_RC(d.upload(&dBb, &p->Bb[(size_t)first * m * np], (size_t)count * m * np, st.s));
+    GPAD_TRY_RC(d.upload(&db0, p->b0.data(), p->b0.size(), st.s));
+    GPAD_TRY_RC(d.upload(&dA, p->A.data(), p->A.size(), st.s));
+    GPAD_TRY_RC(d.upload(&dBm, &p->Bm[(size_t)first * nx * nu], (size_t)count * nx * nu, st.s));
+    GPAD_TRY_RC(d.upload(&dinvL, invL.data(), invL.size(), st.s));
+    GPAD_TRY_RC(d.upload(&dblk, blk.data(), blk.size(), st.s));
+    GPAD_CUDA(cudaStreamSynchronize(st.s));          // invL / blk are locals: their copies must have left
+    return run_loop(h, count, nx, nu, n, m, np, p->N, dKg, (size_t)n * np, dBb, (size_t)m * np, db0, 0.0, dinvL, dA, dBm,
+                    (size_t)nx * nu, dblk, (int)p->blocks.size(), x0, nullptr, samples, theta, beta, max_iter, warm_start, x_traj,
+                    u_traj, st.s);
+}
+
 }  // namespace gpad
+
+extern "C" int gpad_instances_device(gpad_problem_t p, int B, const double* params, float* g_P, float* p_D, float* f, void* stream) {
+    using namespace gpad;
+    GPAD_REQUIRE(p && params && B >= 1 && (g_P || p_D || f), "gpad_instances_device: bad argument");
+    int device = 0;
+    GPAD_CUDA(cudaGetDevice(&device));
+    return instances_device(p, device, B, params, g_P, p->n, p_D, p->m, f, p->n, static_cast<cudaStream_t>(stream));
+}

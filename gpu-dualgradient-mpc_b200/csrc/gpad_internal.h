@@ -30,6 +30,9 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         }                                           \
     } while (0)
 
+#define GPAD_TRY(expr) do { int rc__ = (expr); if (rc__ != GPAD_OK) return rc__; } while (0)
+#define GPAD_TRY_RC(expr) GPAD_TRY(expr)
+
 inline int round_up(int v, int q) { return (v + q - 1) / q * q; }
 inline size_t round_up_sz(size_t v, size_t q) { return (v + q - 1) / q * q; }
 
@@ -66,6 +69,16 @@ struct BatchState {
     int* active_count = nullptr;  // [2] instances still iterating, instances waiting for the dual-gap evaluation
     int* need = nullptr;          // [Bp] instance takes the dual-gap branch at this check
     float* zy = nullptr;          // [Bp][np] z_y scratch of the dual-gap evaluation (CUDA-core path)
+    // tile retirement (tolerance mode): dense ascending list of the 128-row tiles that still hold a running instance
+    int* tile_flags = nullptr;    // [Bp / 128]
+    int* tile_list = nullptr;     // [Bp / 128]
+    int* tile_count = nullptr;    // [1]
+    unsigned long long* stat = nullptr;   // [2] instance-iterations scheduled (tiles x 128 x iterations) / needed (sum of iters)
+    // compaction (tolerance mode, batch_compact.cu): perm[row] = original instance of a working row (-1: dead row)
+    int* perm = nullptr;          // [Bp]
+    int* holes = nullptr;         // [Bp]
+    int* movers = nullptr;        // [Bp]
+    int* compact_counts = nullptr;  // [2] running rows, moves
 };
 
 struct Operators {
@@ -86,6 +99,11 @@ int launch_unpad_y(float* dst_next, float* dst_cur, float* dst_w, int m, int B, 
                    const float* yb2, int mp, const int* iters, const float* beta_dev, cudaStream_t s);
 int launch_batch_init(const BatchState& st, bool checking, cudaStream_t s);
 int launch_batch_reset_term(const BatchState& st, int max_iter, cudaStream_t s);
+int launch_perm_identity(const BatchState& st, cudaStream_t s);
+int launch_compact(const BatchState& st, const BatchState& archive, int rows_bound, bool have_f, cudaStream_t s);
+int launch_archive_all(const BatchState& st, const BatchState& archive, int rows_bound, cudaStream_t s);
+int launch_batch_tiles(const BatchState& st, int iterations, bool rebuild, cudaStream_t s);
+int launch_batch_iter_sum(const BatchState& st, cudaStream_t s);
 int launch_batch_decide(const BatchState& st, int iter_done, float L, float eps_g, float eps_V, bool have_f, cudaStream_t s);
 int launch_batch_decide_dual(const BatchState& st, int iter_done, float L, float eps_V, cudaStream_t s);
 int launch_batch_finite(const BatchState& st, const float* y_next, cudaStream_t s);

@@ -18,13 +18,7 @@ struct Params {
     int lg_a, lg_b;          // log2(lanes per row) in phase A / B
     int res_a, res_b;        // own rows of M_G / G_L resident in shared memory (memory variant)
     int sched_smem;          // latency_small.cu: theta/beta entries staged in shared memory
-    // latency_grid.cu: register-blocked GEMV: cw column-slice warps x rg row groups (cw * rg = 16 warps),
-    // rb rows per warp, ch float4 chunks per lane
-    int cwa, rga, rba, cha, cwb, rgb, rbb, chb;
-    unsigned long long* ll_w;     // [2][m]  {value, stamp} words of the w exchange
-    unsigned long long* ll_z;     // [2][n]  zhat exchange
-    unsigned long long* ll_r;     // [2][G][8] termination partials
-    unsigned stamp_base;          // per-solve epoch so stale words never match
+    int warp_rows, warp_ordered;  // latency_warp.cu schedule override (0 / -1: chosen by batch size)
     int batch;               // SYNC_BLOCK only: independent instances, one CTA each (per-instance operators)
     size_t op_stride_a, op_stride_b;   // elements between consecutive instances' M_G / G_L (0: shared)
     const float* M_G;        // [n][mld] sequential layout, zero padded
@@ -58,9 +52,6 @@ int max_cluster_size(int threads, size_t smem);
 size_t small_smem_bytes(const Params& p);
 int small_sched_capacity();
 int launch_small(const Params& p, int cha, int chb, int cluster, int threads, cudaStream_t stream);
-// latency_grid.cu: lean whole-chip kernel for one large QP (flag-in-data global exchange, no grid barrier)
-size_t grid_smem_bytes(const Params& p);
-int launch_grid(const Params& p, int G, cudaStream_t stream);
 
 // latency_warp.cu: one warp per QP for the tiny problems (n <= 16, m <= 64), latency and per-instance batch modes
 int warp_supported(const Params& p);

@@ -225,10 +225,9 @@ int launch_warp(const Params& p, cudaStream_t stream) {
     // best measured (37 us per 100 iterations; 12 rows: 61 us unordered -- ptxas walks the tree depth-first -- 45 us ordered).
     int nr = (p.n <= 12 && B > 1) ? 12 : kWR;
     bool ord = B > 1;
-    if (const char* e = getenv("GPAD_WARP_PLAN")) {          // experiments: "<rows>,<ordered>"
-        int a = 0, b = 0;
-        if (sscanf(e, "%d,%d", &a, &b) == 2 && (a == 12 || a == kWR) && a >= p.n) { nr = a; ord = b != 0; }
-    }
+    // experiments (GPAD_DEBUG warp_rows / warp_ordered, read at gpad_setup)
+    if ((p.warp_rows == 12 || p.warp_rows == kWR) && p.warp_rows >= p.n) nr = p.warp_rows;
+    if (p.warp_ordered >= 0) ord = p.warp_ordered != 0;
 #define GPAD_WARP_LAUNCH(C, N, O) gpad_warp_kernel<C, N, O><<<grid, 32 * wpc, 0, stream>>>(p, wpc)
     if (nr == 12) {
         if (ord) { if (chk) GPAD_WARP_LAUNCH(true, 12, true); else GPAD_WARP_LAUNCH(false, 12, true); }

@@ -1,5 +1,5 @@
-// tc_epilogue.cuh -- the fused GPAD epilogue of one transposed 32x32 accumulator block, shared by the
-// cta_group::1 and cta_group::2 tcgen05 kernels.  `buf` holds the block transposed in shared memory
+// tc_epilogue.cuh -- the fused GPAD epilogue of one transposed 32x32 accumulator block, shared by the two
+// tcgen05 kernels (batch_tc.cu, batch_tc_p1.cu).  `buf` holds the block transposed in shared memory
 // (buf[row * 33 + col]); lane = output column, rows row_base..row_base+31 of the batch.
 #pragma once
 #include "batch_common.cuh"
@@ -47,7 +47,7 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
                     const size_t o = (size_t)b * args.np + c;
                     gp[j] = ok ? __ldcs(args.g_P + o) : 0.f;
                     zo[j] = ok ? __ldcs(args.z + o) : 0.f;
-                    pp[j] = (ok && args.pform) ? __ldcs(args.P_prev + o) : 0.f;
+                    pp[j] = ok ? __ldcs(args.P_prev + o) : 0.f;
                 }
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j) {
@@ -55,21 +55,15 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
                     if (!(col_ok && b < args.B)) continue;
                     const size_t o = (size_t)b * args.np + c;
                     float acc = buf[(r0 + j) * 33 + lane];
-                    if (args.pform) {
-                        __stcs(args.P_cur + o, acc);
-                        acc = momentum(acc, pp[j], args.it.beta);          // M_G w_v from P_v, P_{v-1}
-                    }
+                    __stcs(args.P_cur + o, acc);
+                    acc = momentum(acc, pp[j], args.it.beta);          // M_G w_v from P_v, P_{v-1}
                     const float zh = acc - gp[j];
                     __stcs(args.z + o, __fadd_rn(__fmul_rn(1.0f - args.it.theta, zo[j]), __fmul_rn(args.it.theta, zh)));
-                    if (args.zh_single) {
-                        args.zhat[o] = zh;       // product 2's A operand (split there) and the zhat output
-                    } else {
-                        if (args.it.store_zhat) __stcs(args.zhat + o, zh);
-                        float hi, lo;
-                        split_tf32(zh, hi, lo);
-                        args.zh_hi[o] = hi;      // re-read by product 2 of this iteration: default caching
-                        args.zh_lo[o] = lo;
-                    }
+                    if (args.it.store_zhat) __stcs(args.zhat + o, zh);
+                    float hi, lo;
+                    split_tf32(zh, hi, lo);
+                    args.zh_hi[o] = hi;      // re-read by product 2 of this iteration: default caching
+                    args.zh_lo[o] = lo;
                 }
             } else {
                 float yc[kChunk], yp[kChunk], pd[kChunk];
@@ -105,7 +99,7 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
                 float f_zhat = 0.f;
                 if (ok) {
                     float acc = val;
-                    if (args.pform && !args.dual) {
+                    if (!args.dual) {
                         const size_t o = (size_t)b * args.np + c;
                         args.P_cur[o] = val;
                         acc = momentum(val, args.P_prev[o], args.it.beta);

@@ -1,6 +1,6 @@
-// tc_ptx.cuh -- inline-PTX wrappers shared by the tcgen05 kernels (batch_tc.cu: cta_group::1,
-// batch_tc2.cu: cta_group::2): mbarrier, TMA (cp.async.bulk.tensor), tcgen05 alloc / mma / commit / ld,
-// UMMA shared-memory and instruction descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp).
+// tc_ptx.cuh -- inline-PTX wrappers shared by the tcgen05 kernels (batch_tc.cu, batch_tc_p1.cu): mbarrier, TMA
+// (cp.async.bulk.tensor), tcgen05 alloc / mma / commit / ld, programmatic dependent launch, UMMA shared-memory and
+// instruction descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -121,75 +121,11 @@ __device__ __forceinline__ uint32_t make_idesc(int bn) {
 }
 
 
-// ---- cluster / cta_group::2 additions ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t rank) {
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait_cluster(bar, parity)) {}
-}
-// multicast TMA load: the box lands at the same shared-memory offset in every CTA of `mask`, each
-// destination CTA's mbarrier (same offset) is credited with the bytes; the L2 -> SM fabric carries it once
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
-// commit of this CTA's MMAs that arrives on the mbarrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
-// 2-SM TMA load: executed by both CTAs of the pair, data lands in the executing CTA's shared memory,
-// the transaction bytes are credited to the LEADER's mbarrier (peer bit of the address cleared)
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t slot_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// commit of the pair's MMAs: arrives on the mbarrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-// instruction descriptor of the pair: M = 256 (128 rows per CTA), N = bn
-__device__ __forceinline__ uint32_t make_idesc_2sm(int bn) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-}
+// programmatic dependent launch: wait until the kernels this one depends on have completed and their memory is
+// visible (a no-op when the launch carried no programmatic attribute) / allow the next kernel in the stream to be
+// scheduled as SMs free up
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 }  // namespace tc
 }  // namespace gpad

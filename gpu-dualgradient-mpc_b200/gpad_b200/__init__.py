@@ -19,6 +19,7 @@ MODE_LATENCY, MODE_BATCH_SHARED, MODE_BATCH_PER_INSTANCE = 1, 2, 3
 PREC_FP32, PREC_TF32X3 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 SCHEDULE_PAPER, SCHEDULE_MATLAB_LAG = 0, 1
+WARM_COLD, WARM_PREVIOUS, WARM_SHIFTED = 0, 1, 2
 STATUS_NAMES = {0: "max_iter", 1: "converged_z", 2: "converged_zhat", 3: "converged_dual", 4: "nonfinite"}
 
 EXPORTS = [
@@ -30,6 +31,11 @@ EXPORTS = [
     "gpad_problem_operators", "gpad_problem_instances", "gpad_problem_plant", "gpad_schedule",
     "gpad_file_read", "gpad_file_write", "gpad_file_free", "gpad_debug_gemm_tf32x3", "gpad_debug_plan_tiles",
     "gpad_flatten_operators", "gpad_expand_operators", "gpad_closed_loop",
+    "gpad_solve_async", "gpad_wait", "gpad_handle_dims", "gpad_solve_stats", "gpad_instances_device",
+    "gpad_plants_battery", "gpad_plants_destroy", "gpad_plants_dims", "gpad_plants_operators", "gpad_plants_instances",
+    "gpad_closed_loop_plants",
+    "gpad_group_setup", "gpad_group_destroy", "gpad_group_solve", "gpad_group_size", "gpad_group_shard",
+    "gpad_file_read_flat", "gpad_file_write_flat", "gpad_fixture_read", "gpad_fixture_write", "gpad_fixture_free",
 ]
 
 _fp = C.POINTER(C.c_float)
@@ -54,7 +60,19 @@ class SolveArgs(C.Structure):
                 ("eps_g", C.c_float), ("eps_V", C.c_float),
                 ("y_next", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p), ("zhat", C.c_void_p), ("w", C.c_void_p),
                 ("iters", C.c_void_p), ("status", C.c_void_p), ("max_viol", C.c_void_p), ("gap", C.c_void_p),
-                ("stream", C.c_void_p), ("reserved", C.c_int * 4)]
+                ("stream", C.c_void_p), ("params", C.c_void_p), ("problem", C.c_void_p), ("build_f", C.c_int),
+                ("reserved", C.c_int * 3)]
+
+
+class SolveStats(C.Structure):
+    _fields_ = [("instance_iterations_scheduled", C.c_double), ("instance_iterations_needed", C.c_double),
+                ("compactions", C.c_int), ("reserved", C.c_int)]
+
+
+class Fixture(C.Structure):
+    _fields_ = [("step", C.c_int), ("n_u", C.c_int), ("N", C.c_int), ("m", C.c_int), ("flat", C.c_int), ("theta", C.c_float),
+                ("op", _fp), ("w", _fp), ("g_P", _fp), ("p_D", _fp), ("zhat_in", _fp), ("z_prev", _fp),
+                ("prod", _fp), ("sum", _fp), ("zhat_out", _fp), ("z_out", _fp), ("y_next", _fp)]
 
 
 class FileData(C.Structure):
@@ -103,6 +121,27 @@ def lib():
         L.gpad_file_read.argtypes = [C.c_char_p, C.POINTER(FileData)]
         L.gpad_file_write.argtypes = [C.c_char_p, C.POINTER(FileData)]
         L.gpad_file_free.argtypes = [C.POINTER(FileData)]
+        L.gpad_solve_async.argtypes = [C.c_void_p, C.POINTER(SolveArgs), C.POINTER(C.c_longlong)]
+        L.gpad_wait.argtypes = [C.c_void_p, C.c_longlong]
+        L.gpad_handle_dims.argtypes = [C.c_void_p] + [_ip] * 6
+        L.gpad_solve_stats.argtypes = [C.c_void_p, C.POINTER(SolveStats)]
+        L.gpad_instances_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gpad_plants_battery.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.POINTER(C.c_void_p)]
+        L.gpad_plants_destroy.argtypes = [C.c_void_p]
+        L.gpad_plants_dims.argtypes = [C.c_void_p] + [_ip] * 5
+        L.gpad_plants_operators.argtypes = [C.c_void_p, C.c_int, _fp, _fp, _fp]
+        L.gpad_plants_instances.argtypes = [C.c_void_p, _dp, _fp, _fp, _fp]
+        L.gpad_closed_loop_plants.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, _dp, C.c_int, _fp, _fp, C.c_int, C.c_int, _dp, _dp]
+        L.gpad_group_setup.argtypes = [C.POINTER(Config), _ip, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.gpad_group_destroy.argtypes = [C.c_void_p]
+        L.gpad_group_solve.argtypes = [C.c_void_p, C.POINTER(SolveArgs)]
+        L.gpad_group_size.argtypes = [C.c_void_p]
+        L.gpad_group_shard.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), _ip, _ip]
+        L.gpad_file_read_flat.argtypes = [C.c_char_p, C.POINTER(FileData)]
+        L.gpad_file_write_flat.argtypes = [C.c_char_p, C.POINTER(FileData)]
+        L.gpad_fixture_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(Fixture)]
+        L.gpad_fixture_write.argtypes = [C.c_char_p, C.POINTER(Fixture)]
+        L.gpad_fixture_free.argtypes = [C.POINTER(Fixture)]
         L.gpad_debug_gemm_tf32x3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.gpad_debug_plan_tiles.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4
         _lib = L
@@ -232,12 +271,18 @@ class Solver:
         return ms.value, cnt.value
 
     def solve_host(self, g_P, p_D, theta, beta, max_iter=None, f=None, y0=None, y_prev0=None, check_every=0,
-                   eps_g=0.0, eps_V=0.0, outputs=("y_next", "y", "z", "zhat", "w")):
-        """numpy in, numpy out (GPAD_MEM_HOST): H2D + solve + D2H + sync inside the call."""
+                   eps_g=0.0, eps_V=0.0, outputs=("y_next", "y", "z", "zhat", "w"), params=None, problem=None, build_f=False):
+        """numpy in, numpy out (GPAD_MEM_HOST): H2D + solve + D2H + sync inside the call.
+        params/problem: build g_P / p_D (and f) on the device from the parameter rows instead."""
         n, m = self.n, self.m
-        g_P = np.ascontiguousarray(g_P, np.float32).reshape(-1, n)
-        B = g_P.shape[0]
-        p_D = np.ascontiguousarray(p_D, np.float32).reshape(B, m)
+        if params is not None:
+            params = np.ascontiguousarray(np.atleast_2d(params), np.float64)
+            B = params.shape[0]
+            g_P = p_D = None
+        else:
+            g_P = np.ascontiguousarray(g_P, np.float32).reshape(-1, n)
+            B = g_P.shape[0]
+            p_D = np.ascontiguousarray(p_D, np.float32).reshape(B, m)
         opt = {k: (None if v is None else np.ascontiguousarray(v, np.float32).reshape(B, -1))
                for k, v in (("f", f), ("y0", y0), ("y_prev0", y_prev0))}
         theta = np.ascontiguousarray(theta, np.float32); beta = np.ascontiguousarray(beta, np.float32)
@@ -248,7 +293,8 @@ class Solver:
         a = SolveArgs(B, MEM_HOST, _ptr(g_P), _ptr(p_D), _ptr(opt["f"]), _ptr(opt["y0"]), _ptr(opt["y_prev0"]),
                       _f32p(theta), _f32p(beta), max_iter, check_every, eps_g, eps_V,
                       _ptr(out.get("y_next")), _ptr(out.get("y")), _ptr(out.get("z")), _ptr(out.get("zhat")),
-                      _ptr(out.get("w")), _ptr(iters), _ptr(status), _ptr(viol), _ptr(gap), None)
+                      _ptr(out.get("w")), _ptr(iters), _ptr(status), _ptr(viol), _ptr(gap), None,
+                      _ptr(params), problem._h if problem is not None else None, 1 if build_f else 0)
         check(lib().gpad_solve(self._h, C.byref(a)), "gpad_solve")
         if B == 1 and self.mode == MODE_LATENCY:
             out = {k: v[0] for k, v in out.items()}
@@ -259,14 +305,31 @@ class Solver:
 
     def solve_device(self, batch, g_P, p_D, theta, beta, max_iter, stream=None, f=None, y0=None, y_prev0=None,
                      check_every=0, eps_g=0.0, eps_V=0.0, y_next=None, y=None, z=None, zhat=None, w=None,
-                     iters=None, status=None, max_viol=None, gap=None):
+                     iters=None, status=None, max_viol=None, gap=None, params=None, problem=None, build_f=False):
         """device pointers (torch tensors or ints) in and out (GPAD_MEM_DEVICE): enqueue only."""
         theta = np.ascontiguousarray(theta, np.float32); beta = np.ascontiguousarray(beta, np.float32)
         a = SolveArgs(batch, MEM_DEVICE, _ptr(g_P), _ptr(p_D), _ptr(f), _ptr(y0), _ptr(y_prev0),
                       _f32p(theta), _f32p(beta), max_iter, check_every, eps_g, eps_V,
                       _ptr(y_next), _ptr(y), _ptr(z), _ptr(zhat), _ptr(w), _ptr(iters), _ptr(status),
-                      _ptr(max_viol), _ptr(gap), stream)
+                      _ptr(max_viol), _ptr(gap), stream, _ptr(params), problem._h if problem is not None else None,
+                      1 if build_f else 0)
         check(lib().gpad_solve(self._h, C.byref(a)), "gpad_solve")
+
+    def solve_async(self, args):
+        """gpad_solve_async on a prepared SolveArgs (host buffers, ideally pinned) -> ticket"""
+        t = C.c_longlong()
+        check(lib().gpad_solve_async(self._h, C.byref(args), C.byref(t)), "gpad_solve_async")
+        return t.value
+
+    def wait(self, ticket):
+        check(lib().gpad_wait(self._h, ticket), "gpad_wait")
+
+    def stats(self):
+        """tolerance-mode bookkeeping of the last shared-operator batch solve"""
+        st = SolveStats()
+        check(lib().gpad_solve_stats(self._h, C.byref(st)), "gpad_solve_stats")
+        return {"scheduled": st.instance_iterations_scheduled, "needed": st.instance_iterations_needed,
+                "compactions": st.compactions}
 
     def close(self):
         if self._h:
@@ -296,6 +359,103 @@ def expand_operators(n_u, N, m, M_G_flat, G_L_flat):
     return M_G, G_L
 
 
+def host_args(batch, theta, beta, max_iter, g_P=None, p_D=None, params=None, problem=None, outputs=None, iters=None, status=None,
+              f=None, y0=None, y_prev0=None, check_every=0, eps_g=0.0, eps_V=0.0, build_f=False):
+    """SolveArgs over caller-owned host arrays (keep them and theta/beta alive while the solve is in flight)"""
+    o = outputs or {}
+    return SolveArgs(batch, MEM_HOST, _ptr(g_P), _ptr(p_D), _ptr(f), _ptr(y0), _ptr(y_prev0), _f32p(theta), _f32p(beta), max_iter,
+                     check_every, eps_g, eps_V, _ptr(o.get("y_next")), _ptr(o.get("y")), _ptr(o.get("z")), _ptr(o.get("zhat")),
+                     _ptr(o.get("w")), _ptr(iters), _ptr(status), None, None, None, _ptr(params),
+                     problem._h if problem is not None else None, 1 if build_f else 0)
+
+
+class Plants:
+    """B battery plants with per-instance cell capacities (BASELINE config 5), condensed on host threads."""
+
+    def __init__(self, n_u, N, capacity_scale, threads=0):
+        cs = np.ascontiguousarray(capacity_scale, np.float64).reshape(-1, n_u)
+        self._h = C.c_void_p()
+        check(lib().gpad_plants_battery(n_u, N, cs.shape[0], cs.ctypes.data_as(_dp), threads, C.byref(self._h)), "gpad_plants_battery")
+        v = [C.c_int() for _ in range(5)]
+        check(lib().gpad_plants_dims(self._h, *[C.byref(x) for x in v]))
+        self.n_u, self.N, self.m, self.n_par, self.B = (x.value for x in v)
+        self.n = self.n_u * self.N
+
+    def operators(self, layout=LAYOUT_SEQUENTIAL):
+        M_G = np.empty((self.B, self.n * self.m), np.float32); G_L = np.empty((self.B, self.n * self.m), np.float32)
+        L = np.empty(self.B, np.float32)
+        check(lib().gpad_plants_operators(self._h, layout, _f32p(M_G), _f32p(G_L), _f32p(L)), "gpad_plants_operators")
+        return M_G, G_L, L
+
+    def instances(self, params, want_f=False):
+        params = np.ascontiguousarray(params, np.float64).reshape(self.B, self.n_par)
+        g_P = np.empty((self.B, self.n), np.float32); p_D = np.empty((self.B, self.m), np.float32)
+        f = np.empty((self.B, self.n), np.float32) if want_f else None
+        check(lib().gpad_plants_instances(self._h, params.ctypes.data_as(_dp), _f32p(g_P), _f32p(p_D), _f32p(f) if want_f else None),
+              "gpad_plants_instances")
+        return g_P, p_D, f
+
+    def closed_loop(self, solver, x0, samples, theta, beta, max_iter=None, warm_start=WARM_COLD, first=0, count=0):
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), np.float64)
+        B = x0.shape[0]
+        theta = np.ascontiguousarray(theta, np.float32); beta = np.ascontiguousarray(beta, np.float32)
+        max_iter = len(theta) if max_iter is None else max_iter
+        xt = np.empty((samples + 1, B, self.n_u)); ut = np.empty((samples, B, self.n_u))
+        check(lib().gpad_closed_loop_plants(self._h, solver._h, first, count, x0.ctypes.data_as(_dp), samples, _f32p(theta), _f32p(beta),
+                                            max_iter, int(warm_start), xt.ctypes.data_as(_dp), ut.ctypes.data_as(_dp)),
+              "gpad_closed_loop_plants")
+        return xt, ut
+
+    def close(self):
+        if self._h:
+            lib().gpad_plants_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Group:
+    """gpad_group_*: one logical solver over several devices of one box (host-memory solves)."""
+
+    def __init__(self, devices, n_u, N, m, L, M_G, G_L, layout=LAYOUT_SEQUENTIAL, mode=MODE_BATCH_SHARED, precision=PREC_TF32X3,
+                 max_batch=1):
+        cfg = Config(n_u, N, m, float(L), layout, mode, precision, max_batch, -1, MEM_HOST)
+        M_G = np.ascontiguousarray(M_G, np.float32); G_L = np.ascontiguousarray(G_L, np.float32)
+        dev = np.ascontiguousarray(devices, np.int32)
+        self._keep = (M_G, G_L)
+        self._h = C.c_void_p()
+        check(lib().gpad_group_setup(C.byref(cfg), dev.ctypes.data_as(_ip), dev.size, _ptr(M_G), _ptr(G_L), C.byref(self._h)),
+              "gpad_group_setup")
+        self.n, self.m, self.size = n_u * N, m, dev.size
+
+    def solve(self, args):
+        check(lib().gpad_group_solve(self._h, C.byref(args)), "gpad_group_solve")
+
+    def shard(self, i, batch):
+        h, first, count = C.c_void_p(), C.c_int(), C.c_int()
+        check(lib().gpad_group_shard(self._h, i, batch, C.byref(h), C.byref(first), C.byref(count)), "gpad_group_shard")
+        return first.value, count.value
+
+    def close(self):
+        if self._h:
+            lib().gpad_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def instances_device(problem, batch, params, g_P=None, p_D=None, f=None, stream=None):
+    check(lib().gpad_instances_device(problem._h, batch, _ptr(params), _ptr(g_P), _ptr(p_D), _ptr(f), stream), "gpad_instances_device")
+
+
 def closed_loop(problem, solver, x0, samples, theta, beta, max_iter=None, xref=None, warm_start=False):
     """receding-horizon simulation (gpad.m:79-95) -> (x_traj [samples+1][B][nx], u_traj [samples][B][n_u])"""
     x0 = np.ascontiguousarray(np.atleast_2d(x0), np.float64)
@@ -305,7 +465,7 @@ def closed_loop(problem, solver, x0, samples, theta, beta, max_iter=None, xref=N
     xr = None if xref is None else np.ascontiguousarray(np.atleast_2d(xref), np.float64)
     xt = np.empty((samples + 1, B, nx)); ut = np.empty((samples, B, problem.n_u))
     check(lib().gpad_closed_loop(problem._h, solver._h, B, x0.ctypes.data_as(_dp), None if xr is None else xr.ctypes.data_as(_dp),
-                                 samples, _f32p(theta), _f32p(beta), max_iter, 1 if warm_start else 0,
+                                 samples, _f32p(theta), _f32p(beta), max_iter, int(warm_start),
                                  xt.ctypes.data_as(_dp), ut.ctypes.data_as(_dp)), "gpad_closed_loop")
     return xt, ut
 
@@ -344,19 +504,52 @@ def debug_plan_tiles(kernel, ncols):
 
 
 # ---- reference data file (main.cu:29-67) ----
-def file_write(path, n_u, N, m, L, M_G, g_P, G_L, p_D, theta, beta):
+def file_write(path, n_u, N, m, L, M_G, g_P, G_L, p_D, theta, beta, flat=False):
     arrs = [np.ascontiguousarray(a, np.float32).ravel() for a in (M_G, g_P, G_L, p_D, theta, beta)]
+    assert arrs[0].size == (N if flat else n_u * N) * m and arrs[2].size == arrs[0].size
     fd = FileData(n_u, N, m, arrs[4].size, float(L), *[_f32p(a) for a in arrs])
-    check(lib().gpad_file_write(path.encode(), C.byref(fd)), "gpad_file_write")
+    fn = lib().gpad_file_write_flat if flat else lib().gpad_file_write
+    check(fn(path.encode(), C.byref(fd)), "gpad_file_write")
 
 
-def file_read(path):
+def file_read(path, flat=False):
     fd = FileData()
-    check(lib().gpad_file_read(path.encode(), C.byref(fd)), "gpad_file_read")
+    fn = lib().gpad_file_read_flat if flat else lib().gpad_file_read
+    check(fn(path.encode(), C.byref(fd)), "gpad_file_read")
     n, m, it = fd.n_u * fd.N, fd.m, fd.num_iterations
+    op = (fd.N if flat else n) * m
     take = lambda p, cnt: np.ctypeslib.as_array(p, shape=(cnt,)).copy()
-    out = dict(n_u=fd.n_u, N=fd.N, m=m, num_iterations=it, L=fd.L, M_G=take(fd.M_G, n * m), g_P=take(fd.g_P, n),
-               G_L=take(fd.G_L, n * m), p_D=take(fd.p_D, m), theta=take(fd.theta, max(it, 1))[:it],
+    out = dict(n_u=fd.n_u, N=fd.N, m=m, num_iterations=it, L=fd.L, M_G=take(fd.M_G, op), g_P=take(fd.g_P, n),
+               G_L=take(fd.G_L, op), p_D=take(fd.p_D, m), theta=take(fd.theta, max(it, 1))[:it],
                beta=take(fd.beta, max(it, 1))[:it])
     lib().gpad_file_free(C.byref(fd))
     return out
+
+
+_FIXTURE_FIELDS = {"op": None, "w": "m", "g_P": "n", "p_D": "m", "zhat_in": "n", "z_prev": "n",
+                   "prod": None, "sum": "m", "zhat_out": "n", "z_out": "n", "y_next": "m"}
+
+
+def fixture_read(directory, step, flat=False):
+    """step-2/3/4 fixture of the reference's harnesses (main_prof.cu:117-156,198-239; step3.cu:59-81) -> dict"""
+    fx = Fixture()
+    check(lib().gpad_fixture_read(directory.encode(), step, 1 if flat else 0, C.byref(fx)), "gpad_fixture_read")
+    n, m = fx.n_u * fx.N, fx.m
+    size = {"n": n, "m": m}
+    out = dict(step=fx.step, n_u=fx.n_u, N=fx.N, m=m, flat=bool(fx.flat), theta=fx.theta)
+    for name, kind in _FIXTURE_FIELDS.items():
+        p = getattr(fx, name)
+        if not p:
+            continue
+        cnt = size[kind] if kind else ((fx.N if fx.flat else n) * m if name == "op" else (n if step == 2 else m))
+        out[name] = np.ctypeslib.as_array(p, shape=(cnt,)).copy()
+    lib().gpad_fixture_free(C.byref(fx))
+    return out
+
+
+def fixture_write(directory, step, n_u, N, m, flat=False, theta=0.0, **vectors):
+    keep = {k: np.ascontiguousarray(v, np.float32).ravel() for k, v in vectors.items()}
+    fx = Fixture(step, n_u, N, m, 1 if flat else 0, float(theta))
+    for k, v in keep.items():
+        setattr(fx, k, _f32p(v))
+    check(lib().gpad_fixture_write(directory.encode(), C.byref(fx)), "gpad_fixture_write")

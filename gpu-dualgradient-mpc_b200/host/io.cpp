@@ -1,12 +1,18 @@
-// io.cpp -- reader / writer of the reference's text data file, main.cu:29-67:
-//   "n_u N m num_iterations L" then M_G (n*m), g_P (n), G_L (n*m), p_D (m),
-//   theta[num_iterations], beta[num_iterations]; whitespace-separated %f-parsable floats.
-// The operator layout inside the file is whatever the consumer expects (the shipped kernels
-// read the flipped one, kernel_functions.cu:50,180); this code does not reorder anything.
-// Unlike readData() every fopen/fscanf result is checked (the reference ignores them, main.cu:32).
+// io.cpp -- readers / writers of the reference's text formats (whitespace-separated %f-parsable floats):
+//   * the full-problem data file, main.cu:29-67: "n_u N m num_iterations L" then M_G (n*m), g_P (n), G_L (n*m),
+//     p_D (m), theta[num_iterations], beta[num_iterations]; with ENABLE_FLATTEN_MATRICES (main.cu:39-41,50-52) the two
+//     operators hold N*m floats each;
+//   * the per-step fixtures of the reference's harnesses: step 2 and step 4 (main_prof.cu:117-156, 198-239), step 3
+//     (Code/CUDA/step3.cu:59-81), each "<dir>/input.txt" + "<dir>/output.txt".
+// The operator layout inside a file is whatever the consumer expects (the shipped kernels read the flipped one,
+// kernel_functions.cu:50,180); nothing is reordered here.  Unlike readData() every fopen / fscanf result is checked
+// (the reference ignores them, main.cu:32) and sizes are validated against the file before anything is allocated.
+#include <sys/stat.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "gpad.h"
 
@@ -18,10 +24,59 @@ bool read_floats(FILE* fp, float* dst, size_t count) {
     return true;
 }
 
-bool write_floats(FILE* fp, const float* src, size_t count) {
+bool write_floats(FILE* fp, const float* src, size_t count, const char* fmt = "%.9g\n") {
     for (size_t i = 0; i < count; ++i)
-        if (fprintf(fp, "%.9g\n", (double)src[i]) < 0) return false;
+        if (fprintf(fp, fmt, (double)src[i]) < 0) return false;
     return true;
+}
+
+// every float takes at least two bytes of text ("0 "): a header that promises more floats than the file can hold is corrupt
+bool plausible(const char* path, size_t floats) {
+    struct stat st;
+    if (stat(path, &st) != 0) return false;
+    return floats <= (size_t)st.st_size / 2 + 16;
+}
+
+float* alloc_floats(size_t count) { return (float*)malloc(sizeof(float) * (count ? count : 1)); }
+
+int file_read(const char* path, gpad_file_t* out, bool flat) {
+    if (!path || !out) return GPAD_ERR_INVALID_ARG;
+    memset(out, 0, sizeof(*out));
+    FILE* fp = fopen(path, "r");
+    if (!fp) return GPAD_ERR_IO;
+    int rc = GPAD_ERR_IO;
+    if (fscanf(fp, "%d %d %d %d %f", &out->n_u, &out->N, &out->m, &out->num_iterations, &out->L) == 5 &&
+        out->n_u > 0 && out->N > 0 && out->m > 0 && out->num_iterations >= 0 &&
+        (size_t)out->n_u * out->N <= (size_t)1 << 24 && (size_t)out->m <= (size_t)1 << 24) {
+        const size_t n = (size_t)out->n_u * out->N, m = (size_t)out->m, it = (size_t)out->num_iterations;
+        const size_t op = (flat ? (size_t)out->N : n) * m;
+        if (plausible(path, 2 * op + n + m + 2 * it)) {
+            out->M_G = alloc_floats(op); out->g_P = alloc_floats(n); out->G_L = alloc_floats(op);
+            out->p_D = alloc_floats(m); out->theta = alloc_floats(it); out->beta = alloc_floats(it);
+            if (out->M_G && out->g_P && out->G_L && out->p_D && out->theta && out->beta &&
+                read_floats(fp, out->M_G, op) && read_floats(fp, out->g_P, n) && read_floats(fp, out->G_L, op) &&
+                read_floats(fp, out->p_D, m) && read_floats(fp, out->theta, it) && read_floats(fp, out->beta, it))
+                rc = GPAD_OK;
+        }
+    }
+    fclose(fp);
+    if (rc != GPAD_OK) gpad_file_free(out);
+    return rc;
+}
+
+int file_write(const char* path, const gpad_file_t* in, bool flat) {
+    if (!path || !in || !in->M_G || !in->g_P || !in->G_L || !in->p_D) return GPAD_ERR_INVALID_ARG;
+    if (in->n_u <= 0 || in->N <= 0 || in->m <= 0 || in->num_iterations < 0) return GPAD_ERR_INVALID_ARG;
+    if (in->num_iterations > 0 && (!in->theta || !in->beta)) return GPAD_ERR_INVALID_ARG;
+    FILE* fp = fopen(path, "w");
+    if (!fp) return GPAD_ERR_IO;
+    const size_t n = (size_t)in->n_u * in->N, m = (size_t)in->m, it = (size_t)in->num_iterations;
+    const size_t op = (flat ? (size_t)in->N : n) * m;
+    bool ok = fprintf(fp, "%d %d %d %d %.9g\n", in->n_u, in->N, in->m, in->num_iterations, (double)in->L) > 0;
+    ok = ok && write_floats(fp, in->M_G, op) && write_floats(fp, in->g_P, n) && write_floats(fp, in->G_L, op) &&
+         write_floats(fp, in->p_D, m) && write_floats(fp, in->theta, it) && write_floats(fp, in->beta, it);
+    ok = (fclose(fp) == 0) && ok;
+    return ok ? GPAD_OK : GPAD_ERR_IO;
 }
 
 }  // namespace
@@ -34,40 +89,88 @@ void gpad_file_free(gpad_file_t* f) {
     memset(f, 0, sizeof(*f));
 }
 
-int gpad_file_read(const char* path, gpad_file_t* out) {
-    if (!path || !out) return GPAD_ERR_INVALID_ARG;
+int gpad_file_read(const char* path, gpad_file_t* out) { return file_read(path, out, false); }
+int gpad_file_write(const char* path, const gpad_file_t* in) { return file_write(path, in, false); }
+int gpad_file_read_flat(const char* path, gpad_file_t* out) { return file_read(path, out, true); }
+int gpad_file_write_flat(const char* path, const gpad_file_t* in) { return file_write(path, in, true); }
+
+void gpad_fixture_free(gpad_fixture_t* f) {
+    if (!f) return;
+    free(f->op); free(f->w); free(f->g_P); free(f->p_D); free(f->zhat_in); free(f->z_prev);
+    free(f->prod); free(f->sum); free(f->zhat_out); free(f->z_out); free(f->y_next);
+    memset(f, 0, sizeof(*f));
+}
+
+int gpad_fixture_read(const char* dir, int step, int flat, gpad_fixture_t* out) {
+    if (!dir || !out || step < 2 || step > 4) return GPAD_ERR_INVALID_ARG;
     memset(out, 0, sizeof(*out));
-    FILE* fp = fopen(path, "r");
-    if (!fp) return GPAD_ERR_IO;
+    out->step = step; out->flat = flat ? 1 : 0;
+    const std::string in_path = std::string(dir) + "/input.txt", out_path = std::string(dir) + "/output.txt";
+    FILE* fi = fopen(in_path.c_str(), "r");
+    FILE* fo = fopen(out_path.c_str(), "r");
     int rc = GPAD_ERR_IO;
-    if (fscanf(fp, "%d %d %d %d %f", &out->n_u, &out->N, &out->m, &out->num_iterations, &out->L) == 5 &&
-        out->n_u > 0 && out->N > 0 && out->m > 0 && out->num_iterations >= 0) {
-        const size_t n = (size_t)out->n_u * out->N, m = (size_t)out->m, it = (size_t)out->num_iterations;
-        out->M_G = (float*)malloc(sizeof(float) * n * m);
-        out->g_P = (float*)malloc(sizeof(float) * n);
-        out->G_L = (float*)malloc(sizeof(float) * n * m);
-        out->p_D = (float*)malloc(sizeof(float) * m);
-        out->theta = (float*)malloc(sizeof(float) * (it ? it : 1));
-        out->beta = (float*)malloc(sizeof(float) * (it ? it : 1));
-        if (out->M_G && out->g_P && out->G_L && out->p_D && out->theta && out->beta &&
-            read_floats(fp, out->M_G, n * m) && read_floats(fp, out->g_P, n) && read_floats(fp, out->G_L, n * m) &&
-            read_floats(fp, out->p_D, m) && read_floats(fp, out->theta, it) && read_floats(fp, out->beta, it))
-            rc = GPAD_OK;
-    }
-    fclose(fp);
-    if (rc != GPAD_OK) gpad_file_free(out);
+    do {
+        if (!fi || !fo) break;
+        const int want = step == 3 ? 4 : 3;
+        int got = fscanf(fi, "%d %d %d", &out->n_u, &out->N, &out->m);
+        if (step == 3 && got == 3) got += fscanf(fi, "%f", &out->theta);                  // step3.cu:59
+        if (got != want || out->n_u <= 0 || out->N <= 0 || out->m <= 0) break;
+        if ((size_t)out->n_u * out->N > (size_t)1 << 24 || (size_t)out->m > (size_t)1 << 24) break;
+        const size_t n = (size_t)out->n_u * out->N, m = (size_t)out->m, op = (flat ? (size_t)out->N : n) * m;
+        bool ok = true;
+        auto take = [&](FILE* fp, float** dst, size_t count) {
+            if (!ok) return;
+            *dst = alloc_floats(count);
+            ok = *dst && read_floats(fp, *dst, count);
+        };
+        if (step == 2) {                                                                   // main_prof.cu:117-156
+            if (!plausible(in_path.c_str(), op + m + n)) break;
+            take(fi, &out->op, op); take(fi, &out->w, m); take(fi, &out->g_P, n);
+            take(fo, &out->prod, n); take(fo, &out->zhat_out, n);
+        } else if (step == 3) {                                                            // step3.cu:79-81
+            if (!plausible(in_path.c_str(), 2 * n)) break;
+            take(fi, &out->z_prev, n); take(fi, &out->zhat_in, n);
+            take(fo, &out->z_out, n);
+        } else {                                                                           // main_prof.cu:198-239
+            if (!plausible(in_path.c_str(), op + 2 * m + n)) break;
+            take(fi, &out->w, m); take(fi, &out->zhat_in, n); take(fi, &out->p_D, m); take(fi, &out->op, op);
+            take(fo, &out->prod, m); take(fo, &out->sum, m); take(fo, &out->y_next, m);
+        }
+        if (ok) rc = GPAD_OK;
+    } while (0);
+    if (fi) fclose(fi);
+    if (fo) fclose(fo);
+    if (rc != GPAD_OK) gpad_fixture_free(out);
     return rc;
 }
 
-int gpad_file_write(const char* path, const gpad_file_t* in) {
-    if (!path || !in || !in->M_G || !in->g_P || !in->G_L || !in->p_D) return GPAD_ERR_INVALID_ARG;
-    FILE* fp = fopen(path, "w");
-    if (!fp) return GPAD_ERR_IO;
-    const size_t n = (size_t)in->n_u * in->N, m = (size_t)in->m, it = (size_t)in->num_iterations;
-    bool ok = fprintf(fp, "%d %d %d %d %.9g\n", in->n_u, in->N, in->m, in->num_iterations, (double)in->L) > 0;
-    ok = ok && write_floats(fp, in->M_G, n * m) && write_floats(fp, in->g_P, n) && write_floats(fp, in->G_L, n * m) &&
-         write_floats(fp, in->p_D, m) && write_floats(fp, in->theta, it) && write_floats(fp, in->beta, it);
-    ok = (fclose(fp) == 0) && ok;
+int gpad_fixture_write(const char* dir, const gpad_fixture_t* in) {
+    if (!dir || !in || in->step < 2 || in->step > 4 || in->n_u <= 0 || in->N <= 0 || in->m <= 0) return GPAD_ERR_INVALID_ARG;
+    const size_t n = (size_t)in->n_u * in->N, m = (size_t)in->m, op = (in->flat ? (size_t)in->N : n) * m;
+    const bool have = in->step == 2 ? (in->op && in->w && in->g_P && in->prod && in->zhat_out)
+                    : in->step == 3 ? (in->z_prev && in->zhat_in && in->z_out)
+                                    : (in->w && in->zhat_in && in->p_D && in->op && in->prod && in->sum && in->y_next);
+    if (!have) return GPAD_ERR_INVALID_ARG;
+    FILE* fi = fopen((std::string(dir) + "/input.txt").c_str(), "w");
+    FILE* fo = fopen((std::string(dir) + "/output.txt").c_str(), "w");
+    bool ok = fi && fo;
+    if (ok) {
+        if (in->step == 3) {
+            // the reference's step-3 fixtures print 8 decimals (build/step3/*/input.txt)
+            ok = fprintf(fi, "%d %d %d %.8f\n", in->n_u, in->N, in->m, (double)in->theta) > 0 &&
+                 write_floats(fi, in->z_prev, n, "%.8f\n") && write_floats(fi, in->zhat_in, n, "%.8f\n") &&
+                 write_floats(fo, in->z_out, n, "%.8f\n");
+        } else if (in->step == 2) {
+            ok = fprintf(fi, "%d %d %d\n", in->n_u, in->N, in->m) > 0 && write_floats(fi, in->op, op) && write_floats(fi, in->w, m) &&
+                 write_floats(fi, in->g_P, n) && write_floats(fo, in->prod, n) && write_floats(fo, in->zhat_out, n);
+        } else {
+            ok = fprintf(fi, "%d %d %d\n", in->n_u, in->N, in->m) > 0 && write_floats(fi, in->w, m) && write_floats(fi, in->zhat_in, n) &&
+                 write_floats(fi, in->p_D, m) && write_floats(fi, in->op, op) && write_floats(fo, in->prod, m) &&
+                 write_floats(fo, in->sum, m) && write_floats(fo, in->y_next, m);
+        }
+    }
+    if (fi) ok = (fclose(fi) == 0) && ok;
+    if (fo) ok = (fclose(fo) == 0) && ok;
     return ok ? GPAD_OK : GPAD_ERR_IO;
 }
 

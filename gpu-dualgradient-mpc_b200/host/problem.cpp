@@ -17,16 +17,11 @@
 
 #include "gpad.h"
 
+#include "problem_internal.h"
+
 namespace {
 
-struct Mat {
-    int r = 0, c = 0;
-    std::vector<double> a;
-    Mat() {}
-    Mat(int r_, int c_) : r(r_), c(c_), a((size_t)r_ * c_, 0.0) {}
-    double& operator()(int i, int j) { return a[(size_t)i * c + j]; }
-    double operator()(int i, int j) const { return a[(size_t)i * c + j]; }
-};
+using gpad::Mat;
 
 Mat eye(int n) { Mat m(n, n); for (int i = 0; i < n; ++i) m(i, i) = 1.0; return m; }
 
@@ -100,24 +95,6 @@ void chol_solve(const Mat& Lc, Mat& X) {
 
 }  // namespace
 
-namespace gpad {
-int closed_loop_device(gpad_handle_t h, int B, int nx, int nu, int n, int m, int npar, double L, const double* Kg,
-                       const double* Bb, const double* b0, const double* A, const double* Bm, const double* x0,
-                       const double* xref, int samples, const float* theta, const float* beta, int max_iter, int warm_start,
-                       double* x_traj, double* u_traj);
-}
-
-struct gpad_problem_s {
-    int n_u = 0, N = 0, n = 0, m = 0, n_par = 0, nx = 0;
-    double L = 0.0;
-    Mat H, G;        // n x n, m x n
-    Mat MG;          // n x m   = -H^-1 G'
-    Mat Ff, Kg;      // n x n_par  (f = Ff p, g_P = Kg p)
-    Mat Bb;          // m x n_par
-    std::vector<double> b0;
-    Mat A, B;        // plant (nx x nx, nx x n_u)
-};
-
 namespace {
 
 // shared tail: Cholesky, M_G, Kg
@@ -166,9 +143,10 @@ void hessian(const Mat& Su, const std::vector<double>& q, const std::vector<doub
 
 }  // namespace
 
-extern "C" {
+namespace gpad {
 
-int gpad_problem_battery(int n_u, int N, gpad_problem_t* out) {
+// battery balancing with cell capacities c_i = 0.027 * 4.1 Ah * cap_scale[i] (cap_scale == nullptr: the reference's pack)
+int build_battery(int n_u, int N, const double* cap_scale, gpad_problem_s** out) {
     if (!out || n_u < 1 || N < 1) return GPAD_ERR_INVALID_ARG;
     gpad_problem_s* P = new gpad_problem_s;
     const int n = n_u * N;
@@ -176,7 +154,11 @@ int gpad_problem_battery(int n_u, int N, gpad_problem_t* out) {
     // plant: A = I, B = diag(-1/(3600 c_i)), c_i = 0.027*4.1 Ah         gpad.m:18,34-35,47-49
     P->A = eye(n_u);
     P->B = Mat(n_u, n_u);
-    for (int i = 0; i < n_u; ++i) P->B(i, i) = -1.0 / (3600.0 * (0.027 * 4.1));
+    for (int i = 0; i < n_u; ++i) {
+        const double scale = cap_scale ? cap_scale[i] : 1.0;
+        if (!(scale > 0.0)) { delete P; return GPAD_ERR_INVALID_ARG; }
+        P->B(i, i) = -1.0 / (3600.0 * (0.027 * 4.1 * scale));
+    }
     Mat Sx, Su;                                                        // M_ak, M_ab gpad.m:50-63
     prediction_matrices(P->A, P->B, N, Sx, Su);
     std::vector<double> q(n_u, 100.0), r(n_u, 1.0);                    // Qx, Qu     gpad.m:36-43
@@ -201,11 +183,19 @@ int gpad_problem_battery(int n_u, int N, gpad_problem_t* out) {
     double fro = 0.0;                                                  // L = ||H||_F^2  acceldualgrad.m:11
     for (double v : P->H.a) fro += v * v;
     P->L = fro;
+    // dual blocks for the receding-horizon shift: {offset, rows per stage}
+    P->blocks = {{0, n_u}, {n, n_u}, {2 * n, n_u}, {3 * n, n_u}, {4 * n, 1}, {4 * n + N, 1}};
     const int rc = finish(P);
     if (rc != GPAD_OK) { delete P; return rc; }
     *out = P;
     return GPAD_OK;
 }
+
+}  // namespace gpad
+
+extern "C" {
+
+int gpad_problem_battery(int n_u, int N, gpad_problem_t* out) { return gpad::build_battery(n_u, N, nullptr, out); }
 
 int gpad_problem_quadrotor(int N, gpad_problem_t* out) {
     if (!out || N < 1) return GPAD_ERR_INVALID_ARG;
@@ -290,6 +280,7 @@ int gpad_problem_quadrotor(int N, gpad_problem_t* out) {
         }
         P->L = 1.02 * lam;
     }
+    P->blocks = {{0, 6}, {ns, 6}, {2 * ns, nu}, {2 * ns + n, nu}, {2 * ns + 2 * n, 4}};
     const int rc = finish(P);
     if (rc != GPAD_OK) { delete P; return rc; }
     *out = P;
@@ -297,6 +288,8 @@ int gpad_problem_quadrotor(int N, gpad_problem_t* out) {
 }
 
 int gpad_problem_destroy(gpad_problem_t p) {
+    if (!p) return GPAD_OK;
+    for (void* d : p->dev_cache) gpad::problem_dev_free(d);
     delete p;
     return GPAD_OK;
 }
@@ -411,11 +404,14 @@ int gpad_expand_operators(int n_u, int N, int m, const float* MGf, const float* 
 int gpad_closed_loop(gpad_problem_t p, gpad_handle_t h, int B, const double* x0, const double* xref, int samples,
                      const float* theta, const float* beta, int max_iter, int warm_start, double* x_traj, double* u_traj) {
     if (!p || !h || !x0 || !theta || !beta || B < 1 || samples < 1 || max_iter < 1) return GPAD_ERR_INVALID_ARG;
+    if (warm_start < GPAD_WARM_COLD || warm_start > GPAD_WARM_SHIFTED) return GPAD_ERR_INVALID_ARG;
     if (p->n_par - p->nx > 0 && !xref) return GPAD_ERR_INVALID_ARG;
+    // the handle must solve THIS problem: a mismatch would run gpad_solve past the ends of the loop's buffers
+    int hn = 0, hN = 0, hm = 0, hmode = 0, hB = 0;
+    if (gpad_handle_dims(h, &hn, &hN, &hm, &hmode, &hB, nullptr) != GPAD_OK) return GPAD_ERR_INVALID_ARG;
+    if (hn != p->n_u || hN != p->N || hm != p->m || B > hB || (hmode == GPAD_MODE_LATENCY && B != 1)) return GPAD_ERR_INVALID_ARG;
     // the whole loop runs on the device (csrc/closed_loop.cu): instance build, solve, state advance
-    return gpad::closed_loop_device(h, B, p->nx, p->n_u, p->n, p->m, p->n_par, p->L, p->Kg.a.data(), p->Bb.a.data(), p->b0.data(),
-                                    p->A.a.data(), p->B.a.data(), x0, xref, samples, theta, beta, max_iter, warm_start, x_traj,
-                                    u_traj);
+    return gpad::closed_loop_device(p, h, B, x0, xref, samples, theta, beta, max_iter, warm_start, x_traj, u_traj);
 }
 
 int gpad_schedule(float* theta, float* beta, int count, int variant) {

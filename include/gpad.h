@@ -16,8 +16,12 @@
  *     vectors back to back).
  *   - there is NO CPU fallback: without a usable CUDA device every compute entry point
  *     returns GPAD_ERR_NO_DEVICE / GPAD_ERR_CUDA.
- *   - a handle is not thread-safe; distinct handles are independent.  The caller owns every
+ *   - a handle is not thread-safe and has ONE solve in flight: its scratch (schedule tables, batch
+ *     state) is shared by all its solves, so a solve enqueued on one stream is ordered by the library
+ *     after the handle's previous solve on any other stream (gpad_solve_async is the one pipelined
+ *     exception and owns its ordering).  Distinct handles are independent.  The caller owns every
  *     buffer it passes; the library owns its handle and its converted operator copies.
+ *   - every call selects the handle's device for its duration and restores the caller's current device.
  */
 #ifndef GPAD_H
 #define GPAD_H
@@ -28,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GPAD_API_VERSION 1
+#define GPAD_API_VERSION 2
 
 typedef enum {
     GPAD_OK = 0,
@@ -110,6 +114,7 @@ int gpad_step_four(const float* G_L, float* y_vp1, const float* w_v, const float
  *    (main.cu:108-180): allocation, H2D, the iteration loop, D2H.
  * ---------------------------------------------------------------------------------------- */
 typedef struct gpad_handle_s* gpad_handle_t;
+typedef struct gpad_problem_s* gpad_problem_t;      /* host-side condensed problem, section 3 */
 
 typedef struct {
     int n_u, N, m;          /* file header, main.cu:34                                        */
@@ -154,13 +159,46 @@ typedef struct {
     float* max_viol;        /* [batch] max_i g(.)_i at the last check (NaN if never checked)   */
     float* gap;             /* [batch] duality-gap figure at the last check (NaN if none)      */
     void* stream;           /* cudaStream_t for GPAD_MEM_DEVICE calls (NULL = default stream)  */
-    int reserved[4];        /* must be zero                                                    */
+    /* on-device instance build (GPAD_MODE_BATCH_SHARED): when params != NULL, g_P / p_D above are ignored
+     * and built on the device from the parameters, g_P = H^-1 F' p, p_D = -(b0 + Bb p) / L
+     * (acceldualgrad.m:21,23; gpad.m:81,85): 8 n_par bytes per instance cross PCIe instead of 4 (n + m) */
+    const double* params;   /* [batch][n_par] (memspace `mem`) or NULL                         */
+    gpad_problem_t problem; /* the problem the parameters belong to (same n_u, N, m as the handle) */
+    int build_f;            /* with params: also build f = F' p and enable the relative / dual gap tests */
+    int reserved[3];        /* must be zero                                                    */
 } gpad_solve_args_t;
 
 /* GPAD_MEM_HOST: copies in, solves, copies out and synchronises before returning.
  * GPAD_MEM_DEVICE: enqueues everything on args->stream and returns without synchronising
- * (iteration-count early exit in tolerance mode synchronises that stream every check). */
+ * (in tolerance mode the host follows the device's stop decisions a few checks behind; stopped
+ * instances are frozen, so the extra iterations it may enqueue change nothing). */
 int gpad_solve(gpad_handle_t h, const gpad_solve_args_t* args);
+
+/* Asynchronous host-memory solves (GPAD_MODE_BATCH_SHARED, fixed iteration count): enqueues copy-in, iterations and
+ * copy-out on three streams over two alternating sets of batch state and returns a ticket at once, so that with
+ * back-to-back calls the H2D copies of solve k+1 and the D2H copies of solve k-1 run under the iterations of solve k
+ * (main.cu:136-147 / 176-180 are serial with its loop).  Host buffers should be page-locked (cudaHostAlloc /
+ * cudaHostRegister); pageable ones work but their copies serialise.  A solve's buffers belong to the library until
+ * gpad_wait(ticket) returns; at most two tickets are in flight (a third call waits on the device for the first). */
+int gpad_solve_async(gpad_handle_t h, const gpad_solve_args_t* args, long long* ticket);
+int gpad_wait(gpad_handle_t h, long long ticket);
+
+/* dimensions a handle was set up with (any pointer may be NULL) */
+int gpad_handle_dims(gpad_handle_t h, int* n_u, int* N, int* m, int* mode, int* max_batch, int* device);
+
+/* tolerance-mode bookkeeping of the handle's last GPAD_MODE_BATCH_SHARED solve (synchronises with it):
+ * instance-iterations the GEMM kernels were scheduled for (128 x iterations per batch tile that still held a running
+ * instance) and instance-iterations the instances needed (sum of iters); their ratio is the share of tensor work that
+ * was useful, the rest rode along on stopped instances of partly finished tiles.  Instances stop at very different
+ * iterations, so the library retires finished tiles and, whenever at most half of the working rows still run, gathers
+ * the running instances into dense tiles (results do not depend on it). */
+typedef struct {
+    double instance_iterations_scheduled;
+    double instance_iterations_needed;
+    int compactions;            /* times the running instances were gathered into dense tiles */
+    int reserved;
+} gpad_solve_stats_t;
+int gpad_solve_stats(gpad_handle_t h, gpad_solve_stats_t* out);
 
 /* Optional per-kernel device timing: when enabled, every hot-path kernel launch of this handle is
  * bracketed by CUDA events on the launching stream (bench.py's roofline figure).
@@ -179,8 +217,6 @@ const char* gpad_describe(gpad_handle_t h);
  * 3. Host-side problem setup (C++ restatement of the MATLAB offline stage: gpad.m:4-85,
  *    acceldualgrad.m:9-23) and the theta/beta schedule the data file carries (main.cu:61-64).
  * ---------------------------------------------------------------------------------------- */
-typedef struct gpad_problem_s* gpad_problem_t;
-
 /* battery balancing, n_u cells, horizon N: m = 4 n_u N + 2 N, L = ||H||_F^2 */
 int gpad_problem_battery(int n_u, int N, gpad_problem_t* out);
 /* hover-linearised quadrotor, nx = 12, nu = 4, horizon N: m = 24 N, L = 1.02 lambda_max(G H^-1 G') */
@@ -194,6 +230,9 @@ int gpad_problem_operators(gpad_problem_t p, int layout, float* M_G, float* G_L)
  * (f may be NULL) -- all host buffers */
 int gpad_problem_instances(gpad_problem_t p, int B, const double* params, float* g_P, float* p_D,
                            float* f);
+/* the same maps evaluated on the CURRENT device: params [B][n_par] (double), g_P [B][n], p_D [B][m], f [B][n] or NULL,
+ * all device pointers, dense rows; enqueued on `stream`.  The problem's matrices are uploaded once per device. */
+int gpad_instances_device(gpad_problem_t p, int B, const double* params, float* g_P, float* p_D, float* f, void* stream);
 /* plant matrices for closed-loop simulation: A [nx][nx], B [nx][n_u] row-major (double) */
 int gpad_problem_plant(gpad_problem_t p, int* nx, double* A, double* B);
 
@@ -208,12 +247,55 @@ int gpad_expand_operators(int n_u, int N, int m, const float* M_G_flat, const fl
 
 /* Closed-loop receding-horizon simulation (gpad.m:79-95): every sample builds g_P / p_D from the current
  * states, solves the batch with h (max_iter iterations, fixed), applies u = z[0:n_u] and advances
- * x <- A x + B u in double.  warm_start != 0 feeds the previous duals (y_I, y_{I-1}) into the next solve; the
- * reference cold-starts every sample (acceldualgrad.m:16-18).  The whole loop runs on the device (instance build, solve,
- * state advance; nx <= 32); only the trajectories are copied back.  x0 [batch][nx]; xref [batch][n_par-nx] or NULL;
- * x_traj [samples+1][batch][nx]; u_traj [samples][batch][n_u] (host, either may be NULL). */
+ * x <- A x + B u in double.  warm_start: 0 = cold start every sample like the reference (acceldualgrad.m:16-18),
+ * GPAD_WARM_PREVIOUS = the previous duals (y_I, y_{I-1}) start the next solve, GPAD_WARM_SHIFTED = the previous duals
+ * moved one stage forward inside every constraint block (the last stage repeats), the receding-horizon shift.
+ * The whole loop runs on the handle's device (instance build, solve, state advance; nx <= 32); only the trajectories
+ * are copied back.  x0 [batch][nx]; xref [batch][n_par-nx] or NULL; x_traj [samples+1][batch][nx];
+ * u_traj [samples][batch][n_u] (host, either may be NULL).  The handle must have been set up for the problem's
+ * n_u, N, m in a batch mode with max_batch >= batch (GPAD_ERR_INVALID_ARG otherwise). */
+enum { GPAD_WARM_COLD = 0, GPAD_WARM_PREVIOUS = 1, GPAD_WARM_SHIFTED = 2 };
 int gpad_closed_loop(gpad_problem_t prob, gpad_handle_t h, int batch, const double* x0, const double* xref, int samples,
                      const float* theta, const float* beta, int max_iter, int warm_start, double* x_traj, double* u_traj);
+
+/* ------------------------------------------------------------------------------------------
+ * 3b. Per-instance plants (BASELINE config 5): B battery packs whose cell capacities differ per instance
+ *     (gpad.m:18 scaled by capacity_scale [B][n_u]), hence B different M_G / G_L / L and affine instance maps.
+ *     Condensed on `threads` host threads (<= 0: all cores).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gpad_plants_s* gpad_plants_t;
+int gpad_plants_battery(int n_u, int N, int B, const double* capacity_scale, int threads, gpad_plants_t* out);
+int gpad_plants_destroy(gpad_plants_t p);
+int gpad_plants_dims(gpad_plants_t p, int* n_u, int* N, int* m, int* n_par, int* B);
+/* operators of all plants back to back ([B][n*m] each) in the requested layout: what gpad_setup takes in
+ * GPAD_MODE_BATCH_PER_INSTANCE; L [B] (may be NULL) */
+int gpad_plants_operators(gpad_plants_t p, int layout, float* M_G, float* G_L, float* L);
+/* per-instance vectors, one parameter row per plant: params [B][n_par] -> g_P [B][n], p_D [B][m], f [B][n] or NULL (host) */
+int gpad_plants_instances(gpad_plants_t p, const double* params, float* g_P, float* p_D, float* f);
+/* gpad_closed_loop with one plant per instance; h is a GPAD_MODE_BATCH_PER_INSTANCE handle built from
+ * gpad_plants_operators of the same plants (max_batch >= B); first <= 0 with count <= 0 means all plants,
+ * otherwise plants [first, first + count) -- the shard this handle owns */
+int gpad_closed_loop_plants(gpad_plants_t p, gpad_handle_t h, int first, int count, const double* x0, int samples,
+                            const float* theta, const float* beta, int max_iter, int warm_start, double* x_traj,
+                            double* u_traj);
+
+/* ------------------------------------------------------------------------------------------
+ * 3c. One logical solver over several devices of one box: the batch is cut into contiguous shards, one per device,
+ *     operators are replicated (per-instance operators are sharded with their instances), every device runs its own
+ *     handle from its own host thread, and results land in the caller's host buffers by asynchronous D2H copies.
+ *     No collective, no NCCL: the path has no exchange step.  cfg->max_batch is the capacity of the
+ *     whole group; cfg->device is ignored.  devices may repeat an ordinal (several shards on one GPU).
+ *     Results do not depend on the number of devices.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gpad_group_s* gpad_group_t;
+int gpad_group_setup(const gpad_config_t* cfg, const int* devices, int device_count, const float* M_G, const float* G_L,
+                     gpad_group_t* out);
+int gpad_group_destroy(gpad_group_t g);
+/* GPAD_MEM_HOST arguments only; shards [0, batch) over the devices and solves them concurrently */
+int gpad_group_solve(gpad_group_t g, const gpad_solve_args_t* args);
+int gpad_group_size(gpad_group_t g);
+/* shard i: its handle and the instance range [first, first + count) it owns for a batch of `batch` */
+int gpad_group_shard(gpad_group_t g, int i, int batch, gpad_handle_t* h, int* first, int* count);
 
 /* theta_v, beta_v for v = 0..count-1 (paper eq. 8e / acceldualgrad.m:55-56) */
 int gpad_schedule(float* theta, float* beta, int count, int variant);
@@ -231,6 +313,28 @@ typedef struct {
 int gpad_file_read(const char* path, gpad_file_t* out);
 int gpad_file_write(const char* path, const gpad_file_t* in);
 void gpad_file_free(gpad_file_t* f);
+/* the ENABLE_FLATTEN_MATRICES variant of the same file (main.cu:39-41,50-52): the two operators hold N*m floats
+ * each (GPAD_LAYOUT_FLAT) instead of n*m; everything else is identical */
+int gpad_file_read_flat(const char* path, gpad_file_t* out);
+int gpad_file_write_flat(const char* path, const gpad_file_t* in);
+
+/* The per-step fixtures of the reference's harnesses, "<dir>/input.txt" + "<dir>/output.txt":
+ *   step 2 (main_prof.cu:117-156)  input: n_u N m, M_G, w[m], g_P[n];  output: M_G w [n], zhat [n]
+ *   step 3 (step3.cu:59-81)        input: n_u N m theta, z_prev[n], zhat[n];  output: z [n]
+ *   step 4 (main_prof.cu:198-239)  input: n_u N m, w[m], zhat[n], p_D[m], G_L;  output: G_L zhat [m], sum [m], y_next [m]
+ * `flat` != 0: the operator holds N*m floats (the default fixtures of main_prof.cu:10, ENABLE_FLATTEN_MATRICES).
+ * Absent vectors are NULL; gpad_fixture_read mallocs, gpad_fixture_free releases. */
+typedef struct {
+    int step;                       /* 2, 3 or 4 */
+    int n_u, N, m, flat;
+    float theta;                    /* step 3 */
+    float *op;                      /* step 2: M_G, step 4: G_L */
+    float *w, *g_P, *p_D, *zhat_in, *z_prev;               /* inputs  */
+    float *prod, *sum, *zhat_out, *z_out, *y_next;         /* outputs */
+} gpad_fixture_t;
+int gpad_fixture_read(const char* dir, int step, int flat, gpad_fixture_t* out);
+int gpad_fixture_write(const char* dir, const gpad_fixture_t* in);
+void gpad_fixture_free(gpad_fixture_t* f);
 
 /* ------------------------------------------------------------------------------------------
  * 5. Test hook: C[M][N] = A[M][K] * B[N][K]^T through the tcgen05 3xTF32 mainloop used by

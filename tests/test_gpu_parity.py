@@ -140,7 +140,7 @@ def test_latency_fixed_iterations_match_oracle(torch_cuda, G, oracle, dims):
     s.close()
 
 
-@pytest.mark.parametrize("plan", ["block", "cluster:2", "cluster:8", "grid:16", "grid:148", "lean:16", "leangrid:148"])
+@pytest.mark.parametrize("plan", ["block", "cluster:2", "cluster:8", "grid:16", "grid:148", "lean:16"])
 def test_latency_every_synchronisation_variant(torch_cuda, G, oracle, plan, monkeypatch):
     """the same QP through single-CTA, cluster/DSMEM and cooperative-grid variants, operators in
     shared memory and streamed from L2"""
@@ -150,11 +150,7 @@ def test_latency_every_synchronisation_variant(torch_cuda, G, oracle, plan, monk
     ora = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta)
     f64 = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta)
     for no_smem in ([True] if plan == "block" else [False] if plan.startswith("lean:") else [False, True]):
-        monkeypatch.setenv("GPAD_LATENCY_PLAN", plan)
-        if no_smem:
-            monkeypatch.setenv("GPAD_LATENCY_NO_SMEM_OPS", "1")
-        else:
-            monkeypatch.delenv("GPAD_LATENCY_NO_SMEM_OPS", raising=False)
+        monkeypatch.setenv("GPAD_DEBUG", f"latency_plan={plan},latency_no_smem_ops={1 if no_smem else 0}")
         s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G_flipped(), pb.G_L_flipped(), layout=G.LAYOUT_FLIPPED, mode=G.MODE_LATENCY)
         print("\n", plan, s.description)
         gpu = s.solve_host(g_P, p_D, theta, beta)
@@ -214,7 +210,7 @@ def test_latency_dual_gap_branch(torch_cuda, G, oracle, plan, monkeypatch):
     default plan (one CTA, latency_small.cu; n = 24 is beyond the one-warp kernel) and forced onto the whole chip
     (latency_grid2.cu)"""
     if plan != "default":
-        monkeypatch.setenv("GPAD_LATENCY_PLAN", plan)
+        monkeypatch.setenv("GPAD_DEBUG", f"latency_plan={plan}")
     hit = 0
     theta, beta = schedule(3000)
     for seed in range(12):
@@ -267,7 +263,7 @@ def test_latency_grid2_matches_generic_grid_kernel(torch_cuda, G, oracle, dims, 
     theta, beta = schedule(50)
     res = {}
     for name, env in (("grid2", "1"), ("generic", "0")):
-        monkeypatch.setenv("GPAD_LATENCY_GRID2", env)
+        monkeypatch.setenv("GPAD_DEBUG", f"latency_grid2={env}")
         s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_LATENCY)
         assert ("column-partitioned" in s.description) == (name == "grid2"), s.description
         cold = s.solve_host(g_P, p_D, theta, beta)
@@ -286,11 +282,11 @@ def test_latency_grid2_matches_generic_grid_kernel(torch_cuda, G, oracle, dims, 
 
 
 # ------------------------------------------------------------------------------------ tensor-core GEMM hook
-@pytest.mark.parametrize("cta_group", ["1", "2"])
+@pytest.mark.parametrize("bk", ["16", "32"])
 @pytest.mark.parametrize("shape", [(128, 16, 16), (128, 256, 64), (300, 200, 1000), (1000, 416, 2400), (257, 2400, 400)])
-def test_tf32x3_gemm_reaches_fp32_accuracy(torch_cuda, G, shape, cta_group, monkeypatch):
-    """both tcgen05 kernels: one CTA per 128-row tile (cta_group::1) and CTA pairs (cta_group::2, M = 256)"""
-    monkeypatch.setenv("GPAD_TC_CG", cta_group)
+def test_tf32x3_gemm_reaches_fp32_accuracy(torch_cuda, G, shape, bk, monkeypatch):
+    """the tcgen05 3xTF32 mainloop with both K-block widths (SWIZZLE_64B / SWIZZLE_128B operand tiles)"""
+    monkeypatch.setenv("GPAD_DEBUG", f"tc_bk={bk}")
     t = torch_cuda
     M, N, K = shape
     rng = np.random.default_rng(M + N + K)
@@ -346,10 +342,8 @@ def test_batch_battery_matches_oracle(torch_cuda, G, oracle, prec, dims, B):
     s.close()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32x3-pairs"])
-def test_batch_quadrotor_matches_oracle(torch_cuda, G, oracle, prec, monkeypatch):
-    monkeypatch.setenv("GPAD_TC_CG", "2" if prec.endswith("pairs") else "1")
-    prec = prec.split("-")[0]
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_batch_quadrotor_matches_oracle(torch_cuda, G, oracle, prec):
     N = 20
     pb = P.quadrotor(N)
     B = 140
@@ -387,12 +381,11 @@ def test_batch_warm_start_matches_oracle(torch_cuda, G, oracle, prec):
     s.close()
 
 
-@pytest.mark.parametrize("knobs", [{"GPAD_TC_P1": "0"}, {"GPAD_TC_P1": "0", "GPAD_TC_PFORM": "0"}, {"GPAD_TC_MC": "2"},
-                                   {"GPAD_TC_XF2": "1"}, {"GPAD_TC_P2TS": "1"}])
+@pytest.mark.parametrize("knobs", ["tc_p1=0", "tc_p1=1", "tc_p1=0,tc_bk=32", "tc_pdl=0", "tc_bn2=128", "tc_stages=2"])
 def test_batch_tc_kernel_variants_match_default(torch_cuda, G, knobs, monkeypatch):
-    """the opt-in / first-generation tcgen05 kernels (legacy product 1 with and without the P-formulation, cluster
-    multicast of the operator tiles, product 2 staging zhat itself, product 2 through the TMEM-A kernel) against the
-    default plan on the same batch: same active sets, iterates within the parity tolerance"""
+    """both product-1 kernels (shared-memory operand / TMEM operand; the default picks one by its waves model), both
+    K-block widths, launches with and without programmatic dependent launch, another product-2 tile width and a shallow
+    ring against the default plan on the same batch: same active sets, iterates within the parity tolerance"""
     N, B = 20, 300
     pb = P.quadrotor(N)
     par = P.quadrotor_params(B, np.random.default_rng(11))
@@ -401,8 +394,7 @@ def test_batch_tc_kernel_variants_match_default(torch_cuda, G, knobs, monkeypatc
     s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
     ref = s.solve_host(g_P, p_D, theta, beta)
     s.close()
-    for k, v in knobs.items():
-        monkeypatch.setenv(k, v)
+    monkeypatch.setenv("GPAD_DEBUG", knobs)
     s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
     print("\n", s.description)
     alt = s.solve_host(g_P, p_D, theta, beta)
@@ -655,7 +647,7 @@ def test_gpad_main_driver_on_reference_format_file(torch_cuda, G, oracle, tmp_pa
 def test_tiny_latency_termination_with_cost_vector(torch_cuda, G, oracle, warp, monkeypatch):
     """battery (3,4) / (4,3) with f: relative-gap and dual-gap branches on the one-warp kernel (latency_warp.cu) and,
     with GPAD_LATENCY_WARP=0, on the one-CTA kernel (latency_small.cu); status and iteration count follow the oracle"""
-    monkeypatch.setenv("GPAD_LATENCY_WARP", warp)
+    monkeypatch.setenv("GPAD_DEBUG", f"latency_warp={warp}")
     theta, beta = schedule(3000)
     seen = {}
     for dims in ((3, 4), (4, 3)):
@@ -678,28 +670,78 @@ def test_tiny_latency_termination_with_cost_vector(torch_cuda, G, oracle, warp, 
 
 
 @pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
-def test_batch_host_pipeline_equals_single_pass(torch_cuda, G, prec, monkeypatch):
-    """opt-in (GPAD_HOST_CHUNK): host-memory fixed-iteration solves cut into ranges whose PCIe copies overlap the iterations
-    of their neighbours (solve_batch_pipelined); an instance's result must not depend on the range it rides in:
-    bit-identical to the single-pass solve, cold and warm started, including a ragged last range"""
-    N, B = 20, 1000
+def test_async_double_buffered_solves_equal_synchronous(torch_cuda, G, prec):
+    """gpad_solve_async / gpad_wait: five back-to-back host-memory solves of different batches alternate over two
+    sets of batch state on three streams; every result must be bit-identical to the synchronous gpad_solve of the same
+    batch (cold and warm started), whatever was in flight around it"""
+    t = torch_cuda
+    N, B = 20, 700
     pb = P.quadrotor(N)
-    par = P.quadrotor_params(B, np.random.default_rng(13))
-    g_P, p_D, _ = pb.instance(par)
     theta, beta = schedule(30)
     code = G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32
-    monkeypatch.delenv("GPAD_HOST_CHUNK", raising=False)
     s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=code, max_batch=B)
-    one = s.solve_host(g_P, p_D, theta, beta)
-    one_w = s.solve_host(g_P, p_D, theta, beta, y0=one["y_next"], y_prev0=one["y"])
-    monkeypatch.setenv("GPAD_HOST_CHUNK", "256")
-    piped = s.solve_host(g_P, p_D, theta, beta)
-    piped_w = s.solve_host(g_P, p_D, theta, beta, y0=one["y_next"], y_prev0=one["y"])
-    s.close()
+    pin = lambda a: t.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    jobs = []
+    for j in range(5):
+        Bj = B - 97 * j                                   # ragged batches: different tile counts per solve
+        g_P, p_D, _ = pb.instance(P.quadrotor_params(Bj, np.random.default_rng(100 + j)))
+        ref = s.solve_host(g_P, p_D, theta, beta)
+        warm = (ref["y_next"], ref["y"]) if j % 2 else (None, None)
+        if j % 2:
+            ref = s.solve_host(g_P, p_D, theta, beta, y0=warm[0], y_prev0=warm[1])
+        jobs.append(dict(B=Bj, g_P=pin(g_P), p_D=pin(p_D), y0=None if warm[0] is None else pin(warm[0]),
+                         yp=None if warm[1] is None else pin(warm[1]), ref=ref,
+                         out={k: pin(np.full((Bj, pb.m if k in ("y_next", "y", "w") else pb.n), np.nan, np.float32)) for k in VECS},
+                         iters=pin(np.zeros(Bj, np.int32)), status=pin(np.full(Bj, -1, np.int32))))
+    tickets = []
+    for jb in jobs:
+        jb["args"] = G.host_args(jb["B"], theta, beta, 30, g_P=jb["g_P"], p_D=jb["p_D"], y0=jb["y0"], y_prev0=jb["yp"],
+                                 outputs=jb["out"], iters=jb["iters"], status=jb["status"])
+        tickets.append(s.solve_async(jb["args"]))
+    for tk in reversed(tickets):                           # any order; old tickets are complete once newer ones are
+        s.wait(tk)
+    for j, jb in enumerate(jobs):
+        for k in VECS:
+            assert np.array_equal(jb["out"][k], jb["ref"][k]), (j, k)
+        assert (jb["iters"] == 30).all() and (jb["status"] == 0).all()
+    # a synchronous solve right after the pipeline still sees consistent state
+    again = s.solve_host(jobs[0]["g_P"], jobs[0]["p_D"], theta, beta)
     for k in VECS:
-        assert np.array_equal(piped[k], one[k]), k
-        assert np.array_equal(piped_w[k], one_w[k]), k
-    assert (piped["iters"] == 30).all() and (piped["status"] == 0).all()
+        assert np.array_equal(again[k], jobs[0]["ref"][k]), k
+    s.close()
+
+
+@pytest.mark.parametrize("kind", ["quadrotor", "battery"])
+def test_on_device_instance_build_equals_host_build(torch_cuda, G, kind):
+    """gpad_solve with params + problem (g_P / p_D built on the device from the parameter rows, acceldualgrad.m:21,23)
+    against gpad_problem_instances on the host followed by the same solve: bit-identical inputs, hence bit-identical
+    iterates; also the stand-alone gpad_instances_device entry point and the f vector"""
+    t = torch_cuda
+    if kind == "quadrotor":
+        prob, B = G.Problem("quadrotor", N=20), 333
+        par = P.quadrotor_params(B, np.random.default_rng(21))
+    else:
+        prob, B = G.Problem("battery", n_u=10, N=15), 200
+        par = np.random.default_rng(22).random((B, 10)) - 0.5
+    M_G, G_L = prob.operators()
+    g_P, p_D, f = prob.instances(par, want_f=True)
+    dpar = t.from_numpy(par).cuda()
+    dg, dp, df = (t.empty((B, k), device="cuda") for k in (prob.n, prob.m, prob.n))
+    G.instances_device(prob, B, dpar, dg, dp, df, stream=t.cuda.current_stream().cuda_stream)
+    t.cuda.synchronize()
+    assert np.array_equal(dg.cpu().numpy(), g_P) and np.array_equal(dp.cpu().numpy(), p_D) and np.array_equal(df.cpu().numpy(), f)
+    theta, beta = schedule(40)
+    s = G.Solver(prob.n_u, prob.N, prob.m, prob.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
+    a = s.solve_host(g_P, p_D, theta, beta)
+    b = s.solve_host(None, None, theta, beta, params=par, problem=prob)
+    for k in VECS:
+        assert np.array_equal(a[k], b[k]), k
+    # tolerance mode with the cost vector built on the device as well
+    a = s.solve_host(g_P, p_D, theta, beta, f=f, check_every=5, eps_g=1e-2, eps_V=1e-2)
+    b = s.solve_host(None, None, theta, beta, params=par, problem=prob, build_f=True, check_every=5, eps_g=1e-2, eps_V=1e-2)
+    for k in list(VECS) + ["iters", "status"]:
+        assert np.array_equal(a[k], b[k]), k
+    s.close()
 
 
 @pytest.mark.parametrize("plan", ["16,0", "16,1", "12,0", "12,1"])
@@ -727,9 +769,10 @@ def test_warp_kernel_plans_are_bit_identical(torch_cuda, G, plan, monkeypatch):
         one.close(); many.close()
         return out
 
-    monkeypatch.delenv("GPAD_WARP_PLAN", raising=False)
+    monkeypatch.delenv("GPAD_DEBUG", raising=False)
     base = run()
-    monkeypatch.setenv("GPAD_WARP_PLAN", plan)
+    rows, ordered = plan.split(",")
+    monkeypatch.setenv("GPAD_DEBUG", f"warp_rows={rows},warp_ordered={ordered}")
     for a, b in zip(base, run()):
         for k in list(VECS) + ["iters", "status"]:
             assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (plan, k)

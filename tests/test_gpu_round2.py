@@ -1,0 +1,291 @@
+"""GPU parity tests (-m gpu), second batch: tolerance mode at batch scale (tile retirement + compaction), the
+multi-device group, per-instance plants with the warm-started receding horizon (BASELINE config 5), the shifted warm
+start, the 1000-sample closed-loop regression of gpad.m:6, and the reference's step fixtures through the C ABI.
+Same oracle, same metric and bounds as tests/test_gpu_parity.py."""
+import os
+
+import numpy as np
+import pytest
+
+import problems as P
+from oracle import Oracle, schedule
+from test_gpu_parity import TOL, VECS, check_parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpad_b200
+    return gpad_b200
+
+
+# ------------------------------------------------------------------------------------ tolerance mode, quadrotor batch
+@pytest.mark.parametrize("check_every", [1, 5])
+@pytest.mark.parametrize("with_f", [False, True])
+def test_quadrotor_batch_tolerance_matches_oracle(torch_cuda, G, oracle, check_every, with_f, monkeypatch):
+    """BASELINE config 4's tolerance variant at test size: quadrotor N = 20 (n = 80, m = 480), 640 QPs, eps = 1e-3.
+    Instances stop between ~40 and ~2500 iterations, so tiles retire and the batch is compacted several times while it
+    runs; status and iteration count must follow the oracle instance by instance, the iterates stay within the
+    noise-aware parity bound, and the result must not depend on retirement / compaction / how far the host runs ahead."""
+    N, B, eps, max_iter = 20, 640, 1e-3, 3000
+    pb = P.quadrotor(N)
+    par = P.quadrotor_params(B, np.random.default_rng(31))
+    g_P, p_D, f = pb.instance(par)
+    theta, beta = schedule(max_iter)
+    kw = dict(check_every=check_every, eps_g=eps, eps_V=eps, f=f if with_f else None)
+    ora = oracle.solve_batch(4, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, **kw)
+    assert ora["iters"].max() > 4 * np.median(ora["iters"]) or np.ptp(ora["iters"]) > 1000       # a wide spread, as in production
+    runs = {}
+    for name, knobs in (("default", ""), ("plain", "tc_retire=0,check_lag=0"), ("retire-only", "tc_compact=0")):
+        if knobs:
+            monkeypatch.setenv("GPAD_DEBUG", knobs)
+        else:
+            monkeypatch.delenv("GPAD_DEBUG", raising=False)
+        s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
+        runs[name] = s.solve_host(g_P, p_D, theta, beta, **kw)
+        runs[name]["stats"] = s.stats()
+        s.close()
+    gpu = runs["default"]
+    print("\n stats:", {k: v["stats"] for k, v in runs.items()})
+    assert gpu["stats"]["compactions"] >= 1
+    assert runs["plain"]["stats"]["compactions"] == 0
+    assert gpu["stats"]["scheduled"] < 0.8 * runs["plain"]["stats"]["scheduled"]           # compaction removes finished rows' work
+    assert gpu["stats"]["needed"] == float(ora["iters"].sum())
+    for other in ("plain", "retire-only"):
+        for k in list(VECS) + ["iters", "status", "max_viol", "gap"]:
+            assert np.array_equal(gpu[k], runs[other][k], equal_nan=True), (other, k)
+    assert np.array_equal(gpu["status"], ora["status"]), np.flatnonzero(gpu["status"] != ora["status"])
+    assert np.array_equal(gpu["iters"], ora["iters"]), (np.flatnonzero(gpu["iters"] != ora["iters"]),
+                                                         (gpu["iters"] - ora["iters"])[gpu["iters"] != ora["iters"]])
+    worst = 0.0
+    for b in list(range(0, B, 37)) + [int(np.argmax(ora["iters"])), int(np.argmin(ora["iters"]))]:
+        it = int(ora["iters"][b])
+        f64 = oracle.solve_f64(4, N, pb.m, pb.M_G, pb.G_L, g_P[b], p_D[b], theta, beta, max_iter=it)
+        worst = max(worst, check_parity({k: gpu[k][b] for k in VECS}, {k: ora[k][b] for k in VECS}, f64, f"tolerance batch [{b}] it={it}"))
+    print(f" worst GPU-vs-oracle rel_inf over the sampled instances {worst:.2e}; iterations {ora['iters'].min()}..{ora['iters'].max()}")
+
+
+def test_battery_batch_tolerance_with_compaction(torch_cuda, G, oracle):
+    """battery (10,15) batch in tolerance mode on both precisions: compaction over several tiles, exact status / count"""
+    n_u, N, B = 10, 15, 520
+    pb = P.battery(n_u, N)
+    X0 = np.random.default_rng(41).random((B, n_u)) - 0.5
+    g_P, p_D, f = pb.instance(X0)
+    theta, beta = schedule(1500)
+    kw = dict(check_every=3, eps_g=1e-2, eps_V=1e-2, f=f)
+    ora = oracle.solve_batch(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, **kw)
+    for prec in (G.PREC_FP32, G.PREC_TF32X3):
+        s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=prec, max_batch=B)
+        gpu = s.solve_host(g_P, p_D, theta, beta, **kw)
+        print("\n", prec, s.stats(), "iterations", ora["iters"].min(), "..", ora["iters"].max())
+        s.close()
+        assert np.array_equal(gpu["status"], ora["status"])
+        assert np.array_equal(gpu["iters"], ora["iters"]), np.flatnonzero(gpu["iters"] != ora["iters"])
+        for k in VECS:
+            assert P.rel_inf(gpu[k], ora[k]) <= 3e-5, k
+
+
+# ------------------------------------------------------------------------------------ multi-device group
+def test_group_results_do_not_depend_on_device_count(torch_cuda, G):
+    """gpad_group_*: the batch cut into 1, 2 and 3 contiguous shards (all on device 0 here; the driver's box has one
+    GPU for tests) gives bit-identical results: shared operators (tcgen05) and per-instance operators"""
+    N, B = 20, 700
+    pb = P.quadrotor(N)
+    g_P, p_D, _ = pb.instance(P.quadrotor_params(B, np.random.default_rng(51)))
+    theta, beta = schedule(25)
+    res = []
+    for devices in ([0], [0, 0], [0, 0, 0]):
+        grp = G.Group(devices, 4, N, pb.m, pb.L, pb.M_G, pb.G_L, max_batch=B)
+        out = {k: np.full((B, pb.m if k in ("y_next", "y", "w") else pb.n), np.nan, np.float32) for k in VECS}
+        iters = np.zeros(B, np.int32); status = np.full(B, -1, np.int32)
+        grp.solve(G.host_args(B, theta, beta, 25, g_P=g_P, p_D=p_D, outputs=out, iters=iters, status=status))
+        spans = [grp.shard(i, B) for i in range(len(devices))]
+        assert sum(c for _, c in spans) == B and spans[0][0] == 0
+        grp.close()
+        assert (iters == 25).all() and (status == 0).all()
+        res.append(out)
+    for other in res[1:]:
+        for k in VECS:
+            assert np.array_equal(res[0][k], other[k]), k
+    # and equal to the plain single handle
+    s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
+    one = s.solve_host(g_P, p_D, theta, beta)
+    s.close()
+    for k in VECS:
+        assert np.array_equal(res[0][k], one[k]), k
+    # per-instance operators are sharded with their instances
+    n_u, Nb, Bp = 3, 4, 300
+    rng = np.random.default_rng(52)
+    plants = G.Plants(n_u, Nb, 1.0 + 0.1 * (2 * rng.random((Bp, n_u)) - 1))
+    M, Gl, L = plants.operators()
+    gp, pd, _ = plants.instances(rng.random((Bp, n_u)) - 0.5)
+    th, be = schedule(60)
+    res = []
+    for devices in ([0], [0, 0, 0]):
+        grp = G.Group(devices, n_u, Nb, plants.m, float(L[0]), M, Gl, mode=G.MODE_BATCH_PER_INSTANCE, precision=G.PREC_FP32, max_batch=Bp)
+        out = {k: np.full((Bp, plants.m if k in ("y_next", "y", "w") else plants.n), np.nan, np.float32) for k in VECS}
+        grp.solve(G.host_args(Bp, th, be, 60, g_P=gp, p_D=pd, outputs=out))
+        grp.close()
+        res.append(out)
+    for k in VECS:
+        assert np.array_equal(res[0][k], res[1][k]), k
+
+
+# ------------------------------------------------------------------------------------ per-instance plants, receding horizon
+def shift_duals(y, blocks, N):
+    out = y.copy()
+    for off, r in blocks:
+        blk = y[..., off:off + r * N].reshape(y.shape[:-1] + (N, r))
+        sh = np.concatenate([blk[..., 1:, :], blk[..., -1:, :]], axis=-2)
+        out[..., off:off + r * N] = sh.reshape(y.shape[:-1] + (N * r,))
+    return out
+
+
+@pytest.mark.parametrize("warm", [0, 1, 2])
+def test_plants_closed_loop_matches_oracle_loop(torch_cuda, G, oracle, warm):
+    """BASELINE config 5 at test size: 48 battery packs with per-instance cell capacities (+-10 %), hence per-instance
+    M_G / G_L / L / instance maps, T = 6 receding-horizon samples, cold / previous-dual / shifted warm start, on the
+    one-warp batched-GEMV kernel; against the same loop driven by the oracle on numpy-built plants"""
+    n_u, N, B, samples, iters = 3, 4, 48, 6, 60
+    rng = np.random.default_rng(61)
+    scale = 1.0 + 0.1 * (2 * rng.random((B, n_u)) - 1)
+    plants = G.Plants(n_u, N, scale)
+    M, Gl, L = plants.operators()
+    theta, beta = schedule(iters)
+    s = G.Solver(n_u, N, plants.m, float(L[0]), M, Gl, mode=G.MODE_BATCH_PER_INSTANCE, max_batch=B)
+    x0 = rng.random((B, n_u)) - 0.5
+    xt, ut = plants.closed_loop(s, x0, samples, theta, beta, warm_start=warm)
+    # a shard of the plants through the same handle layout: plants [16, 40) as their own handle
+    s2 = G.Solver(n_u, N, plants.m, float(L[16]), M[16:40], Gl[16:40], mode=G.MODE_BATCH_PER_INSTANCE, max_batch=24)
+    xt2, ut2 = plants.closed_loop(s2, x0[16:40], samples, theta, beta, warm_start=warm, first=16, count=24)
+    s.close(); s2.close()
+    assert np.array_equal(ut2, ut[:, 16:40]) and np.array_equal(xt2, xt[:, 16:40])
+    blocks = [(0, n_u), (n_u * N, n_u), (2 * n_u * N, n_u), (3 * n_u * N, n_u), (4 * n_u * N, 1), (4 * n_u * N + N, 1)]
+    for b in (0, 7, 23, 47):
+        ref = P.battery(n_u, N, cap_scale=scale[b])
+        assert P.rel_inf(M[b].reshape(ref.n, ref.m), ref.M_G) <= 1e-6 and abs(L[b] - ref.L) <= 1e-6 * ref.L
+        Bm = np.diag(-1.0 / (3600.0 * 0.027 * 4.1 * scale[b]))
+        x = x0[b].copy()
+        y1 = y0 = None
+        for k in range(samples):
+            g_P, p_D, _ = ref.instance(x)
+            kw = {}
+            if warm and k > 0:
+                kw = {"y0": shift_duals(y1, blocks, N), "y_prev0": shift_duals(y0, blocks, N)} if warm == 2 else {"y0": y1, "y_prev0": y0}
+            sol = oracle.solve(n_u, N, ref.m, M[b], Gl[b], g_P, p_D, theta, beta, **kw)
+            y1, y0 = sol["y_next"], sol["y"]
+            u = sol["z"][:n_u].astype(np.float64)
+            assert np.max(np.abs(ut[k, b] - u)) <= 2e-5 * max(1.0, np.abs(u).max()), (b, k, ut[k, b], u)
+            x = x + Bm @ u
+            assert np.max(np.abs(xt[k + 1, b] - x)) <= 1e-6, (b, k)
+
+
+def test_closed_loop_rejects_mismatched_handle(torch_cuda, G):
+    pb = G.Problem("battery", n_u=3, N=4)
+    other = G.Problem("battery", n_u=4, N=3)
+    M_G, G_L = other.operators()
+    theta, beta = schedule(10)
+    s = G.Solver(4, 3, other.m, other.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_FP32, max_batch=2)
+    with pytest.raises(G.GpadError):
+        G.closed_loop(pb, s, np.zeros((2, 3)), 2, theta, beta)          # wrong problem for this handle
+    with pytest.raises(G.GpadError):
+        G.closed_loop(other, s, np.zeros((3, 4)), 2, theta, beta)       # batch larger than the handle's capacity
+    s.close()
+
+
+def test_closed_loop_1000_samples_shifted_warm_start(torch_cuda, G, oracle):
+    """the reference's closed-loop regression length (gpad.m:6: 1000 samples) on the default battery problem (3,4), four
+    packs, with the receding-horizon shifted warm start and 30 iterations per sample, against the oracle-driven loop"""
+    n_u, N, samples, iters = 3, 4, 1000, 30
+    pb = G.Problem("battery", n_u=n_u, N=N)
+    M_G, G_L = pb.operators()
+    theta, beta = schedule(iters)
+    x0 = np.array([[0.41, -0.33, 0.12], [-0.2, 0.05, 0.45], [0.3, 0.3, -0.45], [-0.5, 0.5, 0.0]])
+    s = G.Solver(n_u, N, pb.m, pb.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_FP32, max_batch=4)
+    xt, ut = G.closed_loop(pb, s, x0, samples, theta, beta, warm_start=G.WARM_SHIFTED)
+    s.close()
+    A, Bm = pb.plant()
+    blocks = [(0, n_u), (n_u * N, n_u), (2 * n_u * N, n_u), (3 * n_u * N, n_u), (4 * n_u * N, 1), (4 * n_u * N + N, 1)]
+    x = x0.copy()
+    y1 = y0 = None
+    for k in range(samples):
+        g_P, p_D, _ = pb.instances(x, want_f=False)
+        kw = {"y0": shift_duals(y1, blocks, N), "y_prev0": shift_duals(y0, blocks, N)} if k > 0 else {}
+        sol = oracle.solve_batch(n_u, N, pb.m, M_G, G_L, g_P, p_D, theta, beta, **kw)
+        y1, y0 = sol["y_next"], sol["y"]
+        u = sol["z"][:, :n_u].astype(np.float64)
+        assert np.max(np.abs(ut[k] - u)) <= 2e-5 * max(1.0, np.abs(u).max()), k
+        x = x @ A.T + u @ Bm.T
+        assert np.max(np.abs(xt[k + 1] - x)) <= 2e-6, k
+        x = xt[k + 1].copy()         # follow the device trajectory: differences must not accumulate into the comparison
+    assert np.ptp(xt[-1], axis=1).max() < 0.2 * np.ptp(xt[0], axis=1).max()      # the packs end up balanced
+
+
+# ------------------------------------------------------------------------------------ reference fixtures through the C ABI
+@pytest.mark.parametrize("case", [1, 2, 3, 4, 5])
+def test_step3_reference_fixture_through_shim(torch_cuda, G, golden_dir, case, tmp_path):
+    """the reference's own step-3 vectors (FinalProject/build/step3/<k>, committed as tests/golden/step3_fixtures.npz),
+    written in the reference's text format, read back by gpad_fixture_read (step3.cu:59-81) and pushed through
+    gpad_step_three on the GPU: abs 2e-7 like tests/test_oracle.py (harness bound 1e-7 + %.8f text rounding)"""
+    t = torch_cuda
+    g = np.load(os.path.join(golden_dir, "step3_fixtures.npz"))
+    n_u, N, m = (int(v) for v in g[f"dims{case}"])
+    theta = float(g[f"theta{case}"])
+    d = str(tmp_path)
+    G.fixture_write(d, 3, n_u, N, m, theta=theta, z_prev=g[f"z_prev{case}"], zhat_in=g[f"zhat{case}"], z_out=g[f"z{case}"])
+    fx = G.fixture_read(d, 3)
+    assert (fx["n_u"], fx["N"], fx["m"]) == (n_u, N, m) and abs(fx["theta"] - theta) < 1e-8
+    z = t.from_numpy(fx["z_prev"]).cuda(); zh = t.from_numpy(fx["zhat_in"]).cuda()
+    G.step_three(fx["theta"], zh, z, n_u * N, stream=t.cuda.current_stream().cuda_stream)
+    t.cuda.synchronize()
+    assert np.max(np.abs(z.cpu().numpy() - fx["z_out"])) <= 2e-7
+
+
+@pytest.mark.parametrize("flat", [False, True])
+def test_step2_step4_fixture_formats_through_shims(torch_cuda, G, oracle, flat, tmp_path):
+    """step-2 / step-4 fixtures in the reference's formats (main_prof.cu:117-156, 198-239; the reference's own files are
+    absent from its repository): generated from the oracle, dense ("_unflat") and flat, read back through the C ABI and
+    run through gpad_step_two / gpad_step_four (flat operators are expanded first: the shims take the flipped dense
+    layout the reference kernels read)"""
+    t = torch_cuda
+    n_u, N = 4, 6
+    pb = P.battery(n_u, N)
+    n, m = pb.n, pb.m
+    rng = np.random.default_rng(71)
+    w = np.abs(rng.standard_normal(m)).astype(np.float32) * (rng.random(m) < 0.4)
+    g_P, p_D, _ = pb.instance(rng.random(n_u) - 0.5)
+    zhat = oracle.step_two(pb.M_G, w, g_P, n_u, N)
+    y_next = oracle.step_four(pb.G_L, w, p_D, zhat, n_u, N)
+    prod2 = (pb.M_G.astype(np.float64) @ w).astype(np.float32)
+    prod4 = (pb.G_L.astype(np.float64) @ zhat).astype(np.float32)
+    MGf, GLf, resid = G.flatten_operators(n_u, N, m, pb.M_G, pb.G_L)
+    assert resid == 0.0
+    d2, d4 = str(tmp_path / "s2"), str(tmp_path / "s4")
+    os.makedirs(d2); os.makedirs(d4)
+    G.fixture_write(d2, 2, n_u, N, m, flat=flat, op=MGf if flat else pb.M_G, w=w, g_P=g_P, prod=prod2, zhat_out=zhat)
+    G.fixture_write(d4, 4, n_u, N, m, flat=flat, op=GLf if flat else pb.G_L, w=w, zhat_in=zhat, p_D=p_D, prod=prod4,
+                    sum=prod4 + (w + p_D), y_next=y_next)
+    f2, f4 = G.fixture_read(d2, 2, flat=flat), G.fixture_read(d4, 4, flat=flat)
+    if flat:
+        MG, _ = G.expand_operators(n_u, N, m, f2["op"].reshape(N, m), GLf)
+        _, GL = G.expand_operators(n_u, N, m, MGf, f4["op"].reshape(m, N))
+    else:
+        MG, GL = f2["op"].reshape(n, m), f4["op"].reshape(m, n)
+    dev = lambda a: t.from_numpy(np.ascontiguousarray(a, np.float32)).cuda()
+    st = t.cuda.current_stream().cuda_stream
+    dz = t.empty(n, device="cuda"); dy = t.empty(m, device="cuda")
+    G.step_two(dev(MG.T), dev(f2["w"]), dev(f2["g_P"]), dz, N, n_u, m, stream=st)
+    G.step_four(dev(GL.T), dy, dev(f4["w"]), dev(f4["p_D"]), dev(f4["zhat_in"]), N, n_u, m, stream=st)
+    t.cuda.synchronize()
+    assert np.max(np.abs(dz.cpu().numpy() - f2["zhat_out"])) <= 1e-6          # the harness's own EPSILON (main_prof.cu:8)
+    assert np.max(np.abs(dy.cpu().numpy() - f4["y_next"])) <= 1e-6
+    assert np.array_equal(dy.cpu().numpy() > 0, f4["y_next"] > 0)
