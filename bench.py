@@ -12,15 +12,22 @@ M_G / G_L, random initial states and set-points (seeded), fixed 100 GPAD iterati
 
   value     device-resident: inputs already in HBM, CUDA events around K gpad_solve() calls on the
             launching stream, max over ranks;  solves/s = N_gpus * 65536 * K / T
-  e2e       the same K solves through the C ABI with HOST (pinned) buffers: H2D of g_P / p_D and
-            D2H of the five vectors main.cu:176-180 copies back are inside the timed region
-  roofline  dominant kernel = the tcgen05 3xTF32 GEMM (both products are the same kernel template):
-            algorithmic FLOPs per launch 2*n*m*B divided by its mean launch duration measured with
-            CUDA events inside the library (gpad_profile_*), against the tensor-pipe peak for this
-            precision scheme: MEASURED_PEAKS.json bf16 sustained / 2 (tf32) / 3 (three MMAs/product)
-  cpu_baseline  the reference's own seq_functions.cpp (oracle/_ref, kind "reference") or the C
-            restatement (kind "port") on all host cores, bounded sample of the same workload
-  --impl reference  times that CPU path as the whole arm (no GPU code involved)
+  e2e       the same solves through the C ABI with HOST (pinned) buffers, every step: the step's inputs (the
+            per-instance parameters [x0; xref], from which g_P / p_D are built on the device exactly as the host
+            build does) go host -> device and the five vectors main.cu:176-180 copies back come device -> host,
+            inside the timed region, through gpad_solve_async / gpad_wait (copies of neighbouring steps overlap
+            the iterations).  e2e.variants also times host g_P / p_D inputs (async and synchronous).
+  parity_sample  instances of the timed 64K run itself (first / last tile, tile boundaries, spread) against
+            oracle/_ref (the reference's compiled seq_functions.cpp) with the parity bound of the tests
+  roofline  dominant kernel = the tcgen05 3xTF32 GEMM (both products): algorithmic FLOPs per launch 2*n*m*B over the
+            mean launch duration measured with CUDA events inside the library (gpad_profile_*), against the tensor
+            peak for this precision scheme: MEASURED_PEAKS.json bf16 sustained / 2 (tf32) / 3 (three MMAs/product)
+  cpu_baseline  the reference's own seq_functions.cpp (oracle/_ref, kind "reference") or the C restatement
+            (kind "port") on all host cores, bounded sample of the same workload
+  further legs (rank 0, after the timed region): tolerance mode at 64K, strong scaling of a fixed 64K batch,
+            single-QP latency with the reference's CPU and GPU loops beside it, per-instance plants (config 5),
+            4096 battery QPs (config 3), closed loop
+  --impl reference  times the reference CPU path as the whole arm (no GPU code, no repo library involved)
 Inputs (2.9 GB per GPU per solve with state) are far larger than the 126 MB L2, so no flush is needed.
 """
 import argparse
@@ -131,6 +138,18 @@ def host_problem():
     return prob, dict(n_u=prob.n_u, N=prob.N, m=prob.m, n=prob.n, L=prob.L, M_G=M_G, G_L=G_L)
 
 
+def numpy_problem():
+    """the same quadrotor problem from the numpy restatement (tests/problems.py): the reference arm loads no repo library"""
+    import problems as P
+    pb = P.quadrotor(HORIZON)
+    return pb, dict(n_u=pb.n_u, N=pb.N, m=pb.m, n=pb.n, L=pb.L, M_G=pb.M_G, G_L=pb.G_L)
+
+
+def numpy_schedule(count):
+    from oracle import schedule
+    return schedule(count)
+
+
 def cpu_rate(budget_s, cores=None):
     """solves/s of the CPU path on `cores` threads over a sample sized to ~budget_s seconds"""
     import gpad_b200 as G
@@ -151,17 +170,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import gpad_b200 as G
     solve, kind = cpu_solver()
-    prob, pb = host_problem()
-    theta, beta = G.schedule(ITERS)
+    prob, pb = numpy_problem()
+    theta, beta = numpy_schedule(ITERS)
     cores = os.cpu_count() or 1
-    g1, p1, _ = prob.instances(quad_params(cores, 99), want_f=False)
+    g1, p1, _ = prob.instance(quad_params(cores, 99))
     t0 = time.perf_counter(); solve(pb, g1, p1, theta, beta, cores); t_probe = time.perf_counter() - t0
     total_steps = args.steps + args.warmup
     per_step_s = max(1.0, min(15.0, 150.0 / max(total_steps, 1)))
     count = int(max(cores, per_step_s / max(t_probe, 1e-3) * cores))
-    g, p, _ = prob.instances(quad_params(count, 7), want_f=False)
+    g, p, _ = prob.instance(quad_params(count, 7))
     for _ in range(args.warmup):
         solve(pb, g, p, theta, beta, cores)
     t0 = time.perf_counter()
@@ -174,7 +192,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "step": "bounded sample: " + sample},
+        "config": {"workload": WORKLOAD, "step": "bounded sample: " + sample,
+                   "inputs": "tests/problems.py numpy restatement of the quadrotor problem (no repo library loaded)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(out["threads"]), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -182,18 +201,31 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+def p50(xs):
+    return float(np.median(np.asarray(xs, np.float64)))
+
+
 def latency_probe(torch, G):
-    """single-QP p50 solve latency (second half of the BASELINE metric), latency mode, device-resident"""
+    """single-QP p50 solve latency (second half of the BASELINE metric), latency mode, with the reference beside it:
+    (i) the reference's CPU step functions on one core (oracle/_ref), (ii) the reference's own GPU kernels driven by
+    the loop of main.cu:160-175 (5 launches + 3 device syncs per iteration) on this same B200 (oracle/_ref, compiled
+    unmodified for sm_100a), (iii) our p50 through the C ABI with host buffers, (iv) tolerance mode, (v) a model"""
+    import oracle
+    ref_cpu = oracle.RefLib() if oracle.have_ref() else None
+    ref_gpu = oracle.RefCuda() if oracle.have_refcuda() else None
+    port = oracle.Oracle()
     out = {}
-    for n_u, N in ((3, 4), (10, 100)):
+    sms, clk_ghz = 148, 1.9
+    for n_u, N in ((3, 4), (10, 15), (10, 100)):
         prob = G.Problem("battery", n_u=n_u, N=N)
         M_G, G_L = prob.operators()
+        n, m = prob.n, prob.m
         x0 = np.array([[-0.1, 0.45, -0.09, 0.05, 0, -0.05, 0.3, 0.2, 0.25, -0.45]]) if n_u == 10 else np.array([[0.31, -0.12, 0.44]])
-        g_P, p_D, _ = prob.instances(x0, want_f=False)
+        g_P, p_D, f = prob.instances(x0, want_f=True)
         theta, beta = G.schedule(ITERS)
-        s = G.Solver(n_u, N, prob.m, prob.L, M_G, G_L, mode=G.MODE_LATENCY)
+        s = G.Solver(n_u, N, m, prob.L, M_G, G_L, mode=G.MODE_LATENCY)
         dg, dp = torch.from_numpy(g_P[0]).cuda(), torch.from_numpy(p_D[0]).cuda()
-        dz = torch.empty(prob.n, device="cuda"); dy = torch.empty(prob.m, device="cuda")
+        dz = torch.empty(n, device="cuda"); dy = torch.empty(m, device="cuda")
         st = torch.cuda.current_stream().cuda_stream
         for _ in range(10):
             s.solve_device(1, dg, dp, theta, beta, ITERS, stream=st, z=dz, y_next=dy)
@@ -204,24 +236,65 @@ def latency_probe(torch, G):
             e0.record(); s.solve_device(1, dg, dp, theta, beta, ITERS, stream=st, z=dz, y_next=dy); e1.record()
             e1.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
-        entry = {"p50_us": float(np.median(ts)), "p99_us": float(np.percentile(ts, 99)), "iterations": ITERS, "path": s.description}
-        if "cooperative-grid" in s.description:
-            # SM-cycle model of SURVEY 8(d) for a whole-chip plan: operator bytes through the SMs' shared-memory ports
-            # (phase B reads registers in latency_grid2.cu: only M_G counts) + two grid exchanges of ~1.1 us each
-            sms, clk_ghz, t_exchange_us = 148, 1.9, 1.1
-            t_ops_us = 4.0 * prob.n * prob.m / (sms * 128.0) / (clk_ghz * 1e3)
-            model = t_ops_us + 2 * t_exchange_us
-            entry.update({"us_per_iteration": entry["p50_us"] / ITERS, "model_us_per_iteration": model,
-                          "frac_of_model": model / (entry["p50_us"] / ITERS),
-                          "model": "4nm B / (148 SMs x 128 B/clk) at 1.9 GHz + 2 grid exchanges x 1.1 us"})
-        out[f"battery({n_u},{N}) n={prob.n} m={prob.m}"] = entry
+        entry = {"p50_us": p50(ts), "p99_us": float(np.percentile(ts, 99)), "iterations": ITERS, "path": s.description,
+                 "us_per_iteration": p50(ts) / ITERS}
+        # (iii) through the C ABI with host buffers: H2D of g_P / p_D, the solve, D2H of the five vectors, synchronised
+        th = []
+        for _ in range(200):
+            t0 = time.perf_counter(); s.solve_host(g_P[0], p_D[0], theta, beta); th.append((time.perf_counter() - t0) * 1e6)
+        entry["p50_us_host_buffers_c_abi"] = p50(th[20:])
+        # (iv) tolerance mode (BASELINE config 2): eps_g = eps_V = 1e-3, checked every iteration, N_max guard
+        nmax = 2000
+        th2, be2 = G.schedule(nmax)
+        dit = torch.zeros(1, dtype=torch.int32, device="cuda"); dst = torch.zeros(1, dtype=torch.int32, device="cuda")
+        tt = []
+        for _ in range(60):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); s.solve_device(1, dg, dp, th2, be2, nmax, stream=st, z=dz, y_next=dy, iters=dit, status=dst, check_every=1,
+                                        eps_g=1e-3, eps_V=1e-3); e1.record()
+            e1.synchronize()
+            tt.append(e0.elapsed_time(e1) * 1e3)
+        entry["tolerance_1e-3"] = {"p50_us": p50(tt[10:]), "iterations": int(dit.item()), "status": G.STATUS_NAMES.get(int(dst.item())),
+                                   "n_max": nmax}
+        if n * m < 200000:          # the CPU oracle on the same solve (seconds for the small problems only)
+            ora = port.solve(n_u, N, m, M_G, G_L, g_P[0], p_D[0], th2, be2, L=prob.L, check_every=1, eps_g=1e-3, eps_V=1e-3)
+            entry["tolerance_1e-3"].update({"oracle_iterations": int(ora["iters"]), "oracle_status": G.STATUS_NAMES.get(int(ora["status"]))})
+        # (i) reference CPU loop, one core
+        if ref_cpu is not None:
+            reps = 200 if n * m < 50000 else (20 if n * m < 500000 else 3)
+            tc = []
+            for _ in range(reps):
+                t0 = time.perf_counter(); ref_cpu.solve(n_u, N, m, M_G, G_L, g_P[0], p_D[0], theta, beta); tc.append((time.perf_counter() - t0) * 1e6)
+            entry["reference_cpu_one_core_p50_us"] = p50(tc)
+        # (ii) reference GPU loop on this B200 (operators resident, the loop of main.cu:160-175 alone)
+        if ref_gpu is not None:
+            tg, zref = ref_gpu.loop_times(n_u, N, m, M_G, G_L, g_P[0], p_D[0], theta, beta, ITERS, 40)
+            entry["reference_cuda_loop_p50_us"] = p50(tg[5:])
+            entry["reference_cuda_loop_matches"] = bool(np.max(np.abs(zref - dz.cpu().numpy())) <= 2e-5 * max(1e-3, float(np.abs(zref).max())))
+            entry["speedup_vs_reference_cuda_loop"] = entry["reference_cuda_loop_p50_us"] / entry["p50_us"]
+        # (v) SM-cycle model of SURVEY 8(d): T_iter >= operator bytes through the shared-memory ports of the C
+        # cooperating SMs + 2 exchanges (+ the dependent reduction chain for one warp)
+        if "one warp" in s.description.lower():
+            model = 300.0 / (clk_ghz * 1e3)
+            basis = "dependent chain of one warp: 5 reduction levels x (select + shuffle + add) + broadcast + 16 chained FMAs + projection ~ 300 clk"
+        elif "cluster" in s.description:
+            C = 16
+            model = 8.0 * n * m / (C * 128.0) / (clk_ghz * 1e3) + 2 * (215 + 38 + 60) / (clk_ghz * 1e3)
+            basis = ("8nm B / (16 CTAs x 128 B/clk) + 2 exchanges x (DSMEM cross-CTA 215 clk + local 38 clk + mbarrier wait ~60 clk, "
+                     "B300_MICROARCH.md CGA table) at 1.9 GHz")
+        else:
+            model = 4.0 * n * m / (sms * 128.0) / (clk_ghz * 1e3) + 2 * 1.1
+            basis = "4nm B / (148 SMs x 128 B/clk) at 1.9 GHz + 2 grid exchanges x 1.1 us"
+        entry.update({"model_us_per_iteration": model, "frac_of_model": model / entry["us_per_iteration"], "model": basis})
+        out[f"battery({n_u},{N}) n={n} m={m}"] = entry
         s.close()
     return out
 
 
 def per_instance_probe(torch, G, B=262144):
-    """BASELINE config 5 (per-instance plants, batched-GEMV mode): battery (3,4) QPs each with its own
-    M_G / G_L; HBM roofline against the algorithmic minimum bytes per solve (operators stay on chip)"""
+    """BASELINE config 5 kernel (per-instance plants, batched-GEMV mode): battery (3,4) QPs each with its own
+    M_G / G_L; scored against the HBM roofline with the algorithmic minimum bytes per solve (operators stay
+    on chip), against the fp32 FMA peak with the algorithmic flops, and against the algorithmic instruction minimum"""
     n_u, N = 3, 4
     prob = G.Problem("battery", n_u=n_u, N=N)
     M_G, G_L = prob.operators()
@@ -247,17 +320,55 @@ def per_instance_probe(torch, G, B=262144):
     sec = e0.elapsed_time(e1) * 1e-3 / reps
     bytes_min = ((2 * n * m + n + m) * 4 + (3 * m + 2 * n) * 4) * B
     _, hbm, src = measured_peaks()
+    fp32_peak = 148 * 128 * 2 * 1.965e9
+    flops = 4.0 * n * m * ITERS * B
+    # algorithmic minimum of warp instructions per QP-iteration with one warp per QP: 2 n m / 32 = 42 FMAs; the kernel
+    # issues 174.4 (profiles/r1_ncu_per_instance_warp.csv: smsp__inst_executed / (B x 100)): 48 products, 28 shuffles, the
+    # selects / adds of the transposed reduction, the projection
+    inst_min, inst_issued = 2.0 * n * m / 32.0, 174.4
     res = {"workload": f"battery(3,4) n={n} m={m}, {B} QPs with per-instance operators, 100 iterations", "solves_per_s": B / sec,
            "ms_per_batch": sec * 1e3, "algorithmic_bytes_per_solve": bytes_min // B, "achieved_GBps": bytes_min / sec / 1e9,
            "hbm_peak_GBps": hbm, "frac_of_hbm_roofline": bytes_min / sec / 1e9 / hbm, "path": s.description,
-           # the bound that applies: instruction issue. profiles/r1_ncu_per_instance_warp.csv: 174.4 warp instructions per QP-iteration
-           # (smsp__inst_executed / (B x 100)), issue slots 82 % busy, shuffle (LSU) pipe 58 %, FMA 44 %, DRAM 5 %
-           "warp_instructions_per_iteration": 174.4, "issue_roofline_solves_per_s": 148 * 4 * 1.965e9 / (174.4 * ITERS),
-           "frac_of_issue_roofline": (B / sec) / (148 * 4 * 1.965e9 / (174.4 * ITERS)),
-           "note": "operators stay in registers for all 100 iterations, so HBM carries 5 % of its peak and the SM issue slots are the bound: "
-                   "148 SMs x 4 schedulers x 1.965 GHz / 174.4 instructions per QP-iteration"}
+           "achieved_TFLOPs": flops / sec / 1e12, "frac_of_fp32_fma_peak": flops / sec / fp32_peak,
+           "warp_instructions_per_iteration": inst_issued, "algorithmic_warp_instructions_per_iteration": inst_min,
+           "frac_of_algorithmic_instruction_minimum": inst_min / inst_issued,
+           "note": "operators stay in registers for all 100 iterations, so HBM carries a few % of its peak; the kernel is bound by "
+                   "instruction issue (shuffles of the in-warp reduction and broadcast), at 24 % of the algorithmic instruction minimum"}
     s.close()
     return res
+
+
+def plants_probe(torch, G, world, rank, dist, B=131072, samples=5, iters=100):
+    """BASELINE config 5 as written: a 1 M-instance scenario sweep with per-instance plant matrices (battery (3,4), cell
+    capacities +-10 % per instance) sharded over the GPUs of the box -- 131 072 plants per GPU, so 8 GPUs hold the 1 M --
+    T = 5 receding-horizon samples of 100 iterations, warm-started with the shifted duals of the previous sample.
+    Every rank condenses and owns its shard; nothing is exchanged inside the loop."""
+    n_u, N = 3, 4
+    rng = np.random.default_rng(1000 + rank)
+    t0 = time.perf_counter()
+    plants = G.Plants(n_u, N, 1.0 + 0.1 * (2 * rng.random((B, n_u)) - 1))
+    t_cond = time.perf_counter() - t0
+    M, Gl, L = plants.operators()
+    theta, beta = G.schedule(iters)
+    s = G.Solver(n_u, N, plants.m, float(L[0]), M, Gl, mode=G.MODE_BATCH_PER_INSTANCE, max_batch=B)
+    x0 = rng.random((B, n_u)) - 0.5
+    plants.closed_loop(s, x0, 1, theta, beta, warm_start=G.WARM_SHIFTED)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    xt, ut = plants.closed_loop(s, x0, samples, theta, beta, warm_start=G.WARM_SHIFTED)
+    sec = time.perf_counter() - t0
+    if dist is not None:
+        tmax = torch.tensor([sec], device="cuda"); dist.all_reduce(tmax, op=dist.ReduceOp.MAX); sec = float(tmax.item())
+    ok = bool(np.isfinite(xt).all() and np.isfinite(ut).all() and np.abs(ut).max() <= 0.3 + 1e-3)
+    desc = s.description
+    s.close(); plants.close()
+    return {"workload": f"battery(3,4) per-instance plants, {B} per GPU x {world} GPUs = {B * world} plants, {samples} receding-horizon samples x "
+                        f"{iters} iterations, shifted warm start", "plants_total": B * world, "solves_per_s": B * world * samples / sec,
+            "plant_steps_per_s": B * world * samples / sec, "ms_per_sample": sec / samples * 1e3, "host_condensing_s_per_gpu_shard": t_cond,
+            "timed": "wall clock around gpad_closed_loop_plants (uploads of the shard's maps and the trajectory copy-back included), max over ranks",
+            "finite_and_within_input_box": ok, "path": desc}
 
 
 def battery_batch_probe(torch, G, B=4096):
@@ -301,16 +412,87 @@ def closed_loop_probe(torch, G, B=16384, samples=5, iters=20):
     x0, xref = np.ascontiguousarray(par[:, :nx]), np.ascontiguousarray(par[:, nx:])
     theta, beta = G.schedule(iters)
     s = G.Solver(4, 100, prob.m, prob.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
-    G.closed_loop(prob, s, x0, 1, theta, beta, xref=xref, warm_start=True)
+    G.closed_loop(prob, s, x0, 1, theta, beta, xref=xref, warm_start=G.WARM_SHIFTED)
     sec = float("inf")
     for _ in range(2):                       # best of two (each call also allocates and frees its device buffers)
         t0 = time.perf_counter()
-        xt, ut = G.closed_loop(prob, s, x0, samples, theta, beta, xref=xref, warm_start=True)
+        xt, ut = G.closed_loop(prob, s, x0, samples, theta, beta, xref=xref, warm_start=G.WARM_SHIFTED)
         sec = min(sec, time.perf_counter() - t0)
     s.close()
-    return {"workload": f"quadrotor N=100, {B} plants, {samples} receding-horizon samples x {iters} warm-started iterations",
+    return {"workload": f"quadrotor N=100, {B} plants, {samples} receding-horizon samples x {iters} iterations, shifted warm start",
             "plant_steps_per_s": B * samples / sec, "ms_per_sample": sec / samples * 1e3,
             "finite": bool(np.isfinite(xt).all() and np.isfinite(ut).all())}
+
+
+def parity_sample(solver, prob, pb, params, d_out, theta, beta, B):
+    """instances of the timed run itself against oracle/_ref (the reference's compiled seq_functions.cpp): first and
+    last batch tile, both sides of tile boundaries, and a spread -- same bound as tests/test_gpu_parity.py:check_parity"""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    idx = sorted(set([0, 1, 127, 128, 129, 255, 256, B // 2 - 1, B // 2, B // 2 + 127, B - 257, B - 256, B - 129, B - 128, B - 127, B - 1]
+                     + [int(v) for v in np.random.default_rng(17).integers(0, B, 8)]))
+    idx = [i for i in idx if 0 <= i < B]
+    g_P, p_D, _ = prob.instances(params[idx], want_f=False)
+    ref = oracle.RefLib() if oracle.have_ref() else None
+    port = oracle.Oracle()
+    cores = os.cpu_count() or 1
+    if ref is not None:
+        ora = ref.solve_batch(pb["n_u"], pb["N"], pb["m"], pb["M_G"], pb["G_L"], g_P, p_D, theta, beta, nthreads=cores)
+        kind = "reference"
+    else:
+        ora = port.solve_batch(pb["n_u"], pb["N"], pb["m"], pb["M_G"], pb["G_L"], g_P, p_D, theta, beta, nthreads=cores)
+        kind = "port"
+    with ThreadPoolExecutor(min(cores, len(idx))) as ex:
+        f64 = list(ex.map(lambda j: port.solve_f64(pb["n_u"], pb["N"], pb["m"], pb["M_G"], pb["G_L"], g_P[j], p_D[j], theta, beta), range(len(idx))))
+    names = ("y_next", "y", "z", "zhat", "w")
+    sel = {k: d_out[k][idx].cpu().numpy() for k in names}
+    rel = lambda a, b: float(np.max(np.abs(a.astype(np.float64) - b)) / max(float(np.max(np.abs(b))), 1e-300))
+    worst, worst_over, flips, ok = 0.0, 0.0, 0, True
+    for j in range(len(idx)):
+        for k in names:
+            e_or, noise = rel(sel[k][j], ora[k][j].astype(np.float64)), rel(ora[k][j], f64[j][k])
+            tol = 2e-5 if k == "zhat" else 1e-5
+            bound = max(tol, noise) + noise
+            worst = max(worst, e_or); worst_over = max(worst_over, e_or / bound)
+            ok = ok and e_or <= bound and rel(sel[k][j], f64[j][k]) <= 1.25 * noise + 1e-5
+        fl = np.flatnonzero((sel["y_next"][j] > 0) != (ora["y_next"][j] > 0))
+        flips += int(sum(1 for i in fl if abs(f64[j]["y_next"][i]) >= 1e-6))
+    return {"against": f"oracle/_ref ({kind})", "instances": len(idx), "indices": idx, "worst_rel_inf": worst,
+            "worst_fraction_of_bound": worst_over, "active_set_flips": flips, "within_test_bound": bool(ok and flips == 0),
+            "bound": "GPU vs reference <= noise + max(1e-5 (2e-5 on zhat), noise), noise = reference vs fp64 arbiter; GPU vs arbiter <= 1.25 noise + 1e-5"}
+
+
+def tolerance_probe(torch, G, prob, pb, solver, d_par, B, eps=1e-3, check_every=5, max_iter=4000):
+    """BASELINE config 4's tolerance variant: the same 64K quadrotor batch with eps_g = eps_V = 1e-3, N_max = 4000;
+    instances stop at very different iterations, the library retires finished tiles and compacts the running instances"""
+    theta, beta = G.schedule(max_iter)
+    d_it = torch.zeros(B, dtype=torch.int32, device="cuda"); d_st = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d_z = torch.empty((B, prob.n), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    solver.solve_device(B, None, None, theta, beta, max_iter, stream=st, params=d_par, problem=prob, z=d_z, iters=d_it, status=d_st,
+                        check_every=check_every, eps_g=eps, eps_V=eps)
+    e1.record(); e1.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    stats = solver.stats()
+    it = d_it.cpu().numpy(); stt = d_st.cpu().numpy()
+    edges = [0, 100, 250, 500, 1000, 1500, 2000, 3000, max_iter + 1]
+    hist = np.histogram(it, bins=edges)[0]
+    launched = stats["scheduled"]
+    return {"workload": f"the 64K quadrotor batch, eps_g = eps_V = {eps}, checked every {check_every} iterations, N_max = {max_iter}",
+            "solves_per_s": B / sec, "ms_per_solve_of_the_batch": sec * 1e3,
+            "iterations": {"min": int(it.min()), "median": float(np.median(it)), "mean": float(it.mean()), "p99": float(np.percentile(it, 99)),
+                           "max": int(it.max()), "histogram_edges": edges, "histogram": [int(v) for v in hist]},
+            "status_counts": {G.STATUS_NAMES[int(k)]: int((stt == k).sum()) for k in np.unique(stt)},
+            "instance_iterations_needed": stats["needed"], "instance_iterations_scheduled": launched,
+            "share_of_mma_work_on_finished_rows": 1.0 - stats["needed"] / max(launched, 1.0),
+            "share_without_retirement_or_compaction": 1.0 - stats["needed"] / (float(round_up(B, 128)) * float(it.max())),
+            "compactions": stats["compactions"], "z_finite": bool(torch.isfinite(d_z).all())}
+
+
+def round_up(v, q):
+    return (v + q - 1) // q * q
 
 
 def run_ours(args):
@@ -333,13 +515,17 @@ def run_ours(args):
     n, m, B = prob.n, prob.m, args.batch
     theta, beta = G.schedule(ITERS)
     from gpad_b200 import sharding
-    g_P, p_D, _ = prob.instances(quad_params(B, seed=sharding.shard_seed(0, rank)), want_f=False)
+    params = quad_params(B, seed=sharding.shard_seed(0, rank))
     prec = G.PREC_FP32 if args.precision == "fp32" else G.PREC_TF32X3
     solver = G.Solver(prob.n_u, prob.N, m, prob.L, pb["M_G"], pb["G_L"], mode=G.MODE_BATCH_SHARED, precision=prec,
                       max_batch=B, device=local)
+    desc_main = solver.description
     stream = torch.cuda.current_stream()
     st = stream.cuda_stream
-    d_gP, d_pD = torch.from_numpy(g_P).cuda(), torch.from_numpy(p_D).cuda()
+    # device-resident inputs: g_P / p_D built once on the device from the parameters (bit-identical to the host build)
+    d_par = torch.from_numpy(params).cuda()
+    d_gP, d_pD = torch.empty((B, n), device="cuda"), torch.empty((B, m), device="cuda")
+    G.instances_device(prob, B, d_par, d_gP, d_pD, stream=st)
     names = ("y_next", "y", "z", "zhat", "w")
     d_out = {k: torch.empty((B, m if k in ("y_next", "y", "w") else n), device="cuda") for k in names}
     d_it = torch.zeros(B, dtype=torch.int32, device="cuda"); d_st = torch.zeros(B, dtype=torch.int32, device="cuda")
@@ -383,28 +569,74 @@ def run_ours(args):
     solver.profile(False)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
-    # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region ----
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-    h_gP, h_pD = pin(g_P), pin(p_D)
-    h_out = {k: torch.empty((B, m if k in ("y_next", "y", "w") else n), pin_memory=True).numpy() for k in names}
-    from gpad_b200 import SolveArgs, MEM_HOST, _ptr, _f32p, check, lib
-    import ctypes as C
-    h_it = np.zeros(B, np.int32); h_st = np.zeros(B, np.int32)
-    a = SolveArgs(B, MEM_HOST, _ptr(h_gP), _ptr(h_pD), None, None, None, _f32p(theta), _f32p(beta), ITERS, 0, 0.0, 0.0,
-                  _ptr(h_out["y_next"]), _ptr(h_out["y"]), _ptr(h_out["z"]), _ptr(h_out["zhat"]), _ptr(h_out["w"]),
-                  _ptr(h_it), _ptr(h_st), None, None, None)
-    e2e_steps = max(1, min(args.steps, 3))
-    check(lib().gpad_solve(solver._h, C.byref(a)), "gpad_solve (e2e warm-up)")
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        check(lib().gpad_solve(solver._h, C.byref(a)), "gpad_solve (e2e)")      # synchronises before returning
-    torch.cuda.synchronize()
-    t_e2e = sharding.max_over_ranks(time.perf_counter() - t0, device="cuda")
-    h2d = (g_P.nbytes + p_D.nbytes)
-    d2h = sum(v.nbytes for v in h_out.values()) + h_it.nbytes + h_st.nbytes
-    ok = bool(np.isfinite(h_out["z"]).all() and (h_st == 0).all() and (h_it == ITERS).all())
-    same = bool(np.array_equal(h_out["z"], d_out["z"].cpu().numpy()))
+    # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region, every step ----
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    h_par = pin(params)
+    sets = [dict(out={k: torch.empty((B, m if k in ("y_next", "y", "w") else n), pin_memory=True).numpy() for k in names},
+                 it=pin(np.zeros(B, np.int32)), st=pin(np.full(B, -1, np.int32))) for _ in range(2)]
+    e2e_steps = max(2, min(args.steps, 10))
+
+    def run_async(make_args):
+        """K back-to-back steps, at most two in flight, results of step k land in buffer set k % 2"""
+        argsets = [make_args(sets[j]) for j in range(2)]
+        t = solver.solve_async(argsets[0]); solver.wait(t)                     # warm-up (allocates the second state set on step 2)
+        t = solver.solve_async(argsets[1]); solver.wait(t)
+        barrier()
+        t0 = time.perf_counter()
+        tickets = []
+        for k in range(e2e_steps):
+            if k >= 2:
+                solver.wait(tickets[k - 2])            # the buffer set of step k - 2 is reused: its results must have landed
+            tickets.append(solver.solve_async(argsets[k % 2]))
+        for tk in tickets[-2:]:
+            solver.wait(tk)
+        torch.cuda.synchronize()
+        return sharding.max_over_ranks(time.perf_counter() - t0, device="cuda")
+
+    t_e2e = run_async(lambda S: G.host_args(B, theta, beta, ITERS, params=h_par, problem=prob, outputs=S["out"], iters=S["it"], status=S["st"]))
+    last = sets[(e2e_steps - 1) % 2]
+    ok = bool(np.isfinite(last["out"]["z"]).all() and (last["st"] == 0).all() and (last["it"] == ITERS).all())
+    same = bool(all(np.array_equal(last["out"][k], d_out[k].cpu().numpy()) for k in ("z", "y_next")))
+    h2d = h_par.nbytes
+    d2h = sum(v.nbytes for v in last["out"].values()) + last["it"].nbytes + last["st"].nbytes
+    variants = {}
+    if rank == 0 or world > 1:
+        # the same pipeline with g_P / p_D handed over from the host (734 MB more per step), and the synchronous call
+        h_gP, h_pD = pin(d_gP.cpu().numpy()), pin(d_pD.cpu().numpy())
+        t_v = run_async(lambda S: G.host_args(B, theta, beta, ITERS, g_P=h_gP, p_D=h_pD, outputs=S["out"], iters=S["it"], status=S["st"]))
+        variants["async_host_gP_pD"] = {"value": world * B * e2e_steps / t_v, "h2d_bytes_per_step": int(h_gP.nbytes + h_pD.nbytes)}
+        sync_args = G.host_args(B, theta, beta, ITERS, g_P=h_gP, p_D=h_pD, outputs=sets[0]["out"], iters=sets[0]["it"], status=sets[0]["st"])
+        from gpad_b200 import check, lib
+        import ctypes as C
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            check(lib().gpad_solve(solver._h, C.byref(sync_args)), "gpad_solve (sync e2e)")
+        t_s = sharding.max_over_ranks((time.perf_counter() - t0) / 2, device="cuda")
+        variants["synchronous_gpad_solve_host_gP_pD"] = {"value": world * B / t_s, "h2d_bytes_per_step": int(h_gP.nbytes + h_pD.nbytes)}
+        del h_gP, h_pD
+
+    # ---- strong scaling of a FIXED 64K batch (BASELINE config 4 as written): every rank solves 65536 / N instances ----
+    strong = None
+    if world > 1:
+        Bs = BATCH // world
+        barrier()
+        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ks = max(3, args.steps)
+        for _ in range(2):
+            solver.solve_device(Bs, d_gP, d_pD, theta, beta, ITERS, stream=st, z=d_out["z"])
+        barrier()
+        es0.record(stream)
+        for _ in range(ks):
+            solver.solve_device(Bs, d_gP, d_pD, theta, beta, ITERS, stream=st, z=d_out["z"])
+        sharding.gather_first_moves(d_out["z"][:Bs], prob.n_u, dst=0, equal_shards=True)
+        es1.record(stream)
+        barrier()
+        ms = sharding.max_over_ranks(es0.elapsed_time(es1), device="cuda")
+        strong = {"total_batch": BATCH, "batch_per_gpu": Bs, "steps": ks, "solves_per_s": BATCH * ks / (ms * 1e-3), "ms_per_step": ms / ks,
+                  "note": "fixed 65536-instance batch cut into N shards; compare with the N = 1 value of this metric for the strong-scaling factor"}
+
+    plants = plants_probe(torch, G, world, rank, dist) if not args.no_latency else None
 
     if rank != 0:
         if dist is not None:
@@ -425,7 +657,7 @@ def run_ours(args):
     if prec == G.PREC_TF32X3:
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "kernel": "tc_p1_kernel<1> (product 1) + tc_gemm_kernel<2> (product 2), tcgen05 kind::tf32 x3", "algorithmic_flops_per_launch": flops_per_launch,
+                "kernel": "tc_p1_kernel (product 1) + tc_gemm_kernel<2> (product 2), tcgen05 kind::tf32 x3", "algorithmic_flops_per_launch": flops_per_launch,
                 "mean_launch_ms": k_ms, "launches_timed": int(c1 + c2), "product1_ms": ms1 / max(c1, 1), "product2_ms": ms2 / max(c2, 1),
                 "kernel_share_of_step": (ms1 + ms2) / elapsed_ms,
                 # the tensor pipe itself, measured on this pool's B200 with MMAs only (tests/ubench/ubench_tc.cu,
@@ -437,6 +669,9 @@ def run_ours(args):
         roof = {"bound": "tensor", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if achieved else None,
                 "traffic": traffic, "kernel": "simt_gemm_kernel (CUDA-core FFMA)", "peak_basis": "148 SMs x 128 FMA/clk x 1.965 GHz (nominal fp32)"}
 
+    psample = parity_sample(solver, prob, pb, params, d_out, theta, beta, B)
+    tol = tolerance_probe(torch, G, prob, pb, solver, d_par, B) if (not args.no_latency and prec == G.PREC_TF32X3) else None
+    solver.close()
     cpu_val, cpu_info = cpu_rate(args.cpu_budget)
     lat = latency_probe(torch, G) if not args.no_latency else None
     per_inst = per_instance_probe(torch, G) if not args.no_latency else None
@@ -449,15 +684,22 @@ def run_ours(args):
         "dtype": "f32 (tf32 x3 split products, fp32 accumulate)" if prec == G.PREC_TF32X3 else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "iters_per_solve": ITERS, "n": n, "m": m,
                    "step": "one gpad_solve() of the whole batch = 100 GPAD iterations", "l2": "inputs (>2.9 GB/GPU) exceed the 126 MB L2; no flush",
-                   "precision": args.precision, "path": solver.description},
+                   "precision": args.precision, "path": desc_main},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                "results_finite_and_complete": ok, "matches_device_resident_run": same},
+                "call": "gpad_solve_async / gpad_wait, pinned host buffers, two steps in flight; inputs = per-instance parameters [x0; xref] "
+                        "(g_P / p_D built on the device), outputs = the five vectors of main.cu:176-180 + iters + status",
+                "fraction_of_device_resident_value": e2e_value / value,
+                "results_finite_and_complete": ok, "matches_device_resident_run": same, "variants": variants},
         "gpu_launches": int(launches),
         "roofline": roof,
         "cpu_baseline": dict(value=cpu_val, unit=UNIT, **cpu_info),
         "clocks": clocks,
+        "parity_sample": psample,
+        "quadrotor_64k_eps1e-3": tol,
+        "strong_scaling": strong,
         "single_qp_latency": lat,
         "per_instance_operators": per_inst,
+        "per_instance_plants_1M_sweep": plants,
         "battery_batch_4096": bat3,
         "closed_loop": cloop,
     }

@@ -54,7 +54,6 @@ Knobs parse_knobs() {
         else if (key == "warp_rows") k.warp_rows = iv;
         else if (key == "warp_ordered") k.warp_ordered = iv;
         else if (key == "tc_p1") k.tc_p1 = iv;
-        else if (key == "tc_bk") k.tc_bk = iv;
         else if (key == "tc_stages") k.tc_stages = iv;
         else if (key == "tc_bn2") k.tc_bn2 = iv;
         else if (key == "tc_autotune") k.tc_autotune = iv;
@@ -795,7 +794,7 @@ int gpad_debug_gemm_tf32x3(const float* A, const float* B, float* C, int M, int 
     GPAD_CUDA(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) { set_error("sm_100 device required"); return GPAD_ERR_UNSUPPORTED; }
     const Knobs kn = parse_knobs();
-    const int bk = kn.tc_bk == 32 ? 32 : 16;
+    const int bk = 16;
     tc::GemmDesc g;
     g.bk = bk;
     g.k_pad = round_up(K, 32);

@@ -210,7 +210,7 @@ int iterate(gpad_handle_s* h, BatchSlot& sl, const gpad_solve_args_t* a, cudaStr
         k.it.theta = a->theta[it];
         k.it.beta = a->beta[it];
         k.it.check = check ? 1 : 0;
-        k.it.store_zhat = (checking || it + 1 == a->max_iter) ? 1 : 0;
+        k.it.store_zhat = (check || it + 1 == a->max_iter) ? 1 : 0;      // instances stop at checks only
         k.y_prev = st.yb[(it + 2) % 3];           // y_{v-1}
         k.y_cur = st.yb[it % 3];                  // y_v
         k.y_next = st.yb[(it + 1) % 3];           // y_{v+1} overwrites y_{v-2}
@@ -388,7 +388,7 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
     GPAD_TRY(tc::launch_split(h->op.M_G, h->op.M_G, h->op.M_G_lo, c1, h->own_stream));
     GPAD_TRY(tc::launch_split(h->op.G_L, h->op.G_L, h->op.G_L_lo, c2, h->own_stream));
     GPAD_CUDA(cudaStreamSynchronize(h->own_stream));
-    const int bk = kn.tc_bk == 32 ? 32 : 16;
+    const int bk = 16;
     tc::GemmDesc& g1 = sl.g1; tc::GemmDesc& g2 = sl.g2;
     g1.bk = g2.bk = bk;
     g1.k_pad = mp; g1.bn = bn1; g1.n_tiles = nt1; g1.ncols_valid = n;

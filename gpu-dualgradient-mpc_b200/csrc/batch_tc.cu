@@ -309,14 +309,10 @@ static int launch_one(const GemmDesc& g, const BatchKernelArgs& args, float* C, 
 }
 
 int launch_gemm(int phase, const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s) {
-    if (g.bk == 16) {
-        if (phase == 0) return launch_one<0, 16>(g, args, C, ldc, num_sms, s);
-        if (phase == 1) return launch_one<1, 16>(g, args, C, ldc, num_sms, s);
-        return launch_one<2, 16>(g, args, C, ldc, num_sms, s);
-    }
-    if (phase == 0) return launch_one<0, 32>(g, args, C, ldc, num_sms, s);
-    if (phase == 1) return launch_one<1, 32>(g, args, C, ldc, num_sms, s);
-    return launch_one<2, 32>(g, args, C, ldc, num_sms, s);
+    if (g.bk != 16) { set_error("tcgen05 GEMM: K block %d is not built (16 only)", g.bk); return GPAD_ERR_UNSUPPORTED; }
+    if (phase == 0) return launch_one<0, 16>(g, args, C, ldc, num_sms, s);
+    if (phase == 1) return launch_one<1, 16>(g, args, C, ldc, num_sms, s);
+    return launch_one<2, 16>(g, args, C, ldc, num_sms, s);
 }
 
 int launch_split(const float* src, float* hi, float* lo, size_t count, cudaStream_t s) {

@@ -12,7 +12,7 @@ struct GemmDesc {
     CUtensorMap tmA_hi, tmA_lo;   // A [rows = batch][K] tiles of 128 x bk (product 1: y_v, split in-kernel; product 2: zhat hi / lo)
     CUtensorMap tmY[3];           // product 1: the three rotating y buffers
     CUtensorMap tmB_hi, tmB_lo;   // B [rows = outputs][K] tiles of bn x bk
-    int bk = 16;                  // K block in floats: 16 (SWIZZLE_64B) or 32 (SWIZZLE_128B)
+    int bk = 16;                  // K block in floats (SWIZZLE_64B operand tiles)
     int k_pad = 0;                // K rounded up to bk
     int m_tiles = 0, n_tiles = 0, bn = 0, stages = 0;
     int pdl = 0;                  // launch with programmatic stream serialization

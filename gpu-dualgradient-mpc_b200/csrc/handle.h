@@ -22,7 +22,6 @@ struct Knobs {
     int latency_flat = -1;           // -1 auto; 0 expands flat operators to the dense kernels
     int warp_rows = 0, warp_ordered = -1;   // one-warp kernel schedule (0 / -1: chosen by batch size)
     int tc_p1 = -1;                  // product 1: -1 waves model, 1 TMEM-operand kernel, 0 shared-memory-operand kernel
-    int tc_bk = 16;                  // K block of the shared-memory-operand kernel (16 | 32)
     int tc_stages = 0;               // cap on its ring depth (0: as many as fit)
     int tc_bn2 = 0;                  // product 2 tile width (0: tuned, cached per shape)
     int tc_autotune = 1;             // 0: first candidate width without timing

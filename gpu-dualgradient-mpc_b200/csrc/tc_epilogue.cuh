@@ -23,10 +23,11 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
             const int b = row_base + rr;
             if (col_ok && b < args.B) Cdbg[(size_t)b * ldc + c] = buf[rr * 33 + lane];
         }
-    } else if ((!args.it.check && !args.done) || (PHASE == 1 && args.p_only)) {
-        // fast path (fixed-iteration solves): rows in chunks of kChunk with every global
-        // load of the chunk issued before the first use, so each warp keeps
-        // kChunk * (2 or 3) x 128 B in flight; streaming cache hints keep the operators in L2
+    } else if (!args.it.check && !args.dual) {
+        // fast path (every iteration of a fixed-iteration solve, the iterations between two checks in tolerance mode):
+        // rows in chunks of kChunk with every global load of the chunk issued before the first use, so each warp keeps
+        // kChunk * (2 or 3) x 128 B in flight; streaming cache hints keep the operators in L2.  In tolerance mode stopped
+        // instances (done[b]) are skipped and the averaged residual sbar is carried along.
         constexpr int kChunk = 16;
 #pragma unroll 1
         for (int r0 = 0; r0 < 32; r0 += kChunk) {
@@ -40,10 +41,13 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
                     continue;
                 }
                 float gp[kChunk], zo[kChunk], pp[kChunk];
+                unsigned live = 0;
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j) {
                     const int b = row_base + r0 + j;
-                    const bool ok = col_ok && b < args.B;
+                    bool ok = col_ok && b < args.B;
+                    if (ok && args.done) ok = __ldg(args.done + b) == 0;
+                    live |= (ok ? 1u : 0u) << j;
                     const size_t o = (size_t)b * args.np + c;
                     gp[j] = ok ? __ldcs(args.g_P + o) : 0.f;
                     zo[j] = ok ? __ldcs(args.z + o) : 0.f;
@@ -52,7 +56,7 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j) {
                     const int b = row_base + r0 + j;
-                    if (!(col_ok && b < args.B)) continue;
+                    if (!((live >> j) & 1u)) continue;
                     const size_t o = (size_t)b * args.np + c;
                     float acc = buf[(r0 + j) * 33 + lane];
                     __stcs(args.P_cur + o, acc);
@@ -67,10 +71,13 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
                 }
             } else {
                 float yc[kChunk], yp[kChunk], pd[kChunk];
+                unsigned live = 0;
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j) {
                     const int b = row_base + r0 + j;
-                    const bool ok = col_ok && b < args.B;
+                    bool ok = col_ok && b < args.B;
+                    if (ok && args.done) ok = __ldg(args.done + b) == 0;
+                    live |= (ok ? 1u : 0u) << j;
                     const size_t o = (size_t)b * args.mp + c;
                     yc[j] = ok ? __ldcs(args.y_cur + o) : 0.f;
                     yp[j] = ok ? __ldcs(args.y_prev + o) : 0.f;
@@ -79,11 +86,25 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j) {
                     const int b = row_base + r0 + j;
-                    if (!(col_ok && b < args.B)) continue;
+                    if (!((live >> j) & 1u)) continue;
                     const size_t o = (size_t)b * args.mp + c;
                     const float wv = momentum(yc[j], yp[j], args.it.beta);
                     const float sacc = buf[(r0 + j) * 33 + lane] + (wv + pd[j]);
                     args.y_next[o] = 0.5f * (sacc + fabsf(sacc));   // read back by the next two kernels
+                }
+                if (args.checking) {
+                    // tolerance mode: sbar <- (1 - theta) sbar + theta (acc + p_D), the residual of the averaged iterate
+                    float sb[kChunk];
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j)
+                        sb[j] = ((live >> j) & 1u) ? __ldcs(args.sbar + (size_t)(row_base + r0 + j) * args.mp + c) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j) {
+                        if (!((live >> j) & 1u)) continue;
+                        const float rhat = buf[(r0 + j) * 33 + lane] + pd[j];
+                        __stcs(args.sbar + (size_t)(row_base + r0 + j) * args.mp + c,
+                               __fadd_rn(__fmul_rn(1.0f - args.it.theta, sb[j]), __fmul_rn(args.it.theta, rhat)));
+                    }
                 }
             }
         }

@@ -19,8 +19,9 @@ def build(force=False):
     lib = os.path.join(_HERE, "liboracle.so")
     src = os.path.join(_HERE, "gpad_oracle.c")
     ref = os.path.join(_HERE, "_ref", "libgpad_ref.so")
+    refcuda = os.path.join(_HERE, "_ref", "libgpad_refcuda.so")
     stale = (not os.path.exists(lib)) or os.path.getmtime(lib) < os.path.getmtime(src)
-    want_ref = os.path.isdir("/root/reference/Code/CUDA/FinalProject/src") and not os.path.exists(ref)
+    want_ref = os.path.isdir("/root/reference/Code/CUDA/FinalProject/src") and not (os.path.exists(ref) and os.path.exists(refcuda))
     if force or stale or want_ref:
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
                        stdout=subprocess.DEVNULL)
@@ -29,6 +30,10 @@ def build(force=False):
 
 def have_ref():
     return os.path.exists(os.path.join(_HERE, "_ref", "libgpad_ref.so"))
+
+
+def have_refcuda():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libgpad_refcuda.so"))
 
 
 def _f32(a):
@@ -247,3 +252,43 @@ class RefLib:
                                               _p(out["zhat"]), _p(out["w"]), nthreads)
         out.update(threads=used)
         return out
+
+
+class RefCuda:
+    """The reference's own GPU kernels (kernel_functions.cu, unmodified, compiled for sm_100a) driven by the loop of
+    main.cu:117-180 (oracle/ref_cuda_compose.cu).  Needs a GPU; operators in the sequential layout are flipped here
+    into what the kernels read."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "_ref", "libgpad_refcuda.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        L = self.lib = C.CDLL(path)
+        L.ref_cuda_solve.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int,
+                                     _fp, _fp, _fp, _fp, _fp, _dp, _dp]
+        L.ref_cuda_loop_resident.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _dp, _fp]
+
+    def solve(self, n_u, N, m, M_G, G_L, g_P, p_D, theta, beta, max_iter=None):
+        n = n_u * N
+        max_iter = len(theta) if max_iter is None else max_iter
+        MGf = _f32(np.asarray(M_G, np.float32).reshape(n, m).T); GLf = _f32(np.asarray(G_L, np.float32).reshape(m, n).T)
+        a = [_f32(x) for x in (g_P, p_D, theta, beta)]
+        out = {k: np.zeros(sz, np.float32) for k, sz in (("y_next", m), ("y", m), ("z", n), ("zhat", n), ("w", m))}
+        loop, total = C.c_double(), C.c_double()
+        rc = self.lib.ref_cuda_solve(n_u, N, m, _p(MGf), _p(a[0]), _p(GLf), _p(a[1]), _p(a[2]), _p(a[3]), max_iter,
+                                     _p(out["y_next"]), _p(out["y"]), _p(out["z"]), _p(out["zhat"]), _p(out["w"]),
+                                     C.byref(loop), C.byref(total))
+        assert rc == 0, f"CUDA error {rc} in the reference kernels"
+        out.update(iters=max_iter, status=0, loop_us=loop.value, total_us=total.value)
+        return out
+
+    def loop_times(self, n_u, N, m, M_G, G_L, g_P, p_D, theta, beta, max_iter, reps):
+        """per-solve wall time (us) of the reference loop on resident operators, `reps` solves back to back"""
+        n = n_u * N
+        MGf = _f32(np.asarray(M_G, np.float32).reshape(n, m).T); GLf = _f32(np.asarray(G_L, np.float32).reshape(m, n).T)
+        a = [_f32(x) for x in (g_P, p_D, theta, beta)]
+        t = np.zeros(reps, np.float64); z = np.zeros(n, np.float32)
+        rc = self.lib.ref_cuda_loop_resident(n_u, N, m, _p(MGf), _p(a[0]), _p(GLf), _p(a[1]), _p(a[2]), _p(a[3]), max_iter,
+                                             reps, t.ctypes.data_as(_dp), _p(z))
+        assert rc == 0, f"CUDA error {rc} in the reference kernels"
+        return t, z

@@ -58,6 +58,15 @@ def check_parity(gpu, ora, f64, label=""):
     return worst
 
 
+def check_parity_stopped(oracle, gpu, ora, n_u, N, pb, g_P, p_D, theta, beta, label=""):
+    """tolerance-mode results: the noise-aware bound of check_parity, with the fp64 arbiter run for exactly the
+    iterations the reference ran (no termination test), so `noise` is the reference's own distance from exact arithmetic
+    at its stop iteration"""
+    it = int(ora["iters"])
+    f64 = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta[:it], beta[:it])
+    return check_parity({k: gpu[k] for k in VECS}, {k: ora[k] for k in VECS}, f64, label)
+
+
 def battery_case(n_u, N, seed=0):
     pb = P.battery(n_u, N)
     rng = np.random.default_rng(seed)
@@ -188,11 +197,7 @@ def test_latency_termination_matches_oracle(torch_cuda, G, oracle, dims, eps, wi
     if gpu["iters"] == ora["iters"]:
         # long solves drift: the bound is relative to the reference's own distance from exact arithmetic after the
         # same number of iterations (the fp64 arbiter run for exactly that many iterations, no termination test)
-        it = int(ora["iters"])
-        f64 = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta[:it], beta[:it])
-        for k in VECS:
-            noise = P.rel_inf(ora[k], f64[k])
-            assert P.rel_inf(gpu[k], ora[k]) <= max(3e-5, 1.5 * noise), (k, P.rel_inf(gpu[k], ora[k]), noise)
+        check_parity_stopped(oracle, gpu, ora, n_u, N, pb, g_P, p_D, theta, beta, f"latency termination {dims} eps={eps}")
         # max_viol = L * max(sbar): an fp32 rounding of the (cancelling) residual is scaled by L (1131 for (10,100))
         assert abs(gpu["max_viol"] - ora["max_viol"]) <= max(1e-5, 1e-7 * pb.L) + 1e-3 * abs(ora["max_viol"])
     # check_every = 7 stops on a multiple of 7 and agrees with the oracle under the same setting
@@ -225,8 +230,7 @@ def test_latency_dual_gap_branch(torch_cuda, G, oracle, plan, monkeypatch):
         gpu = s.solve_host(g_P, p_D, theta, beta, f=f, **kw)
         s.close()
         assert gpu["status"] == ora["status"] and gpu["iters"] == ora["iters"], (seed, gpu["status"], ora["status"], gpu["iters"], ora["iters"])
-        for k in VECS:
-            assert P.rel_inf(gpu[k], ora[k]) <= 3e-5
+        check_parity_stopped(oracle, gpu, ora, n_u, N, pb, g_P, p_D, theta, beta, f"latency dual gap seed {seed}")
         hit += ora["status"] == 3
     print("\n dual-gap terminations:", hit)
 
@@ -282,11 +286,11 @@ def test_latency_grid2_matches_generic_grid_kernel(torch_cuda, G, oracle, dims, 
 
 
 # ------------------------------------------------------------------------------------ tensor-core GEMM hook
-@pytest.mark.parametrize("bk", ["16", "32"])
+@pytest.mark.parametrize("stages", ["0", "2"])
 @pytest.mark.parametrize("shape", [(128, 16, 16), (128, 256, 64), (300, 200, 1000), (1000, 416, 2400), (257, 2400, 400)])
-def test_tf32x3_gemm_reaches_fp32_accuracy(torch_cuda, G, shape, bk, monkeypatch):
-    """the tcgen05 3xTF32 mainloop with both K-block widths (SWIZZLE_64B / SWIZZLE_128B operand tiles)"""
-    monkeypatch.setenv("GPAD_DEBUG", f"tc_bk={bk}")
+def test_tf32x3_gemm_reaches_fp32_accuracy(torch_cuda, G, shape, stages, monkeypatch):
+    """the tcgen05 3xTF32 mainloop (test hook of the shared-memory-operand kernel) with a full and a two-slot ring"""
+    monkeypatch.setenv("GPAD_DEBUG", f"tc_stages={stages}")
     t = torch_cuda
     M, N, K = shape
     rng = np.random.default_rng(M + N + K)
@@ -381,10 +385,9 @@ def test_batch_warm_start_matches_oracle(torch_cuda, G, oracle, prec):
     s.close()
 
 
-@pytest.mark.parametrize("knobs", ["tc_p1=0", "tc_p1=1", "tc_p1=0,tc_bk=32", "tc_pdl=0", "tc_bn2=128", "tc_stages=2"])
+@pytest.mark.parametrize("knobs", ["tc_p1=0", "tc_p1=1", "tc_pdl=0", "tc_p1=0,tc_pdl=0", "tc_bn2=128", "tc_stages=2"])
 def test_batch_tc_kernel_variants_match_default(torch_cuda, G, knobs, monkeypatch):
-    """both product-1 kernels (shared-memory operand / TMEM operand; the default picks one by its waves model), both
-    K-block widths, launches with and without programmatic dependent launch, another product-2 tile width and a shallow
+    """both product-1 kernels (shared-memory operand / TMEM operand; the default picks one by its waves model), launches with and without programmatic dependent launch, another product-2 tile width and a shallow
     ring against the default plan on the same batch: same active sets, iterates within the parity tolerance"""
     N, B = 20, 300
     pb = P.quadrotor(N)
@@ -421,8 +424,9 @@ def test_batch_termination_matches_oracle(torch_cuda, G, oracle, prec, with_f):
     assert np.array_equal(gpu["status"], ora["status"])
     assert np.array_equal(gpu["iters"], ora["iters"]), np.flatnonzero(gpu["iters"] != ora["iters"])
     assert len(set(ora["iters"].tolist())) > 3          # instances really stop at different iterations
-    for k in VECS:
-        assert P.rel_inf(gpu[k], ora[k]) <= 3e-5, k
+    for b in range(0, B, 11):
+        check_parity_stopped(oracle, {k: gpu[k][b] for k in VECS}, {k: ora[k][b] for k in list(VECS) + ["iters"]}, n_u, N, pb,
+                             g_P[b], p_D[b], theta, beta, f"batch termination {prec} [{b}]")
     s.close()
 
 
@@ -446,8 +450,9 @@ def test_batch_dual_gap_branch(torch_cuda, G, oracle, prec):
     assert (ora["status"] == 3).sum() > 0, "no instance exercised the dual-gap branch"
     assert np.array_equal(gpu["status"], ora["status"]), np.flatnonzero(gpu["status"] != ora["status"])
     assert np.array_equal(gpu["iters"], ora["iters"]), np.flatnonzero(gpu["iters"] != ora["iters"])
-    for k in VECS:
-        assert P.rel_inf(gpu[k], ora[k]) <= 3e-5, k
+    for b in range(0, B, 5):
+        check_parity_stopped(oracle, {k: gpu[k][b] for k in VECS}, {k: ora[k][b] for k in list(VECS) + ["iters"]}, n_u, N, pb,
+                             g_P[b], p_D[b], theta, beta, f"batch dual gap {prec} [{b}]")
 
 
 
@@ -662,8 +667,7 @@ def test_tiny_latency_termination_with_cost_vector(torch_cuda, G, oracle, warp, 
                 ora = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, f=f, **kw)
                 gpu = s.solve_host(g_P, p_D, theta, beta, f=f, **kw)
                 assert gpu["status"] == ora["status"] and gpu["iters"] == ora["iters"], (dims, seed, eps, gpu["status"], ora["status"], gpu["iters"], ora["iters"])
-                for k in VECS:
-                    assert P.rel_inf(gpu[k], ora[k]) <= 3e-5, (dims, seed, k)
+                check_parity_stopped(oracle, gpu, ora, n_u, N, pb, g_P, p_D, theta, beta, f"tiny latency {dims} seed {seed} eps {eps}")
                 seen[int(ora["status"])] = seen.get(int(ora["status"]), 0) + 1
         s.close()
     print("\n statuses:", seen)
