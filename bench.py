@@ -238,6 +238,7 @@ def latency_probe(torch, G):
             ts.append(e0.elapsed_time(e1) * 1e3)
         entry = {"p50_us": p50(ts), "p99_us": float(np.percentile(ts, 99)), "iterations": ITERS, "path": s.description,
                  "us_per_iteration": p50(ts) / ITERS}
+        z_fixed = dz.cpu().numpy().copy()             # z_99 of the fixed 100-iteration solve
         # (iii) through the C ABI with host buffers: H2D of g_P / p_D, the solve, D2H of the five vectors, synchronised
         th = []
         for _ in range(200):
@@ -270,7 +271,7 @@ def latency_probe(torch, G):
         if ref_gpu is not None:
             tg, zref = ref_gpu.loop_times(n_u, N, m, M_G, G_L, g_P[0], p_D[0], theta, beta, ITERS, 40)
             entry["reference_cuda_loop_p50_us"] = p50(tg[5:])
-            entry["reference_cuda_loop_matches"] = bool(np.max(np.abs(zref - dz.cpu().numpy())) <= 2e-5 * max(1e-3, float(np.abs(zref).max())))
+            entry["reference_cuda_loop_matches"] = bool(np.max(np.abs(zref - z_fixed)) <= 2e-5 * max(1e-3, float(np.abs(zref).max())))
             entry["speedup_vs_reference_cuda_loop"] = entry["reference_cuda_loop_p50_us"] / entry["p50_us"]
         # (v) SM-cycle model of SURVEY 8(d): T_iter >= operator bytes through the shared-memory ports of the C
         # cooperating SMs + 2 exchanges (+ the dependent reduction chain for one warp)
@@ -361,14 +362,15 @@ def plants_probe(torch, G, world, rank, dist, B=131072, samples=5, iters=100):
     sec = time.perf_counter() - t0
     if dist is not None:
         tmax = torch.tensor([sec], device="cuda"); dist.all_reduce(tmax, op=dist.ReduceOp.MAX); sec = float(tmax.item())
-    ok = bool(np.isfinite(xt).all() and np.isfinite(ut).all() and np.abs(ut).max() <= 0.3 + 1e-3)
+    ok = bool(np.isfinite(xt).all() and np.isfinite(ut).all())
+    u_max = float(np.abs(ut).max())
     desc = s.description
     s.close(); plants.close()
     return {"workload": f"battery(3,4) per-instance plants, {B} per GPU x {world} GPUs = {B * world} plants, {samples} receding-horizon samples x "
                         f"{iters} iterations, shifted warm start", "plants_total": B * world, "solves_per_s": B * world * samples / sec,
             "plant_steps_per_s": B * world * samples / sec, "ms_per_sample": sec / samples * 1e3, "host_condensing_s_per_gpu_shard": t_cond,
             "timed": "wall clock around gpad_closed_loop_plants (uploads of the shard's maps and the trajectory copy-back included), max over ranks",
-            "finite_and_within_input_box": ok, "path": desc}
+            "finite": ok, "max_abs_input": u_max, "input_box": 0.3, "path": desc}
 
 
 def battery_batch_probe(torch, G, B=4096):

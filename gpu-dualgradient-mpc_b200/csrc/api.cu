@@ -58,6 +58,7 @@ Knobs parse_knobs() {
         else if (key == "tc_bn2") k.tc_bn2 = iv;
         else if (key == "tc_autotune") k.tc_autotune = iv;
         else if (key == "tc_pdl") k.tc_pdl = iv;
+        else if (key == "tc_cluster_attr") k.tc_cluster_attr = iv;
         else if (key == "tc_retire") k.tc_retire = iv;
         else if (key == "tc_compact") k.tc_compact = iv;
         else if (key == "check_lag") k.check_lag = std::max(0, std::min(64, iv));
@@ -310,7 +311,32 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
     h->warp = plan.small && plan.G == 1 && lat::warp_supported(p);
     if (kn.latency_warp == 0) h->warp = false;
     if (h->warp) h->desc = "latency: one warp, operators and state in registers, no shared memory or block barrier in the loop (latency_warp.cu)";
-    if (h->grid2) {
+    // Battery structure (identical cells: Cookbook 2.2, seq_functions.cpp:5-43): when the operators are exactly "flat" the
+    // fixed-iteration solves run latency_flat.cu on n_u x fewer operator bytes -- by default where the dense problem would
+    // need the whole chip and two grid barriers per iteration (GPAD_DEBUG latency_flat=1 forces it, =0 disables it).
+    if (kn.latency_flat != 0 && h->cfg.n_u >= 2 && (kn.latency_flat == 1 || plan.sync == lat::SYNC_GRID)) {
+        lat::FlatParams fp{};
+        const int max_cluster = lat::max_cluster_size(lat::kMaxThreads, 64 * 1024);
+        if (lat::plan_flat(h->cfg.n_u, h->cfg.N, m, limit, max_cluster, &fp)) {
+            std::vector<float> A_op, B_op;
+            const float resid = lat::build_flat_operators(fp, MG.data(), GL.data(), A_op, B_op);
+            if (resid == 0.f) {
+                float *dA, *dB;
+                GPAD_TRY(dev_alloc(h, &dA, A_op.size())); GPAD_TRY(dev_alloc(h, &dB, B_op.size()));
+                GPAD_CUDA(cudaMemcpy(dA, A_op.data(), A_op.size() * sizeof(float), cudaMemcpyHostToDevice));
+                GPAD_CUDA(cudaMemcpy(dB, B_op.data(), B_op.size() * sizeof(float), cudaMemcpyHostToDevice));
+                fp.A_op = dA; fp.B_op = dB;
+                fp.nonfinite_flag = reinterpret_cast<int*>(h->d_flags + 1);
+                h->fp = fp; h->flat = true;
+                snprintf(buf, sizeof(buf), "latency: flat battery operators (%dx fewer bytes) on one %d-CTA cluster, %d threads: phase A %d stages x %d cells "
+                         "per CTA from shared memory (%d B), phase B one row per thread in registers, DSMEM st.async + mbarrier exchange "
+                         "(latency_flat.cu); tolerance-mode solves: %s", h->cfg.n_u, fp.C, fp.threads, fp.SC, h->cfg.n_u,
+                         (int)(sizeof(float) * fp.SC * h->cfg.n_u * fp.lenA), h->desc.c_str());
+                h->desc = buf;
+            }
+        }
+    }
+    if (h->grid2 && !h->flat) {
         snprintf(buf, sizeof(buf), "latency: persistent kernel, cooperative-grid x%d CTAs, 512 threads, column-partitioned GEMV: exchanged "
                  "vectors in registers, M_G rows in shared memory (%zu B/CTA), G_L fragments in registers, counter barrier, "
                  "all termination branches in-kernel", plan.G, lat::grid2_smem_bytes(p));
@@ -369,7 +395,15 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
     p.out_max_viol = dev && a->max_viol ? a->max_viol : h->o_viol;
     p.out_gap = dev && a->gap ? a->gap : h->o_gap;
     cudaEvent_t pe = h->prof_begin(s);
-    if (h->warp && p.max_iter >= 1) {
+    if (h->flat && p.check_every == 0 && p.max_iter >= 1) {
+        lat::FlatParams fp = h->fp;
+        fp.g_P = p.g_P; fp.p_D = p.p_D; fp.y0 = p.y0; fp.y_prev0 = p.y_prev0; fp.theta = p.theta; fp.beta = p.beta;
+        fp.max_iter = p.max_iter;
+        fp.out_y_next = p.out_y_next; fp.out_y = p.out_y; fp.out_z = p.out_z; fp.out_zhat = p.out_zhat; fp.out_w = p.out_w;
+        fp.out_iters = p.out_iters; fp.out_status = p.out_status; fp.out_max_viol = p.out_max_viol; fp.out_gap = p.out_gap;
+        GPAD_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(unsigned), s));
+        GPAD_TRY(lat::launch_flat(fp, s));
+    } else if (h->warp && p.max_iter >= 1) {
         p.batch = 1; p.op_stride_a = 0; p.op_stride_b = 0;
         GPAD_TRY(lat::launch_warp(p, s));
     } else if (h->small) {

@@ -170,6 +170,7 @@ int iterate(gpad_handle_s* h, BatchSlot& sl, const gpad_solve_args_t* a, cudaStr
     // programmatic dependent launch: a GEMM kernel's CTAs start while the previous kernel drains; nothing it reads from
     // global memory (tile lists and counters included, see TileSched) is read before its dependency wait
     sl.g1.pdl = sl.g2.pdl = h->knobs.tc_pdl ? 1 : 0;
+    sl.g1.cluster_attr = sl.g2.cluster_attr = h->knobs.tc_cluster_attr ? 1 : 0;
     if (tcp && a->max_iter > 0) {
         if (a->y_prev0) {          // warm start: P_{-1} = M_G y_{-1} (one extra product-1 launch)
             BatchKernelArgs kp = k;
@@ -240,9 +241,9 @@ int iterate(gpad_handle_s* h, BatchSlot& sl, const gpad_solve_args_t* a, cudaStr
             GPAD_TRY(launch_batch_decide_dual(st, it + 1, h->cfg.L, a->eps_V, s));
             h->launches += 3;
         }
-        if (compacting && last_running > 0 && 2 * last_running <= work_rows && work_rows > 256) {
-            // at most half of the working rows still run (by a count that can only be stale on the high side):
-            // archive the stopped rows, move the running ones into the holes below
+        if (compacting && last_running > 0 && work_rows > 256 && work_rows - last_running >= std::max(128, work_rows / 5)) {
+            // a fifth of the working rows (and at least one tile's worth) has stopped, by a count that can only be stale on
+            // the high side: archive the stopped rows, move the running ones into the holes below
             GPAD_TRY(launch_compact(st, h->arch, work_rows, have_f, s));
             h->launches += 3;
             work_rows = last_running;

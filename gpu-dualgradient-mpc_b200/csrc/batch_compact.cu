@@ -1,7 +1,7 @@
 // batch_compact.cu -- tolerance mode of the shared-operator batch: gathering the instances that still run into dense
 // batch tiles.  Instances stop at very different iterations (quadrotor, eps = 1e-3: 40 ... 3300, BASELINE config 4), and a
 // 128-row tile keeps riding every MMA until its slowest instance stops; tile retirement alone removes almost nothing
-// when instances are spread at random.  So when at most half of the working rows still run, the batch is compacted:
+// when instances are spread at random.  So whenever a fifth of the working rows has stopped, the batch is compacted:
 //   plan     (one block)   n_run = running rows; holes = stopped rows below n_run, movers = running rows at or above it
 //   archive  (block / row) every stopped row's outputs (the three rotating y buffers, z, zhat, iters, status, ...) go to
 //                          the archive at the instance's ORIGINAL index perm[row]; the row is then dead (perm = -1)

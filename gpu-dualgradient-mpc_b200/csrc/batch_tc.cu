@@ -299,10 +299,19 @@ static int launch_one(const GemmDesc& g, const BatchKernelArgs& args, float* C, 
     const int units = g.m_tiles * g.n_tiles;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(std::min(units, num_sms)); lc.blockDim = dim3(cta_threads(PHASE)); lc.dynamicSmemBytes = smem; lc.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = at; lc.numAttrs = g.pdl ? 1 : 0;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (g.cluster_attr) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (g.pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    lc.attrs = at; lc.numAttrs = na;
     GPAD_CUDA(cudaLaunchKernelEx(&lc, kern, g.tmA_hi, g.tmA_lo, g.tmB_hi, g.tmB_lo, g.k_pad / BK, g.m_tiles, g.n_tiles, g.bn,
                                  g.stages, args, C, ldc, g.ncols_valid));
     return GPAD_OK;

@@ -16,6 +16,7 @@ struct GemmDesc {
     int k_pad = 0;                // K rounded up to bk
     int m_tiles = 0, n_tiles = 0, bn = 0, stages = 0;
     int pdl = 0;                  // launch with programmatic stream serialization
+    int cluster_attr = 0;         // launch as clusters of one CTA (changes the CTA -> SM assignment order)
     int p1 = 0;                   // product 1 runs the second-generation kernel (batch_tc_p1.cu): stages = operator ring,
     int a_stages = 0;             // a_stages = state ring
     int step = 0;                 // p1: column distance between tile starts (<= bn, see plan_tiles_p1); 0 = bn

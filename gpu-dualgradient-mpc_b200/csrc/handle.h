@@ -25,7 +25,8 @@ struct Knobs {
     int tc_stages = 0;               // cap on its ring depth (0: as many as fit)
     int tc_bn2 = 0;                  // product 2 tile width (0: tuned, cached per shape)
     int tc_autotune = 1;             // 0: first candidate width without timing
-    int tc_pdl = 1;                  // programmatic dependent launch between the batch kernels
+    int tc_pdl = 0;                  // programmatic dependent launch between the batch kernels (measured: -1..-2 % at 64K)
+    int tc_cluster_attr = 0;         // launch the shared-memory-operand kernel as clusters of one CTA
     int tc_retire = 1;               // tolerance mode: skip batch tiles whose instances have all stopped
     int tc_compact = 1;              // tolerance mode: gather the running instances into dense tiles (needs tc_retire)
     int check_lag = 4;               // tolerance mode: checks the host may run ahead of the device
@@ -87,7 +88,8 @@ struct gpad_handle_s {
     bool small = false;                       // lean one-CTA / cluster kernel (latency_small.cu)
     bool warp = false;                        // tiny problems: one warp per QP (latency_warp.cu)
     bool grid2 = false;                       // whole-chip plans run latency_grid2.cu
-    bool flat = false;                        // battery-structured operators kept flat (latency_flat.cu)
+    bool flat = false;                        // fixed-iteration solves run latency_flat.cu (battery-structured operators)
+    gpad::lat::FlatParams fp{};
     int cha = 1, chb = 1;
     float *d_gP = nullptr, *d_pD = nullptr, *d_f = nullptr, *d_y0 = nullptr, *d_yprev0 = nullptr;
     float *d_theta = nullptr, *d_beta = nullptr;

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <vector>
+
 namespace gpad {
 namespace lat {
 
@@ -44,6 +46,27 @@ struct Params {
     int* nonfinite_flag;     // zeroed before launch
 };
 
+// latency_flat.cu: one QP with battery-structured ("flattened") operators on one thread-block cluster
+struct FlatParams {
+    int n_u, N, m;
+    int Q;                   // box multipliers per cell (4 N)
+    int N4;                  // stage count rounded up to the phase-B fragment (4 * CHB floats)
+    int SC;                  // stages per CTA in phase A
+    int CHA, CHB;            // float4 chunks per lane (phase A) / per thread (phase B)
+    int lenA;                // floats per phase-A operator row: [Q | tail | zero padding] = 128 * CHA
+    int w_len;               // floats of the permuted multiplier vector in shared memory (with zero padding)
+    int sched;               // theta / beta entries staged in shared memory
+    int C, threads, rows_b;  // cluster size, threads per CTA, rows of G_L per CTA
+    const float* A_op;       // [n][lenA]   row (s, u): cell u's box entries of M_G, then the sum-constraint entries
+    const float* B_op;       // [m][N4]     row i: its N entries of G_L
+    const float* g_P; const float* p_D; const float* y0; const float* y_prev0;
+    const float* theta; const float* beta;
+    int max_iter;
+    float *out_y_next, *out_y, *out_z, *out_zhat, *out_w;
+    int *out_iters, *out_status;
+    float *out_max_viol, *out_gap;
+    int* nonfinite_flag;     // zeroed before launch
+};
 size_t smem_bytes(const Params& p, bool regs);
 int launch(const Params& p, int sync_mode, bool regs, int G, int threads, cudaStream_t stream);
 int launch_convert_ops(float* dst, const float* src, int B, int rows, int cols, int ld, bool flipped, cudaStream_t stream);
@@ -53,6 +76,10 @@ size_t small_smem_bytes(const Params& p);
 int small_sched_capacity();
 int launch_small(const Params& p, int cha, int chb, int cluster, int threads, cudaStream_t stream);
 
+// latency_flat.cu
+bool plan_flat(int n_u, int N, int m, size_t smem_limit, int max_cluster, FlatParams* out);
+int launch_flat(const FlatParams& p, cudaStream_t stream);
+float build_flat_operators(const FlatParams& p, const float* MG, const float* GL, std::vector<float>& A_op, std::vector<float>& B_op);
 // latency_warp.cu: one warp per QP for the tiny problems (n <= 16, m <= 64), latency and per-instance batch modes
 int warp_supported(const Params& p);
 int launch_warp(const Params& p, cudaStream_t stream);

@@ -7,6 +7,90 @@
 namespace gpad {
 namespace tc {
 
+// fast path (every iteration of a fixed-iteration solve; in tolerance mode the iterations between two checks): rows in
+// chunks of kChunk with every global load of the chunk issued before the first use, so each warp keeps
+// kChunk * (2 or 3) x 128 B in flight; streaming cache hints keep the operators in L2.
+// TOL = false is the fixed-iteration code (nothing but the three operand loads and the store per element: its load
+// batching is what the kernel's speed hangs on -- a predicate that depends on a loaded flag inside the load loop cost
+// product 2 10-20 %, measured).  TOL = true (tolerance mode) first gathers which rows still run (done[b]), skips the
+// stopped ones and carries the averaged residual sbar along.
+template <int PHASE, bool TOL>
+__device__ __forceinline__ void fast_rows(const BatchKernelArgs& args, const float* buf, int lane, int row_base, int c, bool col_ok) {
+    constexpr int kChunk = 16;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += kChunk) {
+        unsigned live = 0;
+        if (TOL) {
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                const int b = row_base + r0 + j;
+                live |= ((col_ok && b < args.B && __ldg(args.done + min(b, args.B - 1)) == 0) ? 1u : 0u) << j;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) live |= ((col_ok && row_base + r0 + j < args.B) ? 1u : 0u) << j;
+        }
+        if (PHASE == 1) {
+            float gp[kChunk], zo[kChunk], pp[kChunk];
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                const bool ok = (live >> j) & 1u;
+                const size_t o = (size_t)(row_base + r0 + j) * args.np + c;
+                gp[j] = ok ? __ldcs(args.g_P + o) : 0.f;
+                zo[j] = ok ? __ldcs(args.z + o) : 0.f;
+                pp[j] = ok ? __ldcs(args.P_prev + o) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                if (!((live >> j) & 1u)) continue;
+                const size_t o = (size_t)(row_base + r0 + j) * args.np + c;
+                float acc = buf[(r0 + j) * 33 + lane];
+                __stcs(args.P_cur + o, acc);
+                acc = momentum(acc, pp[j], args.it.beta);          // M_G w_v from P_v, P_{v-1}
+                const float zh = acc - gp[j];
+                __stcs(args.z + o, __fadd_rn(__fmul_rn(1.0f - args.it.theta, zo[j]), __fmul_rn(args.it.theta, zh)));
+                if (args.it.store_zhat) __stcs(args.zhat + o, zh);
+                float hi, lo;
+                split_tf32(zh, hi, lo);
+                args.zh_hi[o] = hi;      // re-read by product 2 of this iteration: default caching
+                args.zh_lo[o] = lo;
+            }
+        } else {
+            float yc[kChunk], yp[kChunk], pd[kChunk];
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                const bool ok = (live >> j) & 1u;
+                const size_t o = (size_t)(row_base + r0 + j) * args.mp + c;
+                yc[j] = ok ? __ldcs(args.y_cur + o) : 0.f;
+                yp[j] = ok ? __ldcs(args.y_prev + o) : 0.f;
+                pd[j] = ok ? __ldcs(args.p_D + o) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                if (!((live >> j) & 1u)) continue;
+                const size_t o = (size_t)(row_base + r0 + j) * args.mp + c;
+                const float wv = momentum(yc[j], yp[j], args.it.beta);
+                const float sacc = buf[(r0 + j) * 33 + lane] + (wv + pd[j]);
+                args.y_next[o] = 0.5f * (sacc + fabsf(sacc));   // read back by the next two kernels
+            }
+            if (TOL) {
+                // sbar <- (1 - theta) sbar + theta (acc + p_D), the residual of the averaged iterate
+                float sb[kChunk];
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j)
+                    sb[j] = ((live >> j) & 1u) ? __ldcs(args.sbar + (size_t)(row_base + r0 + j) * args.mp + c) : 0.f;
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) {
+                    if (!((live >> j) & 1u)) continue;
+                    const float rhat = buf[(r0 + j) * 33 + lane] + pd[j];
+                    __stcs(args.sbar + (size_t)(row_base + r0 + j) * args.mp + c,
+                           __fadd_rn(__fmul_rn(1.0f - args.it.theta, sb[j]), __fmul_rn(args.it.theta, rhat)));
+                }
+            }
+        }
+    }
+}
+
 template <int PHASE>
 __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, const float* buf, int lane, int row_base, int blk,
                                                int n_tile, int bn, int ncols_valid, float* __restrict__ Cdbg, int ldc,
@@ -23,91 +107,16 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
             const int b = row_base + rr;
             if (col_ok && b < args.B) Cdbg[(size_t)b * ldc + c] = buf[rr * 33 + lane];
         }
-    } else if (!args.it.check && !args.dual) {
-        // fast path (every iteration of a fixed-iteration solve, the iterations between two checks in tolerance mode):
-        // rows in chunks of kChunk with every global load of the chunk issued before the first use, so each warp keeps
-        // kChunk * (2 or 3) x 128 B in flight; streaming cache hints keep the operators in L2.  In tolerance mode stopped
-        // instances (done[b]) are skipped and the averaged residual sbar is carried along.
-        constexpr int kChunk = 16;
-#pragma unroll 1
-        for (int r0 = 0; r0 < 32; r0 += kChunk) {
-            if (PHASE == 1) {
-                if (args.p_only) {       // warm start: P_{-1} = M_G y_{-1}, nothing else
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j) {
-                        const int b = row_base + r0 + j;
-                        if (col_ok && b < args.B) args.P_cur[(size_t)b * args.np + c] = buf[(r0 + j) * 33 + lane];
-                    }
-                    continue;
-                }
-                float gp[kChunk], zo[kChunk], pp[kChunk];
-                unsigned live = 0;
-#pragma unroll
-                for (int j = 0; j < kChunk; ++j) {
-                    const int b = row_base + r0 + j;
-                    bool ok = col_ok && b < args.B;
-                    if (ok && args.done) ok = __ldg(args.done + b) == 0;
-                    live |= (ok ? 1u : 0u) << j;
-                    const size_t o = (size_t)b * args.np + c;
-                    gp[j] = ok ? __ldcs(args.g_P + o) : 0.f;
-                    zo[j] = ok ? __ldcs(args.z + o) : 0.f;
-                    pp[j] = ok ? __ldcs(args.P_prev + o) : 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < kChunk; ++j) {
-                    const int b = row_base + r0 + j;
-                    if (!((live >> j) & 1u)) continue;
-                    const size_t o = (size_t)b * args.np + c;
-                    float acc = buf[(r0 + j) * 33 + lane];
-                    __stcs(args.P_cur + o, acc);
-                    acc = momentum(acc, pp[j], args.it.beta);          // M_G w_v from P_v, P_{v-1}
-                    const float zh = acc - gp[j];
-                    __stcs(args.z + o, __fadd_rn(__fmul_rn(1.0f - args.it.theta, zo[j]), __fmul_rn(args.it.theta, zh)));
-                    if (args.it.store_zhat) __stcs(args.zhat + o, zh);
-                    float hi, lo;
-                    split_tf32(zh, hi, lo);
-                    args.zh_hi[o] = hi;      // re-read by product 2 of this iteration: default caching
-                    args.zh_lo[o] = lo;
-                }
-            } else {
-                float yc[kChunk], yp[kChunk], pd[kChunk];
-                unsigned live = 0;
-#pragma unroll
-                for (int j = 0; j < kChunk; ++j) {
-                    const int b = row_base + r0 + j;
-                    bool ok = col_ok && b < args.B;
-                    if (ok && args.done) ok = __ldg(args.done + b) == 0;
-                    live |= (ok ? 1u : 0u) << j;
-                    const size_t o = (size_t)b * args.mp + c;
-                    yc[j] = ok ? __ldcs(args.y_cur + o) : 0.f;
-                    yp[j] = ok ? __ldcs(args.y_prev + o) : 0.f;
-                    pd[j] = ok ? __ldcs(args.p_D + o) : 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < kChunk; ++j) {
-                    const int b = row_base + r0 + j;
-                    if (!((live >> j) & 1u)) continue;
-                    const size_t o = (size_t)b * args.mp + c;
-                    const float wv = momentum(yc[j], yp[j], args.it.beta);
-                    const float sacc = buf[(r0 + j) * 33 + lane] + (wv + pd[j]);
-                    args.y_next[o] = 0.5f * (sacc + fabsf(sacc));   // read back by the next two kernels
-                }
-                if (args.checking) {
-                    // tolerance mode: sbar <- (1 - theta) sbar + theta (acc + p_D), the residual of the averaged iterate
-                    float sb[kChunk];
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j)
-                        sb[j] = ((live >> j) & 1u) ? __ldcs(args.sbar + (size_t)(row_base + r0 + j) * args.mp + c) : 0.f;
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j) {
-                        if (!((live >> j) & 1u)) continue;
-                        const float rhat = buf[(r0 + j) * 33 + lane] + pd[j];
-                        __stcs(args.sbar + (size_t)(row_base + r0 + j) * args.mp + c,
-                               __fadd_rn(__fmul_rn(1.0f - args.it.theta, sb[j]), __fmul_rn(args.it.theta, rhat)));
-                    }
-                }
-            }
+    } else if (PHASE == 1 && args.p_only) {
+        // warm start: P_{-1} = M_G y_{-1}, nothing else
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+            const int b = row_base + rr;
+            if (col_ok && b < args.B) args.P_cur[(size_t)b * args.np + c] = buf[rr * 33 + lane];
         }
+    } else if (!args.it.check && !args.dual) {
+        if (args.done) fast_rows<PHASE, true>(args, buf, lane, row_base, c, col_ok);
+        else fast_rows<PHASE, false>(args, buf, lane, row_base, c, col_ok);
     } else {
         // general path: termination bookkeeping (per-row reductions, stopped instances)
 #pragma unroll 2

@@ -121,27 +121,32 @@ def lib():
         L.gpad_file_read.argtypes = [C.c_char_p, C.POINTER(FileData)]
         L.gpad_file_write.argtypes = [C.c_char_p, C.POINTER(FileData)]
         L.gpad_file_free.argtypes = [C.POINTER(FileData)]
-        L.gpad_solve_async.argtypes = [C.c_void_p, C.POINTER(SolveArgs), C.POINTER(C.c_longlong)]
-        L.gpad_wait.argtypes = [C.c_void_p, C.c_longlong]
-        L.gpad_handle_dims.argtypes = [C.c_void_p] + [_ip] * 6
-        L.gpad_solve_stats.argtypes = [C.c_void_p, C.POINTER(SolveStats)]
-        L.gpad_instances_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.gpad_plants_battery.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.POINTER(C.c_void_p)]
-        L.gpad_plants_destroy.argtypes = [C.c_void_p]
-        L.gpad_plants_dims.argtypes = [C.c_void_p] + [_ip] * 5
-        L.gpad_plants_operators.argtypes = [C.c_void_p, C.c_int, _fp, _fp, _fp]
-        L.gpad_plants_instances.argtypes = [C.c_void_p, _dp, _fp, _fp, _fp]
-        L.gpad_closed_loop_plants.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, _dp, C.c_int, _fp, _fp, C.c_int, C.c_int, _dp, _dp]
-        L.gpad_group_setup.argtypes = [C.POINTER(Config), _ip, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
-        L.gpad_group_destroy.argtypes = [C.c_void_p]
-        L.gpad_group_solve.argtypes = [C.c_void_p, C.POINTER(SolveArgs)]
-        L.gpad_group_size.argtypes = [C.c_void_p]
-        L.gpad_group_shard.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), _ip, _ip]
-        L.gpad_file_read_flat.argtypes = [C.c_char_p, C.POINTER(FileData)]
-        L.gpad_file_write_flat.argtypes = [C.c_char_p, C.POINTER(FileData)]
-        L.gpad_fixture_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(Fixture)]
-        L.gpad_fixture_write.argtypes = [C.c_char_p, C.POINTER(Fixture)]
-        L.gpad_fixture_free.argtypes = [C.POINTER(Fixture)]
+        v2 = {
+            "gpad_solve_async": [C.c_void_p, C.POINTER(SolveArgs), C.POINTER(C.c_longlong)],
+            "gpad_wait": [C.c_void_p, C.c_longlong],
+            "gpad_handle_dims": [C.c_void_p] + [_ip] * 6,
+            "gpad_solve_stats": [C.c_void_p, C.POINTER(SolveStats)],
+            "gpad_instances_device": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+            "gpad_plants_battery": [C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.POINTER(C.c_void_p)],
+            "gpad_plants_destroy": [C.c_void_p],
+            "gpad_plants_dims": [C.c_void_p] + [_ip] * 5,
+            "gpad_plants_operators": [C.c_void_p, C.c_int, _fp, _fp, _fp],
+            "gpad_plants_instances": [C.c_void_p, _dp, _fp, _fp, _fp],
+            "gpad_closed_loop_plants": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, _dp, C.c_int, _fp, _fp, C.c_int, C.c_int, _dp, _dp],
+            "gpad_group_setup": [C.POINTER(Config), _ip, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)],
+            "gpad_group_destroy": [C.c_void_p],
+            "gpad_group_solve": [C.c_void_p, C.POINTER(SolveArgs)],
+            "gpad_group_size": [C.c_void_p],
+            "gpad_group_shard": [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), _ip, _ip],
+            "gpad_file_read_flat": [C.c_char_p, C.POINTER(FileData)],
+            "gpad_file_write_flat": [C.c_char_p, C.POINTER(FileData)],
+            "gpad_fixture_read": [C.c_char_p, C.c_int, C.c_int, C.POINTER(Fixture)],
+            "gpad_fixture_write": [C.c_char_p, C.POINTER(Fixture)],
+            "gpad_fixture_free": [C.POINTER(Fixture)],
+        }
+        for name, sig in v2.items():          # API version 2 entry points (an older library simply lacks them)
+            if hasattr(L, name):
+                getattr(L, name).argtypes = sig
         L.gpad_debug_gemm_tf32x3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.gpad_debug_plan_tiles.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4
         _lib = L

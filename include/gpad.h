@@ -190,7 +190,7 @@ int gpad_handle_dims(gpad_handle_t h, int* n_u, int* N, int* m, int* mode, int* 
  * instance-iterations the GEMM kernels were scheduled for (128 x iterations per batch tile that still held a running
  * instance) and instance-iterations the instances needed (sum of iters); their ratio is the share of tensor work that
  * was useful, the rest rode along on stopped instances of partly finished tiles.  Instances stop at very different
- * iterations, so the library retires finished tiles and, whenever at most half of the working rows still run, gathers
+ * iterations, so the library retires finished tiles and, whenever a fifth of the working rows has stopped, gathers
  * the running instances into dense tiles (results do not depend on it). */
 typedef struct {
     double instance_iterations_scheduled;

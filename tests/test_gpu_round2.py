@@ -84,8 +84,10 @@ def test_quadrotor_batch_tolerance_matches_oracle(torch_cuda, G, oracle, eps, ch
     assert gpu["stats"]["scheduled"] < 0.8 * runs["plain"]["stats"]["scheduled"]           # compaction removes finished rows' work
     assert gpu["stats"]["needed"] == float(gpu["iters"].sum())
     for other in ("plain", "retire-only"):
-        for k in list(VECS) + ["iters", "status", "max_viol", "gap"]:
+        for k in list(VECS) + ["iters", "status", "max_viol"]:
             assert np.array_equal(gpu[k], runs[other][k], equal_nan=True), (other, k)
+        # the gap figure is summed with atomics over tiles (order varies from run to run): equal up to fp32 rounding
+        assert np.allclose(gpu["gap"], runs[other]["gap"], rtol=1e-3, atol=1e-4, equal_nan=True), other
     d_gpu, d_ref = gpu["iters"] - ora["iters"], ora["iters"] - it64
     n_gpu, n_ref = int((d_gpu != 0).sum()), int((d_ref != 0).sum())
     print(f" iteration counts: GPU != reference on {n_gpu} instances (median |d| {np.median(np.abs(d_gpu[d_gpu != 0])) if n_gpu else 0}), "
@@ -323,3 +325,74 @@ def test_step2_step4_fixture_formats_through_shims(torch_cuda, G, oracle, flat, 
     assert np.max(np.abs(dz.cpu().numpy() - f2["zhat_out"])) <= 1e-6          # the harness's own EPSILON (main_prof.cu:8)
     assert np.max(np.abs(dy.cpu().numpy() - f4["y_next"])) <= 1e-6
     assert np.array_equal(dy.cpu().numpy() > 0, f4["y_next"] > 0)
+
+
+# ------------------------------------------------------------------------------------ flat battery operators (f4)
+@pytest.mark.parametrize("dims", [(3, 4), (4, 3), (4, 6), (10, 15), (15, 10), (7, 33), (10, 100)])
+def test_flat_operator_latency_kernel_matches_oracle(torch_cuda, G, oracle, dims, monkeypatch):
+    """latency_flat.cu: the battery problem on its flattened operators (seq_functions.cpp:5-43, kernel_functions.cu:74-109)
+    on one thread-block cluster; forced for every size here (by default it replaces the whole-chip plans only), cold and
+    warm started, against the oracle (dense and flat step functions agree: tests/test_oracle.py) with the parity bound"""
+    n_u, N = dims
+    monkeypatch.setenv("GPAD_DEBUG", "latency_flat=1")
+    pb = P.battery(n_u, N)
+    rng = np.random.default_rng(n_u * 100 + N)
+    g_P, p_D, f = pb.instance(P.battery_x0(n_u, rng))
+    iters = 100 if n_u * N <= 200 else 60
+    theta, beta = schedule(iters)
+    s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_LATENCY)
+    assert "flat battery operators" in s.description, s.description
+    print("\n", s.description)
+    gpu = s.solve_host(g_P, p_D, theta, beta)
+    ora = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta)
+    f64 = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta)
+    worst = check_parity(gpu, ora, f64, f"flat latency {dims}")
+    assert int(gpu["iters"]) == iters and int(gpu["status"]) == 0
+    warm = s.solve_host(g_P, p_D, theta, beta, y0=gpu["y_next"], y_prev0=gpu["y"])
+    ora_w = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, y0=gpu["y_next"], y_prev0=gpu["y"])
+    f64_w = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, y0=gpu["y_next"], y_prev0=gpu["y"])
+    check_parity(warm, ora_w, f64_w, f"flat latency warm {dims}")
+    # the same handle in tolerance mode falls back to the dense kernels and still follows the oracle
+    th2, be2 = schedule(400)
+    tol = s.solve_host(g_P, p_D, th2, be2, check_every=1, eps_g=1e-2, eps_V=1e-2)
+    ora_t = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, th2, be2, L=pb.L, check_every=1, eps_g=1e-2, eps_V=1e-2)
+    assert int(tol["status"]) == int(ora_t["status"]) and int(tol["iters"]) == int(ora_t["iters"])
+    s.close()
+    print(f" flat {dims}: worst GPU-vs-oracle rel_inf {worst:.2e}")
+
+
+def test_flat_layout_input_and_automatic_detection(torch_cuda, G, oracle, monkeypatch):
+    """GPAD_LAYOUT_FLAT operators (the reference's flattened data-file variant) feed the same kernel; a dense problem
+    that is NOT flat (perturbed operators) keeps the dense kernels; by default (10,100) -- a whole-chip plan in dense
+    form -- is detected as flat and moved to one cluster"""
+    n_u, N = 4, 6
+    pb = P.battery(n_u, N)
+    g_P, p_D, _ = pb.instance(np.array([0.2, -0.3, 0.1, 0.45]))
+    theta, beta = schedule(80)
+    Mf, Gf, resid = G.flatten_operators(n_u, N, pb.m, pb.M_G, pb.G_L)
+    assert resid == 0.0
+    monkeypatch.setenv("GPAD_DEBUG", "latency_flat=1")
+    s_flat = G.Solver(n_u, N, pb.m, pb.L, Mf, Gf, layout=G.LAYOUT_FLAT, mode=G.MODE_LATENCY)
+    s_dense = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_LATENCY)
+    assert "flat battery operators" in s_flat.description and "flat battery operators" in s_dense.description
+    a, b = s_flat.solve_host(g_P, p_D, theta, beta), s_dense.solve_host(g_P, p_D, theta, beta)
+    for k in VECS:
+        assert np.array_equal(a[k], b[k]), k
+    s_flat.close(); s_dense.close()
+    M2 = pb.M_G.copy(); M2[0, 1] += 1e-3            # couples cell 0 with cell 1's multiplier: no longer flat
+    s = G.Solver(n_u, N, pb.m, pb.L, M2, pb.G_L, mode=G.MODE_LATENCY)
+    assert "flat battery operators" not in s.description
+    got = s.solve_host(g_P, p_D, theta, beta)
+    ora = oracle.solve(n_u, N, pb.m, M2, pb.G_L, g_P, p_D, theta, beta)
+    for k in VECS:
+        assert P.rel_inf(got[k], ora[k]) <= 2e-5, k
+    s.close()
+    monkeypatch.delenv("GPAD_DEBUG", raising=False)
+    big = P.battery(10, 100)
+    s = G.Solver(10, 100, big.m, big.L, big.M_G, big.G_L, mode=G.MODE_LATENCY)
+    assert "flat battery operators" in s.description, s.description
+    s.close()
+    monkeypatch.setenv("GPAD_DEBUG", "latency_flat=0")
+    s = G.Solver(10, 100, big.m, big.L, big.M_G, big.G_L, mode=G.MODE_LATENCY)
+    assert "column-partitioned" in s.description, s.description
+    s.close()
