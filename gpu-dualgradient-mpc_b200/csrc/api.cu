@@ -690,6 +690,8 @@ int gpad_setup(const gpad_config_t* cfg, const float* M_G, const float* G_L, gpa
         if (rc != GPAD_OK) break;
         rc = cfg->mode == GPAD_MODE_LATENCY ? setup_latency(h, MG, GL) : setup_batch(h, MG, GL);
     } while (0);
+    // setup work ran on several streams (legacy default stream included): everything has landed before the first solve
+    if (rc == GPAD_OK && cudaDeviceSynchronize() != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "gpad_setup", __FILE__, __LINE__); }
     if (rc != GPAD_OK) { gpad_destroy(h); return rc; }
     *out = h;
     return GPAD_OK;

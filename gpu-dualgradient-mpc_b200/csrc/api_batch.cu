@@ -63,6 +63,9 @@ int alloc_slot(gpad_handle_s* h, BatchSlot& sl, const BatchSlot* like) {
     GPAD_CUDA(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
     GPAD_CUDA(cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
     GPAD_CUDA(cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming));
+    // the memsets above ran on the legacy default stream, which the library's non-blocking streams do not wait for:
+    // they must have landed before the first solve copies inputs into these arrays
+    GPAD_CUDA(cudaDeviceSynchronize());
     sl.allocated = true;
     return GPAD_OK;
 }

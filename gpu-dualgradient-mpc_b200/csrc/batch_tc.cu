@@ -63,7 +63,7 @@ __host__ __device__ constexpr int epi_warps(int phase) { return kWorkWarps - xfo
 __host__ __device__ constexpr int cta_threads(int phase) { return 32 * (2 + kWorkWarps); }
 
 // PHASE 0: plain store of C (test hook); 1: GPAD product 1; 2: GPAD product 2
-template <int PHASE, int BK>
+template <int PHASE, int BK, bool TOL>
 __global__ void __launch_bounds__(cta_threads(PHASE), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -209,7 +209,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = __uint_as_float(v[j]);
                 __syncwarp();
-                epilogue_block<PHASE>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, Cdbg, ldc);
+                epilogue_block<PHASE, TOL>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, Cdbg, ldc);
                 __syncwarp();
             }
             tc_fence_before();
@@ -291,9 +291,9 @@ int pick_stages(int bk, int bn, size_t smem_limit) {
     return s;
 }
 
-template <int PHASE, int BK>
+template <int PHASE, int BK, bool TOL>
 static int launch_one(const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s) {
-    auto kern = tc_gemm_kernel<PHASE, BK>;
+    auto kern = tc_gemm_kernel<PHASE, BK, TOL>;
     const size_t smem = smem_bytes(BK, g.bn, g.stages);
     GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int units = g.m_tiles * g.n_tiles;
@@ -319,9 +319,11 @@ static int launch_one(const GemmDesc& g, const BatchKernelArgs& args, float* C, 
 
 int launch_gemm(int phase, const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s) {
     if (g.bk != 16) { set_error("tcgen05 GEMM: K block %d is not built (16 only)", g.bk); return GPAD_ERR_UNSUPPORTED; }
-    if (phase == 0) return launch_one<0, 16>(g, args, C, ldc, num_sms, s);
-    if (phase == 1) return launch_one<1, 16>(g, args, C, ldc, num_sms, s);
-    return launch_one<2, 16>(g, args, C, ldc, num_sms, s);
+    // fixed-iteration solves run the lean instantiation; tolerance mode (stopped rows, reductions, dual-gap launches) its own
+    const bool tol = args.checking || args.dual || args.done;
+    if (phase == 0) return launch_one<0, 16, false>(g, args, C, ldc, num_sms, s);
+    if (phase == 1) return tol ? launch_one<1, 16, true>(g, args, C, ldc, num_sms, s) : launch_one<1, 16, false>(g, args, C, ldc, num_sms, s);
+    return tol ? launch_one<2, 16, true>(g, args, C, ldc, num_sms, s) : launch_one<2, 16, false>(g, args, C, ldc, num_sms, s);
 }
 
 int launch_split(const float* src, float* hi, float* lo, size_t count, cudaStream_t s) {

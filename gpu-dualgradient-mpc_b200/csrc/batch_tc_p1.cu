@@ -69,7 +69,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-template <int EPI>
+template <int EPI, bool TOL>
 __global__ void __launch_bounds__(32 * (kP1FirstEpi + EPI), 1)
 tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmB_hi,
              const __grid_constant__ CUtensorMap tmB_lo, int num_k_blocks, int m_tiles, int n_tiles, int bn,
@@ -240,7 +240,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
 #pragma unroll
                 for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = __uint_as_float(v[j]);
                 __syncwarp();
-                epilogue_block<1>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, nullptr, 0, step);
+                epilogue_block<1, TOL>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, nullptr, 0, step);
                 __syncwarp();
             }
             tc_fence_before();
@@ -293,7 +293,8 @@ int plan_rings_p1(int bn, size_t smem_limit, int* a_stages, int* b_stages) {
 int launch_p1(const GemmDesc& g, const BatchKernelArgs& args, int num_sms, cudaStream_t s) {
     const size_t smem = p1_smem_bytes(g.bn, g.a_stages, g.stages, 8);
     const int tiles = g.m_tiles * g.n_tiles;
-    auto kern = tc_p1_kernel<8>;
+    const bool tol = args.checking || args.dual || args.done;
+    auto kern = tol ? tc_p1_kernel<8, true> : tc_p1_kernel<8, false>;
     GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(std::min(tiles, num_sms)); lc.blockDim = dim3(32 * (kP1FirstEpi + 8)); lc.dynamicSmemBytes = smem; lc.stream = s;
