@@ -72,6 +72,21 @@ affine_kernel(float* __restrict__ out, int ld, const double* __restrict__ M, siz
     }
 }
 
+// one matrix per instance (per-instance plants): every matrix entry is used once, so one thread per output reading its own
+// row is already coalesced across the outputs of an instance
+__global__ void affine_plants_kernel(float* __restrict__ out, int ld, const double* __restrict__ M, size_t mat_stride,
+                                     const double* __restrict__ b0, const double* __restrict__ invL_b, const double* __restrict__ x,
+                                     int nx, int rows, int B) {
+    const size_t total = (size_t)B * rows;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / rows), i = (int)(idx % rows);
+        const double* Mi = M + (size_t)b * mat_stride + (size_t)i * nx;
+        double s = b0 ? b0[i] : 0.0;
+        for (int c = 0; c < nx; ++c) s = __dadd_rn(s, __dmul_rn(Mi[c], x[(size_t)b * nx + c]));
+        out[(size_t)b * ld + i] = b0 ? (float)(-s * invL_b[b]) : (float)s;
+    }
+}
+
 inline dim3 affine_grid(int rows, int B) {
     const int gx = (rows + kAffRows - 1) / kAffRows;
     const int gy = std::max(1, std::min((B + kAffTB - 1) / kAffTB, (148 * 8 + gx - 1) / gx));
@@ -207,8 +222,13 @@ int run_loop(gpad_handle_t h, int B, int nx, int nu, int n, int m, int npar, int
 #undef TRYA
     if (x_traj) GPAD_CUDA(cudaMemcpyAsync(dxt, dx, sizeof(double) * B * nx, cudaMemcpyDeviceToDevice, s));
     for (int k = 0; k < samples; ++k) {
-        affine_kernel<<<affine_grid(n, B), kAffRows, 0, s>>>(gP, n, dKg, kg_stride, nullptr, 0.0, nullptr, dx, nx, dxref, nref, n, B);       // gpad.m:81
-        affine_kernel<<<affine_grid(m, B), kAffRows, 0, s>>>(pD, m, dBb, bb_stride, db0, invL, dinvL, dx, nx, dxref, nref, m, B);            // gpad.m:85
+        if (kg_stride) {        // one plant per instance
+            affine_plants_kernel<<<grid_for((size_t)B * n), 256, 0, s>>>(gP, n, dKg, kg_stride, nullptr, nullptr, dx, nx, n, B);             // gpad.m:81
+            affine_plants_kernel<<<grid_for((size_t)B * m), 256, 0, s>>>(pD, m, dBb, bb_stride, db0, dinvL, dx, nx, m, B);                   // gpad.m:85
+        } else {
+            affine_kernel<<<affine_grid(n, B), kAffRows, 0, s>>>(gP, n, dKg, 0, nullptr, 0.0, nullptr, dx, nx, dxref, nref, n, B);           // gpad.m:81
+            affine_kernel<<<affine_grid(m, B), kAffRows, 0, s>>>(pD, m, dBb, 0, db0, invL, nullptr, dx, nx, dxref, nref, m, B);              // gpad.m:85
+        }
         GPAD_CUDA(cudaGetLastError());
         gpad_solve_args_t a{};
         a.batch = B; a.mem = GPAD_MEM_DEVICE; a.stream = s;
@@ -278,6 +298,54 @@ int closed_loop_device(gpad_problem_t p, gpad_handle_t h, int B, const double* x
                     d->blocks, (int)p->blocks.size(), x0, xref, samples, theta, beta, max_iter, warm_start, x_traj, u_traj, st.s);
 }
 
+// device copies of one shard of plants (uploaded once per (device, first, count): 1.6 KB of maps per plant)
+struct PlantsDev {
+    int device = -1, first = 0, count = 0;
+    DevBufs mem;
+    double *Kg = nullptr, *Bb = nullptr, *b0 = nullptr, *A = nullptr, *Bm = nullptr, *invL = nullptr;
+    int* blocks = nullptr;
+};
+
+void plants_dev_free(void* cache) {
+    PlantsDev* d = static_cast<PlantsDev*>(cache);
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    cudaSetDevice(d->device);
+    delete d;
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+}
+
+static int plants_dev_get(gpad_plants_t p, int device, int first, int count, PlantsDev** out) {
+    std::lock_guard<std::mutex> lock(p->dev_mutex);
+    for (void* c : p->dev_cache) {
+        PlantsDev* d = static_cast<PlantsDev*>(c);
+        if (d->device == device && d->first == first && d->count == count) { *out = d; return GPAD_OK; }
+    }
+    PlantsDev* d = new PlantsDev;
+    d->device = device; d->first = first; d->count = count;
+    const int n = p->n, m = p->m, np = p->n_par, nx = p->nx, nu = p->n_u;
+    std::vector<double> invL(count);
+    for (int b = 0; b < count; ++b) invL[b] = 1.0 / p->L[first + b];
+    std::vector<int> blk;
+    for (auto& b : p->blocks) { blk.push_back(b.first); blk.push_back(b.second); }
+    int rc = GPAD_OK;
+    do {
+        if ((rc = d->mem.upload(&d->Kg, &p->Kg[(size_t)first * n * np], (size_t)count * n * np, nullptr)) != GPAD_OK) break;
+        if ((rc = d->mem.upload(&d->Bb, &p->Bb[(size_t)first * m * np], (size_t)count * m * np, nullptr)) != GPAD_OK) break;
+        if ((rc = d->mem.upload(&d->b0, p->b0.data(), p->b0.size(), nullptr)) != GPAD_OK) break;
+        if ((rc = d->mem.upload(&d->A, p->A.data(), p->A.size(), nullptr)) != GPAD_OK) break;
+        if ((rc = d->mem.upload(&d->Bm, &p->Bm[(size_t)first * nx * nu], (size_t)count * nx * nu, nullptr)) != GPAD_OK) break;
+        if ((rc = d->mem.upload(&d->invL, invL.data(), invL.size(), nullptr)) != GPAD_OK) break;
+        if ((rc = d->mem.upload(&d->blocks, blk.data(), blk.size(), nullptr)) != GPAD_OK) break;
+        if (cudaStreamSynchronize(nullptr) != cudaSuccess) { cudaGetLastError(); rc = GPAD_ERR_CUDA; }     // invL / blk are locals
+    } while (0);
+    if (rc != GPAD_OK) { delete d; return rc; }
+    p->dev_cache.push_back(d);
+    *out = d;
+    return GPAD_OK;
+}
+
 int closed_loop_plants_device(gpad_plants_t p, gpad_handle_t h, int first, int count, const double* x0, int samples,
                               const float* theta, const float* beta, int max_iter, int warm_start, double* x_traj,
                               double* u_traj) {
@@ -287,24 +355,11 @@ int closed_loop_plants_device(gpad_plants_t p, gpad_handle_t h, int first, int c
     GPAD_CUDA(dev.status);
     StreamScope st;
     GPAD_CUDA(st.status);
+    PlantsDev* d = nullptr;
+    GPAD_TRY_RC(plants_dev_get(p, device, first, count, &d));
     const int n = p->n, m = p->m, np = p->n_par, nx = p->nx, nu = p->n_u;
-    DevBufs d;
-    double *dKg, *dBb, *db0, *dA, *dBm, *dinvL;
-    int* dblk;
-    std::vector<double> invL(count);
-    for (int b = 0; b < count; ++b) invL[b] = 1.0 / p->L[first + b];
-    std::vector<int> blk;
-    for (auto& b : p->blocks) { blk.push_back(b.first); blk.push_back(b.second); }
-    GPAD_TRY_RC(d.upload(&dKg, &p->Kg[(size_t)first * n * np], (size_t)count * n * np, st.s));
-    GPAD_TRY_RC(d.upload(&dBb, &p->Bb[(size_t)first * m * np], (size_t)count * m * np, st.s));
-    GPAD_TRY_RC(d.upload(&db0, p->b0.data(), p->b0.size(), st.s));
-    GPAD_TRY_RC(d.upload(&dA, p->A.data(), p->A.size(), st.s));
-    GPAD_TRY_RC(d.upload(&dBm, &p->Bm[(size_t)first * nx * nu], (size_t)count * nx * nu, st.s));
-    GPAD_TRY_RC(d.upload(&dinvL, invL.data(), invL.size(), st.s));
-    GPAD_TRY_RC(d.upload(&dblk, blk.data(), blk.size(), st.s));
-    GPAD_CUDA(cudaStreamSynchronize(st.s));          // invL / blk are locals: their copies must have left
-    return run_loop(h, count, nx, nu, n, m, np, p->N, dKg, (size_t)n * np, dBb, (size_t)m * np, db0, 0.0, dinvL, dA, dBm,
-                    (size_t)nx * nu, dblk, (int)p->blocks.size(), x0, nullptr, samples, theta, beta, max_iter, warm_start, x_traj,
+    return run_loop(h, count, nx, nu, n, m, np, p->N, d->Kg, (size_t)n * np, d->Bb, (size_t)m * np, d->b0, 0.0, d->invL, d->A, d->Bm,
+                    (size_t)nx * nu, d->blocks, (int)p->blocks.size(), x0, nullptr, samples, theta, beta, max_iter, warm_start, x_traj,
                     u_traj, st.s);
 }
 

@@ -20,6 +20,7 @@ struct Knobs {
     int latency_grid2 = -1;          // -1 auto; 0 forces the generic whole-chip kernel
     int latency_warp = -1;           // -1 auto; 0 forces the one-CTA kernel for tiny problems
     int latency_flat = -1;           // -1 auto; 0 expands flat operators to the dense kernels
+    int flat_xchg = 0;               // flat kernel exchange: 0 bulk DSMEM copies, 1 per-entry st.async
     int warp_rows = 0, warp_ordered = -1;   // one-warp kernel schedule (0 / -1: chosen by batch size)
     int tc_p1 = -1;                  // product 1: -1 waves model, 1 TMEM-operand kernel, 0 shared-memory-operand kernel
     int tc_stages = 0;               // cap on its ring depth (0: as many as fit)

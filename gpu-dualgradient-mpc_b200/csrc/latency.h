@@ -57,6 +57,7 @@ struct FlatParams {
     int w_len;               // floats of the permuted multiplier vector in shared memory (with zero padding)
     int sched;               // theta / beta entries staged in shared memory
     int C, threads, rows_b;  // cluster size, threads per CTA, rows of G_L per CTA
+    int xchg;                // 0: bulk copies of each CTA's block, 1: per-entry asynchronous stores
     const float* A_op;       // [n][lenA]   row (s, u): cell u's box entries of M_G, then the sum-constraint entries
     const float* B_op;       // [m][N4]     row i: its N entries of G_L
     const float* g_P; const float* p_D; const float* y0; const float* y_prev0;

@@ -10,17 +10,22 @@
 // 3.4 MB instead of 33.6 MB: the whole problem lives in ONE 16-CTA cluster (shared memory + registers) and the two
 // whole-chip grid barriers per iteration of latency_grid2.cu become two DSMEM exchanges.
 //
-// Layout inside the kernel (everything permuted so that every dot product runs over contiguous, 16-byte aligned data):
-//   w_s   [n_u][Q] cell-major box multipliers (Q = 4N entries per cell), then the tail (sum-constraint multipliers)
-//   zh_s  [n_u + 1][N4] cell-major zhat, then S[s] = sum_u zhat[s,u]
+// Layout inside the kernel (everything permuted so that every dot product runs over contiguous, 16-byte aligned data
+// and every CTA PRODUCES a contiguous block of each exchanged vector):
+//   w_s   [n_u][Q] cell-major box multipliers (Q = 4N entries per cell), then the tail (sum-constraint multipliers);
+//         CTA c owns POSITIONS [c R, (c+1) R) of it, thread t the row of G_L whose multiplier lives at position c R + t
+//   zh_s  [C][n_u + 1][8]: block c holds the (<= 8) stages CTA c owns, cell-major, plus S[s] = sum_u zhat[s,u]
 //   phase A: CTA c owns SC consecutive stages; WARP u handles cell u of those stages: a lane holds float4 chunks of the
 //            row vector [w_s segment u | tail] and accumulates SC rows against them (operator rows in shared memory,
-//            one vector load serves SC rows); lane sl then owns row (s_sl, u): zhat, z average, exchange
-//   S:       one block barrier, SC threads sum their stage over the cells in a fixed order and exchange S
-//   phase B: one THREAD per row of G_L (its N4 operator entries in registers, CHB float4), box rows read cell
-//            i % n_u's segment of zh_s, sum rows read S
-//   exchange: as in latency_small.cu -- every produced entry is an asynchronous 4-byte store into each CTA's shared
-//            memory crediting that CTA's mbarrier; consumers wait on their own barrier, no cluster barrier in the loop.
+//            one vector load serves SC rows); lane sl then owns row (s_sl, u): zhat, z average, into the CTA's own block
+//   S:       one block barrier, SC threads sum their stage over the cells in a fixed order
+//   phase B: one THREAD per row of G_L (its operator entries in registers, stage-padded like zh_s: 2 float4 per CTA
+//            block), box rows read their cell's 8 floats of every block, sum rows read S
+//   exchange: every CTA writes what it produced into its OWN shared memory and ships the block to its 15 peers with one
+//            bulk asynchronous copy each (cp.async.bulk shared::cta -> shared::cluster, completing bytes on the peer's
+//            mbarrier); consumers wait on their own mbarrier, no cluster barrier in the loop.  (The first version stored
+//            every entry into every CTA with st.async.b32, like latency_small.cu: 5.3 k four-byte remote stores per CTA
+//            and iteration took 8 us per iteration -- the remote-store issue rate, ~2.5 clk each, was the bound.)
 // Fixed-iteration solves (the reference's behaviour, main.cu:87); tolerance-mode solves of the same handle run the dense
 // kernels.  Same arithmetic as everywhere else: unfused step 1 / step 3 / (w + p_D) / projection, tree-ordered dots.
 #include <cooperative_groups.h>
@@ -30,6 +35,7 @@
 #include <vector>
 
 #include "gpad_internal.h"
+#include "lat_util.cuh"
 #include "latency.h"
 
 namespace gpad {
@@ -46,11 +52,20 @@ __device__ __forceinline__ uint32_t f_mapa(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void f_st_async_all(uint32_t data0, uint32_t bar0, uint32_t stride, float v, int C) {
+// one 4-byte asynchronous store into every OTHER CTA of the cluster, each crediting that CTA's mbarrier
+__device__ __forceinline__ void f_st_async_peers(uint32_t data0, uint32_t bar0, uint32_t stride, float v, int C, int self) {
     const uint32_t bits = __float_as_uint(v);
     for (int r = 0; r < C; ++r, data0 += stride, bar0 += stride)
-        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
-                     ::"r"(data0), "r"(bits), "r"(bar0) : "memory");
+        if (r != self)
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                         ::"r"(data0), "r"(bits), "r"(bar0) : "memory");
+}
+// one bulk copy of `bytes` (multiple of 16) from this CTA's shared memory to the same offset in CTA `rank`, completing on
+// that CTA's mbarrier
+__device__ __forceinline__ void f_bulk_to_peer(uint32_t src_cta, uint32_t dst_rank0, uint32_t bar_rank0, uint32_t stride, int rank,
+                                               uint32_t bytes) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_rank0 + (uint32_t)rank * stride), "r"(src_cta), "r"(bytes), "r"(bar_rank0 + (uint32_t)rank * stride) : "memory");
 }
 __device__ __forceinline__ void f_mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -72,19 +87,25 @@ __device__ __forceinline__ float f_dot4(const float4 a, const float4 b, float ac
     return acc;
 }
 
-template <int CHB>
-__global__ void __launch_bounds__(kMaxThreads) gpad_flat_kernel(const FlatParams p) {
+// XCHG 0: bulk copies of the CTA's block; XCHG 1: every producing thread stores its entry straight into the peers
+// (st.async.b32; a warp's entries are contiguous in the destination)
+// big clusters hold 2 * CL float4 of G_L per thread in registers: at most 384 threads there, so that ptxas gets 168 registers
+constexpr int flat_max_threads(int cl) { return cl >= 8 ? 384 : kMaxThreads; }
+
+template <int CL, int XCHG>
+__global__ void __launch_bounds__(flat_max_threads(CL)) gpad_flat_kernel(const FlatParams p) {
+    constexpr int CHB = 2 * CL;                          // float4 fragments of a phase-B row: 8 stage slots per CTA block
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const int rank = (int)blockIdx.x, C = (int)gridDim.x;
-    const int n_u = p.n_u, N = p.N, n = n_u * N, m = p.m, Q = p.Q, N4 = p.N4;
-    const int box = n_u * Q, SC = p.SC, CHA = p.CHA, lenA = p.lenA;
+    const int rank = (int)blockIdx.x;
+    const int n_u = p.n_u, N = p.N, m = p.m, Q = p.Q;
+    const int box = n_u * Q, SC = p.SC, CHA = p.CHA, lenA = p.lenA, R = p.rows_b;
+    const int zblk = (n_u + 1) * 8;                      // floats per CTA block of zh_s
     float* w_s = smem;                                  // [w_len]  permuted multipliers (+ zero padding)
-    float* zh_s = w_s + p.w_len;                        // [(n_u + 1) * N4]
-    float* zloc = zh_s + (n_u + 1) * N4;                // [SC * n_u] this CTA's zhat, stage-major (for S)
-    float* th_s = zloc + kFlatMaxSC * 16;               // [sched] theta
+    float* zh_s = w_s + p.w_len;                        // [CL][n_u + 1][8]
+    float* th_s = zh_s + CL * zblk;                     // [sched] theta
     float* be_s = th_s + p.sched;                       // [sched] beta
-    uint64_t* xbar = reinterpret_cast<uint64_t*>(be_s + p.sched);      // [2] mbarriers (8-byte aligned: all counts are even)
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(be_s + p.sched);      // [2] mbarriers
     float* a_s = reinterpret_cast<float*>(xbar + 2);    // [SC * n_u][lenA] this CTA's rows of the phase-A operator
 
     // ---- phase-A operator rows of this CTA: global -> shared memory, once ----
@@ -100,24 +121,30 @@ __global__ void __launch_bounds__(kMaxThreads) gpad_flat_kernel(const FlatParams
             dst[k] = s < N ? __ldg(src + (size_t)(s * n_u + r % n_u) * l4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
-    // ---- phase-B operator row of this thread: global -> registers, once ----
-    const int row_b = rank * p.rows_b + tid;
-    const bool own_b = tid < p.rows_b && row_b < m;
+    // ---- phase-B row of this thread: the row of G_L whose multiplier lives at position rank R + tid of w_s ----
+    const int pos_b = rank * R + tid;
+    int row_b = -1;
+    if (tid < R) {
+        if (pos_b < box) row_b = (pos_b % Q) * n_u + pos_b / Q;
+        else if (pos_b < m) row_b = pos_b;
+    }
+    const bool own_b = row_b >= 0;
     float4 rb[CHB];
     {
-        const float4* src = reinterpret_cast<const float4*>(p.B_op + (size_t)min(row_b, m - 1) * (4 * CHB));
+        const float4* src = reinterpret_cast<const float4*>(p.B_op + (size_t)max(row_b, 0) * (4 * CHB));
 #pragma unroll
         for (int k = 0; k < CHB; ++k) rb[k] = own_b ? __ldg(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const int seg_b = row_b < box ? row_b % n_u : n_u;                        // which segment of zh_s this row reads
-    const int pos_b = row_b < box ? (row_b % n_u) * Q + row_b / n_u : row_b;  // where this row's multiplier lives in w_s
-    const float4* zh4 = reinterpret_cast<const float4*>(zh_s + seg_b * N4);
+    const int seg_b = (own_b && row_b < box) ? row_b % n_u : n_u;               // cell segment, or S for the sum rows
+    const float4* zh4 = reinterpret_cast<const float4*>(zh_s + seg_b * 8);
 
-    // ---- phase-A role: warp u < n_u handles cell u of the CTA's stages; lane sl < SC then owns row (s0 + sl, u) ----
+    // ---- phase-A role: warp u < n_u handles cell u of the CTA's stages; after the transposed butterfly lane 4 sl holds
+    //      the total of stage slot sl and owns row (s0 + sl, u) ----
     const bool warp_a = warp < n_u;
     const int u = warp;
-    const int s_me = s0 + lane;
-    const bool own_a = warp_a && lane < SC && s_me < N;
+    const int sl_me = lane >> 2;                         // stage slot whose row total this lane ends up with
+    const int s_me = s0 + sl_me;
+    const bool own_a = warp_a && (lane & 3) == 0 && sl_me < SC && s_me < N;
     const int row_a = s_me * n_u + u;
     int voff[kFlatMaxCHA];                               // float offset into w_s of this lane's vector chunks
 #pragma unroll
@@ -139,26 +166,49 @@ __global__ void __launch_bounds__(kMaxThreads) gpad_flat_kernel(const FlatParams
         w_r = __fadd_rn(yv, __fmul_rn(beta0, __fsub_rn(yv, yp)));      // step 1 of iteration 0
     }
     for (int i = tid; i < p.w_len; i += nthr) w_s[i] = 0.f;
-    for (int i = tid; i < (n_u + 1) * N4; i += nthr) zh_s[i] = 0.f;
+    for (int i = tid; i < CL * zblk; i += nthr) zh_s[i] = 0.f;
     const bool sched_in_smem = p.max_iter <= p.sched;
     if (sched_in_smem)
         for (int i = tid; i < p.max_iter; i += nthr) { th_s[i] = p.theta[i]; be_s[i] = p.beta[i]; }
     const uint32_t zbar = f_smem_addr(xbar), wbar = f_smem_addr(xbar + 1);
     const uint32_t zbar0 = f_mapa(zbar, 0), wbar0 = f_mapa(wbar, 0);
-    const uint32_t cstride = C > 1 ? f_mapa(zbar, 1) - zbar0 : 0;
-    const uint32_t zh0 = f_mapa(f_smem_addr(zh_s), 0), w0 = f_mapa(f_smem_addr(w_s), 0);
-    const uint32_t zh_dst = zh0 + 4u * (uint32_t)(u * N4 + s_me);              // own_a: zhat[s_me, u]
-    const uint32_t s_dst = zh0 + 4u * (uint32_t)(n_u * N4 + s0 + tid);         // tid < SC: S[s0 + tid]
-    const uint32_t w_dst = w0 + 4u * (uint32_t)pos_b;
+    const uint32_t cstride = CL > 1 ? f_mapa(zbar, 1) - zbar0 : 0;
+    // this CTA's blocks of the two exchanged vectors: local address (source) and rank-0 view of the same offset (destination)
+    float* w_mine = w_s + rank * R;
+    float* zh_mine = zh_s + rank * zblk;
+    const uint32_t w_src = f_smem_addr(w_mine), zh_src = f_smem_addr(zh_mine);
+    const uint32_t w_dst0 = f_mapa(w_src, 0), zh_dst0 = f_mapa(zh_src, 0);
+    const uint32_t w_bytes = 4u * R, zh_bytes = 4u * zblk;
     uint32_t zpar = 0, wpar = 0;
     if (tid == 0) {
         f_mbar_init(zbar, 1); f_mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    f_cluster_sync();                         // every CTA's vectors are zeroed / barriers initialised before anyone stores into them
-    if (own_b) f_st_async_all(w_dst, wbar0, cstride, w_r, C);
-    if (tid == 0) f_mbar_expect(wbar, 4u * m);
-    f_mbar_wait(wbar, wpar); wpar ^= 1;
+    f_cluster_sync();                         // every CTA's vectors are zeroed / barriers initialised before anyone copies into them
+
+    // ships this CTA's block of an exchanged vector to the peers (after every thread's writes to it are visible to the
+    // asynchronous proxy) and waits until the peers' blocks have landed here
+    auto exchange = [&](uint32_t src, uint32_t dst0, uint32_t bar_local, uint32_t bar0, uint32_t bytes, uint32_t& parity) {
+        __syncthreads();
+        if (CL > 1) {
+            if (tid == 0) f_mbar_expect(bar_local, (uint32_t)(CL - 1) * bytes);
+            if (XCHG == 0 && tid < CL && tid != rank) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the block's (barrier-ordered) writes -> async proxy
+                f_bulk_to_peer(src, dst0, bar0, cstride, tid, bytes);
+            }
+            f_mbar_wait(bar_local, parity); parity ^= 1;
+        }
+    };
+    // XCHG 1: rank-0 views of this thread's own entries
+    const uint32_t w_ent0 = w_dst0 + 4u * (uint32_t)tid;                        // tid < R
+    const uint32_t zh_ent0 = zh_dst0 + 4u * (uint32_t)(u * 8 + sl_me);          // lanes 4 sl (zero for the padding slots)
+    const uint32_t s_ent0 = zh_dst0 + 4u * (uint32_t)(n_u * 8 + tid);           // tid < 8
+
+    if (tid < R) {
+        w_mine[tid] = own_b ? w_r : 0.f;
+        if (XCHG == 1) f_st_async_peers(w_ent0, wbar0, cstride, own_b ? w_r : 0.f, CL, rank);
+    }
+    exchange(w_src, w_dst0, wbar, wbar0, w_bytes, wpar);
 
     for (int v = 0; v < p.max_iter; ++v) {
         const float theta = sched_in_smem ? th_s[v] : __ldg(p.theta + v);
@@ -167,69 +217,70 @@ __global__ void __launch_bounds__(kMaxThreads) gpad_flat_kernel(const FlatParams
         const float one_minus = 1.0f - theta;
 
         // ---------------- phase A: zhat = M_G w - g_P, z average ----------------
+        // straight-line code: loads and products of absent chunks / stage slots are predicated off (a branch per slot
+        // would serialise the eight reductions: measured 1.3 us per iteration on a problem that needs 0.4)
         if (warp_a) {
             float acc[kFlatMaxSC];
 #pragma unroll
             for (int sl = 0; sl < kFlatMaxSC; ++sl) acc[sl] = 0.f;
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int ch = 0; ch < kFlatMaxCHA; ++ch) {
-                if (ch < CHA) {
-                    const float4 x = *reinterpret_cast<const float4*>(w_s + voff[ch]);
-                    const float* a = a_s + (size_t)u * lenA + (ch * 32 + lane) * 4;
+                const bool have = ch < CHA;
+                const float4 x = have ? *reinterpret_cast<const float4*>(w_s + voff[ch]) : zero4;
+                const float* a = a_s + (size_t)u * lenA + (ch * 32 + lane) * 4;
 #pragma unroll
-                    for (int sl = 0; sl < kFlatMaxSC; ++sl)
-                        if (sl < SC) acc[sl] = f_dot4(*reinterpret_cast<const float4*>(a + (size_t)sl * n_u * lenA), x, acc[sl]);
+                for (int sl = 0; sl < kFlatMaxSC; ++sl) {
+                    const float4 av = (have && sl < SC) ? *reinterpret_cast<const float4*>(a + (size_t)sl * n_u * lenA) : zero4;
+                    acc[sl] = f_dot4(av, x, acc[sl]);
                 }
             }
-            float mine = 0.f;
-#pragma unroll
-            for (int sl = 0; sl < kFlatMaxSC; ++sl) {
-                if (sl < SC) {
-                    float d = acc[sl];
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                    if (lane == sl) mine = d;
-                }
-            }
+            const float mine = warp_sum_transposed_v<kFlatMaxSC>(acc, lane);      // lane l: total of slot (l >> 2) & 7
             if (own_a) {
                 zh_r = mine - gp_r;
                 z_r = __fadd_rn(__fmul_rn(one_minus, z_r), __fmul_rn(theta, zh_r));
-                zloc[lane * n_u + u] = zh_r;
-                f_st_async_all(zh_dst, zbar0, cstride, zh_r, C);
+                zh_mine[u * 8 + sl_me] = zh_r;
             }
+            // XCHG 1: all 8 slots of the cell's row travel (the padding slots carry zeros), so that every CTA receives
+            // exactly one block's worth of bytes
+            if (XCHG == 1 && (lane & 3) == 0) f_st_async_peers(zh_ent0, zbar0, cstride, own_a ? zh_r : 0.f, CL, rank);
         }
         __syncthreads();
-        if (tid < SC && s0 + tid < N) {      // S[s] = sum_u zhat[s,u], fixed order
+        if (tid < 8) {                        // S[s] = sum_u zhat[s,u], fixed order (zero for the padding slots)
+            float part[16];
+#pragma unroll
+            for (int uu = 0; uu < 16; ++uu) part[uu] = uu < n_u ? zh_mine[uu * 8 + tid] : 0.f;
             float S = 0.f;
-            for (int uu = 0; uu < n_u; ++uu) S += zloc[tid * n_u + uu];
-            f_st_async_all(s_dst, zbar0, cstride, S, C);
+#pragma unroll
+            for (int uu = 0; uu < 16; ++uu) S += part[uu];
+            zh_mine[n_u * 8 + tid] = S;
+            if (XCHG == 1) f_st_async_peers(s_ent0, zbar0, cstride, S, CL, rank);
         }
-        if (tid == 0) f_mbar_expect(zbar, 4u * (n + N));     // all of zhat_v and S
-        f_mbar_wait(zbar, zpar); zpar ^= 1;
+        exchange(zh_src, zh_dst0, zbar, zbar0, zh_bytes, zpar);
 
         // ---------------- phase B: y+ = max(G_L zhat + (w + p_D), 0), momentum ----------------
         {
             float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-            for (int k = 0; k < CHB; k += 2) {
-                d0 = f_dot4(rb[k], zh4[k], d0);
-                if (k + 1 < CHB) d1 = f_dot4(rb[k + 1], zh4[k + 1], d1);
+            for (int c = 0; c < CL; ++c) {
+                const float4* zc = zh4 + c * (zblk / 4);
+                d0 = f_dot4(rb[2 * c], zc[0], d0);
+                d1 = f_dot4(rb[2 * c + 1], zc[1], d1);
             }
             if (own_b) {
                 const float s = (d0 + d1) + (w_r + pd_r);
                 yn = 0.5f * (s + fabsf(s));
                 if (!last) {            // advance; on the last iteration w_v, y_v stay (they are outputs)
                     const float wn = __fadd_rn(yn, __fmul_rn(beta_next, __fsub_rn(yn, yv)));
-                    f_st_async_all(w_dst, wbar0, cstride, wn, C);
+                    w_mine[tid] = wn;
                     w_r = wn;
                     yp = yv; yv = yn;
                 }
             }
+            // XCHG 1: every position of the block travels (positions without a row carry their zero)
+            if (XCHG == 1 && !last && tid < R) f_st_async_peers(w_ent0, wbar0, cstride, own_b ? w_r : 0.f, CL, rank);
         }
-        if (!last) {
-            if (tid == 0) f_mbar_expect(wbar, 4u * m);       // all m entries of w_{v+1}
-            f_mbar_wait(wbar, wpar); wpar ^= 1;
-        }
+        if (!last) exchange(w_src, w_dst0, wbar, wbar0, w_bytes, wpar);
     }
 
     // ---------------- outputs (main.cu:176-180 + termination outputs) ----------------
@@ -244,7 +295,7 @@ __global__ void __launch_bounds__(kMaxThreads) gpad_flat_kernel(const FlatParams
     }
     int bad = __syncthreads_or(own_b && !isfinite(yn));
     if (tid == 0 && bad) atomicExch(p.nonfinite_flag, 1);
-    f_cluster_sync();                          // no CTA exits while a peer may still store into it; flags are published
+    f_cluster_sync();                          // no CTA exits while a peer may still copy into it; flags are published
     if (rank == 0 && tid == 0) {
         __threadfence();
         if (p.out_iters) *p.out_iters = p.max_iter;
@@ -255,16 +306,24 @@ __global__ void __launch_bounds__(kMaxThreads) gpad_flat_kernel(const FlatParams
 }
 
 size_t flat_smem_bytes(const FlatParams& p) {
-    return ((size_t)p.w_len + (size_t)(p.n_u + 1) * p.N4 + kFlatMaxSC * 16 + 2 * (size_t)p.sched + 4 +
-            (size_t)p.SC * p.n_u * p.lenA) * sizeof(float) + 16;
+    return ((size_t)p.w_len + (size_t)p.C * (p.n_u + 1) * 8 + 2 * (size_t)p.sched + 4 + (size_t)p.SC * p.n_u * p.lenA) * sizeof(float) + 16;
 }
 
-template <int CHB>
+template <int CL>
 int launch_flat_t(const FlatParams& p, cudaStream_t stream) {
-    auto kern = gpad_flat_kernel<CHB>;
+    auto kern = p.xchg == 0 ? gpad_flat_kernel<CL, 0> : gpad_flat_kernel<CL, 1>;
     const size_t smem = flat_smem_bytes(p);
-    GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (p.C > 8) GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    // function attributes are set when they have to grow (per device): cudaFuncSetAttribute costs tens of microseconds of
+    // host time, which a single-QP latency solve would pay on every call
+    static size_t smem_set[2][64] = {};
+    int dev = 0;
+    GPAD_CUDA(cudaGetDevice(&dev));
+    size_t& have = smem_set[p.xchg ? 1 : 0][dev & 63];
+    if (smem > have) {
+        GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (p.C > 8) GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        have = smem;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.C); cfg.blockDim = dim3(p.threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -287,22 +346,17 @@ bool plan_flat(int n_u, int N, int m, size_t smem_limit, int max_cluster, FlatPa
     const int T4 = round_up(m - box, 4);
     p.lenA = round_up(p.Q + T4, 128);                  // 32 lanes x float4
     p.CHA = p.lenA / 128;
-    p.N4 = round_up(N, 4);
-    p.CHB = p.N4 / 4;
-    const int chb_built[] = {1, 2, 4, 8, 16, 25, 32};
-    int chb = 0;
-    for (int c : chb_built) if (c >= p.CHB) { chb = c; break; }
-    if (p.CHA > kFlatMaxCHA || chb == 0) return false;
-    p.CHB = chb; p.N4 = 4 * chb;
-    p.w_len = box + T4 + 128;                          // the last chunk of a row vector may read past the tail: zero padding
+    if (p.CHA > kFlatMaxCHA) return false;
     p.sched = 256;
     for (int C : {1, 2, 4, 8, 16}) {
         if (C > max_cluster) break;
         p.C = C;
         p.SC = (N + C - 1) / C;
-        p.rows_b = (m + C - 1) / C;
+        p.rows_b = round_up((m + C - 1) / C, 4);       // positions of w_s per CTA: a 16-byte multiple for the bulk copies
+        p.N4 = 8 * C; p.CHB = 2 * C;
+        p.w_len = std::max(box + T4, C * p.rows_b) + 128;      // the last chunk of a row vector may read past the tail: zero padding
         p.threads = std::max(32 * n_u, round_up(p.rows_b, 32));
-        if (p.SC > kFlatMaxSC || p.threads > kMaxThreads) continue;
+        if (p.SC > kFlatMaxSC || p.threads > flat_max_threads(C)) continue;
         if (flat_smem_bytes(p) > smem_limit) continue;
         *out = p;
         return true;
@@ -322,30 +376,30 @@ float build_flat_operators(const FlatParams& p, const float* MG, const float* GL
             for (int q = 0; q < p.Q; ++q) dst[q] = src[q * n_u + u];              // cell u's box multipliers
             for (int k = box; k < m; ++k) dst[p.Q + (k - box)] = src[k];          // the sum-constraint multipliers
         }
+    // row i of G_L, stage s = c SC + sl -> slot c * 8 + sl (the stage padding of zh_s)
     B_op.assign((size_t)m * p.N4, 0.f);
+    auto slot = [&](int s) { return (s / p.SC) * 8 + s % p.SC; };
     for (int i = 0; i < m; ++i)
-        for (int s = 0; s < N; ++s) B_op[(size_t)i * p.N4 + s] = GL[(size_t)i * n + s * n_u + (i < box ? i % n_u : 0)];
+        for (int s = 0; s < N; ++s) B_op[(size_t)i * p.N4 + slot(s)] = GL[(size_t)i * n + s * n_u + (i < box ? i % n_u : 0)];
     float resid = 0.f;
     for (int r = 0; r < n; ++r)
         for (int k = 0; k < box; ++k)
             if (k % n_u != r % n_u) resid = std::max(resid, std::fabs(MG[(size_t)r * m + k]));
     for (int i = 0; i < m; ++i)
         for (int j = 0; j < n; ++j) {
-            const float flat = (i >= box || j % n_u == i % n_u) ? B_op[(size_t)i * p.N4 + j / n_u] : 0.f;
+            const float flat = (i >= box || j % n_u == i % n_u) ? B_op[(size_t)i * p.N4 + slot(j / n_u)] : 0.f;
             resid = std::max(resid, std::fabs(GL[(size_t)i * n + j] - flat));
         }
     return resid;
 }
 
 int launch_flat(const FlatParams& p, cudaStream_t stream) {
-    switch (p.CHB) {
+    switch (p.C) {
         case 1: return launch_flat_t<1>(p, stream);
         case 2: return launch_flat_t<2>(p, stream);
         case 4: return launch_flat_t<4>(p, stream);
         case 8: return launch_flat_t<8>(p, stream);
-        case 16: return launch_flat_t<16>(p, stream);
-        case 25: return launch_flat_t<25>(p, stream);
-        default: return launch_flat_t<32>(p, stream);
+        default: return launch_flat_t<16>(p, stream);
     }
 }
 

@@ -54,6 +54,8 @@ int gpad_plants_battery(int n_u, int N, int B, const double* capacity_scale, int
 }
 
 int gpad_plants_destroy(gpad_plants_t p) {
+    if (!p) return GPAD_OK;
+    for (void* d : p->dev_cache) gpad::plants_dev_free(d);
     delete p;
     return GPAD_OK;
 }

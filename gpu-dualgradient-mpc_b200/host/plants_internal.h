@@ -14,9 +14,13 @@ struct gpad_plants_s {
     std::vector<double> Bm;              // [B][nx][n_u] plant input matrices
     std::vector<double> b0, A;           // common: [m], [nx][nx]
     std::vector<std::pair<int, int>> blocks;
+    // device copies of a shard's instance maps, one per (device, first, count) that ran a closed loop (csrc/closed_loop.cu)
+    std::mutex dev_mutex;
+    std::vector<void*> dev_cache;
 };
 
 namespace gpad {
+void plants_dev_free(void* cache);
 int closed_loop_plants_device(gpad_plants_t p, gpad_handle_t h, int first, int count, const double* x0, int samples,
                               const float* theta, const float* beta, int max_iter, int warm_start, double* x_traj,
                               double* u_traj);

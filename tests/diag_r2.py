@@ -10,7 +10,7 @@ import torch
 import gpad_b200 as G
 from bench import quad_params
 
-B, ITERS = 65536, 20
+B, ITERS = int(os.environ.get("DIAG_B", "65536")), 20
 sections = sys.argv[1:] or ["kernels", "build", "async"]
 
 
@@ -74,6 +74,58 @@ if "kernels" in sections:
         cmd = [sys.executable, __file__, "one", label, knobs] + ([lib] if lib else [])
         r = subprocess.run(cmd, env={**os.environ, **env}, capture_output=True, text=True)
         print(r.stdout.strip() or f"{label} [{knobs}]: rc={r.returncode} {r.stderr[-400:]}", flush=True)
+
+if "small" in sections:
+    import subprocess
+    for b in (8192, 16384, 32768, 65536):
+        for knobs in ("", "tc_pdl=1"):
+            r = subprocess.run([sys.executable, __file__, "one", f"B={b}", knobs], env={**os.environ, "DIAG_B": str(b)}, capture_output=True, text=True)
+            print(r.stdout.strip() or f"B={b} [{knobs}]: rc={r.returncode} {r.stderr[-400:]}", flush=True)
+
+if "latency" in sections:
+    for n_u, N in ((10, 100), (10, 15), (15, 10), (4, 6)):
+        for knobs in ("latency_flat=1,flat_xchg=1", "latency_flat=1,flat_xchg=0", "latency_flat=0"):
+            os.environ["GPAD_DEBUG"] = knobs
+            prob = G.Problem("battery", n_u=n_u, N=N)
+            M_G, G_L = prob.operators()
+            g_P, p_D, _ = prob.instances(np.random.default_rng(1).random((1, n_u)) - 0.5, want_f=False)
+            theta, beta = G.schedule(100)
+            s = G.Solver(n_u, N, prob.m, prob.L, M_G, G_L, mode=G.MODE_LATENCY)
+            dg, dp = torch.from_numpy(g_P[0]).cuda(), torch.from_numpy(p_D[0]).cuda()
+            dz = torch.empty(prob.n, device="cuda")
+            st = torch.cuda.current_stream().cuda_stream
+            for _ in range(10):
+                s.solve_device(1, dg, dp, theta, beta, 100, stream=st, z=dz)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(200):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); s.solve_device(1, dg, dp, theta, beta, 100, stream=st, z=dz); e1.record(); e1.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3)
+            th11, be11 = G.schedule(1100)
+            s.solve_device(1, dg, dp, th11, be11, 1100, stream=st, z=dz); torch.cuda.synchronize()
+            tl = []
+            for _ in range(20):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); s.solve_device(1, dg, dp, th11, be11, 1100, stream=st, z=dz); e1.record(); e1.synchronize()
+                tl.append(e0.elapsed_time(e1) * 1e3)
+            print(f"latency ({n_u},{N}) [{knobs}]: p50 {np.median(ts):.1f} us, slope {(np.median(tl) - np.median(ts)) / 1000:.3f} us/iteration   {s.description[:90]}", flush=True)
+            s.close()
+
+if "plants" in sections:
+    n_u, N, Bp = 3, 4, 131072
+    rng = np.random.default_rng(3)
+    plants = G.Plants(n_u, N, 1.0 + 0.1 * (2 * rng.random((Bp, n_u)) - 1))
+    M, Gl, L = plants.operators()
+    theta, beta = G.schedule(100)
+    s = G.Solver(n_u, N, plants.m, float(L[0]), M, Gl, mode=G.MODE_BATCH_PER_INSTANCE, max_batch=Bp)
+    x0 = rng.random((Bp, n_u)) - 0.5
+    for samples in (1, 5, 9):
+        for warm in (0, 2):
+            plants.closed_loop(s, x0, samples, theta, beta, warm_start=warm)
+            t0 = time.perf_counter(); plants.closed_loop(s, x0, samples, theta, beta, warm_start=warm); dt = time.perf_counter() - t0
+            print(f"plants closed loop: samples {samples} warm {warm}: {dt * 1e3:.1f} ms total, {dt / samples * 1e3:.2f} ms per sample", flush=True)
+    s.close()
 
 if "build" in sections:
     prob, s = setup("tc_bn2=160")

@@ -328,13 +328,14 @@ def test_step2_step4_fixture_formats_through_shims(torch_cuda, G, oracle, flat, 
 
 
 # ------------------------------------------------------------------------------------ flat battery operators (f4)
+@pytest.mark.parametrize("xchg", [0, 1])
 @pytest.mark.parametrize("dims", [(3, 4), (4, 3), (4, 6), (10, 15), (15, 10), (7, 33), (10, 100)])
-def test_flat_operator_latency_kernel_matches_oracle(torch_cuda, G, oracle, dims, monkeypatch):
+def test_flat_operator_latency_kernel_matches_oracle(torch_cuda, G, oracle, dims, xchg, monkeypatch):
     """latency_flat.cu: the battery problem on its flattened operators (seq_functions.cpp:5-43, kernel_functions.cu:74-109)
     on one thread-block cluster; forced for every size here (by default it replaces the whole-chip plans only), cold and
     warm started, against the oracle (dense and flat step functions agree: tests/test_oracle.py) with the parity bound"""
     n_u, N = dims
-    monkeypatch.setenv("GPAD_DEBUG", "latency_flat=1")
+    monkeypatch.setenv("GPAD_DEBUG", f"latency_flat=1,flat_xchg={xchg}")      # both exchange mechanisms of the kernel
     pb = P.battery(n_u, N)
     rng = np.random.default_rng(n_u * 100 + N)
     g_P, p_D, f = pb.instance(P.battery_x0(n_u, rng))
@@ -387,12 +388,19 @@ def test_flat_layout_input_and_automatic_detection(torch_cuda, G, oracle, monkey
     for k in VECS:
         assert P.rel_inf(got[k], ora[k]) <= 2e-5, k
     s.close()
+    # defaults: operators that ARRIVE flat and would need the whole chip in dense form run the flat kernel; dense input
+    # keeps the (equally fast) whole-chip kernel; latency_flat=0 switches the flat kernel off altogether
     monkeypatch.delenv("GPAD_DEBUG", raising=False)
     big = P.battery(10, 100)
-    s = G.Solver(10, 100, big.m, big.L, big.M_G, big.G_L, mode=G.MODE_LATENCY)
+    bMf, bGf, r = G.flatten_operators(10, 100, big.m, big.M_G, big.G_L)
+    assert r == 0.0
+    s = G.Solver(10, 100, big.m, big.L, bMf, bGf, layout=G.LAYOUT_FLAT, mode=G.MODE_LATENCY)
     assert "flat battery operators" in s.description, s.description
     s.close()
-    monkeypatch.setenv("GPAD_DEBUG", "latency_flat=0")
     s = G.Solver(10, 100, big.m, big.L, big.M_G, big.G_L, mode=G.MODE_LATENCY)
+    assert "column-partitioned" in s.description, s.description
+    s.close()
+    monkeypatch.setenv("GPAD_DEBUG", "latency_flat=0")
+    s = G.Solver(10, 100, big.m, big.L, bMf, bGf, layout=G.LAYOUT_FLAT, mode=G.MODE_LATENCY)
     assert "column-partitioned" in s.description, s.description
     s.close()
