@@ -149,6 +149,29 @@ struct DevBufs {
     ~DevBufs() { for (void* q : p) cudaFree(q); }
 };
 
+// the loop's working buffers: one device allocation that persists with the problem / plants cache and only ever grows
+// (cudaMalloc / cudaFree of ~100 MB per call cost tens to hundreds of milliseconds, more than the loop itself)
+struct Workspace {
+    unsigned char* base = nullptr;
+    size_t cap = 0, used = 0;
+    int reserve(size_t bytes) {
+        used = 0;
+        if (bytes <= cap) return GPAD_OK;
+        if (base) cudaFree(base);
+        base = nullptr; cap = 0;
+        if (cudaMalloc(reinterpret_cast<void**>(&base), bytes) != cudaSuccess) { cudaGetLastError(); set_error("closed loop: cudaMalloc of %zu bytes failed", bytes); return GPAD_ERR_ALLOC; }
+        cap = bytes;
+        return GPAD_OK;
+    }
+    template <typename T> T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + used);
+        used += (count * sizeof(T) + 255) / 256 * 256;
+        return p;
+    }
+    static size_t need(size_t count, size_t elem) { return (count * elem + 255) / 256 * 256; }
+    ~Workspace() { if (base) cudaFree(base); }
+};
+
 struct DeviceScope {             // the handle's device for the duration of the loop, the caller's afterwards
     int prev = -1;
     cudaError_t status = cudaSuccess;
@@ -172,6 +195,7 @@ struct ProblemDev {
     DevBufs mem;
     double *Kg = nullptr, *Ff = nullptr, *Bb = nullptr, *b0 = nullptr, *A = nullptr, *B = nullptr;
     int* blocks = nullptr;
+    Workspace ws;
 };
 
 int problem_dev_get(gpad_problem_t p, int device, ProblemDev** out) {
@@ -206,20 +230,26 @@ int run_loop(gpad_handle_t h, int B, int nx, int nu, int n, int m, int npar, int
              const double* dBb, size_t bb_stride, const double* db0, double invL, const double* dinvL, const double* dA,
              const double* dBm, size_t bm_stride, const int* dblocks, int nblocks, const double* x0, const double* xref,
              int samples, const float* theta, const float* beta, int max_iter, int warm_start, double* x_traj, double* u_traj,
-             cudaStream_t s) {
+             Workspace& ws, cudaStream_t s) {
     if (nx > 32 || npar > kAffMaxNp) { set_error("closed loop: nx = %d / n_par = %d > 32 is not supported", nx, npar); return GPAD_ERR_UNSUPPORTED; }
     const int nref = npar - nx;
-    DevBufs d;
-    double *dx, *dxref = nullptr, *dut, *dxt;
-    float *gP, *pD, *z, *ya[2], *yb[2], *sa = nullptr, *sb = nullptr;
-#define TRYA(e) do { int rc_ = (e); if (rc_ != GPAD_OK) return rc_; } while (0)
-    TRYA(d.upload(&dx, x0, (size_t)B * nx, s));
-    if (nref > 0) TRYA(d.upload(&dxref, xref, (size_t)B * nref, s));
-    TRYA(d.alloc(&dut, u_traj ? (size_t)samples * B * nu : 0)); TRYA(d.alloc(&dxt, x_traj ? (size_t)(samples + 1) * B * nx : 0));
-    TRYA(d.alloc(&gP, (size_t)B * n)); TRYA(d.alloc(&pD, (size_t)B * m)); TRYA(d.alloc(&z, (size_t)B * n));
-    for (int k = 0; k < 2; ++k) { TRYA(d.alloc(&ya[k], (size_t)B * m)); TRYA(d.alloc(&yb[k], (size_t)B * m)); }
-    if (warm_start == GPAD_WARM_SHIFTED) { TRYA(d.alloc(&sa, (size_t)B * m)); TRYA(d.alloc(&sb, (size_t)B * m)); }
-#undef TRYA
+    const size_t Bn = (size_t)B * n, Bm = (size_t)B * m;
+    const size_t n_ut = u_traj ? (size_t)samples * B * nu : 0, n_xt = x_traj ? (size_t)(samples + 1) * B * nx : 0;
+    const bool shifted = warm_start == GPAD_WARM_SHIFTED;
+    size_t bytes = Workspace::need((size_t)B * nx, 8) + Workspace::need((size_t)B * std::max(nref, 1), 8) + Workspace::need(n_ut, 8) +
+                   Workspace::need(n_xt, 8) + 2 * Workspace::need(Bn, 4) + (size_t)(5 + (shifted ? 2 : 0)) * Workspace::need(Bm, 4);
+    GPAD_TRY(ws.reserve(bytes));
+    double* dx = ws.take<double>((size_t)B * nx);
+    double* dxref = ws.take<double>((size_t)B * std::max(nref, 1));
+    double* dut = ws.take<double>(n_ut);
+    double* dxt = ws.take<double>(n_xt);
+    float* gP = ws.take<float>(Bn); float* z = ws.take<float>(Bn); float* pD = ws.take<float>(Bm);
+    float *ya[2], *yb[2], *sa = nullptr, *sb = nullptr;
+    for (int k = 0; k < 2; ++k) { ya[k] = ws.take<float>(Bm); yb[k] = ws.take<float>(Bm); }
+    if (shifted) { sa = ws.take<float>(Bm); sb = ws.take<float>(Bm); }
+    GPAD_CUDA(cudaMemcpyAsync(dx, x0, sizeof(double) * B * nx, cudaMemcpyHostToDevice, s));
+    if (nref > 0) GPAD_CUDA(cudaMemcpyAsync(dxref, xref, sizeof(double) * B * nref, cudaMemcpyHostToDevice, s));
+    else dxref = nullptr;
     if (x_traj) GPAD_CUDA(cudaMemcpyAsync(dxt, dx, sizeof(double) * B * nx, cudaMemcpyDeviceToDevice, s));
     for (int k = 0; k < samples; ++k) {
         if (kg_stride) {        // one plant per instance
@@ -295,7 +325,7 @@ int closed_loop_device(gpad_problem_t p, gpad_handle_t h, int B, const double* x
     ProblemDev* d = nullptr;
     GPAD_TRY_RC(problem_dev_get(p, device, &d));
     return run_loop(h, B, p->nx, p->n_u, p->n, p->m, p->n_par, p->N, d->Kg, 0, d->Bb, 0, d->b0, 1.0 / p->L, nullptr, d->A, d->B, 0,
-                    d->blocks, (int)p->blocks.size(), x0, xref, samples, theta, beta, max_iter, warm_start, x_traj, u_traj, st.s);
+                    d->blocks, (int)p->blocks.size(), x0, xref, samples, theta, beta, max_iter, warm_start, x_traj, u_traj, d->ws, st.s);
 }
 
 // device copies of one shard of plants (uploaded once per (device, first, count): 1.6 KB of maps per plant)
@@ -304,6 +334,7 @@ struct PlantsDev {
     DevBufs mem;
     double *Kg = nullptr, *Bb = nullptr, *b0 = nullptr, *A = nullptr, *Bm = nullptr, *invL = nullptr;
     int* blocks = nullptr;
+    Workspace ws;
 };
 
 void plants_dev_free(void* cache) {
@@ -360,7 +391,7 @@ int closed_loop_plants_device(gpad_plants_t p, gpad_handle_t h, int first, int c
     const int n = p->n, m = p->m, np = p->n_par, nx = p->nx, nu = p->n_u;
     return run_loop(h, count, nx, nu, n, m, np, p->N, d->Kg, (size_t)n * np, d->Bb, (size_t)m * np, d->b0, 0.0, d->invL, d->A, d->Bm,
                     (size_t)nx * nu, d->blocks, (int)p->blocks.size(), x0, nullptr, samples, theta, beta, max_iter, warm_start, x_traj,
-                    u_traj, st.s);
+                    u_traj, d->ws, st.s);
 }
 
 }  // namespace gpad

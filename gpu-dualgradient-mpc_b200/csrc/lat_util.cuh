@@ -58,6 +58,28 @@ __device__ __forceinline__ float warp_sum_transposed_v(float (&v)[R], int lane) 
     for (; o >= 1; o >>= 1) t += shfl_bfly_v(t, o);
     return t;
 }
+// The same reduction WITHOUT the selects: when lane l keeps its R values in the order v'[k] = v[k ^ mask(l)], with mask(l) the
+// lane bits the butterfly pairs on (for R = 16 over 32 lanes: mask = (l >> 1) & 15), the element to hand over is at a fixed
+// index at every level -- the partner's mask differs in exactly the bit that swaps the halves.  The kernel gets the permuted
+// order for free by loading its operator rows in that order once.  Same pairing, hence the same sums bit for bit; lane l
+// ends with the total of value mask(l).  ORD: shuffles as volatile asm (program order), see above.
+template <int R, bool ORD>
+__device__ __forceinline__ float warp_sum_prepermuted(float (&v)[R]) {
+    static_assert(R == 8 || R == 16 || R == 32, "R");
+    int o = 16;
+#pragma unroll
+    for (int s = R / 2; s >= 1; s >>= 1, o >>= 1) {
+        float got[R / 2];
+#pragma unroll
+        for (int i = 0; i < s; ++i) got[i] = ORD ? shfl_bfly_v(v[i + s], o) : __shfl_xor_sync(0xffffffffu, v[i + s], o);
+#pragma unroll
+        for (int i = 0; i < s; ++i) v[i] = v[i] + got[i];
+    }
+    float t = v[0];
+#pragma unroll
+    for (; o >= 1; o >>= 1) t += ORD ? shfl_bfly_v(t, o) : __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+}
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 

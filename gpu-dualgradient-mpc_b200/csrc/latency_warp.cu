@@ -5,8 +5,9 @@
 // The lean one-CTA kernel (latency_small.cu) spends two __syncthreads and two shared-memory exchanges per iteration on
 // a problem whose whole state fits one warp.  Here lane l owns dual entries i = l and l + 32:
 //   phase A (step 2, kernel_functions.cu:16-64): lane l holds COLUMNS l, l+32 of M_G, so its own w_i never leaves
-//            the lane; the 16 (padded) row sums are reduced with the transposed butterfly (16 shuffles) and the
-//            owner lanes apply -g_P and the z average (step 3);
+//            the lane; the 16 (padded) row sums are reduced with the transposed butterfly (16 shuffles; the rows sit in
+//            each lane's registers in the lane-dependent order r ^ ((l >> 1) & 15), which makes the butterfly free of
+//            selects: lat_util.cuh warp_sum_prepermuted) and the owner lanes apply -g_P and the z average (step 3);
 //   phase B (step 4 + step 1, kernel_functions.cu:142-200, 7-14): zhat is broadcast with n shuffles, lane l holds
 //            ROWS l, l+32 of G_L and finishes y_{v+1}, w_{v+1} for its own entries.
 // No shared memory, no block barrier, no global traffic in the loop except the (cached) theta / beta schedule.
@@ -45,7 +46,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp_kernel(const Para
     const int n = p.n, m = p.m;
 
     // ---- operators and state into registers ----
-    float mg[kMR][kWR], gl[kMR][kWR];
+    float mg[kMR][kWR], gl[kMR][kWR];      // mg[j][k] = M_G[row k ^ rmask][column], gl[j][c] = G_L[row][column c]
+    const int rmask = (lane >> 1) & (kWR - 1);
     float yv[kMR], yp[kMR], pd[kMR], w[kMR], yn[kMR], sb[kMR];
     bool own[kMR];
     const float beta0 = p.beta[0];
@@ -55,7 +57,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp_kernel(const Para
         own[j] = i < m;
 #pragma unroll
         for (int r = 0; r < kWR; ++r) {
-            mg[j][r] = (own[j] && r < n) ? __ldg(p.M_G + (size_t)r * p.mld + i) : 0.f;
+            const int rp = r ^ rmask;          // the row this register slot holds for the reduction
+            mg[j][r] = (own[j] && rp < n) ? __ldg(p.M_G + (size_t)rp * p.mld + i) : 0.f;
             gl[j][r] = (own[j] && r < n) ? __ldg(p.G_L + (size_t)i * p.nld + r) : 0.f;
         }
         yv[j] = (own[j] && p.y0) ? p.y0[i] : 0.f;
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp_kernel(const Para
         yn[j] = yv[j];
         sb[j] = 0.f;
     }
-    const int r_me = (lane >> 1) & (kWR - 1);          // the row whose total this lane holds after the reduction
+    const int r_me = rmask;                            // the row whose total this lane holds after the reduction
     const float gp_me = r_me < n ? p.g_P[r_me] : 0.f;
     const float f_me = (p.f && r_me < n && (lane & 1) == 0) ? p.f[r_me] : 0.f;      // one lane per row carries f_r
     float z_me = 0.f, zh_me = 0.f;
@@ -88,8 +91,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp_kernel(const Para
         // ---------------- phase A ----------------
         float acc[kWR];
 #pragma unroll
-        for (int r = 0; r < kWR; ++r) acc[r] = r < NR ? fmaf(mg[1][r], w[1], mg[0][r] * w[0]) : 0.f;
-        const float tot = ORD ? warp_sum_transposed_v<kWR>(acc, lane) : warp_sum_transposed<kWR>(acc, lane);
+        for (int r = 0; r < kWR; ++r) acc[r] = fmaf(mg[1][r], w[1], mg[0][r] * w[0]);
+        const float tot = warp_sum_prepermuted<kWR, ORD>(acc);
         zh_me = tot - gp_me;
         z_me = __fadd_rn(__fmul_rn(one_minus, z_me), __fmul_rn(theta, zh_me));
 
@@ -149,8 +152,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp_kernel(const Para
                     // dual branch: Phi(y_{v+1}) with z_y = M_G y+ - g_P and G_L z_y -- the two phases once more, on y+
                     float a2[kWR];
 #pragma unroll
-                    for (int r = 0; r < kWR; ++r) a2[r] = r < NR ? fmaf(mg[1][r], yn[1], mg[0][r] * yn[0]) : 0.f;
-                    const float zy_me = warp_sum_transposed<kWR>(a2, lane) - gp_me;
+                    for (int r = 0; r < kWR; ++r) a2[r] = fmaf(mg[1][r], yn[1], mg[0][r] * yn[0]);
+                    const float zy_me = warp_sum_prepermuted<kWR, false>(a2) - gp_me;
                     float fzy = f_me * zy_me, y_gz = 0.f, y_pd = 0.f;
                     float d2[kMR] = {0.f, 0.f};
 #pragma unroll
