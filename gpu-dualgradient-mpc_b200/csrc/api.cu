@@ -54,6 +54,7 @@ Knobs parse_knobs() {
         else if (key == "flat_xchg") k.flat_xchg = iv;
         else if (key == "warp_rows") k.warp_rows = iv;
         else if (key == "warp_ordered") k.warp_ordered = iv;
+        else if (key == "warp_pack") k.warp_pack = iv;
         else if (key == "tc_p1") k.tc_p1 = iv;
         else if (key == "tc_stages") k.tc_stages = iv;
         else if (key == "tc_bn2") k.tc_bn2 = iv;
@@ -276,7 +277,7 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
     h->small = plan.small; h->cha = plan.cha; h->chb = plan.chb;
     p.L = h->cfg.L;
     p.batch = 1; p.op_stride_a = p.op_stride_b = 0;
-    p.warp_rows = kn.warp_rows; p.warp_ordered = kn.warp_ordered;
+    p.warp_rows = kn.warp_rows; p.warp_ordered = kn.warp_ordered; p.warp_pack = kn.warp_pack;
     float *dMG, *dGL;
     GPAD_TRY(upload_padded(h, MG.data(), n, m, n, p.mld, &dMG));
     GPAD_TRY(upload_padded(h, GL.data(), m, n, m, p.nld, &dGL));
@@ -503,11 +504,14 @@ int setup_per_instance(gpad_handle_s* h, const float* M_G, const float* G_L) {
              plan.small ? "and per-row state read once into registers (lean kernel)" : plan.regs ? "read once into registers" : "in shared memory / streamed",
              plan.small ? lat::small_smem_bytes(p) : lat::smem_bytes(p, plan.regs));
     h->desc = buf;
-    p.warp_rows = h->knobs.warp_rows; p.warp_ordered = h->knobs.warp_ordered;
+    p.warp_rows = h->knobs.warp_rows; p.warp_ordered = h->knobs.warp_ordered; p.warp_pack = h->knobs.warp_pack;
     h->warp = lat::warp_supported(p);
     if (h->knobs.latency_warp == 0) h->warp = false;
-    if (h->warp) h->desc = "batch-per-instance: one WARP per QP (batched GEMV), 4 QPs per CTA, operators and state read once into registers, "
-                           "no shared memory or block barrier in the loop (latency_warp.cu)";
+    if (h->warp) h->desc = h->knobs.warp_pack
+        ? "batch-per-instance: batched GEMV in registers (latency_warp.cu): fixed-iteration solves pack TWO QPs per warp (16 lanes each, "
+          "8 QPs per CTA), tolerance-mode solves one QP per warp; operators and state read once, no shared memory or block barrier in the loop"
+        : "batch-per-instance: one WARP per QP (batched GEMV), 4 QPs per CTA, operators and state read once into registers, "
+          "no shared memory or block barrier in the loop (latency_warp.cu)";
     return GPAD_OK;
 }
 

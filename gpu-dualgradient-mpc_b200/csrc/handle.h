@@ -22,6 +22,7 @@ struct Knobs {
     int latency_flat = -1;           // -1 auto; 0 expands flat operators to the dense kernels
     int flat_xchg = 0;               // flat kernel exchange: 0 bulk DSMEM copies, 1 per-entry st.async
     int warp_rows = 0, warp_ordered = -1;   // one-warp kernel schedule (0 / -1: chosen by batch size)
+    int warp_pack = 1;               // fixed-iteration per-instance batches: two QPs per warp
     int tc_p1 = -1;                  // product 1: -1 waves model, 1 TMEM-operand kernel, 0 shared-memory-operand kernel
     int tc_stages = 0;               // cap on its ring depth (0: as many as fit)
     int tc_bn2 = 0;                  // product 2 tile width (0: tuned, cached per shape)

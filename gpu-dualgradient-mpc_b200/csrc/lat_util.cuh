@@ -80,6 +80,21 @@ __device__ __forceinline__ float warp_sum_prepermuted(float (&v)[R]) {
     for (; o >= 1; o >>= 1) t += ORD ? shfl_bfly_v(t, o) : __shfl_xor_sync(0xffffffffu, t, o);
     return t;
 }
+// the same over HALF a warp (two independent problems per warp, 16 lanes each): R = 16 values, four levels, no tail;
+// lane h = lane & 15 keeps its values in the order v'[k] = v[k ^ h] and ends with the total of value h
+template <bool ORD>
+__device__ __forceinline__ float halfwarp_sum_prepermuted(float (&v)[16]) {
+    int o = 8;
+#pragma unroll
+    for (int s = 8; s >= 1; s >>= 1, o >>= 1) {
+        float got[8];
+#pragma unroll
+        for (int i = 0; i < s; ++i) got[i] = ORD ? shfl_bfly_v(v[i + s], o) : __shfl_xor_sync(0xffffffffu, v[i + s], o);
+#pragma unroll
+        for (int i = 0; i < s; ++i) v[i] = v[i] + got[i];
+    }
+    return v[0];
+}
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 

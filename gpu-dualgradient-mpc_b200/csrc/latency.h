@@ -21,6 +21,7 @@ struct Params {
     int res_a, res_b;        // own rows of M_G / G_L resident in shared memory (memory variant)
     int sched_smem;          // latency_small.cu: theta/beta entries staged in shared memory
     int warp_rows, warp_ordered;  // latency_warp.cu schedule override (0 / -1: chosen by batch size)
+    int warp_pack;                // fixed-iteration batches: two QPs per warp (1 default / 0 off)
     int batch;               // SYNC_BLOCK only: independent instances, one CTA each (per-instance operators)
     size_t op_stride_a, op_stride_b;   // elements between consecutive instances' M_G / G_L (0: shared)
     const float* M_G;        // [n][mld] sequential layout, zero padded

@@ -213,6 +213,119 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp_kernel(const Para
     }
 }
 
+// ---- TWO QPs per warp (fixed-iteration batches): 16 lanes per QP, lane h = lane & 15 owns dual entries h, h+16, h+32, h+48.
+// The reduction and the zhat broadcast then serve two QPs per shuffle: per QP-iteration 15 + 12 shuffles become 7.5 + 6
+// (the products, 2 n m / 32 per QP, stay).  Same arithmetic per QP as gpad_warp_kernel except the order of the four
+// products per row and of the 16-lane butterfly; results sit within rounding of it (tests compare both with the oracle).
+constexpr int kMR2 = 4;
+
+template <int NR, bool ORD>
+__global__ void __launch_bounds__(32 * kWarpsPerCta) gpad_warp2_kernel(const Params p_in, int warps_per_cta) {
+    Params p = p_in;
+    const int lane = threadIdx.x & 31, h = lane & 15;
+    const size_t B = (size_t)p.batch;
+    const size_t pair = (size_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    if (2 * pair >= B) return;                                  // whole warps leave together
+    const size_t inst_raw = 2 * pair + (lane >> 4);
+    const bool live = inst_raw < B;                              // an odd batch leaves the last half-warp idle
+    const size_t inst = live ? inst_raw : B - 1;                 // (it shadows the last QP and stores nothing)
+    p.M_G += inst * p.op_stride_a; p.G_L += inst * p.op_stride_b;
+    p.g_P += inst * p.n; p.p_D += inst * p.m;
+    if (p.y0) p.y0 += inst * p.m;
+    if (p.y_prev0) p.y_prev0 += inst * p.m;
+    const int n = p.n, m = p.m;
+
+    float mg[kMR2][kWR], gl[kMR2][NR];     // mg[j][k] = M_G[row k ^ h][column], gl[j][c] = G_L[row][column c]
+    float yv[kMR2], yp[kMR2], pd[kMR2], w[kMR2], yn[kMR2];
+    bool own[kMR2];
+    const float beta0 = p.beta[0];
+#pragma unroll
+    for (int j = 0; j < kMR2; ++j) {
+        const int i = h + 16 * j;
+        own[j] = i < m;
+#pragma unroll
+        for (int r = 0; r < kWR; ++r) {
+            const int rp = r ^ h;
+            mg[j][r] = (own[j] && rp < n) ? __ldg(p.M_G + (size_t)rp * p.mld + i) : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < NR; ++c) gl[j][c] = (own[j] && c < n) ? __ldg(p.G_L + (size_t)i * p.nld + c) : 0.f;
+        yv[j] = (own[j] && p.y0) ? p.y0[i] : 0.f;
+        yp[j] = (own[j] && p.y_prev0) ? p.y_prev0[i] : 0.f;
+        pd[j] = own[j] ? p.p_D[i] : 0.f;
+        w[j] = __fadd_rn(yv[j], __fmul_rn(beta0, __fsub_rn(yv[j], yp[j])));     // step 1 of iteration 0
+        yn[j] = yv[j];
+    }
+    const float gp_me = h < n ? p.g_P[h] : 0.f;              // lane h ends the reduction with the total of row h
+    float z_me = 0.f, zh_me = 0.f;
+
+    float theta_pf = __ldg(p.theta), beta_pf = p.max_iter > 1 ? __ldg(p.beta + 1) : 0.f;
+    for (int v = 0; v < p.max_iter; ++v) {
+        const float theta = theta_pf, one_minus = 1.0f - theta;
+        const bool last = (v + 1 == p.max_iter);
+        const float beta_next = last ? 0.f : beta_pf;
+        if (!last) {
+            theta_pf = __ldg(p.theta + v + 1);
+            beta_pf = (v + 2 < p.max_iter) ? __ldg(p.beta + v + 2) : 0.f;
+        }
+        // ---------------- phase A ----------------
+        float acc[kWR];
+#pragma unroll
+        for (int r = 0; r < kWR; ++r) acc[r] = fmaf(mg[3][r], w[3], fmaf(mg[2][r], w[2], fmaf(mg[1][r], w[1], mg[0][r] * w[0])));
+        const float tot = halfwarp_sum_prepermuted<ORD>(acc);
+        zh_me = tot - gp_me;
+        z_me = __fadd_rn(__fmul_rn(one_minus, z_me), __fmul_rn(theta, zh_me));
+        // ---------------- phase B ----------------
+        float d[kMR2] = {0.f, 0.f, 0.f, 0.f};
+        float zc[NR];
+#pragma unroll
+        for (int c = 0; c < NR; ++c) zc[c] = __shfl_sync(0xffffffffu, zh_me, c, 16);       // lane c of this half
+#pragma unroll
+        for (int c = 0; c < NR; ++c) {
+#pragma unroll
+            for (int j = 0; j < kMR2; ++j) d[j] = fmaf(gl[j][c], zc[c], d[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kMR2; ++j) {
+            const float s = d[j] + (w[j] + pd[j]);
+            yn[j] = 0.5f * (s + fabsf(s));
+        }
+        if (!last) {
+#pragma unroll
+            for (int j = 0; j < kMR2; ++j) {
+                w[j] = __fadd_rn(yn[j], __fmul_rn(beta_next, __fsub_rn(yn[j], yv[j])));
+                yp[j] = yv[j];
+                yv[j] = yn[j];
+            }
+        }
+    }
+
+    // ---------------- outputs (main.cu:176-180 + termination outputs) ----------------
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < kMR2; ++j) {
+        const int i = h + 16 * j;
+        if (own[j] && live) {
+            if (p.out_y_next) p.out_y_next[inst * m + i] = yn[j];
+            if (p.out_y) p.out_y[inst * m + i] = yv[j];
+            if (p.out_w) p.out_w[inst * m + i] = w[j];
+            bad = bad || !isfinite(yn[j]);
+        }
+    }
+    if (h < n && live) {
+        if (p.out_z) p.out_z[inst * n + h] = z_me;
+        if (p.out_zhat) p.out_zhat[inst * n + h] = zh_me;
+    }
+    const unsigned bad_lanes = __ballot_sync(0xffffffffu, bad);
+    const bool bad_half = (bad_lanes >> (lane & 16)) & 0xffffu;
+    if (h == 0 && live) {
+        if (p.out_iters) p.out_iters[inst] = p.max_iter;
+        if (p.out_status) p.out_status[inst] = bad_half ? GPAD_STATUS_NONFINITE : GPAD_STATUS_MAX_ITER;
+        if (p.out_max_viol) p.out_max_viol[inst] = __int_as_float(0x7fc00000);
+        if (p.out_gap) p.out_gap[inst] = __int_as_float(0x7fc00000);
+    }
+}
+
 }  // namespace
 
 int warp_supported(const Params& p) { return p.n <= kWR && p.m <= 32 * kMR; }
@@ -228,9 +341,19 @@ int launch_warp(const Params& p, cudaStream_t stream) {
     // best measured (37 us per 100 iterations; 12 rows: 61 us unordered -- ptxas walks the tree depth-first -- 45 us ordered).
     int nr = (p.n <= 12 && B > 1) ? 12 : kWR;
     bool ord = B > 1;
-    // experiments (GPAD_DEBUG warp_rows / warp_ordered, read at gpad_setup)
+    // experiments (GPAD_DEBUG warp_rows / warp_ordered / warp_pack, read at gpad_setup)
     if ((p.warp_rows == 12 || p.warp_rows == kWR) && p.warp_rows >= p.n) nr = p.warp_rows;
     if (p.warp_ordered >= 0) ord = p.warp_ordered != 0;
+    // fixed-iteration batches: two QPs per warp (halves the reduction and broadcast shuffles per QP)
+    if (B > 1 && !chk && p.warp_pack != 0 && p.max_iter >= 1) {
+        const int grid2 = (int)(((size_t)(B + 1) / 2 + kWarpsPerCta - 1) / kWarpsPerCta);
+        if (nr == 12) { if (ord) gpad_warp2_kernel<12, true><<<grid2, 32 * kWarpsPerCta, 0, stream>>>(p, kWarpsPerCta);
+                        else gpad_warp2_kernel<12, false><<<grid2, 32 * kWarpsPerCta, 0, stream>>>(p, kWarpsPerCta); }
+        else          { if (ord) gpad_warp2_kernel<kWR, true><<<grid2, 32 * kWarpsPerCta, 0, stream>>>(p, kWarpsPerCta);
+                        else gpad_warp2_kernel<kWR, false><<<grid2, 32 * kWarpsPerCta, 0, stream>>>(p, kWarpsPerCta); }
+        GPAD_CUDA(cudaGetLastError());
+        return GPAD_OK;
+    }
 #define GPAD_WARP_LAUNCH(C, N, O) gpad_warp_kernel<C, N, O><<<grid, 32 * wpc, 0, stream>>>(p, wpc)
     if (nr == 12) {
         if (ord) { if (chk) GPAD_WARP_LAUNCH(true, 12, true); else GPAD_WARP_LAUNCH(false, 12, true); }
