@@ -323,18 +323,20 @@ def per_instance_probe(torch, G, B=262144):
     _, hbm, src = measured_peaks()
     fp32_peak = 148 * 128 * 2 * 1.965e9
     flops = 4.0 * n * m * ITERS * B
-    # algorithmic minimum of warp instructions per QP-iteration with one warp per QP: 2 n m / 32 = 42 FMAs; the kernel
-    # issues 174.4 (profiles/r1_ncu_per_instance_warp.csv: smsp__inst_executed / (B x 100)): 48 products, 28 shuffles, the
-    # selects / adds of the transposed reduction, the projection
-    inst_min, inst_issued = 2.0 * n * m / 32.0, 174.4
+    # algorithmic minimum of warp instructions per QP-iteration: 2 n m / 32 = 42 FMAs; the two-QPs-per-warp kernel issues
+    # 112.3 (profiles/r2_ncu_per_instance_warp2.csv: smsp__inst_executed / (B x 100); round 1's one-warp kernel: 174.4):
+    # 56 products, 13.5 shuffles, the adds of the select-free transposed reduction, the projection and momentum updates
+    inst_min, inst_issued = 2.0 * n * m / 32.0, 112.3
     res = {"workload": f"battery(3,4) n={n} m={m}, {B} QPs with per-instance operators, 100 iterations", "solves_per_s": B / sec,
            "ms_per_batch": sec * 1e3, "algorithmic_bytes_per_solve": bytes_min // B, "achieved_GBps": bytes_min / sec / 1e9,
            "hbm_peak_GBps": hbm, "frac_of_hbm_roofline": bytes_min / sec / 1e9 / hbm, "path": s.description,
            "achieved_TFLOPs": flops / sec / 1e12, "frac_of_fp32_fma_peak": flops / sec / fp32_peak,
            "warp_instructions_per_iteration": inst_issued, "algorithmic_warp_instructions_per_iteration": inst_min,
            "frac_of_algorithmic_instruction_minimum": inst_min / inst_issued,
+           "issue_roofline_solves_per_s": 148 * 4 * 1.965e9 / (inst_issued * ITERS),
+           "frac_of_issue_roofline": (B / sec) / (148 * 4 * 1.965e9 / (inst_issued * ITERS)),
            "note": "operators stay in registers for all 100 iterations, so HBM carries a few % of its peak; the kernel is bound by "
-                   "instruction issue (shuffles of the in-warp reduction and broadcast), at 24 % of the algorithmic instruction minimum"}
+                   "instruction issue (ncu: issue slots 80 % busy), at 37 % of the algorithmic instruction minimum (round 1: 24 %)"}
     s.close()
     return res
 
