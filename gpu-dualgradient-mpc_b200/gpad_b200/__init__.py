@@ -20,6 +20,7 @@ PREC_FP32, PREC_TF32X3 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 SCHEDULE_PAPER, SCHEDULE_MATLAB_LAG = 0, 1
 WARM_COLD, WARM_PREVIOUS, WARM_SHIFTED = 0, 1, 2
+L_REFERENCE, L_LAMBDA_MAX = 0, 1
 STATUS_NAMES = {0: "max_iter", 1: "converged_z", 2: "converged_zhat", 3: "converged_dual", 4: "nonfinite"}
 
 EXPORTS = [
@@ -36,6 +37,7 @@ EXPORTS = [
     "gpad_closed_loop_plants",
     "gpad_group_setup", "gpad_group_destroy", "gpad_group_solve", "gpad_group_size", "gpad_group_shard",
     "gpad_file_read_flat", "gpad_file_write_flat", "gpad_fixture_read", "gpad_fixture_write", "gpad_fixture_free",
+    "gpad_problem_set_lipschitz",
 ]
 
 _fp = C.POINTER(C.c_float)
@@ -143,6 +145,7 @@ def lib():
             "gpad_fixture_read": [C.c_char_p, C.c_int, C.c_int, C.POINTER(Fixture)],
             "gpad_fixture_write": [C.c_char_p, C.POINTER(Fixture)],
             "gpad_fixture_free": [C.POINTER(Fixture)],
+            "gpad_problem_set_lipschitz": [C.c_void_p, C.c_int, _fp],
         }
         for name, sig in v2.items():          # API version 2 entry points (an older library simply lacks them)
             if hasattr(L, name):
@@ -201,6 +204,13 @@ class Problem:
         check(L.gpad_problem_dims(self._h, C.byref(nu), C.byref(N), C.byref(m), C.byref(npar), C.byref(Lc)))
         self.kind, self.n_u, self.N, self.m, self.n_par, self.L = kind, nu.value, N.value, m.value, npar.value, Lc.value
         self.n = self.n_u * self.N
+
+    def set_lipschitz(self, which):
+        """L_REFERENCE: ||H||_F^2 (acceldualgrad.m:11); L_LAMBDA_MAX: 1.02 lambda_max(G H^-1 G') (paper section 4)"""
+        Lc = C.c_float()
+        check(lib().gpad_problem_set_lipschitz(self._h, which, C.byref(Lc)), "gpad_problem_set_lipschitz")
+        self.L = Lc.value
+        return self.L
 
     def operators(self, layout=LAYOUT_SEQUENTIAL):
         M_G = np.empty(self.n * self.m, np.float32)

@@ -141,6 +141,32 @@ void hessian(const Mat& Su, const std::vector<double>& q, const std::vector<doub
         for (int j = i + 1; j < H.c; ++j) { const double s = 0.5 * (H(i, j) + H(j, i)); H(i, j) = s; H(j, i) = s; }
 }
 
+// lambda_max(G H^-1 G') = lambda_max(H^-1 G'G) by 400 power iterations from a fixed start vector (paper section 4)
+bool lambda_max_dual(const gpad_problem_s* P, double* out) {
+    const int n = P->n;
+    Mat Lc = P->H;
+    if (!cholesky(Lc)) return false;
+    Mat T = matmul(transpose(P->G), P->G);
+    chol_solve(Lc, T);
+    std::vector<double> v(n, 1.0 / std::sqrt((double)n)), u(n);
+    double lam = 0.0;
+    for (int it = 0; it < 400; ++it) {
+        for (int i = 0; i < n; ++i) {
+            double s = 0.0;
+            const double* row = &T.a[(size_t)i * n];
+            for (int j = 0; j < n; ++j) s += row[j] * v[j];
+            u[i] = s;
+        }
+        double nrm = 0.0;
+        for (double x : u) nrm += x * x;
+        lam = std::sqrt(nrm);
+        if (!(lam > 0.0)) return false;
+        for (int i = 0; i < n; ++i) v[i] = u[i] / lam;
+    }
+    *out = lam;
+    return true;
+}
+
 }  // namespace
 
 namespace gpad {
@@ -260,24 +286,8 @@ int gpad_problem_quadrotor(int N, gpad_problem_t* out) {
         }
     // L = 1.02 lambda_max(G H^-1 G') by power iteration on T = H^-1 (G'G), fixed start vector
     {
-        Mat Lc = P->H;
-        if (!cholesky(Lc)) { delete P; return GPAD_ERR_INVALID_ARG; }
-        Mat T = matmul(transpose(P->G), P->G);
-        chol_solve(Lc, T);
-        std::vector<double> v(n, 1.0 / std::sqrt((double)n)), u(n);
         double lam = 0.0;
-        for (int it = 0; it < 400; ++it) {
-            for (int i = 0; i < n; ++i) {
-                double s = 0.0;
-                const double* row = &T.a[(size_t)i * n];
-                for (int j = 0; j < n; ++j) s += row[j] * v[j];
-                u[i] = s;
-            }
-            double nrm = 0.0;
-            for (double x : u) nrm += x * x;
-            lam = std::sqrt(nrm);
-            for (int i = 0; i < n; ++i) v[i] = u[i] / lam;
-        }
+        if (!lambda_max_dual(P, &lam)) { delete P; return GPAD_ERR_INVALID_ARG; }
         P->L = 1.02 * lam;
     }
     P->blocks = {{0, 6}, {ns, 6}, {2 * ns, nu}, {2 * ns + n, nu}, {2 * ns + 2 * n, 4}};
@@ -291,6 +301,23 @@ int gpad_problem_destroy(gpad_problem_t p) {
     if (!p) return GPAD_OK;
     for (void* d : p->dev_cache) gpad::problem_dev_free(d);
     delete p;
+    return GPAD_OK;
+}
+
+int gpad_problem_set_lipschitz(gpad_problem_t p, int which, float* L_out) {
+    if (!p) return GPAD_ERR_INVALID_ARG;
+    double L = 0.0;
+    if (which == GPAD_L_REFERENCE) {                  // L = ||H||_F^2, acceldualgrad.m:11
+        for (double v : p->H.a) L += v * v;
+    } else if (which == GPAD_L_LAMBDA_MAX) {          // L = 1.02 lambda_max(G H^-1 G'), paper section 4
+        double lam = 0.0;
+        if (!lambda_max_dual(p, &lam)) return GPAD_ERR_INVALID_ARG;
+        L = 1.02 * lam;
+    } else {
+        return GPAD_ERR_INVALID_ARG;
+    }
+    p->L = L;
+    if (L_out) *L_out = (float)L;
     return GPAD_OK;
 }
 

@@ -224,6 +224,13 @@ int gpad_problem_quadrotor(int N, gpad_problem_t* out);
 int gpad_problem_destroy(gpad_problem_t p);
 /* n_par = length of the per-instance parameter vector (battery: x0 [n_u]; quadrotor: [x0;xref] [24]) */
 int gpad_problem_dims(gpad_problem_t p, int* n_u, int* N, int* m, int* n_par, float* L);
+/* Lipschitz constant of the dual gradient, the L of G_L = G / L and p_D = -b / L: GPAD_L_REFERENCE = ||H||_F^2 with H the
+ * PRIMAL Hessian (acceldualgrad.m:11: the reference's choice, the battery default; only a valid bound by accident of the
+ * battery scaling, 1.5x ... 50x above the dual Hessian's largest eigenvalue), GPAD_L_LAMBDA_MAX = 1.02 lambda_max(G H^-1 G')
+ * (paper section 4; the quadrotor default).  Changes what gpad_problem_dims / _operators / _instances return and what the
+ * on-device instance build uses from then on; handles built from the earlier operators keep the earlier L. */
+enum { GPAD_L_REFERENCE = 0, GPAD_L_LAMBDA_MAX = 1 };
+int gpad_problem_set_lipschitz(gpad_problem_t p, int which, float* L_out);
 /* operators to host buffers of n*m floats each, in the requested gpad_layout */
 int gpad_problem_operators(gpad_problem_t p, int layout, float* M_G, float* G_L);
 /* per-instance vectors from parameters [B][n_par] (double): g_P [B][n], p_D [B][m], f [B][n]

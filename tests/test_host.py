@@ -282,3 +282,25 @@ def test_group_and_async_entry_points_fail_loudly_without_a_device():
     pb = P.battery(3, 4)
     with pytest.raises(G.GpadError, match="no CUDA device|no usable"):
         G.Group([0, 1], 3, 4, pb.m, pb.L, pb.M_G, pb.G_L, max_batch=256)
+
+
+def test_lipschitz_constant_is_selectable():
+    """acceldualgrad.m:11 uses L = ||H||_F^2; the paper (section 4) lambda_max(G H^-1 G'): both on request"""
+    ref = P.battery(3, 4)
+    pb = G.Problem("battery", n_u=3, N=4)
+    assert abs(pb.L - ref.L) <= 1e-6 * ref.L                                # the reference's choice is the battery default
+    M0, G0 = pb.operators()
+    lam = np.linalg.eigvalsh(ref.G @ np.linalg.solve(ref.H, ref.G.T)).max()
+    L1 = pb.set_lipschitz(G.L_LAMBDA_MAX)
+    # power iteration approaches lambda_max from below (clustered eigenvalues: 0.1 % short after 400 steps), hence the 2 % margin
+    assert lam <= L1 <= 1.021 * lam and L1 < 0.8 * ref.L                    # SURVEY: 7.9986 against 12.0379
+    M1, G1 = pb.operators()
+    assert np.array_equal(M0, M1)                                           # M_G does not depend on L
+    assert np.allclose(G1, G0 * (ref.L / L1), rtol=2e-6)
+    g0, p0, _ = G.Problem("battery", n_u=3, N=4).instances(np.array([[0.1, -0.2, 0.3]]))
+    g1, p1, _ = pb.instances(np.array([[0.1, -0.2, 0.3]]))
+    assert np.array_equal(g0, g1) and np.allclose(p1, p0 * (ref.L / L1), rtol=2e-6)
+    assert abs(pb.set_lipschitz(G.L_REFERENCE) - ref.L) <= 1e-6 * ref.L
+    quad = G.Problem("quadrotor", N=10)
+    Lq = quad.L
+    assert abs(quad.set_lipschitz(G.L_LAMBDA_MAX) - Lq) <= 1e-6 * Lq        # the quadrotor default already is the paper's
