@@ -335,12 +335,12 @@ int launch_warp(const Params& p, cudaStream_t stream) {
     const int wpc = B > 1 ? kWarpsPerCta : 1;
     const int grid = (B + wpc - 1) / wpc;
     const bool chk = p.check_every > 0;
-    // Batches are issue-bound: NR = 12 covers the reference's default battery problem (n = 12) with 10 % fewer
-    // instructions, and program-ordered shuffles keep the reduction breadth-first at 79 registers (50.6 -> 56.4 M solves/s).
-    // ONE QP is bound by the dependent chain of a lone warp, and there ptxas' own schedule of the 16-row kernel is the
-    // best measured (37 us per 100 iterations; 12 rows: 61 us unordered -- ptxas walks the tree depth-first -- 45 us ordered).
-    int nr = (p.n <= 12 && B > 1) ? 12 : kWR;
-    bool ord = B > 1;
+    // NR = 12 covers the reference's default battery problem (n = 12): 12 instead of 16 zhat broadcasts and 12-long FMA
+    // chains in phase B; program-ordered shuffles keep the reduction breadth-first.  Measured with the select-free reduction,
+    // one QP, 100 iterations: (12, ordered) 35.3 us, (12, ptxas) 40.4 us, (16, either) 55 us; batches are issue-bound and
+    // prefer the same plan.
+    int nr = p.n <= 12 ? 12 : kWR;
+    bool ord = true;
     // experiments (GPAD_DEBUG warp_rows / warp_ordered / warp_pack, read at gpad_setup)
     if ((p.warp_rows == 12 || p.warp_rows == kWR) && p.warp_rows >= p.n) nr = p.warp_rows;
     if (p.warp_ordered >= 0) ord = p.warp_ordered != 0;
