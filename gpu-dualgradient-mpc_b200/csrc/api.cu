@@ -58,6 +58,7 @@ Knobs parse_knobs() {
         else if (key == "tc_p1") k.tc_p1 = iv;
         else if (key == "tc_stages") k.tc_stages = iv;
         else if (key == "tc_bn2") k.tc_bn2 = iv;
+        else if (key == "tc_p2") k.tc_p2 = iv;
         else if (key == "tc_autotune") k.tc_autotune = iv;
         else if (key == "tc_pdl") k.tc_pdl = iv;
         else if (key == "tc_cluster_attr") k.tc_cluster_attr = iv;
@@ -660,11 +661,12 @@ int gpad_setup(const gpad_config_t* cfg, const float* M_G, const float* G_L, gpa
     GPAD_REQUIRE(cfg->layout != GPAD_LAYOUT_FLAT || (cfg->mode != GPAD_MODE_BATCH_PER_INSTANCE && cfg->m >= 4 * cfg->n_u * cfg->N),
                  "gpad_setup: GPAD_LAYOUT_FLAT needs m >= 4 n_u N and shared operators");
     GPAD_REQUIRE(cfg->mode >= GPAD_MODE_LATENCY && cfg->mode <= GPAD_MODE_BATCH_PER_INSTANCE, "gpad_setup: bad mode");
-    GPAD_REQUIRE(cfg->precision == GPAD_PREC_FP32 || cfg->precision == GPAD_PREC_TF32X3, "gpad_setup: bad precision");
+    GPAD_REQUIRE(cfg->precision == GPAD_PREC_FP32 || cfg->precision == GPAD_PREC_TF32X3 || cfg->precision == GPAD_PREC_FP16X3,
+                 "gpad_setup: bad precision");
     GPAD_REQUIRE(cfg->max_batch >= 1, "gpad_setup: max_batch must be >= 1");
     GPAD_REQUIRE(cfg->mode != GPAD_MODE_LATENCY || cfg->max_batch == 1, "gpad_setup: latency mode solves one QP (max_batch = 1)");
     GPAD_REQUIRE(cfg->precision == GPAD_PREC_FP32 || cfg->mode == GPAD_MODE_BATCH_SHARED,
-                 "gpad_setup: GPAD_PREC_TF32X3 is only available in GPAD_MODE_BATCH_SHARED");
+                 "gpad_setup: GPAD_PREC_TF32X3 / GPAD_PREC_FP16X3 are only available in GPAD_MODE_BATCH_SHARED");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -871,6 +873,62 @@ int gpad_debug_gemm_tf32x3(const float* A, const float* B, float* C, int M, int 
     cudaError_t e = cudaStreamSynchronize(s);
     cudaFree(Ap); cudaFree(Al); cudaFree(Bp); cudaFree(Bl);
     if (rc == GPAD_OK && e != cudaSuccess) return cuda_fail(e, "gpad_debug_gemm_tf32x3", __FILE__, __LINE__);
+    return rc;
+}
+
+int gpad_debug_gemm_f16x3(const float* A, const float* B, float* C, int M, int N, int K, int kernel, void* stream) {
+    GPAD_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && (kernel == 0 || kernel == 1), "gpad_debug_gemm_f16x3: bad argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0;
+    GPAD_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    GPAD_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) { set_error("sm_100 device required"); return GPAD_ERR_UNSUPPORTED; }
+    tc::GemmDesc g;
+    g.f16 = 1; g.bk = 16;
+    g.k_pad = round_up(K, 32);
+    if (kernel == 1) { tc::plan_tiles_p1(N, &g.bn, &g.n_tiles, &g.step); g.p1 = 1; }
+    else tc::plan_tiles(N, &g.bn, &g.n_tiles);
+    g.m_tiles = round_up(M, 128) / 128;
+    g.ncols_valid = N;
+    const int Mp = g.m_tiles * 128, Np = round_up(g.bn * g.n_tiles, 128);
+    const size_t ca = (size_t)Mp * g.k_pad, cb = (size_t)Np * g.k_pad;
+    float *Ap = nullptr, *Bp = nullptr, *ainv = nullptr, *binv = nullptr, *amax = nullptr;
+    uint16_t *Ah = nullptr, *Al = nullptr, *Bh = nullptr, *Bl = nullptr;
+    GPAD_CUDA(cudaMalloc(&Ap, ca * 4)); GPAD_CUDA(cudaMalloc(&Bp, cb * 4));
+    GPAD_CUDA(cudaMalloc(&Ah, ca * 2)); GPAD_CUDA(cudaMalloc(&Al, ca * 2));
+    GPAD_CUDA(cudaMalloc(&Bh, cb * 2)); GPAD_CUDA(cudaMalloc(&Bl, cb * 2));
+    GPAD_CUDA(cudaMalloc(&ainv, Mp * 4)); GPAD_CUDA(cudaMalloc(&amax, Mp * 4)); GPAD_CUDA(cudaMalloc(&binv, Np * 4));
+    int rc = GPAD_OK;
+    do {
+        if ((rc = launch_pad_rows(Ap, g.k_pad, Mp, A, K, M, s)) != GPAD_OK) break;
+        if ((rc = launch_pad_rows(Bp, g.k_pad, Np, B, K, N, s)) != GPAD_OK) break;
+        if ((rc = tc::launch_quantize_rows(Bp, g.k_pad, Np, Bh, Bl, binv, nullptr, s)) != GPAD_OK) break;
+        if ((rc = tc::make_tmap_bytes(&g.tmB_hi, Bh, 2, g.k_pad, Np, g.k_pad, 32, g.bn)) != GPAD_OK) break;
+        if ((rc = tc::make_tmap_bytes(&g.tmB_lo, Bl, 2, g.k_pad, Np, g.k_pad, 32, g.bn)) != GPAD_OK) break;
+        BatchKernelArgs k{};
+        k.B = M;
+        k.b_colinv = binv;
+        if (kernel == 0) {
+            g.stages = tc::pick_stages(16, g.bn, prop.sharedMemPerBlockOptin);
+            if ((rc = tc::launch_quantize_rows(Ap, g.k_pad, Mp, Ah, Al, ainv, nullptr, s)) != GPAD_OK) break;
+            if ((rc = tc::make_tmap_bytes(&g.tmA_hi, Ah, 2, g.k_pad, Mp, g.k_pad, 32, 128)) != GPAD_OK) break;
+            if ((rc = tc::make_tmap_bytes(&g.tmA_lo, Al, 2, g.k_pad, Mp, g.k_pad, 32, 128)) != GPAD_OK) break;
+            k.a_rowinv = ainv;
+            rc = tc::launch_gemm(0, g, k, C, N, prop.multiProcessorCount, s);
+        } else {
+            // the TMEM-operand kernel quantises A itself; its warm-start launch (p_only) is a plain P = A B^T
+            if ((rc = tc::plan_rings_p1(g.bn, prop.sharedMemPerBlockOptin, &g.a_stages, &g.stages, true)) != GPAD_OK) break;
+            if ((rc = tc::launch_rowmax(Ap, g.k_pad, Mp, amax, s)) != GPAD_OK) break;
+            if ((rc = tc::make_tmap(&g.tmA_hi, Ap, g.k_pad, Mp, g.k_pad, 32, 128)) != GPAD_OK) break;
+            k.a_rowmax = amax;
+            k.p_only = 1; k.np = N; k.P_cur = C;
+            rc = tc::launch_p1(g, k, prop.multiProcessorCount, s);
+        }
+    } while (0);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(Ap); cudaFree(Bp); cudaFree(Ah); cudaFree(Al); cudaFree(Bh); cudaFree(Bl); cudaFree(ainv); cudaFree(amax); cudaFree(binv);
+    if (rc == GPAD_OK && e != cudaSuccess) return cuda_fail(e, "gpad_debug_gemm_f16x3", __FILE__, __LINE__);
     return rc;
 }
 

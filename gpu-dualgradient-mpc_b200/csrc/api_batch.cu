@@ -22,9 +22,23 @@ namespace {
 std::mutex g_tune_mutex;
 std::map<std::tuple<int, int, int, int>, std::pair<int, std::string>> g_tune_cache;
 
+// tensor maps over a slot's own state for the fp16 plans: y_v as fp32 tiles of 128 x 32 (quantised in-kernel), zhat hi / lo
+// as fp16 tiles of 128 x 32
+int make_f16_state_maps(BatchSlot& sl) {
+    const BatchState& st = sl.st;
+    for (int k = 0; k < 3; ++k) GPAD_TRY(tc::make_tmap(&sl.g1h.tmY[k], st.yb[k], st.mp, st.Bp, st.mp, 32, 128));
+    GPAD_TRY(tc::make_tmap_bytes(&sl.g2h.tmA_hi, st.zq_hi, 2, st.np, st.Bp, st.np, 32, 128));
+    GPAD_TRY(tc::make_tmap_bytes(&sl.g2h.tmA_lo, st.zq_lo, 2, st.np, st.Bp, st.np, 32, 128));
+    // epilogue operands of product 2: only the m real columns exist for the maps (zero fill / clipped stores beyond)
+    for (int k = 0; k < 3; ++k) GPAD_TRY(tc::make_tmap(&sl.g2h.tmEy[k], st.yb[k], st.m, st.Bp, st.mp, 32, 128));
+    GPAD_TRY(tc::make_tmap(&sl.g2h.tmEpd, st.p_D, st.m, st.Bp, st.mp, 32, 128));
+    return GPAD_OK;
+}
+
 int alloc_slot(gpad_handle_s* h, BatchSlot& sl, const BatchSlot* like) {
     const int n = h->n, m = h->cfg.m;
-    const bool tcp = h->cfg.precision == GPAD_PREC_TF32X3;
+    const bool f16 = h->cfg.precision == GPAD_PREC_FP16X3;
+    const bool tcp = h->cfg.precision == GPAD_PREC_TF32X3 || f16;
     BatchState& st = sl.st;
     st.n = n; st.m = m; st.np = round_up(n, 32); st.mp = round_up(m, 32);
     st.Bp = round_up(h->cfg.max_batch, 256);
@@ -58,6 +72,17 @@ int alloc_slot(gpad_handle_s* h, BatchSlot& sl, const BatchSlot* like) {
             for (int k = 0; k < 3; ++k) GPAD_TRY(tc::make_tmap(&sl.g1.tmY[k], st.yb[k], st.mp, st.Bp, st.mp, sl.g1.bk, 128));
             GPAD_TRY(tc::make_tmap(&sl.g2.tmA_hi, st.zh_hi, st.np, st.Bp, st.np, sl.g2.bk, 128));
             GPAD_TRY(tc::make_tmap(&sl.g2.tmA_lo, st.zh_lo, st.np, st.Bp, st.np, sl.g2.bk, 128));
+        }
+        if (f16) {
+            GPAD_TRY(dev_alloc(h, &st.zq_hi, bnn)); GPAD_TRY(dev_alloc(h, &st.zq_lo, bnn));
+            GPAD_CUDA(cudaMemset(st.zq_hi, 0, bnn * sizeof(uint16_t))); GPAD_CUDA(cudaMemset(st.zq_lo, 0, bnn * sizeof(uint16_t)));
+            GPAD_TRY(dev_alloc(h, &st.zinv, st.Bp)); GPAD_TRY(dev_alloc(h, &st.ymax[0], st.Bp)); GPAD_TRY(dev_alloc(h, &st.ymax[1], st.Bp));
+            GPAD_CUDA(cudaMemset(st.zinv, 0, st.Bp * sizeof(float)));
+            GPAD_CUDA(cudaMemset(st.ymax[0], 0, st.Bp * sizeof(unsigned))); GPAD_CUDA(cudaMemset(st.ymax[1], 0, st.Bp * sizeof(unsigned)));
+            if (like) {
+                sl.g1h = like->g1h; sl.g2h = like->g2h;
+                GPAD_TRY(make_f16_state_maps(sl));
+            }
         }
     }
     GPAD_CUDA(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
@@ -141,8 +166,12 @@ int inputs(gpad_handle_s* h, BatchSlot& sl, const gpad_solve_args_t* a, bool hos
     return GPAD_OK;
 }
 
-int launch_product(gpad_handle_s* h, BatchSlot& sl, int phase, const BatchKernelArgs& k, cudaStream_t s) {
-    if (h->cfg.precision == GPAD_PREC_TF32X3) {
+// `it`: the iteration (selects the rotating y buffers for the TMA-fed epilogue of the fp16 product 2)
+int launch_product(gpad_handle_s* h, BatchSlot& sl, int phase, const BatchKernelArgs& k, cudaStream_t s, bool f16 = false, int it = 0) {
+    if (f16 && phase == 1) return tc::launch_p1(sl.g1h, k, h->num_sms, s);
+    if (f16 && sl.g2h.p2) return tc::launch_p2(sl.g2h, k, it % 3, (it + 2) % 3, (it + 1) % 3, h->num_sms, s);
+    if (f16) return tc::launch_gemm(2, sl.g2h, k, nullptr, 0, h->num_sms, s);
+    if (h->cfg.precision == GPAD_PREC_TF32X3 || h->cfg.precision == GPAD_PREC_FP16X3) {
         if (phase == 1 && sl.g1.p1) return tc::launch_p1(sl.g1, k, h->num_sms, s);
         return tc::launch_gemm(phase, phase == 1 ? sl.g1 : sl.g2, k, nullptr, 0, h->num_sms, s);
     }
@@ -153,8 +182,9 @@ int launch_product(gpad_handle_s* h, BatchSlot& sl, int phase, const BatchKernel
 int iterate(gpad_handle_s* h, BatchSlot& sl, const gpad_solve_args_t* a, cudaStream_t s) {
     BatchState& st = sl.st;
     const int B = st.B;
-    const bool tcp = h->cfg.precision == GPAD_PREC_TF32X3;
     const bool checking = a->check_every > 0;
+    const bool f16 = h->cfg.precision == GPAD_PREC_FP16X3 && !checking;      // tolerance mode runs the tf32 kernels
+    const bool tcp = h->cfg.precision == GPAD_PREC_TF32X3 || h->cfg.precision == GPAD_PREC_FP16X3;
     const bool have_f = a->f != nullptr || a->build_f;
     // compaction needs the tile list (the compacted layout is only visible to the kernels through it)
     const bool compacting = checking && h->knobs.tc_retire && h->knobs.tc_compact && B > 256;
@@ -170,6 +200,14 @@ int iterate(gpad_handle_s* h, BatchSlot& sl, const gpad_solve_args_t* a, cudaStr
     BatchKernelArgs k = kernel_args(h, st, a, checking);
     const int m_tiles = round_up(B, 128) / 128;
     sl.g1.m_tiles = m_tiles; sl.g2.m_tiles = m_tiles;
+    sl.g1h.m_tiles = m_tiles; sl.g2h.m_tiles = m_tiles;
+    sl.g1h.pdl = sl.g2h.pdl = h->knobs.tc_pdl ? 1 : 0;
+    const int q_rows = m_tiles * 128;          // rows the quantisation kernels cover: whole batch tiles
+    if (f16 && a->max_iter > 0) {
+        // row maxima of y_0 (product 2 reduces those of every later iterate)
+        if (a->y0) { GPAD_TRY(tc::launch_rowmax(st.yb[0], st.mp, q_rows, reinterpret_cast<float*>(st.ymax[0]), s)); h->launches += 1; }
+        else GPAD_CUDA(cudaMemsetAsync(st.ymax[0], 0, sizeof(unsigned) * q_rows, s));
+    }
     // programmatic dependent launch: a GEMM kernel's CTAs start while the previous kernel drains; nothing it reads from
     // global memory (tile lists and counters included, see TileSched) is read before its dependency wait
     sl.g1.pdl = sl.g2.pdl = h->knobs.tc_pdl ? 1 : 0;
@@ -180,7 +218,13 @@ int iterate(gpad_handle_s* h, BatchSlot& sl, const gpad_solve_args_t* a, cudaStr
             kp.p_only = 1; kp.P_cur = st.Pb[1]; kp.P_prev = st.Pb[0];
             kp.tile_list = nullptr; kp.tile_count = nullptr;
             sl.g1.tmA_hi = sl.g1.tmY[2]; sl.g1.tmA_lo = sl.g1.tmY[2];
-            GPAD_TRY(launch_product(h, sl, 1, kp, s));
+            if (f16) {
+                GPAD_TRY(tc::launch_rowmax(st.yb[2], st.mp, q_rows, reinterpret_cast<float*>(st.ymax[1]), s));
+                h->launches += 1;
+                sl.g1h.tmA_hi = sl.g1h.tmY[2];
+                kp.a_rowmax = reinterpret_cast<const float*>(st.ymax[1]); kp.b_colinv = h->op.M_G_inv;
+            }
+            GPAD_TRY(launch_product(h, sl, 1, kp, s, f16));
             h->launches += 1;
         } else {
             GPAD_CUDA(cudaMemsetAsync(st.Pb[1], 0, sizeof(float) * (size_t)st.Bp * st.np, s));
@@ -220,11 +264,24 @@ int iterate(gpad_handle_s* h, BatchSlot& sl, const gpad_solve_args_t* a, cudaStr
         k.y_next = st.yb[(it + 1) % 3];           // y_{v+1} overwrites y_{v-2}
         k.P_cur = st.Pb[it & 1]; k.P_prev = st.Pb[(it + 1) & 1];
         if (tcp) { sl.g1.tmA_hi = sl.g1.tmY[it % 3]; sl.g1.tmA_lo = sl.g1.tmY[it % 3]; }
+        if (f16) {
+            sl.g1h.tmA_hi = sl.g1h.tmY[it % 3];
+            k.a_rowmax = reinterpret_cast<const float*>(st.ymax[it & 1]);
+            k.b_colinv = h->op.M_G_inv;
+        }
         cudaEvent_t pe = h->prof_begin(s);
-        GPAD_TRY(launch_product(h, sl, 1, k, s));
+        GPAD_TRY(launch_product(h, sl, 1, k, s, f16));
         h->prof_end(1, pe, s);
+        if (f16) {
+            // zhat_v -> row scale, fp16 hi / lo; also clears the row maxima product 2 is about to reduce
+            pe = h->prof_begin(s);
+            GPAD_TRY(tc::launch_quantize_rows(st.zhat, st.np, q_rows, st.zq_hi, st.zq_lo, st.zinv, st.ymax[(it + 1) & 1], s));
+            h->prof_end(0, pe, s);
+            h->launches += 1;
+            k.a_rowinv = st.zinv; k.b_colinv = h->op.G_L_inv; k.next_rowmax = st.ymax[(it + 1) & 1];
+        }
         pe = h->prof_begin(s);
-        GPAD_TRY(launch_product(h, sl, 2, k, s));
+        GPAD_TRY(launch_product(h, sl, 2, k, s, f16, it));
         h->prof_end(2, pe, s);
         h->launches += 2;
         ++since_check;
@@ -347,7 +404,8 @@ int wait_all_async(gpad_handle_s* h) {
 // ------------------------------------------------------------------ setup
 int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vector<float>& GL) {
     const int n = h->n, m = h->cfg.m;
-    const bool tcp = h->cfg.precision == GPAD_PREC_TF32X3;
+    const bool f16 = h->cfg.precision == GPAD_PREC_FP16X3;
+    const bool tcp = h->cfg.precision == GPAD_PREC_TF32X3 || f16;
     const Knobs& kn = h->knobs;
     BatchSlot& sl = h->slot[0];
     const int np = round_up(n, 32), mp = round_up(m, 32);
@@ -359,7 +417,8 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
     // tiles.  With few tiles the number of waves over the SMs decides (battery (10,100), 4096 QPs: 160 tiles = 2 waves
     // against 128 tiles = 1 wave: measured 98.7 k against 112 k solves/s), with many tiles the per-tile cost does.
     bool p1 = tcp;
-    if (tcp && kn.tc_p1 >= 0) p1 = kn.tc_p1 != 0;
+    if (f16) p1 = true;       // the fp16 product 1 exists as the TMEM-operand kernel only: one tiling for both families
+    else if (tcp && kn.tc_p1 >= 0) p1 = kn.tc_p1 != 0;
     else if (tcp) {
         int bn_ts = 0, nt_ts = 0;
         tc::plan_tiles_p1(n, &bn_ts, &nt_ts);
@@ -388,6 +447,15 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         return GPAD_OK;
     }
     const size_t c1 = (size_t)h->op.n_rows_pad * mp, c2 = (size_t)h->op.m_rows_pad * np;
+    if (f16) {
+        // fp16 hi / lo of the row-scaled operators, from the fp32 values (before the tf32 split below rewrites them)
+        GPAD_TRY(dev_alloc(h, &h->op.M_Gq_hi, c1)); GPAD_TRY(dev_alloc(h, &h->op.M_Gq_lo, c1));
+        GPAD_TRY(dev_alloc(h, &h->op.G_Lq_hi, c2)); GPAD_TRY(dev_alloc(h, &h->op.G_Lq_lo, c2));
+        GPAD_TRY(dev_alloc(h, &h->op.M_G_inv, h->op.n_rows_pad)); GPAD_TRY(dev_alloc(h, &h->op.G_L_inv, h->op.m_rows_pad));
+        GPAD_TRY(tc::launch_quantize_rows(h->op.M_G, mp, h->op.n_rows_pad, h->op.M_Gq_hi, h->op.M_Gq_lo, h->op.M_G_inv, nullptr, h->own_stream));
+        GPAD_TRY(tc::launch_quantize_rows(h->op.G_L, np, h->op.m_rows_pad, h->op.G_Lq_hi, h->op.G_Lq_lo, h->op.G_L_inv, nullptr, h->own_stream));
+        GPAD_CUDA(cudaStreamSynchronize(h->own_stream));
+    }
     GPAD_TRY(dev_alloc(h, &h->op.M_G_lo, c1)); GPAD_TRY(dev_alloc(h, &h->op.G_L_lo, c2));
     GPAD_TRY(tc::launch_split(h->op.M_G, h->op.M_G, h->op.M_G_lo, c1, h->own_stream));
     GPAD_TRY(tc::launch_split(h->op.G_L, h->op.G_L, h->op.G_L_lo, c2, h->own_stream));
@@ -409,65 +477,97 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
     GPAD_TRY(tc::make_tmap(&g1.tmB_lo, h->op.M_G_lo, mp, h->op.n_rows_pad, mp, g1.bk, bn1));
     GPAD_TRY(tc::make_tmap(&g2.tmA_hi, st.zh_hi, np, st.Bp, np, g2.bk, 128));
     GPAD_TRY(tc::make_tmap(&g2.tmA_lo, st.zh_lo, np, st.Bp, np, g2.bk, 128));
-    auto config_g2 = [&](int b) -> int {
-        bn2 = b; nt2 = (m + b - 1) / b;
-        g2.bn = bn2; g2.n_tiles = nt2;
-        g2.stages = cap_stages(tc::pick_stages(bk, bn2, h->smem_optin));
-        GPAD_TRY(tc::make_tmap(&g2.tmB_hi, h->op.G_L, np, h->op.m_rows_pad, np, g2.bk, bn2));
-        GPAD_TRY(tc::make_tmap(&g2.tmB_lo, h->op.G_L_lo, np, h->op.m_rows_pad, np, g2.bk, bn2));
+    // product 2 tiling of width b for the tf32 (half = false) or the fp16 plan
+    auto config_g2 = [&](tc::GemmDesc& g, bool half, int b) -> int {
+        g.bn = b; g.n_tiles = (m + b - 1) / b;
+        g.stages = cap_stages(tc::pick_stages(bk, b, h->smem_optin));
+        if (half && g.p2) {
+            GPAD_TRY(tc::plan_rings_p2(b, h->smem_optin, &g.stages, &g.e_stages));
+            g.stages = cap_stages(g.stages);
+        }
+        if (half) {
+            GPAD_TRY(tc::make_tmap_bytes(&g.tmB_hi, h->op.G_Lq_hi, 2, np, h->op.m_rows_pad, np, 32, b));
+            GPAD_TRY(tc::make_tmap_bytes(&g.tmB_lo, h->op.G_Lq_lo, 2, np, h->op.m_rows_pad, np, 32, b));
+        } else {
+            GPAD_TRY(tc::make_tmap(&g.tmB_hi, h->op.G_L, np, h->op.m_rows_pad, np, g.bk, b));
+            GPAD_TRY(tc::make_tmap(&g.tmB_lo, h->op.G_L_lo, np, h->op.m_rows_pad, np, g.bk, b));
+        }
         return GPAD_OK;
     };
-    GPAD_TRY(config_g2(bn2));
-    // ---- product 2 tile width: timed once per (device, n, m, batch) in this process on the handle's own zeroed buffers
-    // and own stream (first launch untimed, three timed); results do not depend on the width: every output element sums
-    // over K in the same order.  GPAD_DEBUG tc_bn2=<w> fixes it, tc_autotune=0 keeps the first candidate. ----
-    std::string tune_note;
-    if (kn.tc_bn2 > 0) {
-        GPAD_TRY(config_g2(std::max(16, std::min(256, kn.tc_bn2 / 16 * 16))));
-        tune_note = "fixed by tc_bn2";
-    } else if (h->cfg.max_batch >= 1024 && kn.tc_autotune) {
-        const auto key = std::make_tuple(h->device, n, m, round_up(h->cfg.max_batch, 128));
+    // ---- product 2 tile width: timed once per (device, n, m, batch, kernel family) in this process on the handle's own
+    // zeroed buffers and own stream (first launch untimed, three timed); results do not depend on the width: every output
+    // element sums over K in the same order.  GPAD_DEBUG tc_bn2=<w> fixes it, tc_autotune=0 keeps the first candidate. ----
+    auto tune_g2 = [&](tc::GemmDesc& g, bool half, int bn_default, std::string& tune_note) -> int {
+        GPAD_TRY(config_g2(g, half, bn_default));
+        if (kn.tc_bn2 > 0) {
+            GPAD_TRY(config_g2(g, half, std::max(g.p2 ? 32 : 16, std::min(256, kn.tc_bn2 / (g.p2 ? 32 : 16) * (g.p2 ? 32 : 16)))));
+            tune_note = "fixed by tc_bn2";
+            return GPAD_OK;
+        }
+        if (h->cfg.max_batch < 1024 || !kn.tc_autotune) return GPAD_OK;
+        const auto key = std::make_tuple(h->device, n, m, round_up(h->cfg.max_batch, 128) + (half ? 1 : 0));
         std::lock_guard<std::mutex> lock(g_tune_mutex);
         auto hit = g_tune_cache.find(key);
         if (hit != g_tune_cache.end()) {
-            GPAD_TRY(config_g2(hit->second.first));
+            GPAD_TRY(config_g2(g, half, hit->second.first));
             tune_note = hit->second.second + " (cached)";
-        } else {
-            const int bn_default = bn2;
-            st.B = h->cfg.max_batch;
-            BatchKernelArgs k = kernel_args(h, st, nullptr, false);
-            k.y_prev = st.yb[2]; k.y_cur = st.yb[0]; k.y_next = st.yb[1];
-            k.it.theta = 1.f; k.it.beta = 0.f;
-            cudaEvent_t e0, e1;
-            GPAD_CUDA(cudaEventCreate(&e0)); GPAD_CUDA(cudaEventCreate(&e1));
-            float best_ms = 1e30f; int best_bn = bn_default;
-            std::vector<int> cand = {bn_default};
-            // multiples of 32 columns: every 32-column block of the epilogue then starts on a 128-byte line (widths that
-            // are only multiples of 16 -- 144, 176, 208, 240 -- measured 0.73 .. 1.04 ms against 0.66 .. 0.69 for 160 / 192)
-            for (int b : {256, 224, 192, 160, 128}) if (b != bn_default && (m + b - 1) / b <= 64) cand.push_back(b);
-            for (int b : cand) {
-                if (config_g2(b) != GPAD_OK) continue;
-                g2.m_tiles = (h->cfg.max_batch + 127) / 128;
-                float ms = 1e30f;
-                bool ok = true;
-                for (int rep = 0; rep < 4 && ok; ++rep) {
-                    if (rep == 1) cudaEventRecord(e0, h->own_stream);
-                    ok = tc::launch_gemm(2, g2, k, nullptr, 0, h->num_sms, h->own_stream) == GPAD_OK;
-                }
-                cudaEventRecord(e1, h->own_stream);
-                if (cudaEventSynchronize(e1) != cudaSuccess || !ok) { cudaGetLastError(); continue; }
-                cudaEventElapsedTime(&ms, e0, e1);
-                char t[48];
-                snprintf(t, sizeof(t), "%s%d:%.3f", tune_note.empty() ? "" : " ", b, ms / 3.0f);
-                tune_note += t;
-                if (ms < best_ms) { best_ms = ms; best_bn = b; }
-            }
-            cudaEventDestroy(e0); cudaEventDestroy(e1);
-            GPAD_TRY(config_g2(best_bn));
-            GPAD_CUDA(cudaMemset(st.yb[1], 0, (size_t)st.Bp * mp * sizeof(float)));      // the timed launches wrote y_next
-            tune_note = "timed, ms per launch by width: " + tune_note;
-            g_tune_cache[key] = {best_bn, tune_note};
+            return GPAD_OK;
         }
+        st.B = h->cfg.max_batch;
+        BatchKernelArgs k = kernel_args(h, st, nullptr, false);
+        k.y_prev = st.yb[2]; k.y_cur = st.yb[0]; k.y_next = st.yb[1];
+        k.it.theta = 1.f; k.it.beta = 0.f;
+        k.a_rowinv = st.zinv; k.b_colinv = h->op.G_L_inv; k.next_rowmax = st.ymax[1];
+        cudaEvent_t e0, e1;
+        GPAD_CUDA(cudaEventCreate(&e0)); GPAD_CUDA(cudaEventCreate(&e1));
+        float best_ms = 1e30f; int best_bn = bn_default;
+        std::vector<int> cand = {bn_default};
+        // multiples of 32 columns: every 32-column block of the epilogue then starts on a 128-byte line (widths that
+        // are only multiples of 16 -- 144, 176, 208, 240 -- measured 0.73 .. 1.04 ms against 0.66 .. 0.69 for 160 / 192)
+        for (int b : {256, 224, 192, 160, 128}) if (b != bn_default && (m + b - 1) / b <= 64) cand.push_back(b);
+        for (int b : cand) {
+            if (config_g2(g, half, b) != GPAD_OK) continue;
+            g.m_tiles = (h->cfg.max_batch + 127) / 128;
+            float ms = 1e30f;
+            bool ok = true;
+            for (int rep = 0; rep < 4 && ok; ++rep) {
+                if (rep == 1) cudaEventRecord(e0, h->own_stream);
+                ok = (g.p2 ? tc::launch_p2(g, k, 0, 2, 1, h->num_sms, h->own_stream)
+                           : tc::launch_gemm(2, g, k, nullptr, 0, h->num_sms, h->own_stream)) == GPAD_OK;
+            }
+            cudaEventRecord(e1, h->own_stream);
+            if (cudaEventSynchronize(e1) != cudaSuccess || !ok) { cudaGetLastError(); continue; }
+            cudaEventElapsedTime(&ms, e0, e1);
+            char t[48];
+            snprintf(t, sizeof(t), "%s%d:%.3f", tune_note.empty() ? "" : " ", b, ms / 3.0f);
+            tune_note += t;
+            if (ms < best_ms) { best_ms = ms; best_bn = b; }
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        GPAD_TRY(config_g2(g, half, best_bn));
+        GPAD_CUDA(cudaMemset(st.yb[1], 0, (size_t)st.Bp * mp * sizeof(float)));      // the timed launches wrote y_next
+        if (half) GPAD_CUDA(cudaMemset(st.ymax[1], 0, st.Bp * sizeof(unsigned)));
+        tune_note = "timed, ms per launch by width: " + tune_note;
+        g_tune_cache[key] = {best_bn, tune_note};
+        return GPAD_OK;
+    };
+    std::string tune_note, tune_note_h;
+    GPAD_TRY(tune_g2(g2, false, bn2, tune_note));
+    bn2 = g2.bn; nt2 = g2.n_tiles;
+    if (f16) {
+        tc::GemmDesc& g1h = sl.g1h; tc::GemmDesc& g2h = sl.g2h;
+        g1h = tc::GemmDesc{}; g2h = tc::GemmDesc{};
+        g1h.f16 = g2h.f16 = 1; g1h.bk = g2h.bk = bk;
+        g1h.k_pad = mp; g1h.bn = bn1; g1h.n_tiles = nt1; g1h.ncols_valid = n; g1h.p1 = 1; g1h.step = step1;
+        GPAD_TRY(tc::plan_rings_p1(bn1, h->smem_optin, &g1h.a_stages, &g1h.stages, true));
+        g2h.k_pad = np; g2h.ncols_valid = m;
+        GPAD_TRY(make_f16_state_maps(sl));
+        GPAD_TRY(tc::make_tmap_bytes(&g1h.tmB_hi, h->op.M_Gq_hi, 2, mp, h->op.n_rows_pad, mp, 32, bn1));
+        GPAD_TRY(tc::make_tmap_bytes(&g1h.tmB_lo, h->op.M_Gq_lo, 2, mp, h->op.n_rows_pad, mp, 32, bn1));
+        int bnh = 0, nth = 0;
+        g2h.p2 = kn.tc_p2 ? 1 : 0;
+        if (g2h.p2) tc::plan_tiles_p2(m, &bnh, &nth); else tc::plan_tiles(m, &bnh, &nth);
+        GPAD_TRY(tune_g2(g2h, true, bnh, tune_note_h));
     }
     if (p1)
         snprintf(buf, sizeof(buf),
@@ -484,6 +584,17 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
                  bk, bn1, nt1, g1.stages, bn2, nt2, g2.stages, tune_note.empty() ? "by plan" : tune_note.c_str(), h->num_sms,
                  kn.tc_pdl ? "on" : "off");
     h->desc = buf;
+    if (f16) {
+        snprintf(buf, sizeof(buf),
+                 "batch-shared, fixed-iteration solves: tcgen05 cta_group::1 kind::f16 x3 (fp16 hi/lo of power-of-two row-scaled operands, "
+                 "scales undone on the fp32 accumulator); product1 = P-formulation, y_v quantised in registers into a TMEM A ring (state "
+                 "ring %d x 16 KB + operator ring %d stages), tiles 128x%d x%d, k-blocks of 32; zhat row quantisation kernel; product2 "
+                 "%s, tiles 128x%d x%d (%d stages; width %s); tolerance-mode solves: ",
+                 sl.g1h.a_stages, sl.g1h.stages, sl.g1h.bn, sl.g1h.n_tiles,
+                 sl.g2h.p2 ? "with TMA-streamed epilogue operands and stores" : "(first-generation kernel)", sl.g2h.bn, sl.g2h.n_tiles,
+                 sl.g2h.stages, tune_note_h.empty() ? "by plan" : tune_note_h.c_str());
+        h->desc = std::string(buf) + h->desc;
+    }
     return GPAD_OK;
 }
 

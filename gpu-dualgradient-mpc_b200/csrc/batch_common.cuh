@@ -54,6 +54,11 @@ struct BatchKernelArgs {
     const int* tile_list;
     const int* tile_count;
     const int* dual_count; // dual-gap launches return at once when no instance waits for the evaluation
+    // GPAD_PREC_FP16X3 (fp16 hi / lo operands scaled per row by powers of two; tc_ptx.cuh:f16_scale_exp)
+    const float* a_rowmax;   // product 1: [Bp] max_k y_v[b][k], the transform warps derive the row scale from it
+    const float* a_rowinv;   // product 2: [Bp] 2^-e of the zhat row scale (written by zsplit_kernel)
+    const float* b_colinv;   // [rows_pad] 2^-e of the operator row (= output column) scales
+    unsigned* next_rowmax;   // product 2: [Bp] bit pattern of max_k y_{v+1}[b][k] (atomicMax; zeroed by zsplit_kernel)
 };
 
 __device__ __forceinline__ float tf32_rn(float x) {

@@ -63,7 +63,9 @@ __host__ __device__ constexpr int epi_warps(int phase) { return kWorkWarps - xfo
 __host__ __device__ constexpr int cta_threads(int phase) { return 32 * (2 + kWorkWarps); }
 
 // PHASE 0: plain store of C (test hook); 1: GPAD product 1; 2: GPAD product 2
-template <int PHASE, int BK, bool TOL>
+// F16 (GPAD_PREC_FP16X3): the operand tiles hold fp16 hi / lo of row-scaled values -- the same 64-byte rows, twice the K
+// per row (BK counts 4-byte units), kind::f16 MMAs; the epilogue undoes the row and column scales on the accumulator
+template <int PHASE, int BK, bool TOL, bool F16>
 __global__ void __launch_bounds__(cta_threads(PHASE), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -73,6 +75,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t a_bytes = kBM * BK * 4, b_bytes = (uint32_t)bn * BK * 4;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    constexpr int kElemsPerBlock = F16 ? 2 * BK : BK;      // K elements of one k-block (TMA coordinates count elements)
     constexpr bool kXform = PHASE == 1;    // transform warps: the A tile is y_v (fp32) -> tf32 hi in place, lo next to it
     constexpr int kXW = xform_warps(PHASE);
     constexpr int kEpi = epi_warps(PHASE);
@@ -118,10 +121,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (elect_one()) {
                     // product 1 stages one fp32 tile (y_v); its lo half is produced in place by the transform warps
                     mbar_expect_tx(fb, kXform ? stage_bytes - a_bytes : stage_bytes);
-                    tma_load_2d(base, &tmA_hi, kb * BK, row_a, fb);
-                    if (!kXform) tma_load_2d(base + a_bytes, &tmA_lo, kb * BK, row_a, fb);
-                    tma_load_2d(base + 2 * a_bytes, &tmB_hi, kb * BK, row_b, fb);
-                    tma_load_2d(base + 2 * a_bytes + b_bytes, &tmB_lo, kb * BK, row_b, fb);
+                    tma_load_2d(base, &tmA_hi, kb * kElemsPerBlock, row_a, fb);
+                    if (!kXform) tma_load_2d(base + a_bytes, &tmA_lo, kb * kElemsPerBlock, row_a, fb);
+                    tma_load_2d(base + 2 * a_bytes, &tmB_hi, kb * kElemsPerBlock, row_b, fb);
+                    tma_load_2d(base + 2 * a_bytes + b_bytes, &tmB_lo, kb * kElemsPerBlock, row_b, fb);
                 }
                 __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -130,7 +133,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
         // warp-uniform loop (waits and descriptor arithmetic in uniform registers), one elected lane issues
-        const uint32_t idesc = make_idesc(bn);
+        const uint32_t idesc = make_idesc_k<F16>(bn);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (TileSched ts(m_tiles, n_tiles, args); ts.valid(); ts.next()) {
@@ -148,9 +151,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         const uint64_t a_lo = make_smem_desc<BK>(base + a_bytes + ks * 32);
                         const uint64_t b_hi = make_smem_desc<BK>(base + 2 * a_bytes + ks * 32);
                         const uint64_t b_lo = make_smem_desc<BK>(base + 2 * a_bytes + b_bytes + ks * 32);
-                        umma_tf32(d_tmem, a_hi, b_lo, idesc, (kb | ks) != 0 ? 1u : 0u);
-                        umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
-                        umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+                        umma_ss<F16>(d_tmem, a_hi, b_lo, idesc, (kb | ks) != 0 ? 1u : 0u);
+                        umma_ss<F16>(d_tmem, a_lo, b_hi, idesc, 1u);
+                        umma_ss<F16>(d_tmem, a_hi, b_hi, idesc, 1u);
                     }
                     umma_commit(smem_u32(empty_bar + stage));     // frees the ring slot when these MMAs retire
                 }
@@ -203,15 +206,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tc_fence_after();
             const int row_base = ts.m_tile() * kBM + q * 32;
+            // F16: this thread's accumulator row (TMEM lane = batch row) carries the row scale of the A operand
+            float row_inv = 1.f;
+            if (F16) row_inv = __ldg(args.a_rowinv + row_base + lane);
+            uint32_t row_max = 0;                     // F16 product 2: lane r keeps max_c y+[row_base + r][c] of this tile
             for (int blk = part; blk < nblk; blk += kParts) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride + blk * 32), v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = __uint_as_float(v[j]);
+                for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = F16 ? __uint_as_float(v[j]) * row_inv : __uint_as_float(v[j]);
                 __syncwarp();
-                epilogue_block<PHASE, TOL>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, Cdbg, ldc);
+                epilogue_block<PHASE, TOL, F16>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, Cdbg, ldc, 0, &row_max);
                 __syncwarp();
             }
+            if (F16 && PHASE == 2 && row_max != 0u) atomicMax(args.next_rowmax + row_base + lane, row_max);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
@@ -257,15 +265,21 @@ EncodeTiledFn encode_fn() {
 }  // namespace
 
 int make_tmap(CUtensorMap* map, const float* ptr, int k_elems, int rows, int ld, int box_k, int box_rows) {
+    return make_tmap_bytes(map, ptr, 4, k_elems, rows, ld, box_k, box_rows);
+}
+
+// elem_bytes 4: fp32 rows, 2: fp16 rows; k_elems / ld / box_k count elements.  The swizzle span is the box row.
+int make_tmap_bytes(CUtensorMap* map, const void* ptr, int elem_bytes, int k_elems, int rows, int ld, int box_k, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return GPAD_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)k_elems, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
     cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapSwizzle sw = box_k == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                 : box_k == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+    const int row_bytes = box_k * elem_bytes;
+    const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return GPAD_ERR_CUDA; }
@@ -291,9 +305,9 @@ int pick_stages(int bk, int bn, size_t smem_limit) {
     return s;
 }
 
-template <int PHASE, int BK, bool TOL>
+template <int PHASE, int BK, bool TOL, bool F16 = false>
 static int launch_one(const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s) {
-    auto kern = tc_gemm_kernel<PHASE, BK, TOL>;
+    auto kern = tc_gemm_kernel<PHASE, BK, TOL, F16>;
     const size_t smem = smem_bytes(BK, g.bn, g.stages);
     GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int units = g.m_tiles * g.n_tiles;
@@ -312,8 +326,8 @@ static int launch_one(const GemmDesc& g, const BatchKernelArgs& args, float* C, 
         ++na;
     }
     lc.attrs = at; lc.numAttrs = na;
-    GPAD_CUDA(cudaLaunchKernelEx(&lc, kern, g.tmA_hi, g.tmA_lo, g.tmB_hi, g.tmB_lo, g.k_pad / BK, g.m_tiles, g.n_tiles, g.bn,
-                                 g.stages, args, C, ldc, g.ncols_valid));
+    GPAD_CUDA(cudaLaunchKernelEx(&lc, kern, g.tmA_hi, g.tmA_lo, g.tmB_hi, g.tmB_lo, g.k_pad / (F16 ? 2 * BK : BK), g.m_tiles,
+                                 g.n_tiles, g.bn, g.stages, args, C, ldc, g.ncols_valid));
     return GPAD_OK;
 }
 
@@ -321,6 +335,11 @@ int launch_gemm(int phase, const GemmDesc& g, const BatchKernelArgs& args, float
     if (g.bk != 16) { set_error("tcgen05 GEMM: K block %d is not built (16 only)", g.bk); return GPAD_ERR_UNSUPPORTED; }
     // fixed-iteration solves run the lean instantiation; tolerance mode (stopped rows, reductions, dual-gap launches) its own
     const bool tol = args.checking || args.dual || args.done;
+    if (g.f16) {
+        // fp16 hi / lo operands: fixed-iteration product 2 and the test hook (tolerance mode runs the tf32 kernels)
+        if (tol || phase == 1) { set_error("tcgen05 GEMM: no fp16 instantiation for this launch"); return GPAD_ERR_UNSUPPORTED; }
+        return phase == 0 ? launch_one<0, 16, false, true>(g, args, C, ldc, num_sms, s) : launch_one<2, 16, false, true>(g, args, C, ldc, num_sms, s);
+    }
     if (phase == 0) return launch_one<0, 16, false>(g, args, C, ldc, num_sms, s);
     if (phase == 1) return tol ? launch_one<1, 16, true>(g, args, C, ldc, num_sms, s) : launch_one<1, 16, false>(g, args, C, ldc, num_sms, s);
     return tol ? launch_one<2, 16, true>(g, args, C, ldc, num_sms, s) : launch_one<2, 16, false>(g, args, C, ldc, num_sms, s);

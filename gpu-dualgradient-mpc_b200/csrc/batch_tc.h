@@ -21,16 +21,32 @@ struct GemmDesc {
     int a_stages = 0;             // a_stages = state ring
     int step = 0;                 // p1: column distance between tile starts (<= bn, see plan_tiles_p1); 0 = bn
     int ncols_valid = 0;          // output columns that exist (n or m)
+    int f16 = 0;                  // GPAD_PREC_FP16X3: operand maps over fp16 hi / lo arrays (k_pad counts K elements)
+    // second-generation product 2 (batch_tc_p2.cu): epilogue operands by TMA -- the rotating y buffers and p_D as
+    // [rows = batch][m] fp32 maps with boxes of 128 rows x 32 columns (loads and the store of y_{v+1})
+    int p2 = 0;
+    CUtensorMap tmEy[3], tmEpd;
+    int e_stages = 0;
 };
 
 int make_tmap(CUtensorMap* map, const float* ptr, int k_elems, int rows, int ld, int box_k, int box_rows);
+int make_tmap_bytes(CUtensorMap* map, const void* ptr, int elem_bytes, int k_elems, int rows, int ld, int box_k, int box_rows);
 void plan_tiles(int ncols, int* bn, int* n_tiles);
 size_t smem_bytes(int bk, int bn, int stages);
 int pick_stages(int bk, int bn, size_t smem_limit);
 int launch_gemm(int phase, const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s);
 void plan_tiles_p1(int ncols, int* bn, int* n_tiles, int* step = nullptr);
-int plan_rings_p1(int bn, size_t smem_limit, int* a_stages, int* b_stages);
+int plan_rings_p1(int bn, size_t smem_limit, int* a_stages, int* b_stages, bool f16 = false);
+// GPAD_PREC_FP16X3 helpers (batch_f16.cu)
+// rows of fp32 -> per-row power-of-two scale, fp16 hi / lo of the scaled rows, inv[r] = 2^-e
+int launch_quantize_rows(const float* src, int ld, int rows, uint16_t* hi, uint16_t* lo, float* inv, unsigned* zero_rows,
+                         cudaStream_t s);
+// rowmax[r] = max_k |x[r][k]|
+int launch_rowmax(const float* src, int ld, int rows, float* rowmax, cudaStream_t s);
 int launch_p1(const GemmDesc& g, const BatchKernelArgs& args, int num_sms, cudaStream_t s);
+void plan_tiles_p2(int ncols, int* bn, int* n_tiles);
+int plan_rings_p2(int bn, size_t smem_limit, int* stages, int* e_stages);
+int launch_p2(const GemmDesc& g, const BatchKernelArgs& args, int cur, int prev, int next, int num_sms, cudaStream_t s);
 int launch_split(const float* src, float* hi, float* lo, size_t count, cudaStream_t s);
 
 }  // namespace tc

@@ -50,13 +50,6 @@ struct P1Sched {
     __device__ int n_tile() const { return tile % n_tiles; }
 };
 
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -69,15 +62,20 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-template <int EPI, bool TOL>
+// F16 (GPAD_PREC_FP16X3, fixed-iteration solves): a k-block is 32 K elements.  The y tile arrives as 128 x 32 fp32
+// (128-byte rows, SWIZZLE_128B), the transform warps scale each row by its power of two (from the row maximum the
+// previous product 2 reduced), split it into fp16 hi | lo pairs -- the same 32 TMEM columns per slot -- and the MMAs are
+// kind::f16 with K = 16: half the instructions and half the operator bytes per flop of the tf32 form.
+template <int EPI, bool TOL, bool F16>
 __global__ void __launch_bounds__(32 * (kP1FirstEpi + EPI), 1)
 tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmB_hi,
              const __grid_constant__ CUtensorMap tmB_lo, int num_k_blocks, int m_tiles, int n_tiles, int bn,
              int a_stages, int b_stages, const BatchKernelArgs args, int ncols_valid, int step) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr int BK = kP1BK;
-    constexpr uint32_t a_bytes = kBM * BK * 4;
+    constexpr int BK = kP1BK;                                       // operator tile rows are BK * 4 = 64 bytes
+    constexpr int kElems = F16 ? 2 * BK : BK;                       // K elements per k-block
+    constexpr uint32_t a_bytes = kBM * kElems * 4;                  // fp32 y tile
     const uint32_t b_bytes = (uint32_t)bn * BK * 4;                 // one of hi / lo
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + (size_t)a_stages * a_bytes;
@@ -124,8 +122,8 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
                     const uint32_t fb = smem_u32(bfull + s);
                     const uint32_t bb = smem_u32(b_ring + (size_t)s * 2 * b_bytes);
                     mbar_expect_tx(fb, 2 * b_bytes);
-                    tma_load_2d(bb, &tmB_hi, kb * BK, row_b, fb);
-                    tma_load_2d(bb + b_bytes, &tmB_lo, kb * BK, row_b, fb);
+                    tma_load_2d(bb, &tmB_hi, kb * kElems, row_b, fb);
+                    tma_load_2d(bb + b_bytes, &tmB_lo, kb * kElems, row_b, fb);
                 }
                 __syncwarp();
                 if (++s == b_stages) { s = 0; ph ^= 1; }
@@ -141,7 +139,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
                 if (elect_one()) {
                     const uint32_t fb = smem_u32(afull + s);
                     mbar_expect_tx(fb, a_bytes);
-                    tma_load_2d(smem_u32(a_ring + (size_t)s * a_bytes), &tmY, kb * BK, row_a, fb);
+                    tma_load_2d(smem_u32(a_ring + (size_t)s * a_bytes), &tmY, kb * kElems, row_a, fb);
                 }
                 __syncwarp();
                 if (++s == a_stages) { s = 0; ph ^= 1; }
@@ -149,7 +147,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
-        const uint32_t idesc = make_idesc(bn);
+        const uint32_t idesc = make_idesc_k<F16>(bn);
         int s = 0; uint32_t ph = 0;
         int t = 0; uint32_t tph = 0;
         int acc = 0; uint32_t acc_phase = 0;
@@ -168,9 +166,9 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
                     for (int ks = 0; ks < BK / 8; ++ks) {
                         const uint64_t b_hi = make_smem_desc<BK>(bb + ks * 32);
                         const uint64_t b_lo = make_smem_desc<BK>(bb + b_bytes + ks * 32);
-                        umma_tf32_ts(d_tmem, at + ks * 8, b_lo, idesc, (kb | ks) != 0 ? 1u : 0u);        // hi * lo
-                        umma_tf32_ts(d_tmem, at + 16 + ks * 8, b_hi, idesc, 1u);                         // lo * hi
-                        umma_tf32_ts(d_tmem, at + ks * 8, b_hi, idesc, 1u);                              // hi * hi
+                        umma_ts<F16>(d_tmem, at + ks * 8, b_lo, idesc, (kb | ks) != 0 ? 1u : 0u);        // hi * lo
+                        umma_ts<F16>(d_tmem, at + 16 + ks * 8, b_hi, idesc, 1u);                         // lo * hi
+                        umma_ts<F16>(d_tmem, at + ks * 8, b_hi, idesc, 1u);                              // hi * hi
                     }
                     umma_commit(smem_u32(bempty + s));
                     umma_commit(smem_u32(tfree + t));
@@ -191,15 +189,32 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         int s = 0; uint32_t ph = 0;
         int t = 0; uint32_t tph = 0;
         for (P1Sched ts(m_tiles, n_tiles, args); ts.valid(); ts.next()) {
+            float row_scale = 1.f;
+            if (F16) row_scale = pow2f(f16_scale_exp(__ldg(args.a_rowmax + ts.m_tile() * kBM + row)));
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 mbar_wait(smem_u32(afull + s), ph);
+                uint32_t v[32];
+                if (F16) {
+                    // SWIZZLE_128B: 16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) << 4)
+                    const uint8_t* tile = a_ring + (size_t)s * a_bytes + row * 128;
+                    float4 y[8];
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) y[ch] = *reinterpret_cast<const float4*>(tile + ((ch ^ (row & 7)) << 4));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(aempty + s));       // the shared-memory slot is free again
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {
+                        // TMEM column j of the slot holds K elements 2j, 2j + 1 (hi), column 16 + j their lo parts
+                        split_f16x2(y[ch].x * row_scale, y[ch].y * row_scale, v[ch * 2], v[16 + ch * 2]);
+                        split_f16x2(y[ch].z * row_scale, y[ch].w * row_scale, v[ch * 2 + 1], v[16 + ch * 2 + 1]);
+                    }
+                } else {
                 const uint8_t* tile = a_ring + (size_t)s * a_bytes + row * 64;
                 float4 y[4];
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) y[ch] = *reinterpret_cast<const float4*>(tile + ((ch ^ ((row >> 1) & 3)) << 4));
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(aempty + s));       // the shared-memory slot is free again
-                uint32_t v[32];
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
                     const float e[4] = {y[ch].x, y[ch].y, y[ch].z, y[ch].w};
@@ -210,6 +225,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
                         v[ch * 4 + j] = __float_as_uint(hi);
                         v[16 + ch * 4 + j] = __float_as_uint(lo);
                     }
+                }
                 }
                 mbar_wait(smem_u32(tfree + t), tph ^ 1);                // the MMAs that read this TMEM slot have retired
                 tc_fence_after();
@@ -234,13 +250,15 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tc_fence_after();
             const int row_base = ts.m_tile() * kBM + q * 32;
+            float row_inv = 1.f;         // F16: this thread's accumulator row carries the scale of its y row
+            if (F16) row_inv = pow2f(-f16_scale_exp(__ldg(args.a_rowmax + row_base + lane)));
             for (int blk = part; blk < nblk; blk += kParts) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_stride + (uint32_t)(blk * 32), v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = __uint_as_float(v[j]);
+                for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = F16 ? __uint_as_float(v[j]) * row_inv : __uint_as_float(v[j]);
                 __syncwarp();
-                epilogue_block<1, TOL>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, nullptr, 0, step);
+                epilogue_block<1, TOL, F16>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, nullptr, 0, step);
                 __syncwarp();
             }
             tc_fence_before();
@@ -259,8 +277,8 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     }
 }
 
-size_t p1_smem_bytes(int bn, int a_stages, int b_stages, int epi) {
-    return 1024 + (size_t)a_stages * kBM * kP1BK * 4 + (size_t)b_stages * 2 * bn * kP1BK * 4 +
+size_t p1_smem_bytes(int bn, int a_stages, int b_stages, int epi, bool f16 = false) {
+    return 1024 + (size_t)a_stages * kBM * (f16 ? 2 : 1) * kP1BK * 4 + (size_t)b_stages * 2 * bn * kP1BK * 4 +
            (size_t)epi * kEpiBufFloats * 4 + (2 * a_stages + 2 * b_stages + 2 * kP1TStages + 4) * 8 + 16;
 }
 
@@ -278,23 +296,24 @@ void plan_tiles_p1(int ncols, int* bn, int* n_tiles, int* step) {
     if (step) *step = (nt > 1 && s32 > 0 && (nt - 1) * s32 + b >= ncols) ? s32 : b;
 }
 
-int plan_rings_p1(int bn, size_t smem_limit, int* a_stages, int* b_stages) {
+int plan_rings_p1(int bn, size_t smem_limit, int* a_stages, int* b_stages, bool f16) {
     const int epi = 8;
-    int b = 5, a = 8;
-    while (b > 2 && p1_smem_bytes(bn, a, b, epi) > smem_limit) --b;
-    while (a > 2 && p1_smem_bytes(bn, a, b, epi) > smem_limit) --a;
-    if (p1_smem_bytes(bn, a, b, epi) > smem_limit) return GPAD_ERR_UNSUPPORTED;
-    while (a < 12 && p1_smem_bytes(bn, a + 1, b, epi) <= smem_limit) ++a;     // spare shared memory deepens the HBM-facing ring
+    int b = 5, a = f16 ? 4 : 8;
+    while (b > 2 && p1_smem_bytes(bn, a, b, epi, f16) > smem_limit) --b;
+    while (a > 2 && p1_smem_bytes(bn, a, b, epi, f16) > smem_limit) --a;
+    if (p1_smem_bytes(bn, a, b, epi, f16) > smem_limit) return GPAD_ERR_UNSUPPORTED;
+    while (a < 12 && p1_smem_bytes(bn, a + 1, b, epi, f16) <= smem_limit) ++a;     // spare shared memory deepens the HBM-facing ring
     *a_stages = a; *b_stages = b;
     return GPAD_OK;
 }
 
 // P_v = Y_v M_G^T (A = y_v)
 int launch_p1(const GemmDesc& g, const BatchKernelArgs& args, int num_sms, cudaStream_t s) {
-    const size_t smem = p1_smem_bytes(g.bn, g.a_stages, g.stages, 8);
+    const size_t smem = p1_smem_bytes(g.bn, g.a_stages, g.stages, 8, g.f16 != 0);
     const int tiles = g.m_tiles * g.n_tiles;
     const bool tol = args.checking || args.dual || args.done;
-    auto kern = tol ? tc_p1_kernel<8, true> : tc_p1_kernel<8, false>;
+    if (g.f16 && tol) { set_error("tcgen05 product 1: the fp16 kernel serves fixed-iteration solves only"); return GPAD_ERR_UNSUPPORTED; }
+    auto kern = g.f16 ? tc_p1_kernel<8, false, true> : tol ? tc_p1_kernel<8, true, false> : tc_p1_kernel<8, false, false>;
     GPAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(std::min(tiles, num_sms)); lc.blockDim = dim3(32 * (kP1FirstEpi + 8)); lc.dynamicSmemBytes = smem; lc.stream = s;
@@ -302,7 +321,7 @@ int launch_p1(const GemmDesc& g, const BatchKernelArgs& args, int num_sms, cudaS
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at; lc.numAttrs = g.pdl ? 1 : 0;
-    GPAD_CUDA(cudaLaunchKernelEx(&lc, kern, g.tmA_hi, g.tmB_hi, g.tmB_lo, g.k_pad / kP1BK, g.m_tiles, g.n_tiles, g.bn, g.a_stages,
+    GPAD_CUDA(cudaLaunchKernelEx(&lc, kern, g.tmA_hi, g.tmB_hi, g.tmB_lo, g.k_pad / (g.f16 ? 2 * kP1BK : kP1BK), g.m_tiles, g.n_tiles, g.bn, g.a_stages,
                                  g.stages, args, g.ncols_valid, g.step > 0 ? g.step : g.bn));
     return GPAD_OK;
 }

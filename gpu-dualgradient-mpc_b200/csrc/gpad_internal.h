@@ -59,6 +59,12 @@ struct BatchState {
     float* zh_hi = nullptr; // TF32X3 only
     float* zh_lo = nullptr;
     float* Pb[2] = {nullptr, nullptr};  // TF32X3 only: P_v = M_G y_v lives in Pb[v & 1] (P-formulation of product 1)
+    // FP16X3 only (fixed-iteration solves): fp16 hi / lo of the row-scaled zhat, the inverse row scales, and the row
+    // maxima of y_v (bit patterns; y_v's live in ymax[v & 1])
+    uint16_t* zq_hi = nullptr;   // [Bp][np]
+    uint16_t* zq_lo = nullptr;
+    float* zinv = nullptr;       // [Bp]
+    unsigned* ymax[2] = {nullptr, nullptr};   // [Bp]
     float* sbar = nullptr;  // [Bp][mp] averaged residual (termination only)
     float* red = nullptr;   // [Bp][8] per-instance reductions (termination only)
     int* done = nullptr;    // [Bp] instance stopped (termination mode)
@@ -88,6 +94,9 @@ struct Operators {
     float* M_G_lo = nullptr;  // TF32X3: M_G holds RN-tf32(M_G), *_lo the tf32-rounded remainder
     float* G_L_lo = nullptr;
     int n_rows_pad = 0, m_rows_pad = 0;
+    // FP16X3: fp16 hi / lo of the operators, every row scaled by its own power of two, and 2^-e per row
+    uint16_t *M_Gq_hi = nullptr, *M_Gq_lo = nullptr, *G_Lq_hi = nullptr, *G_Lq_lo = nullptr;
+    float *M_G_inv = nullptr, *G_L_inv = nullptr;
 };
 
 struct BatchKernelArgs;

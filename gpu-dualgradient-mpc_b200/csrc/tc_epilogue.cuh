@@ -91,33 +91,99 @@ __device__ __forceinline__ void fast_rows(const BatchKernelArgs& args, const flo
     }
 }
 
+// GPAD_PREC_FP16X3 (fixed-iteration solves): the accumulator block arrives with the A row scale already undone (the
+// epilogue warp applies it while transposing: TMEM lane = batch row); `cinv` undoes the operator row's scale (lane =
+// output column).  Product 1 stores zhat in fp32 only -- its fp16 split needs the maximum of the WHOLE row, which no
+// single tile sees, and is made by zsplit_kernel between the products.  Product 2 additionally reduces the row maxima of
+// y_{v+1} (>= 0, so the bit patterns order like the values): lane r of the warp keeps row r's maximum in *row_max.
+template <int PHASE>
+__device__ __forceinline__ void fast_rows_f16(const BatchKernelArgs& args, const float* buf, int lane, int row_base, int c, bool col_ok,
+                                              float cinv, uint32_t* row_max) {
+    constexpr int kChunk = 16;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += kChunk) {
+        unsigned live = 0;
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) live |= ((col_ok && row_base + r0 + j < args.B) ? 1u : 0u) << j;
+        if (PHASE == 1) {
+            float gp[kChunk], zo[kChunk], pp[kChunk];
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                const bool ok = (live >> j) & 1u;
+                const size_t o = (size_t)(row_base + r0 + j) * args.np + c;
+                gp[j] = ok ? __ldcs(args.g_P + o) : 0.f;
+                zo[j] = ok ? __ldcs(args.z + o) : 0.f;
+                pp[j] = ok ? __ldcs(args.P_prev + o) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                if (!((live >> j) & 1u)) continue;
+                const size_t o = (size_t)(row_base + r0 + j) * args.np + c;
+                float acc = buf[(r0 + j) * 33 + lane] * cinv;
+                __stcs(args.P_cur + o, acc);
+                acc = momentum(acc, pp[j], args.it.beta);          // M_G w_v from P_v, P_{v-1}
+                const float zh = acc - gp[j];
+                __stcs(args.z + o, __fadd_rn(__fmul_rn(1.0f - args.it.theta, zo[j]), __fmul_rn(args.it.theta, zh)));
+                args.zhat[o] = zh;       // re-read by zsplit_kernel right after this launch: default caching
+            }
+        } else {
+            float yc[kChunk], yp[kChunk], pd[kChunk];
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                const bool ok = (live >> j) & 1u;
+                const size_t o = (size_t)(row_base + r0 + j) * args.mp + c;
+                yc[j] = ok ? __ldcs(args.y_cur + o) : 0.f;
+                yp[j] = ok ? __ldcs(args.y_prev + o) : 0.f;
+                pd[j] = ok ? __ldcs(args.p_D + o) : 0.f;
+            }
+            uint32_t mx = *row_max;
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                const bool ok = (live >> j) & 1u;
+                const size_t o = (size_t)(row_base + r0 + j) * args.mp + c;
+                const float wv = momentum(yc[j], yp[j], args.it.beta);
+                const float sacc = buf[(r0 + j) * 33 + lane] * cinv + (wv + pd[j]);
+                const float yn = 0.5f * (sacc + fabsf(sacc));
+                if (ok) args.y_next[o] = yn;                    // read back by the next two kernels
+                const uint32_t rm = __reduce_max_sync(0xffffffffu, ok ? __float_as_uint(yn) : 0u);
+                if (lane == r0 + j) mx = max(mx, rm);
+            }
+            *row_max = mx;
+        }
+    }
+}
+
 // TOL = false: the kernel of fixed-iteration solves carries nothing but the fast path (the epilogue code of the
 // tolerance mode -- stopped rows, residual average, reductions, dual-gap launches -- lives in the TOL = true
 // instantiation: a 30 % larger kernel measured 10-17 % slower on product 2, whose 14 warps run four different roles
 // out of one instruction cache)
-template <int PHASE, bool TOL>
+template <int PHASE, bool TOL, bool F16 = false>
 __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, const float* buf, int lane, int row_base, int blk,
                                                int n_tile, int bn, int ncols_valid, float* __restrict__ Cdbg, int ldc,
-                                               int step = 0) {
+                                               int step = 0, uint32_t* row_max = nullptr) {
     // tiles start every `step` columns (default: bn).  step < bn (a multiple of 32) keeps every 32-column block on a
     // 128-byte line; the bn - step columns a tile shares with its predecessor belong to the predecessor
     const int cin = blk * 32 + lane;            // column inside the tile
     const int stp = step > 0 ? step : bn;
     const int c = n_tile * stp + cin;      // global output column
     const bool col_ok = cin < bn && c < ncols_valid && (n_tile == 0 || cin >= bn - stp);
+    float cinv = 1.f;
+    if (F16) cinv = col_ok ? __ldg(args.b_colinv + c) : 0.f;
     if (PHASE == 0) {
 #pragma unroll 8
         for (int rr = 0; rr < 32; ++rr) {
             const int b = row_base + rr;
-            if (col_ok && b < args.B) Cdbg[(size_t)b * ldc + c] = buf[rr * 33 + lane];
+            if (col_ok && b < args.B) Cdbg[(size_t)b * ldc + c] = F16 ? buf[rr * 33 + lane] * cinv : buf[rr * 33 + lane];
         }
     } else if (PHASE == 1 && args.p_only) {
         // warm start: P_{-1} = M_G y_{-1}, nothing else
 #pragma unroll 8
         for (int rr = 0; rr < 32; ++rr) {
             const int b = row_base + rr;
-            if (col_ok && b < args.B) args.P_cur[(size_t)b * args.np + c] = buf[rr * 33 + lane];
+            if (col_ok && b < args.B) args.P_cur[(size_t)b * args.np + c] = F16 ? buf[rr * 33 + lane] * cinv : buf[rr * 33 + lane];
         }
+    } else if (F16) {
+        fast_rows_f16<PHASE>(args, buf, lane, row_base, c, col_ok, cinv, row_max);
     } else if (!TOL) {
         fast_rows<PHASE, false>(args, buf, lane, row_base, c, col_ok);
     } else if (!args.it.check && !args.dual && args.done) {

@@ -82,6 +82,38 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::f16 (fp16 operands, fp32 accumulate): K = 16 per instruction, twice the MACs of a kind::tf32 instruction for
+// the same operand bytes
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// A operand from tensor memory (TS form)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void umma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if (F16) umma_f16(d, a, b, idesc, acc); else umma_tf32(d, a, b, idesc, acc);
+}
+template <bool F16>
+__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if (F16) umma_f16_ts(d, a, b, idesc, acc); else umma_tf32_ts(d, a, b, idesc, acc);
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -118,6 +150,34 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = bn
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+// same for kind::f16 with fp16 operands (a_format = b_format = 0)
+__device__ __forceinline__ uint32_t make_idesc_f16(int bn) {
+    return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t make_idesc_k(int bn) { return F16 ? make_idesc_f16(bn) : make_idesc(bn); }
+
+// ---- GPAD_PREC_FP16X3: x * 2^e = hi + lo with fp16 hi, lo (11 + 11 significant bits, what the tf32 split keeps) ----
+// The power-of-two scale brings the largest magnitude of a row into [2^14, 2^15): entries down to 2^-18 of it keep
+// the full 22 bits, smaller ones an absolute error of 2^-40 of the row maximum (fp16 subnormal spacing 2^-24).
+// Scaling by powers of two is exact, and so is undoing it on the fp32 accumulator.
+__device__ __forceinline__ int f16_scale_exp(float row_max) {
+    // row_max >= 0.  exponent field of row_max -> e with row_max * 2^e in [2^14, 2^15); zero / subnormal / non-finite
+    // maxima (nothing to scale, or a row that has already diverged) get e = 0
+    const int ex = (int)((__float_as_uint(row_max) >> 23) & 0xffu);
+    if (ex == 0 || ex == 255) return 0;
+    int e = 14 - (ex - 127);
+    return max(-100, min(100, e));
+}
+__device__ __forceinline__ float pow2f(int e) { return __uint_as_float((uint32_t)(127 + e) << 23); }
+// two scaled fp32 values -> packed fp16x2 hi and lo (low half = first element)
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    float h0, h1;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi));
+    const float r0 = x0 - h0, r1 = x1 - h1;          // exact in fp32
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 
 

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgpad_b200.so")
 # enums of include/gpad.h
 LAYOUT_FLIPPED, LAYOUT_SEQUENTIAL, LAYOUT_FLAT = 0, 1, 2
 MODE_LATENCY, MODE_BATCH_SHARED, MODE_BATCH_PER_INSTANCE = 1, 2, 3
-PREC_FP32, PREC_TF32X3 = 0, 1
+PREC_FP32, PREC_TF32X3, PREC_FP16X3 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 SCHEDULE_PAPER, SCHEDULE_MATLAB_LAG = 0, 1
 WARM_COLD, WARM_PREVIOUS, WARM_SHIFTED = 0, 1, 2
@@ -30,7 +30,7 @@ EXPORTS = [
     "gpad_profile_enable", "gpad_profile_read",
     "gpad_problem_battery", "gpad_problem_quadrotor", "gpad_problem_destroy", "gpad_problem_dims",
     "gpad_problem_operators", "gpad_problem_instances", "gpad_problem_plant", "gpad_schedule",
-    "gpad_file_read", "gpad_file_write", "gpad_file_free", "gpad_debug_gemm_tf32x3", "gpad_debug_plan_tiles",
+    "gpad_file_read", "gpad_file_write", "gpad_file_free", "gpad_debug_gemm_tf32x3", "gpad_debug_gemm_f16x3", "gpad_debug_plan_tiles",
     "gpad_flatten_operators", "gpad_expand_operators", "gpad_closed_loop",
     "gpad_solve_async", "gpad_wait", "gpad_handle_dims", "gpad_solve_stats", "gpad_instances_device",
     "gpad_plants_battery", "gpad_plants_destroy", "gpad_plants_dims", "gpad_plants_operators", "gpad_plants_instances",
@@ -151,6 +151,7 @@ def lib():
             if hasattr(L, name):
                 getattr(L, name).argtypes = sig
         L.gpad_debug_gemm_tf32x3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.gpad_debug_gemm_f16x3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.gpad_debug_plan_tiles.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4
         _lib = L
     return _lib
@@ -509,6 +510,10 @@ def step_four(G_L, y_vp1, w, p_D, zhat, N, n_u, m, max_threads=0, stream=None):
 
 def debug_gemm_tf32x3(A, B, Cout, M, N, K, stream=None):
     check(lib().gpad_debug_gemm_tf32x3(_ptr(A), _ptr(B), _ptr(Cout), M, N, K, stream), "gpad_debug_gemm_tf32x3")
+
+
+def debug_gemm_f16x3(A, B, Cout, M, N, K, kernel=0, stream=None):
+    check(lib().gpad_debug_gemm_f16x3(_ptr(A), _ptr(B), _ptr(Cout), M, N, K, kernel, stream), "gpad_debug_gemm_f16x3")
 
 
 def debug_plan_tiles(kernel, ncols):

@@ -62,8 +62,13 @@ typedef enum {
 
 typedef enum {
     GPAD_PREC_FP32 = 0,    /* CUDA-core FFMA, fp32 accumulate                                   */
-    GPAD_PREC_TF32X3 = 1   /* tcgen05 kind::tf32, hi/lo split of both operands (3 MMAs/product),
+    GPAD_PREC_TF32X3 = 1,  /* tcgen05 kind::tf32, hi/lo split of both operands (3 MMAs/product),
                               fp32 accumulate in TMEM -- BATCH_SHARED only                      */
+    GPAD_PREC_FP16X3 = 2   /* tcgen05 kind::f16: the same 11 + 11 bit hi/lo split held in fp16, every operand
+                              row scaled by an exact power of two taken from its largest magnitude (scales
+                              undone on the fp32 accumulator): half the operand bytes and MMA instructions
+                              of TF32X3 at the same accuracy.  Fixed-iteration solves; tolerance-mode solves
+                              of such a handle run the TF32X3 kernels -- BATCH_SHARED only          */
 } gpad_precision;
 
 typedef enum { GPAD_MEM_HOST = 0, GPAD_MEM_DEVICE = 1 } gpad_memspace;
@@ -349,6 +354,11 @@ void gpad_fixture_free(gpad_fixture_t* f);
  * ---------------------------------------------------------------------------------------- */
 int gpad_debug_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int K,
                            void* stream);
+/* The same through the GPAD_PREC_FP16X3 path: rows of A and B scaled and split into fp16 hi / lo, kind::f16
+ * MMAs, scales undone in the epilogue.  kernel 0 = shared-memory-operand kernel (product 2's mainloop),
+ * 1 = TMEM-operand kernel (product 1's: A quantised by the transform warps inside the kernel). */
+int gpad_debug_gemm_f16x3(const float* A, const float* B, float* C, int M, int N, int K, int kernel,
+                          void* stream);
 
 /* Test hook, host only (no device call): the column tiling the batch kernels use for an operator with
  * `ncols` output columns. kernel 0 = shared-memory-operand kernel (tiles <= 256 columns), 1 = the

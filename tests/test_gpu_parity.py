@@ -285,7 +285,43 @@ def test_latency_grid2_matches_generic_grid_kernel(torch_cuda, G, oracle, dims, 
 
 
 
+def prec_code(G, prec):
+    return {"fp32": G.PREC_FP32, "tf32x3": G.PREC_TF32X3, "fp16x3": G.PREC_FP16X3}[prec]
+
+
 # ------------------------------------------------------------------------------------ tensor-core GEMM hook
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("shape", [(128, 16, 32), (128, 256, 64), (300, 200, 1000), (1000, 416, 2400), (257, 2400, 400), (130, 1000, 4200)])
+def test_f16x3_gemm_reaches_fp32_accuracy(torch_cuda, G, shape, kernel):
+    """GPAD_PREC_FP16X3 mainloops (kernel 0: shared-memory operands = product 2; 1: A quantised in-kernel into tensor
+    memory = product 1) on operands whose ROWS differ by many orders of magnitude, with zeros and an all-zero row:
+    the power-of-two row scales must make fp16 hi + lo as good as the tf32 split"""
+    t = torch_cuda
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K + kernel)
+    A = rng.standard_normal((M, K)) * 10.0 ** rng.uniform(-6, 6, (M, 1))
+    B = rng.standard_normal((N, K)) * 10.0 ** rng.uniform(-5, 3, (N, 1))
+    A[rng.random((M, K)) < 0.3] = 0.0                      # duals: many exact zeros
+    A *= 10.0 ** rng.uniform(-3, 0, (M, K))                # and a wide range inside a row
+    A[M // 2] = 0.0
+    B[N // 3] = 0.0
+    A = A.astype(np.float32); B = B.astype(np.float32)
+    dA, dB = t.from_numpy(A).cuda(), t.from_numpy(B).cuda()
+    dC = t.full((M, N), float("nan"), device="cuda")
+    G.debug_gemm_f16x3(dA, dB, dC, M, N, K, kernel)
+    t.cuda.synchronize()
+    C = dC.cpu().numpy()
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T     # sum |a||b|
+    scale[scale == 0] = 1.0
+    err = np.max(np.abs(C - ref) / scale)
+    fp32 = np.max(np.abs((A @ B.T).astype(np.float64) - ref) / scale)
+    print(f"\n {shape} kernel {kernel}: 3xFP16 err {err:.2e} of sum|a||b|  (numpy fp32 {fp32:.2e})")
+    assert np.isfinite(C).all()
+    assert (C[M // 2] == 0).all() and (C[:, N // 3] == 0).all()
+    assert err <= 1e-6 + 1e-9 * K
+
+
 @pytest.mark.parametrize("stages", ["0", "2"])
 @pytest.mark.parametrize("shape", [(128, 16, 16), (128, 256, 64), (300, 200, 1000), (1000, 416, 2400), (257, 2400, 400)])
 def test_tf32x3_gemm_reaches_fp32_accuracy(torch_cuda, G, shape, stages, monkeypatch):
@@ -323,7 +359,7 @@ def batch_reference(oracle, pb, n_u, N, g_P, p_D, theta, beta, **kw):
     return ora, f64
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "fp16x3"])
 @pytest.mark.parametrize("dims,B", [((3, 4), 300), ((10, 15), 130), ((15, 10), 129)])
 def test_batch_battery_matches_oracle(torch_cuda, G, oracle, prec, dims, B):
     n_u, N = dims
@@ -332,7 +368,7 @@ def test_batch_battery_matches_oracle(torch_cuda, G, oracle, prec, dims, B):
     g_P, p_D, _ = pb.instance(X0)
     theta, beta = schedule(100)
     s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED,
-                 precision=G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32, max_batch=B)
+                 precision=prec_code(G, prec), max_batch=B)
     print("\n", s.description)
     gpu = s.solve_host(g_P, p_D, theta, beta)
     ora, f64 = batch_reference(oracle, pb, n_u, N, g_P, p_D, theta, beta)
@@ -346,7 +382,7 @@ def test_batch_battery_matches_oracle(torch_cuda, G, oracle, prec, dims, B):
     s.close()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "fp16x3"])
 def test_batch_quadrotor_matches_oracle(torch_cuda, G, oracle, prec):
     N = 20
     pb = P.quadrotor(N)
@@ -355,7 +391,7 @@ def test_batch_quadrotor_matches_oracle(torch_cuda, G, oracle, prec):
     g_P, p_D, _ = pb.instance(par)
     theta, beta = schedule(100)
     s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED,
-                 precision=G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32, max_batch=B)
+                 precision=prec_code(G, prec), max_batch=B)
     gpu = s.solve_host(g_P, p_D, theta, beta)
     ora, f64 = batch_reference(oracle, pb, 4, N, g_P, p_D, theta, beta)
     worst = check_parity(gpu, ora, f64, f"batch {prec} quadrotor N={N}")
@@ -363,7 +399,7 @@ def test_batch_quadrotor_matches_oracle(torch_cuda, G, oracle, prec):
     s.close()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "fp16x3"])
 def test_batch_warm_start_matches_oracle(torch_cuda, G, oracle, prec):
     """y_0 / y_{-1} handed in (receding-horizon warm start): the tcgen05 path needs P_{-1} = M_G y_{-1} first
     (one extra product-1 launch, batch_tc_p1.cu), the result must match the oracle started from the same pair"""
@@ -373,7 +409,7 @@ def test_batch_warm_start_matches_oracle(torch_cuda, G, oracle, prec):
     g_P, p_D, _ = pb.instance(X0)
     theta, beta = schedule(40)
     s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED,
-                 precision=G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32, max_batch=B)
+                 precision=prec_code(G, prec), max_batch=B)
     cold = s.solve_host(g_P, p_D, theta, beta)
     warm = s.solve_host(g_P, p_D, theta, beta, y0=cold["y_next"], y_prev0=cold["y"])
     worst = 0.0
@@ -409,7 +445,7 @@ def test_batch_tc_kernel_variants_match_default(torch_cuda, G, knobs, monkeypatc
 
 
 @pytest.mark.parametrize("with_f", [False, True])
-@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "fp16x3"])
 def test_batch_termination_matches_oracle(torch_cuda, G, oracle, prec, with_f):
     n_u, N, B = 3, 4, 200
     pb = P.battery(n_u, N)
@@ -418,7 +454,7 @@ def test_batch_termination_matches_oracle(torch_cuda, G, oracle, prec, with_f):
     theta, beta = schedule(400)
     kw = dict(check_every=2, eps_g=1e-3, eps_V=1e-3, f=f if with_f else None)
     s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED,
-                 precision=G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32, max_batch=B)
+                 precision=prec_code(G, prec), max_batch=B)
     gpu = s.solve_host(g_P, p_D, theta, beta, **kw)
     ora = oracle.solve_batch(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, **kw)
     assert np.array_equal(gpu["status"], ora["status"])
@@ -430,7 +466,7 @@ def test_batch_termination_matches_oracle(torch_cuda, G, oracle, prec, with_f):
     s.close()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "fp16x3"])
 def test_batch_dual_gap_branch(torch_cuda, G, oracle, prec):
     """shared-operator batch with the cost vector f: instances that reach a check with a feasible zhat and a negative
     entry in w take the V(zhat) - Phi(y) branch (two extra operator products for the flagged instances); statuses and
@@ -443,7 +479,7 @@ def test_batch_dual_gap_branch(torch_cuda, G, oracle, prec):
     kw = dict(check_every=1, eps_g=5e-2, eps_V=5e-2, f=f)
     ora = oracle.solve_batch(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, **kw)
     s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED,
-                 precision=G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32, max_batch=B)
+                 precision=prec_code(G, prec), max_batch=B)
     gpu = s.solve_host(g_P, p_D, theta, beta, **kw)
     s.close()
     print("\n statuses (oracle):", {int(k): int((ora["status"] == k).sum()) for k in np.unique(ora["status"])})
@@ -466,16 +502,17 @@ def test_batch_battery_main_size_matches_oracle(torch_cuda, G, oracle):
     g_P, p_D, _ = pb.instance(X0)
     theta, beta = schedule(25)
     res = {}
-    for prec, code in (("fp32", G.PREC_FP32), ("tf32x3", G.PREC_TF32X3)):
+    for prec, code in (("fp32", G.PREC_FP32), ("tf32x3", G.PREC_TF32X3), ("fp16x3", G.PREC_FP16X3)):
         s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=code, max_batch=B)
         res[prec] = s.solve_host(g_P, p_D, theta, beta)
         s.close()
-    for k in VECS:
-        assert P.rel_inf(res["tf32x3"][k], res["fp32"][k]) <= (2 * TOL if k == "zhat" else TOL), k
-    for b in (0, 131, 299):
-        d = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P[b], p_D[b], theta, beta)
-        o32 = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P[b], p_D[b], theta, beta)
-        check_parity({k: res["tf32x3"][k][b] for k in VECS}, o32, d, f"battery (10,100) batch instance {b}")
+    for tcp in ("tf32x3", "fp16x3"):
+        for k in VECS:
+            assert P.rel_inf(res[tcp][k], res["fp32"][k]) <= (2 * TOL if k == "zhat" else TOL), (tcp, k)
+        for b in (0, 131, 299):
+            d = oracle.solve_f64(n_u, N, pb.m, pb.M_G, pb.G_L, g_P[b], p_D[b], theta, beta)
+            o32 = oracle.solve(n_u, N, pb.m, pb.M_G, pb.G_L, g_P[b], p_D[b], theta, beta)
+            check_parity({k: res[tcp][k][b] for k in VECS}, o32, d, f"battery (10,100) batch {tcp} instance {b}")
 
 
 
@@ -493,19 +530,20 @@ def test_full_size_quadrotor_properties(torch_cuda, G, oracle):
     g_P, p_D, _ = pb.instances(par, want_f=False)
     theta, beta = schedule(30)
     res = {}
-    for prec, code in (("fp32", G.PREC_FP32), ("tf32x3", G.PREC_TF32X3)):
+    for prec, code in (("fp32", G.PREC_FP32), ("tf32x3", G.PREC_TF32X3), ("fp16x3", G.PREC_FP16X3)):
         s = G.Solver(4, N, pb.m, pb.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=code, max_batch=B)
         res[prec] = s.solve_host(g_P, p_D, theta, beta)
         s.close()
-    for k in VECS:
-        assert P.rel_inf(res["tf32x3"][k], res["fp32"][k]) <= (2 * TOL if k == "zhat" else TOL), k
-        assert np.array_equal(res["tf32x3"][k][B - 5:], res["tf32x3"][k][:5]), k
-    assert np.array_equal(res["tf32x3"]["y_next"] > 0, res["fp32"]["y_next"] > 0) or \
-        (np.abs(res["fp32"]["y_next"][(res["tf32x3"]["y_next"] > 0) != (res["fp32"]["y_next"] > 0)]) < 1e-6).all()
-    for b in (0, 517):
-        d = oracle.solve_f64(4, N, pb.m, M_G, G_L, g_P[b], p_D[b], theta, beta)
-        o32 = oracle.solve(4, N, pb.m, M_G, G_L, g_P[b], p_D[b], theta, beta)
-        check_parity({k: res["tf32x3"][k][b] for k in VECS}, o32, d, f"full-size quadrotor instance {b}")
+    for tcp in ("tf32x3", "fp16x3"):
+        for k in VECS:
+            assert P.rel_inf(res[tcp][k], res["fp32"][k]) <= (2 * TOL if k == "zhat" else TOL), (tcp, k)
+            assert np.array_equal(res[tcp][k][B - 5:], res[tcp][k][:5]), (tcp, k)
+        assert np.array_equal(res[tcp]["y_next"] > 0, res["fp32"]["y_next"] > 0) or \
+            (np.abs(res["fp32"]["y_next"][(res[tcp]["y_next"] > 0) != (res["fp32"]["y_next"] > 0)]) < 1e-6).all()
+        for b in (0, 517):
+            d = oracle.solve_f64(4, N, pb.m, M_G, G_L, g_P[b], p_D[b], theta, beta)
+            o32 = oracle.solve(4, N, pb.m, M_G, G_L, g_P[b], p_D[b], theta, beta)
+            check_parity({k: res[tcp][k][b] for k in VECS}, o32, d, f"full-size quadrotor {tcp} instance {b}")
 
 
 # ------------------------------------------------------------------------------------ batch, per-instance operators
@@ -673,7 +711,7 @@ def test_tiny_latency_termination_with_cost_vector(torch_cuda, G, oracle, warp, 
     print("\n statuses:", seen)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "fp16x3"])
 def test_async_double_buffered_solves_equal_synchronous(torch_cuda, G, prec):
     """gpad_solve_async / gpad_wait: five back-to-back host-memory solves of different batches alternate over two
     sets of batch state on three streams; every result must be bit-identical to the synchronous gpad_solve of the same
@@ -682,7 +720,7 @@ def test_async_double_buffered_solves_equal_synchronous(torch_cuda, G, prec):
     N, B = 20, 700
     pb = P.quadrotor(N)
     theta, beta = schedule(30)
-    code = G.PREC_TF32X3 if prec == "tf32x3" else G.PREC_FP32
+    code = prec_code(G, prec)
     s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=code, max_batch=B)
     pin = lambda a: t.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     jobs = []
