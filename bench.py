@@ -108,6 +108,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def round_up32(v):
+    return (v + 31) // 32 * 32
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -385,7 +389,7 @@ def battery_batch_probe(torch, G, B=4096):
     rng = np.random.default_rng(3)
     g_P, p_D, _ = prob.instances(rng.random((B, n_u)) - 0.5, want_f=False)
     theta, beta = G.schedule(ITERS)
-    s = G.Solver(n_u, N, m, prob.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
+    s = G.Solver(n_u, N, m, prob.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_FP16X3, max_batch=B)
     dg, dp = torch.from_numpy(g_P).cuda(), torch.from_numpy(p_D).cuda()
     dz = torch.empty((B, n), device="cuda")
     st = torch.cuda.current_stream().cuda_stream
@@ -415,7 +419,7 @@ def closed_loop_probe(torch, G, B=16384, samples=5, iters=20):
     nx = prob.plant()[0].shape[0]
     x0, xref = np.ascontiguousarray(par[:, :nx]), np.ascontiguousarray(par[:, nx:])
     theta, beta = G.schedule(iters)
-    s = G.Solver(4, 100, prob.m, prob.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
+    s = G.Solver(4, 100, prob.m, prob.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_FP16X3, max_batch=B)
     G.closed_loop(prob, s, x0, 1, theta, beta, xref=xref, warm_start=G.WARM_SHIFTED)
     sec = float("inf")
     for _ in range(2):                       # best of two (each call also allocates and frees its device buffers)
@@ -540,7 +544,7 @@ def run_ours(args):
     theta, beta = G.schedule(ITERS)
     from gpad_b200 import sharding
     params = quad_params(B, seed=sharding.shard_seed(0, rank))
-    prec = G.PREC_FP32 if args.precision == "fp32" else G.PREC_TF32X3
+    prec = {"fp32": G.PREC_FP32, "tf32x3": G.PREC_TF32X3, "fp16x3": G.PREC_FP16X3}[args.precision]
     solver = G.Solver(prob.n_u, prob.N, m, prob.L, pb["M_G"], pb["G_L"], mode=G.MODE_BATCH_SHARED, precision=prec,
                       max_batch=B, device=local)
     desc_main = solver.description
@@ -568,7 +572,7 @@ def run_ours(args):
     sharding.gather_first_moves(d_out["z"], prob.n_u, dst=0, equal_shards=True)   # NCCL connections set up outside the timed region
     barrier()
     solver.profile(True)
-    solver.profile_read(1); solver.profile_read(2)
+    solver.profile_read(0); solver.profile_read(1); solver.profile_read(2)
     launches0 = solver.launches
     sampler = ClockSampler(local)
     if rank == 0:
@@ -588,6 +592,7 @@ def run_ours(args):
     elapsed_ms = sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
     assert rank != 0 or u0_all.shape[0] == world * B
     launches = solver.launches - launches0
+    ms0, c0 = solver.profile_read(0)          # fp16x3: the zhat row-quantisation kernel between the products
     ms1, c1 = solver.profile_read(1)
     ms2, c2 = solver.profile_read(2)
     solver.profile(False)
@@ -675,10 +680,46 @@ def run_ours(args):
     k_ms = (ms1 + ms2) / max(c1 + c2, 1)
     achieved = flops_per_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
     traffic = None
+    traffic_all = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    if prec == G.PREC_TF32X3:
+        traffic_all = json.load(open(tpath))
+        traffic = traffic_all.get("dram_bytes_per_launch")
+    if prec == G.PREC_FP16X3:
+        # fp16 hi/lo operands double the tensor rate and halve the operand bytes: the iteration's arithmetic intensity
+        # nm / (4m + 3n) = 89 flop/B now sits BELOW the ridge (3xFP16: 732 TF/s / 6.5 TB/s = 112 flop/B), so the
+        # path is HBM bound.  Dominant kernel = product 2 (tc_p2_kernel): its share of the algorithmic bytes of SURVEY 8(d)
+        # is the 4m floats per instance (read y_v, y_{v-1}, p_D, write y_{v+1}); product 1 carries the 3n (read g_P, r/w z).
+        p1_ms, p2_ms, q_ms = ms1 / max(c1, 1), ms2 / max(c2, 1), ms0 / max(c0, 1)
+        bytes_p2 = 4.0 * m * 4.0 * B
+        bytes_iter = (4.0 * m + 3.0 * n) * 4.0 * B
+        ach = bytes_p2 / (p2_ms * 1e-3) / 1e9 if p2_ms > 0 else None
+        iter_ms = elapsed_ms / (args.steps * ITERS)
+        tf_peak = bf16_sus / 3.0
+        p1_tf = flops_per_launch / (p1_ms * 1e-3) / 1e12 if p1_ms > 0 else None
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None,
+                "traffic": (traffic_all or {}).get("product2_f16", {}).get("dram_bytes_per_launch"),
+                "kernel": "tc_p2_kernel (product 2, tcgen05 kind::f16 x3, TMA-streamed epilogue)",
+                "algorithmic_bytes_per_launch": bytes_p2, "mean_launch_ms": p2_ms, "launches_timed": int(c2),
+                "kernel_share_of_step": ms2 / elapsed_ms,
+                "peak_basis": f"{peak_src}: hbm_gbs (copy bandwidth, of measured)",
+                "product1": {"bound": "tensor", "kernel": "tc_p1_kernel<8,false,true> (kind::f16 x3, A operand quantised into TMEM)",
+                             "mean_launch_ms": p1_ms, "achieved": p1_tf, "peak": tf_peak, "unit": "TFLOP/s",
+                             "frac": (p1_tf / tf_peak) if p1_tf else None, "algorithmic_flops_per_launch": flops_per_launch,
+                             "tcgen05_f16x3_peak_measured": 732.0, "frac_of_tcgen05_peak": (p1_tf / 732.0) if p1_tf else None,
+                             "kernel_share_of_step": ms1 / elapsed_ms,
+                             "traffic": (traffic_all or {}).get("product1_f16", {}).get("dram_bytes_per_launch"),
+                             "peak_basis": f"{peak_src}: bf16 sustained {bf16_sus} TF/s / 3 MMAs per product; the tensor pipe itself "
+                                           "does 4096 fp16 MAC/clk/SM = 732 TF/s of 3xFP16-effective at 1.81 GHz (ubench, twice the tf32 rate)"},
+                "zhat_quantize_kernel": {"mean_launch_ms": q_ms, "bytes_per_launch": 2.0 * round_up32(n) * 4.0 * B,
+                                         "GBps": 2.0 * round_up32(n) * 4.0 * B / (q_ms * 1e-3) / 1e9 if q_ms > 0 else None,
+                                         "kernel_share_of_step": ms0 / elapsed_ms},
+                "whole_iteration": {"algorithmic_bytes": bytes_iter, "ms": iter_ms, "GBps": bytes_iter / (iter_ms * 1e-3) / 1e9,
+                                    "frac_of_hbm_peak": bytes_iter / (iter_ms * 1e-3) / 1e9 / hbm,
+                                    "algorithmic_TFLOPs": 2.0 * flops_per_launch / (iter_ms * 1e-3) / 1e12,
+                                    "note": "(4m + 3n) * 4 B per instance-iteration (SURVEY 8d) over the device-timed iteration: launch gaps, "
+                                            "the quantisation kernel and product 1 included"}}
+    elif prec == G.PREC_TF32X3:
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "kernel": "tc_p1_kernel (product 1) + tc_gemm_kernel<2> (product 2), tcgen05 kind::tf32 x3", "algorithmic_flops_per_launch": flops_per_launch,
@@ -694,7 +735,7 @@ def run_ours(args):
                 "traffic": traffic, "kernel": "simt_gemm_kernel (CUDA-core FFMA)", "peak_basis": "148 SMs x 128 FMA/clk x 1.965 GHz (nominal fp32)"}
 
     psample = parity_sample(solver, prob, pb, params, d_out, theta, beta, B)
-    tol = tolerance_probe(torch, G, prob, pb, solver, d_par, B) if (not args.no_latency and prec == G.PREC_TF32X3) else None
+    tol = tolerance_probe(torch, G, prob, pb, solver, d_par, B) if (not args.no_latency and prec != G.PREC_FP32) else None
     solver.close()
     cpu_val, cpu_info = cpu_rate(args.cpu_budget)
     lat = latency_probe(torch, G) if not args.no_latency else None
@@ -705,7 +746,9 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (tf32 x3 split products, fp32 accumulate)" if prec == G.PREC_TF32X3 else "f32", "data": "synthetic",
+        "dtype": {G.PREC_TF32X3: "f32 (tf32 x3 split products, fp32 accumulate)",
+                  G.PREC_FP16X3: "f32 (fp32 state; products as 3 kind::f16 MMAs on fp16 hi/lo splits of power-of-two row-scaled operands, "
+                                 "11 + 11 significant bits like the tf32 split, fp32 accumulate)"}.get(prec, "f32"), "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "iters_per_solve": ITERS, "n": n, "m": m,
                    "step": "one gpad_solve() of the whole batch = 100 GPAD iterations", "l2": "inputs (>2.9 GB/GPU) exceed the 126 MB L2; no flush",
                    "precision": args.precision, "path": desc_main, "host_placement": numa_note},
@@ -755,7 +798,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "fp32"])
+    ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "tf32x3", "fp32"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()

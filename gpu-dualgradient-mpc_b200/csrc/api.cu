@@ -58,7 +58,6 @@ Knobs parse_knobs() {
         else if (key == "tc_p1") k.tc_p1 = iv;
         else if (key == "tc_stages") k.tc_stages = iv;
         else if (key == "tc_bn2") k.tc_bn2 = iv;
-        else if (key == "tc_p2") k.tc_p2 = iv;
         else if (key == "tc_autotune") k.tc_autotune = iv;
         else if (key == "tc_pdl") k.tc_pdl = iv;
         else if (key == "tc_cluster_attr") k.tc_cluster_attr = iv;

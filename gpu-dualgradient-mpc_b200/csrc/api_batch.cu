@@ -169,8 +169,7 @@ int inputs(gpad_handle_s* h, BatchSlot& sl, const gpad_solve_args_t* a, bool hos
 // `it`: the iteration (selects the rotating y buffers for the TMA-fed epilogue of the fp16 product 2)
 int launch_product(gpad_handle_s* h, BatchSlot& sl, int phase, const BatchKernelArgs& k, cudaStream_t s, bool f16 = false, int it = 0) {
     if (f16 && phase == 1) return tc::launch_p1(sl.g1h, k, h->num_sms, s);
-    if (f16 && sl.g2h.p2) return tc::launch_p2(sl.g2h, k, it % 3, (it + 2) % 3, (it + 1) % 3, h->num_sms, s);
-    if (f16) return tc::launch_gemm(2, sl.g2h, k, nullptr, 0, h->num_sms, s);
+    if (f16) return tc::launch_p2(sl.g2h, k, it % 3, (it + 2) % 3, (it + 1) % 3, h->num_sms, s);
     if (h->cfg.precision == GPAD_PREC_TF32X3 || h->cfg.precision == GPAD_PREC_FP16X3) {
         if (phase == 1 && sl.g1.p1) return tc::launch_p1(sl.g1, k, h->num_sms, s);
         return tc::launch_gemm(phase, phase == 1 ? sl.g1 : sl.g2, k, nullptr, 0, h->num_sms, s);
@@ -565,8 +564,8 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         GPAD_TRY(tc::make_tmap_bytes(&g1h.tmB_hi, h->op.M_Gq_hi, 2, mp, h->op.n_rows_pad, mp, 32, bn1));
         GPAD_TRY(tc::make_tmap_bytes(&g1h.tmB_lo, h->op.M_Gq_lo, 2, mp, h->op.n_rows_pad, mp, 32, bn1));
         int bnh = 0, nth = 0;
-        g2h.p2 = kn.tc_p2 ? 1 : 0;
-        if (g2h.p2) tc::plan_tiles_p2(m, &bnh, &nth); else tc::plan_tiles(m, &bnh, &nth);
+        g2h.p2 = 1;
+        tc::plan_tiles_p2(m, &bnh, &nth);
         GPAD_TRY(tune_g2(g2h, true, bnh, tune_note_h));
     }
     if (p1)
@@ -589,10 +588,9 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
                  "batch-shared, fixed-iteration solves: tcgen05 cta_group::1 kind::f16 x3 (fp16 hi/lo of power-of-two row-scaled operands, "
                  "scales undone on the fp32 accumulator); product1 = P-formulation, y_v quantised in registers into a TMEM A ring (state "
                  "ring %d x 16 KB + operator ring %d stages), tiles 128x%d x%d, k-blocks of 32; zhat row quantisation kernel; product2 "
-                 "%s, tiles 128x%d x%d (%d stages; width %s); tolerance-mode solves: ",
-                 sl.g1h.a_stages, sl.g1h.stages, sl.g1h.bn, sl.g1h.n_tiles,
-                 sl.g2h.p2 ? "with TMA-streamed epilogue operands and stores" : "(first-generation kernel)", sl.g2h.bn, sl.g2h.n_tiles,
-                 sl.g2h.stages, tune_note_h.empty() ? "by plan" : tune_note_h.c_str());
+                 "with TMA-streamed epilogue operands and stores, tiles 128x%d x%d (%d + %d stages; width %s); tolerance-mode solves: ",
+                 sl.g1h.a_stages, sl.g1h.stages, sl.g1h.bn, sl.g1h.n_tiles, sl.g2h.bn, sl.g2h.n_tiles,
+                 sl.g2h.stages, sl.g2h.e_stages, tune_note_h.empty() ? "by plan" : tune_note_h.c_str());
         h->desc = std::string(buf) + h->desc;
     }
     return GPAD_OK;

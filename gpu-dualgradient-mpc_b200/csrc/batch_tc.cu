@@ -63,8 +63,9 @@ __host__ __device__ constexpr int epi_warps(int phase) { return kWorkWarps - xfo
 __host__ __device__ constexpr int cta_threads(int phase) { return 32 * (2 + kWorkWarps); }
 
 // PHASE 0: plain store of C (test hook); 1: GPAD product 1; 2: GPAD product 2
-// F16 (GPAD_PREC_FP16X3): the operand tiles hold fp16 hi / lo of row-scaled values -- the same 64-byte rows, twice the K
-// per row (BK counts 4-byte units), kind::f16 MMAs; the epilogue undoes the row and column scales on the accumulator
+// F16 (GPAD_PREC_FP16X3, test hook of the mainloop batch_tc_p2.cu shares): the operand tiles hold fp16 hi / lo of row-scaled
+// values -- the same 64-byte rows, twice the K per row (BK counts 4-byte units), kind::f16 MMAs; the epilogue undoes the row
+// and column scales on the accumulator
 template <int PHASE, int BK, bool TOL, bool F16>
 __global__ void __launch_bounds__(cta_threads(PHASE), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -209,17 +210,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             // F16: this thread's accumulator row (TMEM lane = batch row) carries the row scale of the A operand
             float row_inv = 1.f;
             if (F16) row_inv = __ldg(args.a_rowinv + row_base + lane);
-            uint32_t row_max = 0;                     // F16 product 2: lane r keeps max_c y+[row_base + r][c] of this tile
             for (int blk = part; blk < nblk; blk += kParts) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride + blk * 32), v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = F16 ? __uint_as_float(v[j]) * row_inv : __uint_as_float(v[j]);
                 __syncwarp();
-                epilogue_block<PHASE, TOL, F16>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, Cdbg, ldc, 0, &row_max);
+                epilogue_block<PHASE, TOL, F16>(args, buf, lane, row_base, blk, ts.n_tile(), bn, ncols_valid, Cdbg, ldc);
                 __syncwarp();
             }
-            if (F16 && PHASE == 2 && row_max != 0u) atomicMax(args.next_rowmax + row_base + lane, row_max);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
@@ -336,9 +335,9 @@ int launch_gemm(int phase, const GemmDesc& g, const BatchKernelArgs& args, float
     // fixed-iteration solves run the lean instantiation; tolerance mode (stopped rows, reductions, dual-gap launches) its own
     const bool tol = args.checking || args.dual || args.done;
     if (g.f16) {
-        // fp16 hi / lo operands: fixed-iteration product 2 and the test hook (tolerance mode runs the tf32 kernels)
-        if (tol || phase == 1) { set_error("tcgen05 GEMM: no fp16 instantiation for this launch"); return GPAD_ERR_UNSUPPORTED; }
-        return phase == 0 ? launch_one<0, 16, false, true>(g, args, C, ldc, num_sms, s) : launch_one<2, 16, false, true>(g, args, C, ldc, num_sms, s);
+        // fp16 hi / lo operands: the test hook of this mainloop only (product 1: batch_tc_p1.cu, product 2: batch_tc_p2.cu)
+        if (phase != 0) { set_error("tcgen05 GEMM: no fp16 instantiation for this launch"); return GPAD_ERR_UNSUPPORTED; }
+        return launch_one<0, 16, false, true>(g, args, C, ldc, num_sms, s);
     }
     if (phase == 0) return launch_one<0, 16, false>(g, args, C, ldc, num_sms, s);
     if (phase == 1) return tol ? launch_one<1, 16, true>(g, args, C, ldc, num_sms, s) : launch_one<1, 16, false>(g, args, C, ldc, num_sms, s);

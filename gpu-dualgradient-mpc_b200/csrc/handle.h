@@ -26,7 +26,6 @@ struct Knobs {
     int tc_p1 = -1;                  // product 1: -1 waves model, 1 TMEM-operand kernel, 0 shared-memory-operand kernel
     int tc_stages = 0;               // cap on its ring depth (0: as many as fit)
     int tc_bn2 = 0;                  // product 2 tile width (0: tuned, cached per shape)
-    int tc_p2 = 1;                   // fp16 product 2: 1 TMA-streamed epilogue (batch_tc_p2.cu), 0 first-generation kernel
     int tc_autotune = 1;             // 0: first candidate width without timing
     int tc_pdl = 0;                  // programmatic dependent launch between the batch kernels (measured: -1..-2 % at 64K)
     int tc_cluster_attr = 0;         // launch the shared-memory-operand kernel as clusters of one CTA

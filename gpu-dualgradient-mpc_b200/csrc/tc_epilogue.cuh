@@ -91,14 +91,15 @@ __device__ __forceinline__ void fast_rows(const BatchKernelArgs& args, const flo
     }
 }
 
-// GPAD_PREC_FP16X3 (fixed-iteration solves): the accumulator block arrives with the A row scale already undone (the
-// epilogue warp applies it while transposing: TMEM lane = batch row); `cinv` undoes the operator row's scale (lane =
-// output column).  Product 1 stores zhat in fp32 only -- its fp16 split needs the maximum of the WHOLE row, which no
-// single tile sees, and is made by zsplit_kernel between the products.  Product 2 additionally reduces the row maxima of
-// y_{v+1} (>= 0, so the bit patterns order like the values): lane r of the warp keeps row r's maximum in *row_max.
+// GPAD_PREC_FP16X3 (fixed-iteration solves), product 1: the accumulator block arrives with the A row scale already
+// undone (the epilogue warp applies it while transposing: TMEM lane = batch row); `cinv` undoes the operator row's
+// scale (lane = output column).  zhat is stored in fp32 only -- its fp16 split needs the maximum of the WHOLE row,
+// which no single tile sees, and is made by quantize_rows_kernel between the products (batch_f16.cu).  Product 2 of
+// this precision has its own kernel and epilogue (batch_tc_p2.cu).
 template <int PHASE>
 __device__ __forceinline__ void fast_rows_f16(const BatchKernelArgs& args, const float* buf, int lane, int row_base, int c, bool col_ok,
-                                              float cinv, uint32_t* row_max) {
+                                              float cinv) {
+    static_assert(PHASE == 1, "fp16 product 2 runs batch_tc_p2.cu");
     constexpr int kChunk = 16;
 #pragma unroll 1
     for (int r0 = 0; r0 < 32; r0 += kChunk) {
@@ -126,29 +127,6 @@ __device__ __forceinline__ void fast_rows_f16(const BatchKernelArgs& args, const
                 __stcs(args.z + o, __fadd_rn(__fmul_rn(1.0f - args.it.theta, zo[j]), __fmul_rn(args.it.theta, zh)));
                 args.zhat[o] = zh;       // re-read by zsplit_kernel right after this launch: default caching
             }
-        } else {
-            float yc[kChunk], yp[kChunk], pd[kChunk];
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j) {
-                const bool ok = (live >> j) & 1u;
-                const size_t o = (size_t)(row_base + r0 + j) * args.mp + c;
-                yc[j] = ok ? __ldcs(args.y_cur + o) : 0.f;
-                yp[j] = ok ? __ldcs(args.y_prev + o) : 0.f;
-                pd[j] = ok ? __ldcs(args.p_D + o) : 0.f;
-            }
-            uint32_t mx = *row_max;
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j) {
-                const bool ok = (live >> j) & 1u;
-                const size_t o = (size_t)(row_base + r0 + j) * args.mp + c;
-                const float wv = momentum(yc[j], yp[j], args.it.beta);
-                const float sacc = buf[(r0 + j) * 33 + lane] * cinv + (wv + pd[j]);
-                const float yn = 0.5f * (sacc + fabsf(sacc));
-                if (ok) args.y_next[o] = yn;                    // read back by the next two kernels
-                const uint32_t rm = __reduce_max_sync(0xffffffffu, ok ? __float_as_uint(yn) : 0u);
-                if (lane == r0 + j) mx = max(mx, rm);
-            }
-            *row_max = mx;
         }
     }
 }
@@ -160,7 +138,7 @@ __device__ __forceinline__ void fast_rows_f16(const BatchKernelArgs& args, const
 template <int PHASE, bool TOL, bool F16 = false>
 __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, const float* buf, int lane, int row_base, int blk,
                                                int n_tile, int bn, int ncols_valid, float* __restrict__ Cdbg, int ldc,
-                                               int step = 0, uint32_t* row_max = nullptr) {
+                                               int step = 0) {
     // tiles start every `step` columns (default: bn).  step < bn (a multiple of 32) keeps every 32-column block on a
     // 128-byte line; the bn - step columns a tile shares with its predecessor belong to the predecessor
     const int cin = blk * 32 + lane;            // column inside the tile
@@ -183,7 +161,7 @@ __device__ __forceinline__ void epilogue_block(const BatchKernelArgs& args, cons
             if (col_ok && b < args.B) args.P_cur[(size_t)b * args.np + c] = F16 ? buf[rr * 33 + lane] * cinv : buf[rr * 33 + lane];
         }
     } else if (F16) {
-        fast_rows_f16<PHASE>(args, buf, lane, row_base, c, col_ok, cinv, row_max);
+        if constexpr (PHASE == 1) fast_rows_f16<1>(args, buf, lane, row_base, c, col_ok, cinv);
     } else if (!TOL) {
         fast_rows<PHASE, false>(args, buf, lane, row_base, c, col_ok);
     } else if (!args.it.check && !args.dual && args.done) {

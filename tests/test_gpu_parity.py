@@ -316,10 +316,19 @@ def test_f16x3_gemm_reaches_fp32_accuracy(torch_cuda, G, shape, kernel):
     scale[scale == 0] = 1.0
     err = np.max(np.abs(C - ref) / scale)
     fp32 = np.max(np.abs((A @ B.T).astype(np.float64) - ref) / scale)
-    print(f"\n {shape} kernel {kernel}: 3xFP16 err {err:.2e} of sum|a||b|  (numpy fp32 {fp32:.2e})")
+    # the tf32 split on the same operands: the yardstick (same 11 + 11 bits per operand, same three products)
+    dT = t.full((M, N), float("nan"), device="cuda")
+    G.debug_gemm_tf32x3(dA, dB, dT, M, N, K)
+    t.cuda.synchronize()
+    err_tf32 = np.max(np.abs(dT.cpu().numpy() - ref) / scale)
+    print(f"\n {shape} kernel {kernel}: 3xFP16 err {err:.2e} of sum|a||b|  (3xTF32 {err_tf32:.2e}, numpy fp32 {fp32:.2e})")
     assert np.isfinite(C).all()
     assert (C[M // 2] == 0).all() and (C[:, N // 3] == 0).all()
-    assert err <= 1e-6 + 1e-9 * K
+    # rows with a wide range concentrate sum|a||b| in a few terms, so the per-product error (<= 3 * 2^-22 = 7e-7: two
+    # 22-bit representations and the dropped lo*lo) does not average out as it does on the normal operands of the tf32
+    # test above; the tensor core's truncating fp32 accumulation adds ~1e-9 per K element
+    assert err <= 2e-6 + 1e-9 * K
+    assert err <= 1.5 * err_tf32 + 2e-7
 
 
 @pytest.mark.parametrize("stages", ["0", "2"])

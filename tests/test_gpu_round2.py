@@ -117,7 +117,7 @@ def test_battery_batch_tolerance_with_compaction(torch_cuda, G, oracle):
     theta, beta = schedule(1500)
     kw = dict(check_every=3, eps_g=1e-2, eps_V=1e-2, f=f)
     ora = oracle.solve_batch(n_u, N, pb.m, pb.M_G, pb.G_L, g_P, p_D, theta, beta, L=pb.L, **kw)
-    for prec in (G.PREC_FP32, G.PREC_TF32X3):
+    for prec in (G.PREC_FP32, G.PREC_TF32X3, G.PREC_FP16X3):      # an FP16X3 handle runs its tolerance-mode solves on the tf32 kernels
         s = G.Solver(n_u, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=prec, max_batch=B)
         gpu = s.solve_host(g_P, p_D, theta, beta, **kw)
         print("\n", prec, s.stats(), "iterations", ora["iters"].min(), "..", ora["iters"].max())
