@@ -820,8 +820,12 @@ long long gpad_launch_count(gpad_handle_t h) { return h ? h->launches : 0; }
 const char* gpad_describe(gpad_handle_t h) { return h ? h->desc.c_str() : ""; }
 
 int gpad_debug_plan_tiles(int kernel, int ncols, int* bn, int* n_tiles, int* step, int* tmem_cols) {
-    GPAD_REQUIRE(bn && n_tiles && step && tmem_cols && ncols > 0 && (kernel == 0 || kernel == 1), "gpad_debug_plan_tiles: bad argument");
-    if (kernel == 1) {
+    GPAD_REQUIRE(bn && n_tiles && step && tmem_cols && ncols > 0 && kernel >= 0 && kernel <= 2, "gpad_debug_plan_tiles: bad argument");
+    if (kernel == 2) {
+        tc::plan_tiles_p2(ncols, bn, n_tiles);
+        *step = *bn;
+        *tmem_cols = 2 * 256;                      // two accumulators at a fixed 256-column stride (batch_tc_p2.cu)
+    } else if (kernel == 1) {
         tc::plan_tiles_p1(ncols, bn, n_tiles, step);
         *tmem_cols = 2 * *bn + 96;                 // two accumulators + 3 state slots of 32 columns (batch_tc_p1.cu)
     } else {

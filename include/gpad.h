@@ -362,7 +362,8 @@ int gpad_debug_gemm_f16x3(const float* A, const float* B, float* C, int M, int N
 
 /* Test hook, host only (no device call): the column tiling the batch kernels use for an operator with
  * `ncols` output columns. kernel 0 = shared-memory-operand kernel (tiles <= 256 columns), 1 = the
- * TMEM-operand kernel (tiles <= 208 columns, 96 TMEM columns kept for the state ring).
+ * TMEM-operand kernel (tiles <= 208 columns, 96 TMEM columns kept for the state ring), 2 = the
+ * fp16 product 2 with the TMA-streamed epilogue (tiles of whole 32-column blocks, <= 256).
  * Tile t covers columns [t*step, t*step + bn); tmem_cols = TMEM columns the plan occupies (<= 512). */
 int gpad_debug_plan_tiles(int kernel, int ncols, int* bn, int* n_tiles, int* step, int* tmem_cols);
 

@@ -165,7 +165,19 @@ def test_batch_column_tiling_covers_every_width(kernel, max_bn):
         assert tmem <= 512, (ncols, bn, tmem)
     assert G.debug_plan_tiles(1, 400)[:3] == (208, 2, 192)                  # quadrotor product 1: aligned second tile
     with pytest.raises(G.GpadError):
-        G.debug_plan_tiles(2, 400)
+        G.debug_plan_tiles(3, 400)
+
+
+def test_fp16_product2_tiling_is_whole_epilogue_blocks():
+    """batch_tc_p2.cu plan_tiles_p2: the TMA-fed epilogue works in 32-column blocks, so tiles are multiples of 32
+    columns (<= 256, a legal UMMA N), cover every width without a tile entirely past the end, and two 256-column
+    accumulator stages fit the 512 TMEM columns"""
+    for ncols in list(range(1, 1200)) + [2399, 2400, 2401, 4200, 4799, 4800]:
+        bn, nt, step, tmem = G.debug_plan_tiles(2, ncols)
+        assert bn % 32 == 0 and 32 <= bn <= 256 and step == bn, (ncols, bn, step)
+        assert nt * bn >= ncols and (nt - 1) * bn < ncols, (ncols, bn, nt)
+        assert tmem <= 512
+    assert G.debug_plan_tiles(2, 2400)[:2] == (256, 10)
 
 
 # ------------------------------------------------------------------------------------ round 2: formats, plants, groups
