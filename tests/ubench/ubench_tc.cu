@@ -37,14 +37,31 @@ struct Cfg {
     int bulk_b;      // 1: operator k-blocks are contiguous pre-packed images fetched with ONE cp.async.bulk (no per-row TMA requests)
     int bk;          // K floats per k-block: 16 (64 B rows, SWIZZLE_64B) or 32 (128 B rows, SWIZZLE_128B)
     int warp_issue;  // 0: the whole issue loop runs under `if (lane == 0)`; 1: warp-uniform loop, elect.sync around each MMA
+    int f16 = 0;     // 1 (warp_issue = 1 only): kind::f16 MMAs (K = 16 per instruction from the same 32 operand bytes per row)
 };
 
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// cluster helpers (the product kernels no longer use clusters / multicast: measured no gain)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile(
@@ -129,7 +146,7 @@ ub_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     } else if (warp == 1 && c.warp_issue) {
         // CUTLASS-style: every lane runs the loop (uniform control flow and address arithmetic),
         // one elected lane executes each tcgen05 instruction
-        const uint32_t idesc = make_idesc(c.bn_mma);
+        const uint32_t idesc = c.f16 ? make_idesc_f16(c.bn_mma) : make_idesc(c.bn_mma);
         const int nh = c.bn / c.bn_mma;
         int stage = 0; uint32_t phase = 0;
         for (int t = 0; t < c.tiles; ++t) {
@@ -140,6 +157,31 @@ ub_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                 }
                 const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint32_t bb = base + c.a_tiles * a_bytes;
+                if (c.f16) {
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint64_t a_hi = make_smem_desc<BK>(base + ks * 32);
+                        const uint64_t a_lo = make_smem_desc<BK>(base + a_bytes + ks * 32);
+                        for (int h = 0; h < nh; ++h) {
+                            const uint32_t off = (uint32_t)h * c.bn_mma * BK * 4;
+                            const uint64_t b_hi = make_smem_desc<BK>(bb + off + ks * 32);
+                            const uint64_t b_lo = make_smem_desc<BK>(bb + b_bytes + off + ks * 32);
+                            const uint32_t d = tmem_base + (uint32_t)h * c.bn_mma;
+                            if (elect_one()) {
+                                if (c.do_xform == 2) {
+                                    const uint32_t at = tmem_base + (uint32_t)((c.bn + 31) & ~31) + (uint32_t)stage * 32u + (uint32_t)ks * 8u;
+                                    umma_f16_ts(d, at, b_lo, idesc, (t | kb | ks) != 0 ? 1u : 0u);
+                                    umma_f16_ts(d, at + 16u, b_hi, idesc, 1u);
+                                    umma_f16_ts(d, at, b_hi, idesc, 1u);
+                                } else {
+                                    umma_f16(d, a_hi, b_lo, idesc, (t | kb | ks) != 0 ? 1u : 0u);
+                                    umma_f16(d, a_lo, b_hi, idesc, 1u);
+                                    umma_f16(d, a_hi, b_hi, idesc, 1u);
+                                }
+                            }
+                        }
+                    }
+                } else
 #pragma unroll
                 for (int ks = 0; ks < BK / 8; ++ks) {
                     const uint64_t a_hi = make_smem_desc<BK>(base + ks * 32);
@@ -521,7 +563,8 @@ static void run(const char* name, Cfg c) {
     unsigned long long cmax = 0; for (auto v : cyc) if (v > cmax) cmax = v;
     const double kb_total = (double)c.tiles * c.kblocks;
     const double clk_per_kb = cmax / kb_total;
-    const double ideal_mma_clk = 3.0 * (c.bk / 8) * 128.0 * c.bn * 8 / 2048.0;            // 2048 tf32 MAC / clk / SM
+    // 2048 tf32 MAC / clk / SM; kind::f16: twice the K per instruction, util is quoted against 4096 fp16 MAC / clk / SM
+    const double ideal_mma_clk = 3.0 * (c.bk / 8) * 128.0 * c.bn * 8 / 2048.0;
     const double bytes_per_kb_sm = c.a_tiles * 128 * 4.0 * c.bk + 2.0 * c.bn * 4.0 * c.bk / c.cluster;   // L2 -> SM fabric bytes
     const double smem_wr = c.a_tiles * 128 * 4.0 * c.bk + 2.0 * c.bn * 4.0 * c.bk;
     const double flops = 2.0 * 128 * c.bn * c.bk * kb_total * grid;                 // algorithmic (one product)
@@ -588,6 +631,19 @@ int main(int argc, char** argv) {
     CK(cudaMemset(dA0, 0, (size_t)ROWS_A * K * 4)); CK(cudaMemset(dA1, 0, (size_t)ROWS_A * K * 4));
     CK(cudaMemset(dB0, 0, (size_t)ROWS_B * K * 4)); CK(cudaMemset(dB1, 0, (size_t)ROWS_B * K * 4));
     const int KB = K / 16, T = 4;
+    auto f16_section = [&]() {
+        printf("---- kind::f16 (GPAD_PREC_FP16X3): the same operand bytes per MMA, K = 16 (twice the MACs); clk per k-block of 6 MMAs\n");
+        for (int f16 = 0; f16 < 2; ++f16) {
+            for (int n : {128, 160, 192, 208, 256}) {
+                char nm[64]; snprintf(nm, sizeof nm, "%s mma only SS 128x%d", f16 ? "f16 " : "tf32", n);
+                run(nm, Cfg{n, n, n / 2, 2, 2, KB, T, 0, 1, 0, 1, 512, 0, 0, 16, 1, f16});
+            }
+            run(f16 ? "f16  mma only TS 128x208" : "tf32 mma only TS 128x208", Cfg{208, 208, 104, 1, 3, KB, T, 0, 1, 2, 1, 512, 0, 0, 16, 1, f16});
+            run(f16 ? "f16  mma only TS 128x256" : "tf32 mma only TS 128x256", Cfg{256, 256, 128, 1, 3, KB, T, 0, 1, 2, 1, 512, 0, 0, 16, 1, f16});
+            run(f16 ? "f16  mma only TS 2x208" : "tf32 mma only TS 2x208",     Cfg{416, 208, 104, 1, 3, KB, T, 0, 1, 2, 1, 512, 0, 0, 16, 1, f16});
+        }
+    };
+    if (argc == 2 && !strcmp(argv[1], "f16")) { f16_section(); return 0; }
     if (argc > 1) {      // name bn bn_mma box a_tiles stages kblocks tiles tma mma xform cluster order warp_issue
         for (int i = 1; i + 13 < argc; i += 14) {
             Cfg c{atoi(argv[i + 1]), atoi(argv[i + 2]), atoi(argv[i + 3]), atoi(argv[i + 4]), atoi(argv[i + 5]), atoi(argv[i + 6]),
@@ -623,6 +679,7 @@ int main(int argc, char** argv) {
         run("p2: tma+mma bn=480",             Cfg{480, 240, 120, 2, 2, 26, 20, 1, 1, 0, 1, 512, 0, 0, 16, wi});
         run("p2: tma+mma bn=480 cluster2",    Cfg{480, 240, 120, 2, 2, 26, 20, 1, 1, 0, 2, 512, 0, 0, 16, wi});
     }
+    f16_section();
     printf("---- product 1 candidates: A = y only (one state tile), hi/lo built by transform warps into a TMEM A ring (TS MMAs)\n");
     run("y-only smem-xform bn=208 (A2 layout)", Cfg{208, 208, 104, 2, 3, KB, T, 1, 1, 1, 1, 512, 0, 0, 16, 1});
     run("y-only tmem-A bn=208",            Cfg{208, 208, 104, 1, 3, KB, T, 1, 1, 2, 1, 512, 0, 0, 16, 1});
