@@ -75,7 +75,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-template <int BK>
+template <int BK, bool F16 = false>
 __global__ void __launch_bounds__(192, 1)
 ub_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
           const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const Cfg c,
@@ -146,7 +146,7 @@ ub_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     } else if (warp == 1 && c.warp_issue) {
         // CUTLASS-style: every lane runs the loop (uniform control flow and address arithmetic),
         // one elected lane executes each tcgen05 instruction
-        const uint32_t idesc = c.f16 ? make_idesc_f16(c.bn_mma) : make_idesc(c.bn_mma);
+        const uint32_t idesc = F16 ? make_idesc_f16(c.bn_mma) : make_idesc(c.bn_mma);
         const int nh = c.bn / c.bn_mma;
         int stage = 0; uint32_t phase = 0;
         for (int t = 0; t < c.tiles; ++t) {
@@ -157,7 +157,7 @@ ub_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
                 }
                 const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint32_t bb = base + c.a_tiles * a_bytes;
-                if (c.f16) {
+                if constexpr (F16) {
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
                         const uint64_t a_hi = make_smem_desc<BK>(base + ks * 32);
@@ -526,7 +526,7 @@ static void run(const char* name, Cfg c) {
     CUtensorMap a0 = make_map(dA0, K, ROWS_A, K, 128, c.bk), a1 = make_map(dA1, K, ROWS_A, K, 128, c.bk);
     CUtensorMap b0 = make_map(dB0, K, ROWS_B, K, c.box_rows, c.bk), b1 = make_map(dB1, K, ROWS_B, K, c.box_rows, c.bk);
     const size_t stage_bytes = (size_t)c.a_tiles * 128 * c.bk * 4 + 2 * (size_t)c.bn * c.bk * 4;
-    auto kern = c.bk == 32 ? ub_kernel<32> : c.bk == 8 ? ub_kernel<8> : ub_kernel<16>;
+    auto kern = c.f16 ? ub_kernel<16, true> : c.bk == 32 ? ub_kernel<32> : c.bk == 8 ? ub_kernel<8> : ub_kernel<16>;
     const size_t smem = 1024 + c.stages * stage_bytes + (3 * c.stages + 2) * 8 + 16;
     if (smem > 232448) { printf("%-44s skipped (smem %zu)\n", name, smem); return; }
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
