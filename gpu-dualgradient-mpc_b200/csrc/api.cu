@@ -880,7 +880,7 @@ int gpad_debug_gemm_tf32x3(const float* A, const float* B, float* C, int M, int 
 }
 
 int gpad_debug_gemm_f16x3(const float* A, const float* B, float* C, int M, int N, int K, int kernel, void* stream) {
-    GPAD_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && (kernel == 0 || kernel == 1), "gpad_debug_gemm_f16x3: bad argument");
+    GPAD_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && kernel >= 0 && kernel <= 2, "gpad_debug_gemm_f16x3: bad argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int dev = 0;
     GPAD_CUDA(cudaGetDevice(&dev));
@@ -890,7 +890,8 @@ int gpad_debug_gemm_f16x3(const float* A, const float* B, float* C, int M, int N
     tc::GemmDesc g;
     g.f16 = 1; g.bk = 16;
     g.k_pad = round_up(K, 32);
-    if (kernel == 1) { tc::plan_tiles_p1(N, &g.bn, &g.n_tiles, &g.step); g.p1 = 1; }
+    if (kernel == 2) { tc::plan_tiles_p1(N, &g.bn, &g.n_tiles, &g.step, 256); g.p1 = 1; g.acc_stages = 1; }
+    else if (kernel == 1) { tc::plan_tiles_p1(N, &g.bn, &g.n_tiles, &g.step); g.p1 = 1; }
     else tc::plan_tiles(N, &g.bn, &g.n_tiles);
     g.m_tiles = round_up(M, 128) / 128;
     g.ncols_valid = N;

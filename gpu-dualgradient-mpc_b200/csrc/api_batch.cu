@@ -20,7 +20,7 @@ namespace {
 // ---- product 2 tile width: measured once per (device, n, m, batch) in this process, not modelled: the landscape is
 // irregular (64K quadrotor batch, ms per launch: 256 -> 0.74, 224 -> 0.93, 192 -> 0.69, 160 -> 0.66, 128 -> 0.81) ----
 std::mutex g_tune_mutex;
-std::map<std::tuple<int, int, int, int>, std::pair<int, std::string>> g_tune_cache;
+std::map<std::tuple<int, int, int, int, int>, std::pair<int, std::string>> g_tune_cache;     // (device, n, m, batch, fp16 kernel)
 
 // tensor maps over a slot's own state for the fp16 plans: y_v as fp32 tiles of 128 x 32 (quantised in-kernel), zhat hi / lo
 // as fp16 tiles of 128 x 32
@@ -427,7 +427,17 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         p1 = cost_ts <= cost_ss;
     }
     if (p1) tc::plan_tiles_p1(n, &bn1, &nt1, &step1);
-    h->op.n_rows_pad = round_up(std::max(bn1 * nt1, n), 128);
+    // fp16 product 1: when wider tiles (<= 256 columns, ONE accumulator stage) bring the whole launch into a single wave over
+    // the SMs and the default plan needs more, take them -- a single wave has no next tile to overlap the epilogue with
+    // (battery (10,100), 4096 QPs: 160 tiles of 208 = 2 waves against 128 tiles of 256 = 1 wave)
+    int bn1h = bn1, nt1h = nt1, step1h = step1, acc1h = 2;
+    if (f16) {
+        int bw = 0, nw = 0, sw = 0;
+        tc::plan_tiles_p1(n, &bw, &nw, &sw, 256);
+        const int mt = (h->cfg.max_batch + 127) / 128;
+        if (mt * nw <= h->num_sms && mt * nt1 > h->num_sms) { bn1h = bw; nt1h = nw; step1h = sw; acc1h = 1; }
+    }
+    h->op.n_rows_pad = round_up(std::max(std::max(bn1 * nt1, bn1h * nt1h), n), 128);
     h->op.m_rows_pad = round_up(m + 256, 128);      // any product-2 tiling of width <= 256 stays inside
     GPAD_TRY(upload_padded(h, MG.data(), n, m, h->op.n_rows_pad, mp, &h->op.M_G));
     GPAD_TRY(upload_padded(h, GL.data(), m, n, h->op.m_rows_pad, np, &h->op.G_L));
@@ -504,7 +514,7 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
             return GPAD_OK;
         }
         if (h->cfg.max_batch < 1024 || !kn.tc_autotune) return GPAD_OK;
-        const auto key = std::make_tuple(h->device, n, m, round_up(h->cfg.max_batch, 128) + (half ? 1 : 0));
+        const auto key = std::make_tuple(h->device, n, m, round_up(h->cfg.max_batch, 128), half ? 1 : 0);
         std::lock_guard<std::mutex> lock(g_tune_mutex);
         auto hit = g_tune_cache.find(key);
         if (hit != g_tune_cache.end()) {
@@ -557,12 +567,12 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         tc::GemmDesc& g1h = sl.g1h; tc::GemmDesc& g2h = sl.g2h;
         g1h = tc::GemmDesc{}; g2h = tc::GemmDesc{};
         g1h.f16 = g2h.f16 = 1; g1h.bk = g2h.bk = bk;
-        g1h.k_pad = mp; g1h.bn = bn1; g1h.n_tiles = nt1; g1h.ncols_valid = n; g1h.p1 = 1; g1h.step = step1;
-        GPAD_TRY(tc::plan_rings_p1(bn1, h->smem_optin, &g1h.a_stages, &g1h.stages, true));
+        g1h.k_pad = mp; g1h.bn = bn1h; g1h.n_tiles = nt1h; g1h.ncols_valid = n; g1h.p1 = 1; g1h.step = step1h; g1h.acc_stages = acc1h;
+        GPAD_TRY(tc::plan_rings_p1(bn1h, h->smem_optin, &g1h.a_stages, &g1h.stages, true));
         g2h.k_pad = np; g2h.ncols_valid = m;
         GPAD_TRY(make_f16_state_maps(sl));
-        GPAD_TRY(tc::make_tmap_bytes(&g1h.tmB_hi, h->op.M_Gq_hi, 2, mp, h->op.n_rows_pad, mp, 32, bn1));
-        GPAD_TRY(tc::make_tmap_bytes(&g1h.tmB_lo, h->op.M_Gq_lo, 2, mp, h->op.n_rows_pad, mp, 32, bn1));
+        GPAD_TRY(tc::make_tmap_bytes(&g1h.tmB_hi, h->op.M_Gq_hi, 2, mp, h->op.n_rows_pad, mp, 32, bn1h));
+        GPAD_TRY(tc::make_tmap_bytes(&g1h.tmB_lo, h->op.M_Gq_lo, 2, mp, h->op.n_rows_pad, mp, 32, bn1h));
         int bnh = 0, nth = 0;
         g2h.p2 = 1;
         tc::plan_tiles_p2(m, &bnh, &nth);
@@ -587,9 +597,10 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         snprintf(buf, sizeof(buf),
                  "batch-shared, fixed-iteration solves: tcgen05 cta_group::1 kind::f16 x3 (fp16 hi/lo of power-of-two row-scaled operands, "
                  "scales undone on the fp32 accumulator); product1 = P-formulation, y_v quantised in registers into a TMEM A ring (state "
-                 "ring %d x 16 KB + operator ring %d stages), tiles 128x%d x%d, k-blocks of 32; zhat row quantisation kernel; product2 "
+                 "ring %d x 16 KB + operator ring %d stages), tiles 128x%d x%d (%d accumulator stage%s), k-blocks of 32; zhat row quantisation kernel; product2 "
                  "with TMA-streamed epilogue operands and stores, tiles 128x%d x%d (%d + %d stages; width %s); tolerance-mode solves: ",
-                 sl.g1h.a_stages, sl.g1h.stages, sl.g1h.bn, sl.g1h.n_tiles, sl.g2h.bn, sl.g2h.n_tiles,
+                 sl.g1h.a_stages, sl.g1h.stages, sl.g1h.bn, sl.g1h.n_tiles, sl.g1h.acc_stages, sl.g1h.acc_stages > 1 ? "s" : "",
+                 sl.g2h.bn, sl.g2h.n_tiles,
                  sl.g2h.stages, sl.g2h.e_stages, tune_note_h.empty() ? "by plan" : tune_note_h.c_str());
         h->desc = std::string(buf) + h->desc;
     }

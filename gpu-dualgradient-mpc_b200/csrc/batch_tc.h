@@ -20,6 +20,7 @@ struct GemmDesc {
     int p1 = 0;                   // product 1 runs the second-generation kernel (batch_tc_p1.cu): stages = operator ring,
     int a_stages = 0;             // a_stages = state ring
     int step = 0;                 // p1: column distance between tile starts (<= bn, see plan_tiles_p1); 0 = bn
+    int acc_stages = 2;           // p1: TMEM accumulator stages (1: single-wave plans with tiles of up to 256 columns)
     int ncols_valid = 0;          // output columns that exist (n or m)
     int f16 = 0;                  // GPAD_PREC_FP16X3: operand maps over fp16 hi / lo arrays (k_pad counts K elements)
     // second-generation product 2 (batch_tc_p2.cu): epilogue operands by TMA -- the rotating y buffers and p_D as
@@ -35,7 +36,7 @@ void plan_tiles(int ncols, int* bn, int* n_tiles);
 size_t smem_bytes(int bk, int bn, int stages);
 int pick_stages(int bk, int bn, size_t smem_limit);
 int launch_gemm(int phase, const GemmDesc& g, const BatchKernelArgs& args, float* C, int ldc, int num_sms, cudaStream_t s);
-void plan_tiles_p1(int ncols, int* bn, int* n_tiles, int* step = nullptr);
+void plan_tiles_p1(int ncols, int* bn, int* n_tiles, int* step = nullptr, int max_bn = 208);
 int plan_rings_p1(int bn, size_t smem_limit, int* a_stages, int* b_stages, bool f16 = false);
 // GPAD_PREC_FP16X3 helpers (batch_f16.cu)
 // rows of fp32 -> per-row power-of-two scale, fp16 hi / lo of the scaled rows, inv[r] = 2^-e

@@ -70,7 +70,7 @@ template <int EPI, bool TOL, bool F16>
 __global__ void __launch_bounds__(32 * (kP1FirstEpi + EPI), 1)
 tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmB_hi,
              const __grid_constant__ CUtensorMap tmB_lo, int num_k_blocks, int m_tiles, int n_tiles, int bn,
-             int a_stages, int b_stages, const BatchKernelArgs args, int ncols_valid, int step) {
+             int a_stages, int b_stages, const BatchKernelArgs args, int ncols_valid, int step, int acc_stages) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int BK = kP1BK;                                       // operator tile rows are BK * 4 = 64 bytes
@@ -92,8 +92,10 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t acc_stride = (uint32_t)bn;                      // bn <= 208 is a multiple of 16: 2 * 208 + 96 = 512
-    const uint32_t a_col0 = 2 * acc_stride;
+    // two accumulator stages of bn <= 208 columns (2 * 208 + 96 = 512), or ONE of up to 256 columns for plans whose tiles
+    // fit a single wave over the SMs (nothing to overlap the epilogue with; fewer, wider tiles)
+    const uint32_t acc_stride = (uint32_t)bn;
+    const uint32_t a_col0 = (uint32_t)acc_stages * acc_stride;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
@@ -179,7 +181,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
             }
             if (elect_one()) umma_commit(smem_u32(tfull_bar + acc));
             __syncwarp();
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= kP1FirstXform && warp < kP1FirstEpi) {
         // ============================ transform warps: y tile -> tf32 hi | lo -> TMEM A ring ============================
@@ -264,7 +266,7 @@ tc_p1_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
         }
     }
 
@@ -285,8 +287,9 @@ size_t p1_smem_bytes(int bn, int a_stages, int b_stages, int epi, bool f16 = fal
 }  // namespace
 
 // tiles of at most 208 columns: 2 x 208 accumulator columns + 96 columns of A ring fill the 512 TMEM columns
-void plan_tiles_p1(int ncols, int* bn, int* n_tiles, int* step) {
-    const int nt = (ncols + 207) / 208;
+// (max_bn = 256 for the single-accumulator plan)
+void plan_tiles_p1(int ncols, int* bn, int* n_tiles, int* step, int max_bn) {
+    const int nt = (ncols + max_bn - 1) / max_bn;
     int b = ((ncols + nt - 1) / nt + 15) / 16 * 16;
     if (b < 16) b = 16;
     *bn = b;
@@ -322,7 +325,7 @@ int launch_p1(const GemmDesc& g, const BatchKernelArgs& args, int num_sms, cudaS
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at; lc.numAttrs = g.pdl ? 1 : 0;
     GPAD_CUDA(cudaLaunchKernelEx(&lc, kern, g.tmA_hi, g.tmB_hi, g.tmB_lo, g.k_pad / (g.f16 ? 2 * kP1BK : kP1BK), g.m_tiles, g.n_tiles, g.bn, g.a_stages,
-                                 g.stages, args, g.ncols_valid, g.step > 0 ? g.step : g.bn));
+                                 g.stages, args, g.ncols_valid, g.step > 0 ? g.step : g.bn, g.acc_stages));
     return GPAD_OK;
 }
 

@@ -356,7 +356,8 @@ int gpad_debug_gemm_tf32x3(const float* A, const float* B, float* C, int M, int 
                            void* stream);
 /* The same through the GPAD_PREC_FP16X3 path: rows of A and B scaled and split into fp16 hi / lo, kind::f16
  * MMAs, scales undone in the epilogue.  kernel 0 = shared-memory-operand kernel (product 2's mainloop),
- * 1 = TMEM-operand kernel (product 1's: A quantised by the transform warps inside the kernel). */
+ * 1 = TMEM-operand kernel (product 1's: A quantised by the transform warps inside the kernel),
+ * 2 = the same with one accumulator stage and tiles of up to 256 columns (its single-wave plan). */
 int gpad_debug_gemm_f16x3(const float* A, const float* B, float* C, int M, int N, int K, int kernel,
                           void* stream);
 

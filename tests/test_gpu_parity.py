@@ -290,11 +290,11 @@ def prec_code(G, prec):
 
 
 # ------------------------------------------------------------------------------------ tensor-core GEMM hook
-@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(128, 16, 32), (128, 256, 64), (300, 200, 1000), (1000, 416, 2400), (257, 2400, 400), (130, 1000, 4200)])
 def test_f16x3_gemm_reaches_fp32_accuracy(torch_cuda, G, shape, kernel):
     """GPAD_PREC_FP16X3 mainloops (kernel 0: shared-memory operands = product 2; 1: A quantised in-kernel into tensor
-    memory = product 1) on operands whose ROWS differ by many orders of magnitude, with zeros and an all-zero row:
+    memory = product 1; 2: product 1's single-wave plan, one accumulator stage of up to 256 columns) on operands whose ROWS differ by many orders of magnitude, with zeros and an all-zero row:
     the power-of-two row scales must make fp16 hi + lo as good as the tf32 split"""
     t = torch_cuda
     M, N, K = shape
@@ -406,6 +406,45 @@ def test_batch_quadrotor_matches_oracle(torch_cuda, G, oracle, prec):
     worst = check_parity(gpu, ora, f64, f"batch {prec} quadrotor N={N}")
     print(f"\n quadrotor N={N} {prec}: worst GPU-vs-oracle rel_inf {worst:.2e}")
     s.close()
+
+
+def test_fp16x3_row_scales_follow_instance_magnitudes(torch_cuda, G, oracle):
+    """GPAD_PREC_FP16X3 scales every operand row by a power of two taken from its largest magnitude.  A batch whose
+    instances differ by five orders of magnitude (states and setpoints from 1e-4 of nominal -- nothing active, duals
+    identically zero -- to 10x nominal, most constraints active) must come out as accurate, instance by instance, as the
+    uniform batches of the other tests: against the CUDA-core fp32 path on every instance and against the oracle on a
+    spread of them"""
+    N, B = 20, 260
+    pb = P.quadrotor(N)
+    rng = np.random.default_rng(77)
+    par = P.quadrotor_params(B, rng) * 10.0 ** rng.uniform(-4, 1, (B, 1))
+    par[3] = 0.0                                           # the origin: g_P = 0, an all-zero zhat row
+    g_P, p_D, _ = pb.instance(par)
+    theta, beta = schedule(80)
+    res = {}
+    for prec in ("fp32", "fp16x3"):
+        s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=prec_code(G, prec), max_batch=B)
+        res[prec] = s.solve_host(g_P, p_D, theta, beta)
+        s.close()
+    assert np.isfinite(res["fp16x3"]["y_next"]).all() and (res["fp16x3"]["status"] == 0).all()
+    active = (res["fp32"]["y_next"] > 0).sum(axis=1)
+    assert active.min() == 0 and active.max() > 100        # from nothing active to heavily constrained
+    worst = 0.0
+    for b in range(B):
+        for k in VECS:
+            ref = res["fp32"][k][b]
+            if np.abs(ref).max() == 0.0:
+                assert np.abs(res["fp16x3"][k][b]).max() == 0.0, (b, k)
+                continue
+            e = P.rel_inf(res["fp16x3"][k][b], ref)
+            worst = max(worst, e)
+            assert e <= (2 * TOL if k == "zhat" else TOL), (b, k, e)
+    order = np.argsort(np.abs(par).max(axis=1))
+    for b in [int(order[0]), int(order[1]), int(order[B // 4]), int(order[B // 2]), int(order[-2]), int(order[-1])]:
+        ora = oracle.solve(4, N, pb.m, pb.M_G, pb.G_L, g_P[b], p_D[b], theta, beta)
+        f64 = oracle.solve_f64(4, N, pb.m, pb.M_G, pb.G_L, g_P[b], p_D[b], theta, beta)
+        check_parity({k: res["fp16x3"][k][b] for k in VECS}, ora, f64, f"fp16x3 scaled instance {b} (|par| {np.abs(par[b]).max():.1e})")
+    print(f"\n fp16x3 vs fp32 over instance magnitudes 1e-4 .. 10: worst per-instance rel_inf {worst:.2e}")
 
 
 @pytest.mark.parametrize("prec", ["fp32", "tf32x3", "fp16x3"])
