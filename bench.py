@@ -644,6 +644,12 @@ def run_ours(args):
         t_s = sharding.max_over_ranks((time.perf_counter() - t0) / 2, device="cuda")
         variants["synchronous_gpad_solve_host_gP_pD"] = {"value": world * B / t_s, "h2d_bytes_per_step": int(h_gP.nbytes + h_pD.nbytes)}
         del h_gP, h_pD
+        # what a receding-horizon controller reads back: the primal solution z (its first n_u entries are the control move),
+        # iteration counts and status -- the same pipeline with 105 MB instead of 2.1 GB of results per step
+        t_z = run_async(lambda S: G.host_args(B, theta, beta, ITERS, params=h_par, problem=prob, outputs={"z": S["out"]["z"]},
+                                              iters=S["it"], status=S["st"]))
+        variants["async_params_outputs_z_only"] = {"value": world * B * e2e_steps / t_z, "h2d_bytes_per_step": int(h2d),
+                                                   "d2h_bytes_per_step": int(last["out"]["z"].nbytes + last["it"].nbytes + last["st"].nbytes)}
 
     # ---- strong scaling of a FIXED 64K batch (BASELINE config 4 as written): every rank solves 65536 / N instances ----
     strong = None
