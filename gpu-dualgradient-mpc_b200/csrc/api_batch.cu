@@ -200,7 +200,9 @@ int iterate(gpad_handle_s* h, BatchSlot& sl, const gpad_solve_args_t* a, cudaStr
     const int m_tiles = round_up(B, 128) / 128;
     sl.g1.m_tiles = m_tiles; sl.g2.m_tiles = m_tiles;
     sl.g1h.m_tiles = m_tiles; sl.g2h.m_tiles = m_tiles;
-    sl.g1h.pdl = sl.g2h.pdl = h->knobs.tc_pdl ? 1 : 0;
+    // fp16 plan: three launches per iteration; below ~16K instances the launch boundaries are 4 % of a solve (measured: 8K
+    // instances 15.3 -> 14.7 ms, 64K within noise), so small solves launch their kernels programmatically dependent
+    sl.g1h.pdl = sl.g2h.pdl = (h->knobs.tc_pdl > 0 || (h->knobs.tc_pdl < 0 && m_tiles <= 128)) ? 1 : 0;
     const int q_rows = m_tiles * 128;          // rows the quantisation kernels cover: whole batch tiles
     if (f16 && a->max_iter > 0) {
         // row maxima of y_0 (product 2 reduces those of every later iterate)
@@ -209,7 +211,7 @@ int iterate(gpad_handle_s* h, BatchSlot& sl, const gpad_solve_args_t* a, cudaStr
     }
     // programmatic dependent launch: a GEMM kernel's CTAs start while the previous kernel drains; nothing it reads from
     // global memory (tile lists and counters included, see TileSched) is read before its dependency wait
-    sl.g1.pdl = sl.g2.pdl = h->knobs.tc_pdl ? 1 : 0;
+    sl.g1.pdl = sl.g2.pdl = h->knobs.tc_pdl > 0 ? 1 : 0;
     sl.g1.cluster_attr = sl.g2.cluster_attr = h->knobs.tc_cluster_attr ? 1 : 0;
     if (tcp && a->max_iter > 0) {
         if (a->y_prev0) {          // warm start: P_{-1} = M_G y_{-1} (one extra product-1 launch)
@@ -274,7 +276,8 @@ int iterate(gpad_handle_s* h, BatchSlot& sl, const gpad_solve_args_t* a, cudaStr
         if (f16) {
             // zhat_v -> row scale, fp16 hi / lo; also clears the row maxima product 2 is about to reduce
             pe = h->prof_begin(s);
-            GPAD_TRY(tc::launch_quantize_rows(st.zhat, st.np, q_rows, st.zq_hi, st.zq_lo, st.zinv, st.ymax[(it + 1) & 1], s));
+            GPAD_TRY(tc::launch_quantize_rows(st.zhat, st.np, q_rows, st.zq_hi, st.zq_lo, st.zinv, st.ymax[(it + 1) & 1], s,
+                                              sl.g1h.pdl != 0));
             h->prof_end(0, pe, s);
             h->launches += 1;
             k.a_rowinv = st.zinv; k.b_colinv = h->op.G_L_inv; k.next_rowmax = st.ymax[(it + 1) & 1];
@@ -584,14 +587,14 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
                  "through a TMEM ring, state ring %d x 8 KB + operator ring %d stages), tiles 128x%d x%d; product2 tiles 128x%d x%d "
                  "(%d stages, TMA ring bk=%d; width %s), TMEM 512 cols, persistent over %d SMs, programmatic dependent launch %s",
                  g1.a_stages, g1.stages, bn1, nt1, bn2, nt2, g2.stages, bk, tune_note.empty() ? "by plan" : tune_note.c_str(),
-                 h->num_sms, kn.tc_pdl ? "on" : "off");
+                 h->num_sms, kn.tc_pdl > 0 ? "on" : "off");
     else
         snprintf(buf, sizeof(buf),
                  "batch-shared: tcgen05 cta_group::1 kind::tf32 x3 (P-formulation, y_v split in shared memory), TMA ring bk=%d, product1 tiles "
                  "128x%d x%d (%d stages), product2 tiles 128x%d x%d (%d stages; width %s), TMEM 2x256 cols, persistent over %d SMs, "
                  "programmatic dependent launch %s",
                  bk, bn1, nt1, g1.stages, bn2, nt2, g2.stages, tune_note.empty() ? "by plan" : tune_note.c_str(), h->num_sms,
-                 kn.tc_pdl ? "on" : "off");
+                 kn.tc_pdl > 0 ? "on" : "off");
     h->desc = buf;
     if (f16) {
         snprintf(buf, sizeof(buf),

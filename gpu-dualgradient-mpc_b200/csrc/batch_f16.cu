@@ -27,6 +27,10 @@ __global__ void __launch_bounds__(32 * kRowWarps)
 quantize_rows_kernel(const float* __restrict__ src, int ld, int rows, uint2* __restrict__ hi, uint2* __restrict__ lo,
                      float* __restrict__ inv, unsigned* __restrict__ zero_rows) {
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    // programmatic dependent launch (a no-op without the launch attribute): the previous kernel's zhat is needed from here
+    // on; the next kernel may start its prologue (its own dependency wait covers this grid's writes)
+    grid_dependency_wait();
+    grid_launch_dependents();
     if (row >= rows) return;
     const float4* x = reinterpret_cast<const float4*>(src + (size_t)row * ld);
     const int nv = ld >> 2;
@@ -90,15 +94,20 @@ rowmax_kernel(const float* __restrict__ src, int ld, int rows, float* __restrict
 }  // namespace
 
 int launch_quantize_rows(const float* src, int ld, int rows, uint16_t* hi, uint16_t* lo, float* inv, unsigned* zero_rows,
-                         cudaStream_t s) {
+                         cudaStream_t s, bool pdl) {
     if (rows <= 0) return GPAD_OK;
     if (ld % 4) { set_error("quantize_rows: leading dimension %d is not a multiple of 4", ld); return GPAD_ERR_INVALID_ARG; }
-    const int grid = (rows + kRowWarps - 1) / kRowWarps;
-    if (ld <= 512)
-        quantize_rows_kernel<4><<<grid, 32 * kRowWarps, 0, s>>>(src, ld, rows, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), inv, zero_rows);
-    else
-        quantize_rows_kernel<0><<<grid, 32 * kRowWarps, 0, s>>>(src, ld, rows, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), inv, zero_rows);
-    GPAD_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((rows + kRowWarps - 1) / kRowWarps); lc.blockDim = dim3(32 * kRowWarps); lc.dynamicSmemBytes = 0; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;
+    const float* src_c = src;
+    uint2* h2 = reinterpret_cast<uint2*>(hi);
+    uint2* l2 = reinterpret_cast<uint2*>(lo);
+    if (ld <= 512) GPAD_CUDA(cudaLaunchKernelEx(&lc, quantize_rows_kernel<4>, src_c, ld, rows, h2, l2, inv, zero_rows));
+    else GPAD_CUDA(cudaLaunchKernelEx(&lc, quantize_rows_kernel<0>, src_c, ld, rows, h2, l2, inv, zero_rows));
     return GPAD_OK;
 }
 

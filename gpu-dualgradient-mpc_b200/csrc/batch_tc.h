@@ -41,7 +41,7 @@ int plan_rings_p1(int bn, size_t smem_limit, int* a_stages, int* b_stages, bool 
 // GPAD_PREC_FP16X3 helpers (batch_f16.cu)
 // rows of fp32 -> per-row power-of-two scale, fp16 hi / lo of the scaled rows, inv[r] = 2^-e
 int launch_quantize_rows(const float* src, int ld, int rows, uint16_t* hi, uint16_t* lo, float* inv, unsigned* zero_rows,
-                         cudaStream_t s);
+                         cudaStream_t s, bool pdl = false);
 // rowmax[r] = max_k |x[r][k]|
 int launch_rowmax(const float* src, int ld, int rows, float* rowmax, cudaStream_t s);
 int launch_p1(const GemmDesc& g, const BatchKernelArgs& args, int num_sms, cudaStream_t s);

@@ -27,7 +27,8 @@ struct Knobs {
     int tc_stages = 0;               // cap on its ring depth (0: as many as fit)
     int tc_bn2 = 0;                  // product 2 tile width (0: tuned, cached per shape)
     int tc_autotune = 1;             // 0: first candidate width without timing
-    int tc_pdl = 0;                  // programmatic dependent launch between the batch kernels (measured: -1..-2 % at 64K)
+    int tc_pdl = -1;                 // programmatic dependent launch between the batch kernels: -1 auto (fp16 plan, solves of
+                                     // <= 16K instances), 0 off, 1 on (measured: -4 % at 8K instances, within noise at 64K)
     int tc_cluster_attr = 0;         // launch the shared-memory-operand kernel as clusters of one CTA
     int tc_retire = 1;               // tolerance mode: skip batch tiles whose instances have all stopped
     int tc_compact = 1;              // tolerance mode: gather the running instances into dense tiles (needs tc_retire)

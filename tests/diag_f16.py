@@ -97,3 +97,42 @@ if "time" in sections:
     for name in outs:
         d = np.abs(outs[name] - outs["tf32x3"]).max() / np.abs(outs["tf32x3"]).max()
         print(f"z after {ITERS} iterations, {name} vs tf32x3 rel_inf {d:.2e}", flush=True)
+
+if "small" in sections:
+    # strong-scaling shards: one handle sized for 64K instances solving 8K .. 64K, with and without programmatic dependent launch
+    prob = G.Problem("quadrotor", N=100)
+    M_G, G_L = prob.operators()
+    par = quad_params(65536, 0)
+    g_P, p_D, _ = prob.instances(par, want_f=False)
+    dg, dp = torch.from_numpy(g_P).cuda(), torch.from_numpy(p_D).cuda()
+    dz = torch.empty((65536, prob.n), device="cuda")
+    theta, beta = G.schedule(100)
+    st = torch.cuda.current_stream().cuda_stream
+    for knobs in os.environ.get("DIAG_KNOBS", ";tc_pdl=1").split(";"):
+        if knobs:
+            os.environ["GPAD_DEBUG"] = knobs
+        else:
+            os.environ.pop("GPAD_DEBUG", None)
+        s = G.Solver(4, 100, prob.m, prob.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_FP16X3, max_batch=65536)
+        base = None
+        for b in (65536, 32768, 16384, 8192, 4096):
+            for _ in range(2):
+                s.solve_device(b, dg, dp, theta, beta, 100, stream=st, z=dz)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                s.solve_device(b, dg, dp, theta, beta, 100, stream=st, z=dz)
+            e1.record(); e1.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            base = base or ms / b
+            s.profile(True)
+            for w in range(3):
+                s.profile_read(w)
+            s.solve_device(b, dg, dp, theta, beta, 100, stream=st, z=dz)
+            torch.cuda.synchronize()
+            (m0, c0), (m1, c1), (m2, c2) = s.profile_read(0), s.profile_read(1), s.profile_read(2)
+            s.profile(False)
+            print(f"[{knobs or 'default'}] B={b:6d}: {ms:8.3f} ms per solve, {ms / 100:.4f} ms/iteration, per-instance efficiency {base / (ms / b):.3f}"
+                  f"   event-timed: product1 {m1 / max(c1, 1):.4f} quantise {m0 / max(c0, 1):.4f} product2 {m2 / max(c2, 1):.4f}", flush=True)
+        s.close()

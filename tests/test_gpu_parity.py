@@ -489,25 +489,32 @@ def test_batch_warm_start_matches_oracle(torch_cuda, G, oracle, prec):
     s.close()
 
 
-@pytest.mark.parametrize("knobs", ["tc_p1=0", "tc_p1=1", "tc_pdl=0", "tc_p1=0,tc_pdl=0", "tc_bn2=128", "tc_stages=2"])
-def test_batch_tc_kernel_variants_match_default(torch_cuda, G, knobs, monkeypatch):
-    """both product-1 kernels (shared-memory operand / TMEM operand; the default picks one by its waves model), launches with and without programmatic dependent launch, another product-2 tile width and a shallow
-    ring against the default plan on the same batch: same active sets, iterates within the parity tolerance"""
+@pytest.mark.parametrize("prec,knobs", [("tf32x3", "tc_p1=0"), ("tf32x3", "tc_p1=1"), ("tf32x3", "tc_pdl=1"), ("tf32x3", "tc_p1=0,tc_pdl=1"),
+                                        ("tf32x3", "tc_bn2=128"), ("tf32x3", "tc_stages=2"),
+                                        ("fp16x3", "tc_pdl=0"), ("fp16x3", "tc_pdl=1"), ("fp16x3", "tc_bn2=64"), ("fp16x3", "tc_bn2=256"),
+                                        ("fp16x3", "tc_stages=2")])
+def test_batch_tc_kernel_variants_match_default(torch_cuda, G, prec, knobs, monkeypatch):
+    """both product-1 kernels of the tf32 family (shared-memory operand / TMEM operand; the default picks one by its waves
+    model), launches with and without programmatic dependent launch (the fp16 family uses it by default for small solves),
+    other product-2 tile widths and shallow rings against the default plan on the same batch: same active sets, iterates
+    within the parity tolerance; the fp16 product 2 bit for bit (its results do not depend on the tile width)"""
     N, B = 20, 300
     pb = P.quadrotor(N)
     par = P.quadrotor_params(B, np.random.default_rng(11))
     g_P, p_D, _ = pb.instance(par)
     theta, beta = schedule(60)
-    s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
+    s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=prec_code(G, prec), max_batch=B)
     ref = s.solve_host(g_P, p_D, theta, beta)
     s.close()
     monkeypatch.setenv("GPAD_DEBUG", knobs)
-    s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
+    s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=prec_code(G, prec), max_batch=B)
     print("\n", s.description)
     alt = s.solve_host(g_P, p_D, theta, beta)
     s.close()
     for k in VECS:
         assert P.rel_inf(alt[k], ref[k]) <= 2e-5, (knobs, k, P.rel_inf(alt[k], ref[k]))
+        if prec == "fp16x3":
+            assert np.array_equal(alt[k], ref[k]), (knobs, k)
     assert np.array_equal(alt["y_next"] > 0, ref["y_next"] > 0)
 
 
