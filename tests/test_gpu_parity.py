@@ -733,7 +733,8 @@ def test_closed_loop_battery_matches_oracle_loop(torch_cuda, G, oracle, warm):
     assert (spread1 < spread0).all()                               # the cells are being balanced
 
 
-def test_closed_loop_quadrotor_device_resident(torch_cuda, G, oracle):
+@pytest.mark.parametrize("prec", ["tf32x3", "fp16x3"])
+def test_closed_loop_quadrotor_device_resident(torch_cuda, G, oracle, prec):
     """the device-resident loop (csrc/closed_loop.cu: instance build, tcgen05 solve, state advance, warm start) on a
     quadrotor batch with set-point parameters, against the same loop orchestrated on the host with the oracle"""
     N, B, samples = 10, 130, 6
@@ -743,7 +744,7 @@ def test_closed_loop_quadrotor_device_resident(torch_cuda, G, oracle):
     par = P.quadrotor_params(B, np.random.default_rng(5))
     nx = pb.plant()[0].shape[0]
     x0, xref = np.ascontiguousarray(par[:, :nx]), np.ascontiguousarray(par[:, nx:])
-    s = G.Solver(4, N, pb.m, pb.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
+    s = G.Solver(4, N, pb.m, pb.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=prec_code(G, prec), max_batch=B)
     xt, ut = G.closed_loop(pb, s, x0, samples, theta, beta, xref=xref, warm_start=True)
     s.close()
     A, Bm = pb.plant()

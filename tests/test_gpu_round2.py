@@ -138,26 +138,27 @@ def test_group_results_do_not_depend_on_device_count(torch_cuda, G):
     pb = P.quadrotor(N)
     g_P, p_D, _ = pb.instance(P.quadrotor_params(B, np.random.default_rng(51)))
     theta, beta = schedule(25)
-    res = []
-    for devices in ([0], [0, 0], [0, 0, 0]):
-        grp = G.Group(devices, 4, N, pb.m, pb.L, pb.M_G, pb.G_L, max_batch=B)
-        out = {k: np.full((B, pb.m if k in ("y_next", "y", "w") else pb.n), np.nan, np.float32) for k in VECS}
-        iters = np.zeros(B, np.int32); status = np.full(B, -1, np.int32)
-        grp.solve(G.host_args(B, theta, beta, 25, g_P=g_P, p_D=p_D, outputs=out, iters=iters, status=status))
-        spans = [grp.shard(i, B) for i in range(len(devices))]
-        assert sum(c for _, c in spans) == B and spans[0][0] == 0
-        grp.close()
-        assert (iters == 25).all() and (status == 0).all()
-        res.append(out)
-    for other in res[1:]:
+    for prec in (G.PREC_TF32X3, G.PREC_FP16X3):
+        res = []
+        for devices in ([0], [0, 0], [0, 0, 0]):
+            grp = G.Group(devices, 4, N, pb.m, pb.L, pb.M_G, pb.G_L, precision=prec, max_batch=B)
+            out = {k: np.full((B, pb.m if k in ("y_next", "y", "w") else pb.n), np.nan, np.float32) for k in VECS}
+            iters = np.zeros(B, np.int32); status = np.full(B, -1, np.int32)
+            grp.solve(G.host_args(B, theta, beta, 25, g_P=g_P, p_D=p_D, outputs=out, iters=iters, status=status))
+            spans = [grp.shard(i, B) for i in range(len(devices))]
+            assert sum(c for _, c in spans) == B and spans[0][0] == 0
+            grp.close()
+            assert (iters == 25).all() and (status == 0).all()
+            res.append(out)
+        for other in res[1:]:
+            for k in VECS:
+                assert np.array_equal(res[0][k], other[k]), (prec, k)
+        # and equal to the plain single handle
+        s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=prec, max_batch=B)
+        one = s.solve_host(g_P, p_D, theta, beta)
+        s.close()
         for k in VECS:
-            assert np.array_equal(res[0][k], other[k]), k
-    # and equal to the plain single handle
-    s = G.Solver(4, N, pb.m, pb.L, pb.M_G, pb.G_L, mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3, max_batch=B)
-    one = s.solve_host(g_P, p_D, theta, beta)
-    s.close()
-    for k in VECS:
-        assert np.array_equal(res[0][k], one[k]), k
+            assert np.array_equal(res[0][k], one[k]), (prec, k)
     # per-instance operators are sharded with their instances
     n_u, Nb, Bp = 3, 4, 300
     rng = np.random.default_rng(52)
