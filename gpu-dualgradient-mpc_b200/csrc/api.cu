@@ -283,13 +283,23 @@ int setup_latency(gpad_handle_s* h, const std::vector<float>& MG, const std::vec
     GPAD_TRY(upload_padded(h, GL.data(), m, n, m, p.nld, &dGL));
     p.M_G = dMG; p.G_L = dGL;
 
-    // per-solve device buffers
-    GPAD_TRY(dev_alloc(h, &h->d_gP, n)); GPAD_TRY(dev_alloc(h, &h->d_pD, m)); GPAD_TRY(dev_alloc(h, &h->d_f, n));
-    GPAD_TRY(dev_alloc(h, &h->d_y0, m)); GPAD_TRY(dev_alloc(h, &h->d_yprev0, m));
-    GPAD_TRY(dev_alloc(h, &h->o_ynext, m)); GPAD_TRY(dev_alloc(h, &h->o_y, m)); GPAD_TRY(dev_alloc(h, &h->o_w, m));
-    GPAD_TRY(dev_alloc(h, &h->o_z, n)); GPAD_TRY(dev_alloc(h, &h->o_zhat, n));
-    GPAD_TRY(dev_alloc(h, &h->o_iters, 1)); GPAD_TRY(dev_alloc(h, &h->o_status, 1));
-    GPAD_TRY(dev_alloc(h, &h->o_viol, 1)); GPAD_TRY(dev_alloc(h, &h->o_gap, 1));
+    // per-solve device buffers: ONE input block [g_P | p_D | y0 | y_prev0 | f] and ONE output block [y_next | y | w | z | zhat |
+    // iters, status, max_viol, gap] (sub-arrays on 16-byte boundaries), each mirrored by a pinned host block, so that a
+    // host-memory solve costs one H2D and one D2H copy instead of up to five and nine (main.cu:136-147, 176-180 copy vector by
+    // vector; on a 35 us solve those copies were 110 us)
+    {
+        const size_t na = round_up_sz(n, 4), ma = round_up_sz(m, 4);
+        h->lat_in_floats = 2 * na + 3 * ma;
+        h->lat_out_floats = 3 * ma + 2 * na + 4;
+        float *din = nullptr, *dout = nullptr;
+        GPAD_TRY(dev_alloc(h, &din, h->lat_in_floats)); GPAD_TRY(dev_alloc(h, &dout, h->lat_out_floats));
+        h->d_gP = din; h->d_pD = din + na; h->d_y0 = h->d_pD + ma; h->d_yprev0 = h->d_y0 + ma; h->d_f = h->d_yprev0 + ma;
+        h->o_ynext = dout; h->o_y = dout + ma; h->o_w = h->o_y + ma; h->o_z = h->o_w + ma; h->o_zhat = h->o_z + na;
+        float* tail = h->o_zhat + na;
+        h->o_iters = reinterpret_cast<int*>(tail); h->o_status = reinterpret_cast<int*>(tail + 1); h->o_viol = tail + 2; h->o_gap = tail + 3;
+        GPAD_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->lat_h_in), sizeof(float) * h->lat_in_floats));
+        GPAD_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->lat_h_out), sizeof(float) * h->lat_out_floats));
+    }
     GPAD_TRY(dev_alloc(h, &p.x_w, p.mld)); GPAD_TRY(dev_alloc(h, &p.x_zhat, p.nld));
     GPAD_CUDA(cudaMemset(p.x_w, 0, sizeof(float) * p.mld));          // the zero padding is gathered too
     GPAD_CUDA(cudaMemset(p.x_zhat, 0, sizeof(float) * p.nld));
@@ -376,11 +386,16 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
     GPAD_TRY(upload_schedule(h, a->theta, a->beta, a->max_iter, s));
     lat::Params p = h->lp;
     if (host) {
-        GPAD_CUDA(cudaMemcpyAsync(h->d_gP, a->g_P, sizeof(float) * n, cudaMemcpyHostToDevice, s));
-        GPAD_CUDA(cudaMemcpyAsync(h->d_pD, a->p_D, sizeof(float) * m, cudaMemcpyHostToDevice, s));
-        if (a->f) GPAD_CUDA(cudaMemcpyAsync(h->d_f, a->f, sizeof(float) * n, cudaMemcpyHostToDevice, s));
-        if (a->y0) GPAD_CUDA(cudaMemcpyAsync(h->d_y0, a->y0, sizeof(float) * m, cudaMemcpyHostToDevice, s));
-        if (a->y_prev0) GPAD_CUDA(cudaMemcpyAsync(h->d_yprev0, a->y_prev0, sizeof(float) * m, cudaMemcpyHostToDevice, s));
+        // gather the inputs that exist into the pinned mirror of the device block, one copy of its used prefix
+        // (block order: g_P, p_D, y0, y_prev0, f -- the optional ones last)
+        float* hi = h->lat_h_in;
+        memcpy(hi + (h->d_gP - h->d_gP), a->g_P, sizeof(float) * n);
+        memcpy(hi + (h->d_pD - h->d_gP), a->p_D, sizeof(float) * m);
+        size_t used = (size_t)(h->d_y0 - h->d_gP);
+        if (a->y0) { memcpy(hi + (h->d_y0 - h->d_gP), a->y0, sizeof(float) * m); used = (size_t)(h->d_yprev0 - h->d_gP); }
+        if (a->y_prev0) { memcpy(hi + (h->d_yprev0 - h->d_gP), a->y_prev0, sizeof(float) * m); used = (size_t)(h->d_f - h->d_gP); }
+        if (a->f) { memcpy(hi + (h->d_f - h->d_gP), a->f, sizeof(float) * n); used = h->lat_in_floats; }
+        GPAD_CUDA(cudaMemcpyAsync(h->d_gP, hi, sizeof(float) * used, cudaMemcpyHostToDevice, s));
         p.g_P = h->d_gP; p.p_D = h->d_pD; p.f = a->f ? h->d_f : nullptr;
         p.y0 = a->y0 ? h->d_y0 : nullptr; p.y_prev0 = a->y_prev0 ? h->d_yprev0 : nullptr;
     } else {
@@ -425,19 +440,22 @@ int solve_latency(gpad_handle_s* h, const gpad_solve_args_t* a) {
     }
     h->prof_end(0, pe, s);
     h->launches += 1;
-    if (host) {
-        if (a->y_next) GPAD_CUDA(cudaMemcpyAsync(a->y_next, h->o_ynext, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
-        if (a->y) GPAD_CUDA(cudaMemcpyAsync(a->y, h->o_y, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
-        if (a->w) GPAD_CUDA(cudaMemcpyAsync(a->w, h->o_w, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
-        if (a->z) GPAD_CUDA(cudaMemcpyAsync(a->z, h->o_z, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
-        if (a->zhat) GPAD_CUDA(cudaMemcpyAsync(a->zhat, h->o_zhat, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
-        if (a->iters) GPAD_CUDA(cudaMemcpyAsync(a->iters, h->o_iters, sizeof(int), cudaMemcpyDeviceToHost, s));
-        if (a->status) GPAD_CUDA(cudaMemcpyAsync(a->status, h->o_status, sizeof(int), cudaMemcpyDeviceToHost, s));
-        if (a->max_viol) GPAD_CUDA(cudaMemcpyAsync(a->max_viol, h->o_viol, sizeof(float), cudaMemcpyDeviceToHost, s));
-        if (a->gap) GPAD_CUDA(cudaMemcpyAsync(a->gap, h->o_gap, sizeof(float), cudaMemcpyDeviceToHost, s));
-    }
+    if (host) GPAD_CUDA(cudaMemcpyAsync(h->lat_h_out, h->o_ynext, sizeof(float) * h->lat_out_floats, cudaMemcpyDeviceToHost, s));
     GPAD_TRY(solve_end(h, s));
-    if (host) GPAD_CUDA(cudaStreamSynchronize(s));
+    if (host) {
+        GPAD_CUDA(cudaStreamSynchronize(s));
+        const float* ho = h->lat_h_out;
+        if (a->y_next) memcpy(a->y_next, ho + (h->o_ynext - h->o_ynext), sizeof(float) * m);
+        if (a->y) memcpy(a->y, ho + (h->o_y - h->o_ynext), sizeof(float) * m);
+        if (a->w) memcpy(a->w, ho + (h->o_w - h->o_ynext), sizeof(float) * m);
+        if (a->z) memcpy(a->z, ho + (h->o_z - h->o_ynext), sizeof(float) * n);
+        if (a->zhat) memcpy(a->zhat, ho + (h->o_zhat - h->o_ynext), sizeof(float) * n);
+        const float* tail = ho + (h->o_viol - 2 - h->o_ynext);
+        if (a->iters) memcpy(a->iters, tail, sizeof(int));
+        if (a->status) memcpy(a->status, tail + 1, sizeof(int));
+        if (a->max_viol) *a->max_viol = tail[2];
+        if (a->gap) *a->gap = tail[3];
+    }
     return GPAD_OK;
 }
 
@@ -717,6 +735,8 @@ int gpad_destroy(gpad_handle_t h) {
         for (auto& pr : h->ev_used[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     destroy_batch(h);
+    if (h->lat_h_in) cudaFreeHost(h->lat_h_in);
+    if (h->lat_h_out) cudaFreeHost(h->lat_h_out);
     if (h->ev_last) cudaEventDestroy(h->ev_last);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->stream_in) cudaStreamDestroy(h->stream_in);

@@ -103,6 +103,8 @@ struct gpad_handle_s {
     int *o_iters = nullptr, *o_status = nullptr;
     float *o_viol = nullptr, *o_gap = nullptr;
     unsigned* d_flags = nullptr;              // [0] barrier counter, [1] nonfinite flag
+    float *lat_h_in = nullptr, *lat_h_out = nullptr;   // pinned mirrors of the input block (d_gP ...) and the output block (o_ynext ...)
+    size_t lat_in_floats = 0, lat_out_floats = 0;
 
     // ---- per-instance mode ----
     float *pi_gP = nullptr, *pi_pD = nullptr, *pi_f = nullptr, *pi_y0 = nullptr, *pi_yprev0 = nullptr;   // host-mode staging
