@@ -60,6 +60,7 @@ Knobs parse_knobs() {
         else if (key == "tc_bn2") k.tc_bn2 = iv;
         else if (key == "tc_autotune") k.tc_autotune = iv;
         else if (key == "tc_pdl") k.tc_pdl = iv;
+        else if (key == "sync_split") k.sync_split = iv;
         else if (key == "tc_cluster_attr") k.tc_cluster_attr = iv;
         else if (key == "tc_retire") k.tc_retire = iv;
         else if (key == "tc_compact") k.tc_compact = iv;

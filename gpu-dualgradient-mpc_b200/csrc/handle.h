@@ -33,6 +33,7 @@ struct Knobs {
     int tc_retire = 1;               // tolerance mode: skip batch tiles whose instances have all stopped
     int tc_compact = 1;              // tolerance mode: gather the running instances into dense tiles (needs tc_retire)
     int check_lag = 4;               // tolerance mode: checks the host may run ahead of the device
+    int sync_split = 1;              // synchronous host-memory solves of >= 16K instances run as two pipelined halves
 };
 Knobs parse_knobs();
 

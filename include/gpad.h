@@ -173,7 +173,11 @@ typedef struct {
     int reserved[3];        /* must be zero                                                    */
 } gpad_solve_args_t;
 
-/* GPAD_MEM_HOST: copies in, solves, copies out and synchronises before returning.
+/* GPAD_MEM_HOST: copies in, solves, copies out and synchronises before returning.  In GPAD_MODE_BATCH_SHARED a
+ * fixed-iteration solve of >= 16384 instances on the tensor-core precisions runs as two halves over the
+ * double-buffered path of gpad_solve_async (the second half's inputs arrive and the first half's results leave under
+ * the other half's iterations); results are those of the single solve bit for bit, and the handle holds a second set of
+ * batch state from the first such call on.
  * GPAD_MEM_DEVICE: enqueues everything on args->stream and returns without synchronising
  * (in tolerance mode the host follows the device's stop decisions a few checks behind; stopped
  * instances are frozen, so the extra iterations it may enqueue change nothing). */
@@ -207,7 +211,8 @@ int gpad_solve_stats(gpad_handle_t h, gpad_solve_stats_t* out);
 
 /* Optional per-kernel device timing: when enabled, every hot-path kernel launch of this handle is
  * bracketed by CUDA events on the launching stream (bench.py's roofline figure).
- * which: 0 = latency persistent kernel, 1 = product-1 kernel, 2 = product-2 kernel.
+ * which: 0 = latency persistent kernel (GPAD_PREC_FP16X3 batch handles: the zhat row-quantisation kernel between
+ * the products), 1 = product-1 kernel, 2 = product-2 kernel.
  * gpad_profile_read synchronises, returns the accumulated milliseconds and launch count since the
  * last read, and resets them. */
 int gpad_profile_enable(gpad_handle_t h, int enable);

@@ -405,3 +405,38 @@ def test_flat_layout_input_and_automatic_detection(torch_cuda, G, oracle, monkey
     s = G.Solver(10, 100, big.m, big.L, bMf, bGf, layout=G.LAYOUT_FLAT, mode=G.MODE_LATENCY)
     assert "column-partitioned" in s.description, s.description
     s.close()
+
+
+@pytest.mark.parametrize("prec", ["tf32x3", "fp16x3"])
+def test_big_synchronous_host_solve_runs_as_two_halves(torch_cuda, G, prec, monkeypatch):
+    """gpad_solve with host buffers and >= 16K instances runs as two pipelined halves over the double-buffered path
+    (api_batch.cu:solve_batch): every output -- cold start, warm start and the on-device instance build from parameters --
+    is bit-identical to the single serial solve (GPAD_DEBUG sync_split=0), ragged batch included"""
+    N, B = 10, 16384 + 777
+    code = {"tf32x3": G.PREC_TF32X3, "fp16x3": G.PREC_FP16X3}[prec]
+    prob = G.Problem("quadrotor", N=N)
+    M_G, G_L = prob.operators()
+    par = P.quadrotor_params(B, np.random.default_rng(61))
+    g_P, p_D, _ = prob.instances(par, want_f=False)
+    theta, beta = schedule(12)
+    runs = {}
+    for name, knobs in (("split", ""), ("serial", "sync_split=0")):
+        if knobs:
+            monkeypatch.setenv("GPAD_DEBUG", knobs)
+        else:
+            monkeypatch.delenv("GPAD_DEBUG", raising=False)
+        s = G.Solver(4, N, prob.m, prob.L, M_G, G_L, mode=G.MODE_BATCH_SHARED, precision=code, max_batch=B)
+        cold = s.solve_host(g_P, p_D, theta, beta)
+        warm = s.solve_host(g_P, p_D, theta, beta, y0=cold["y_next"], y_prev0=cold["y"])
+        built = s.solve_host(None, None, theta, beta, params=par, problem=prob)
+        small = s.solve_host(g_P[:300], p_D[:300], theta, beta)          # below the threshold: the plain path on the same handle
+        runs[name] = (cold, warm, built, small)
+        s.close()
+    for a, b in zip(runs["split"], runs["serial"]):
+        for k in list(VECS) + ["iters", "status"]:
+            assert np.array_equal(a[k], b[k]), k
+    cold, _, built, small = runs["split"]
+    assert (cold["iters"] == 12).all() and (cold["status"] == 0).all()
+    for k in VECS:
+        assert np.array_equal(cold[k], built[k]), k                      # device-built instances are bit-identical to the host build
+        assert np.array_equal(cold[k][:300], small[k]), k
