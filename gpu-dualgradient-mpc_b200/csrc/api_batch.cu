@@ -494,8 +494,7 @@ int setup_batch(gpad_handle_s* h, const std::vector<float>& MG, const std::vecto
         g.bn = b; g.n_tiles = (m + b - 1) / b;
         g.stages = cap_stages(tc::pick_stages(bk, b, h->smem_optin));
         if (half && g.p2) {
-            GPAD_TRY(tc::plan_rings_p2(b, h->smem_optin, &g.stages, &g.e_stages));
-            g.stages = cap_stages(g.stages);
+            GPAD_TRY(tc::plan_rings_p2(b, h->smem_optin, &g.stages, &g.e_stages, kn.tc_stages));
         }
         if (half) {
             GPAD_TRY(tc::make_tmap_bytes(&g.tmB_hi, h->op.G_Lq_hi, 2, np, h->op.m_rows_pad, np, 32, b));

@@ -46,7 +46,7 @@ int launch_quantize_rows(const float* src, int ld, int rows, uint16_t* hi, uint1
 int launch_rowmax(const float* src, int ld, int rows, float* rowmax, cudaStream_t s);
 int launch_p1(const GemmDesc& g, const BatchKernelArgs& args, int num_sms, cudaStream_t s);
 void plan_tiles_p2(int ncols, int* bn, int* n_tiles);
-int plan_rings_p2(int bn, size_t smem_limit, int* stages, int* e_stages);
+int plan_rings_p2(int bn, size_t smem_limit, int* stages, int* e_stages, int max_stages = 0);
 int launch_p2(const GemmDesc& g, const BatchKernelArgs& args, int cur, int prev, int next, int num_sms, cudaStream_t s);
 int launch_split(const float* src, float* hi, float* lo, size_t count, cudaStream_t s);
 

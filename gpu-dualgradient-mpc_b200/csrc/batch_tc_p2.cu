@@ -277,11 +277,12 @@ void plan_tiles_p2(int ncols, int* bn, int* n_tiles) {
     *n_tiles = (ncols + *bn - 1) / *bn;
 }
 
-int plan_rings_p2(int bn, size_t smem_limit, int* stages, int* e_stages) {
+int plan_rings_p2(int bn, size_t smem_limit, int* stages, int* e_stages, int max_stages) {
     int e = 2, s = 6;
     while (s > 2 && p2_smem_bytes(bn, s, e) > smem_limit) --s;
     if (p2_smem_bytes(bn, s, e) > smem_limit) return GPAD_ERR_UNSUPPORTED;
     if (s > 4) s = 4;
+    if (max_stages >= 2 && s > max_stages) s = max_stages;
     while (e < 4 && p2_smem_bytes(bn, s, e + 1) <= smem_limit) ++e;      // spare shared memory deepens the HBM-facing ring
     *stages = s; *e_stages = e;
     return GPAD_OK;
