@@ -741,6 +741,27 @@ def run_ours(args):
                 "traffic": traffic, "kernel": "simt_gemm_kernel (CUDA-core FFMA)", "peak_basis": "148 SMs x 128 FMA/clk x 1.965 GHz (nominal fp32)"}
 
     psample = parity_sample(solver, prob, pb, params, d_out, theta, beta, B)
+    # the other tensor-core family on the same box, same inputs (a tolerance-mode solve of this handle runs its kernels):
+    # device-resident steps only, for the comparison of DESIGN.md section 4.1d
+    alt = None
+    if world == 1 and prec == G.PREC_FP16X3 and not args.no_latency:
+        s2 = G.Solver(prob.n_u, prob.N, m, prob.L, pb["M_G"], pb["G_L"], mode=G.MODE_BATCH_SHARED, precision=G.PREC_TF32X3,
+                      max_batch=B, device=local)
+        d_z2 = torch.empty((B, n), device="cuda")
+        for _ in range(2):
+            s2.solve_device(B, d_gP, d_pD, theta, beta, ITERS, stream=st, z=d_z2)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(5):
+            s2.solve_device(B, d_gP, d_pD, theta, beta, ITERS, stream=st, z=d_z2)
+        a1.record(stream); a1.synchronize()
+        ms_alt = a0.elapsed_time(a1) / 5
+        dz = (d_z2 - d_out["z"]).abs().max().item() / d_out["z"].abs().max().item()
+        alt = {"precision": "tf32x3", "value": B / (ms_alt * 1e-3), "unit": UNIT, "ms_per_step": ms_alt, "steps": 5,
+               "z_rel_inf_vs_fp16x3": dz, "path": s2.description}
+        s2.close()
+        del d_z2
     tol = tolerance_probe(torch, G, prob, pb, solver, d_par, B) if (not args.no_latency and prec != G.PREC_FP32) else None
     solver.close()
     cpu_val, cpu_info = cpu_rate(args.cpu_budget)
@@ -768,6 +789,7 @@ def run_ours(args):
         "cpu_baseline": dict(value=cpu_val, unit=UNIT, **cpu_info),
         "clocks": clocks,
         "parity_sample": psample,
+        "same_box_tf32x3": alt,
         "quadrotor_64k_eps1e-3": tol,
         "strong_scaling": strong,
         "single_qp_latency": lat,
