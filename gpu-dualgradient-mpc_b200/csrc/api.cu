@@ -931,12 +931,18 @@ int gpad_debug_gemm_f16x3(const float* A, const float* B, float* C, int M, int N
     g.ncols_valid = N;
     const int Mp = g.m_tiles * 128, Np = round_up(g.bn * g.n_tiles, 128);
     const size_t ca = (size_t)Mp * g.k_pad, cb = (size_t)Np * g.k_pad;
-    float *Ap = nullptr, *Bp = nullptr, *ainv = nullptr, *binv = nullptr, *amax = nullptr;
-    uint16_t *Ah = nullptr, *Al = nullptr, *Bh = nullptr, *Bl = nullptr;
-    GPAD_CUDA(cudaMalloc(&Ap, ca * 4)); GPAD_CUDA(cudaMalloc(&Bp, cb * 4));
-    GPAD_CUDA(cudaMalloc(&Ah, ca * 2)); GPAD_CUDA(cudaMalloc(&Al, ca * 2));
-    GPAD_CUDA(cudaMalloc(&Bh, cb * 2)); GPAD_CUDA(cudaMalloc(&Bl, cb * 2));
-    GPAD_CUDA(cudaMalloc(&ainv, Mp * 4)); GPAD_CUDA(cudaMalloc(&amax, Mp * 4)); GPAD_CUDA(cudaMalloc(&binv, Np * 4));
+    // one scratch allocation, carved up (256-byte aligned pieces): nothing to leak on an early error
+    auto piece = [](size_t bytes) { return round_up_sz(bytes, 256); };
+    const size_t total = piece(ca * 4) + piece(cb * 4) + 2 * piece(ca * 2) + 2 * piece(cb * 2) + 2 * piece((size_t)Mp * 4) + piece((size_t)Np * 4);
+    char* scratch = nullptr;
+    GPAD_CUDA(cudaMalloc(&scratch, total));
+    char* cur = scratch;
+    auto take = [&](size_t bytes) { char* p = cur; cur += piece(bytes); return p; };
+    float* Ap = reinterpret_cast<float*>(take(ca * 4)); float* Bp = reinterpret_cast<float*>(take(cb * 4));
+    uint16_t* Ah = reinterpret_cast<uint16_t*>(take(ca * 2)); uint16_t* Al = reinterpret_cast<uint16_t*>(take(ca * 2));
+    uint16_t* Bh = reinterpret_cast<uint16_t*>(take(cb * 2)); uint16_t* Bl = reinterpret_cast<uint16_t*>(take(cb * 2));
+    float* ainv = reinterpret_cast<float*>(take((size_t)Mp * 4)); float* amax = reinterpret_cast<float*>(take((size_t)Mp * 4));
+    float* binv = reinterpret_cast<float*>(take((size_t)Np * 4));
     int rc = GPAD_OK;
     do {
         if ((rc = launch_pad_rows(Ap, g.k_pad, Mp, A, K, M, s)) != GPAD_OK) break;
@@ -965,7 +971,7 @@ int gpad_debug_gemm_f16x3(const float* A, const float* B, float* C, int M, int N
         }
     } while (0);
     cudaError_t e = cudaStreamSynchronize(s);
-    cudaFree(Ap); cudaFree(Bp); cudaFree(Ah); cudaFree(Al); cudaFree(Bh); cudaFree(Bl); cudaFree(ainv); cudaFree(amax); cudaFree(binv);
+    cudaFree(scratch);
     if (rc == GPAD_OK && e != cudaSuccess) return cuda_fail(e, "gpad_debug_gemm_f16x3", __FILE__, __LINE__);
     return rc;
 }
