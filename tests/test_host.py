@@ -316,3 +316,65 @@ def test_lipschitz_constant_is_selectable():
     quad = G.Problem("quadrotor", N=10)
     Lq = quad.L
     assert abs(quad.set_lipschitz(G.L_LAMBDA_MAX) - Lq) <= 1e-6 * Lq        # the quadrotor default already is the paper's
+
+
+def test_fp16x3_split_numerics_emulated():
+    """GPAD_PREC_FP16X3 in numpy (csrc/tc_ptx.cuh:f16_scale_exp / split_f16x2, csrc/batch_f16.cu): every row is scaled by
+    the power of two that brings its largest magnitude into [2^14, 2^15), split into fp16 hi + lo, and the product of two
+    such operands is hi*lo + lo*hi + hi*hi accumulated in fp32.  Checked here without a GPU: (a) the scale is exact and
+    puts the row maximum where claimed; (b) hi + lo reproduces entries within 2^-18 of the row maximum to 22 bits and
+    smaller ones to 2^-40 of the row maximum; (c) the three-term product of wide-range rows is as close to the exact
+    product as the same construction with tf32 (10 explicit mantissa bits, fp32 exponent range) operands"""
+    rng = np.random.default_rng(5)
+
+    def scale_exp(row_max):
+        e = np.zeros(row_max.shape, np.int64)
+        ok = (row_max > 0) & np.isfinite(row_max)
+        ex = np.floor(np.log2(row_max[ok])).astype(np.int64)
+        e[ok] = np.clip(14 - ex, -100, 100)
+        return e
+
+    def split_f16(x):
+        e = scale_exp(np.abs(x).max(axis=1))
+        xs = (x.astype(np.float64) * 2.0 ** e[:, None]).astype(np.float32)      # power of two: exact in fp32
+        hi = xs.astype(np.float16)
+        lo = (xs - hi.astype(np.float32)).astype(np.float16)                  # the remainder is exact in fp32
+        return hi, lo, e, xs
+
+    def rn_tf32(x):
+        b = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+        b = (b + 0x1000) & 0xFFFFE000                                          # round to nearest (ties away), 10 mantissa bits
+        return b.astype(np.uint32).view(np.float32)
+
+    M, N, K = 40, 24, 512
+    A = (rng.standard_normal((M, K)) * 10.0 ** rng.uniform(-6, 6, (M, 1)) * 10.0 ** rng.uniform(-3, 0, (M, K))).astype(np.float32)
+    A[rng.random((M, K)) < 0.3] = 0.0
+    A[7] = 0.0
+    B = (rng.standard_normal((N, K)) * 10.0 ** rng.uniform(-5, 3, (N, 1))).astype(np.float32)
+    ah, al, ea, axs = split_f16(A)
+    bh, bl, eb, _ = split_f16(B)
+    # (a)
+    amax = np.abs(axs).max(axis=1)
+    nz = amax > 0
+    assert (amax[nz] >= 2.0 ** 14).all() and (amax[nz] < 2.0 ** 15).all() and ea[7] == 0
+    assert np.array_equal((axs.astype(np.float64) * 2.0 ** (-ea[:, None])).astype(np.float32), A)      # undoing the scale is exact
+    assert np.isfinite(ah.astype(np.float32)).all() and np.isfinite(al.astype(np.float32)).all()
+    # (b)
+    rec = ah.astype(np.float64) + al.astype(np.float64)
+    err = np.abs(rec - axs.astype(np.float64))
+    big = np.abs(axs) >= 2.0 ** -3
+    assert (err[big] <= 2.0 ** -22 * np.abs(axs[big])).all()
+    assert (err[~big] <= 2.0 ** -25).all()                                     # half an fp16 subnormal step = 2^-40 of 2^15
+    # (c)
+    def three_products(xh, xl, yh, yl):
+        f = lambda v: v.astype(np.float32).astype(np.float64)
+        return (f(xh) @ f(yl).T + f(xl) @ f(yh).T + f(xh) @ f(yh).T)
+    c16 = three_products(ah, al, bh, bl) * 2.0 ** (-ea[:, None]) * 2.0 ** (-eb[None, :])
+    th = rn_tf32(A); tl = rn_tf32(A - th); uh = rn_tf32(B); ul = rn_tf32(B - uh)
+    c32 = three_products(th, tl, uh, ul)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T
+    scale[scale == 0] = 1.0
+    e16, e32 = np.max(np.abs(c16 - ref) / scale), np.max(np.abs(c32 - ref) / scale)
+    assert e16 <= 3 * 2.0 ** -22 and e16 <= 1.5 * e32 + 1e-8, (e16, e32)
+    assert (c16[7] == 0).all()
