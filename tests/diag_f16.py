@@ -66,7 +66,7 @@ if "time" in sections:
     st = torch.cuda.current_stream().cuda_stream
     outs = {}
     variants = [("tf32x3", G.PREC_TF32X3, ""), ("fp16x3", G.PREC_FP16X3, "")] + \
-        [("fp16x3 " + k, G.PREC_FP16X3, k) for k in os.environ.get("DIAG_KNOBS", "tc_p2=0").split(";") if k]
+        [("fp16x3 " + k, G.PREC_FP16X3, k) for k in os.environ.get("DIAG_KNOBS", "tc_pdl=1").split(";") if k]
     for name, code, knobs in variants:
         if knobs:
             os.environ["GPAD_DEBUG"] = knobs
